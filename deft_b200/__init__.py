@@ -1,0 +1,19 @@
+"""deft_b200 -- B200-native (sm_100a) tree-attention decode for DeFT.
+
+Only what the tree-attention path needs lives here:
+
+* ``csrc/``        hand-written CUDA kernels + the C ABI (``include/deft_b200.h``) -> ``lib/libdeft_b200.so``
+* ``attention``    ``tree_attention_fwd`` / ``tree_attention_subtree_fwd`` with the reference's signatures
+* ``tree_cache``   ``TreeCache`` / ``TreeMetadata`` mirror (host bookkeeping, C++ table builder)
+* ``memory_pool``  paged KV pool with the reference's layout and allocation order
+* ``install``      rebinding of the reference's operator names to this package (drop-in)
+
+Importing the package loads the shared library and fails loudly if it is missing.
+"""
+from . import _lib  # noqa: F401  (raises ImportError when libdeft_b200.so is absent)
+from .attention import kv_append, tree_attention_fwd, tree_attention_subtree_fwd  # noqa: F401
+from .memory_pool import ReqToTokenPool, TokenToKVPool, TreeIndexPool  # noqa: F401
+from .tree_cache import (BLOCK_CONFIG, KVCacheUpdater, TreeCache, TreeMetadata, TreeNode,  # noqa: F401
+                         get_global_tree_metadata, register_tree_metadata, unregister_tree_metadata)
+
+__version__ = "0.1.0"

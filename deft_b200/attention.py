@@ -1,0 +1,129 @@
+"""The tree-attention operators, with the reference's Python signatures.
+
+``tree_attention_fwd`` (DeFT-Node / Node-Chunk / Tree-Index) and ``tree_attention_subtree_fwd``
+(DeFT-Flatten) keep the positional signatures of ``deft/layers/attention/tree_attention.py:14-25``
+and ``:552-568`` so that ``DeFTAttention.deft_node_forward`` / ``deft_flatten_forward``
+(``deft_attention.py:94-105, 136-148``) can call them unchanged.  Each call is a thin shim over the
+C ABI (``deft_b200_node_fwd`` / ``deft_b200_flatten_fwd``): it passes raw device pointers, strides
+and the current CUDA stream.  There is no PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Plan
+
+_SUPPORTED_HEAD_DIMS = (32, 64, 128)
+_WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(device: torch.device, stream: int, nbytes: int) -> torch.Tensor:
+    """Per (device, stream) scratch for the partial-softmax buffers; grows, never shrinks.
+
+    Calls on one stream are ordered, so reusing the buffer between calls is race-free (the
+    reference allocates and zero-fills its partial buffers on every call).
+    """
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _check_qkvo(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor) -> Tuple[int, int, int, int]:
+    if not (q.is_cuda and k.is_cuda and v.is_cuda and o.is_cuda):
+        raise _lib.DeftError("deft_b200 tree attention needs CUDA tensors (there is no CPU fallback)")
+    assert q.dtype == torch.float16 and k.dtype == torch.float16 and v.dtype == torch.float16 and o.dtype == torch.float16
+    nq, H, D = q.shape
+    HKV = k.shape[1]
+    assert D in _SUPPORTED_HEAD_DIMS, f"head_dim {D} not in {_SUPPORTED_HEAD_DIMS}"
+    assert k.shape[2] == D and v.shape == k.shape and tuple(o.shape) == (nq, H, D) and H % HKV == 0
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1 and o.stride(2) == 1
+    assert k.stride() == v.stride(), "K and V views must share one layout (kv_data[layer][:, 0] / [:, 1])"
+    return nq, H, HKV, D
+
+
+def _i64(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.int64 and t.is_cuda
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, value_buffer: torch.Tensor,
+                               output: torch.Tensor, block_len: int, block_q: torch.Tensor,
+                               block_q_cnts: torch.Tensor, block_q_offset: torch.Tensor,
+                               block_bitmasks: torch.Tensor, block_kv: torch.Tensor, block_lens: torch.Tensor,
+                               plan: Optional[Plan] = None) -> None:
+    """DeFT-Flatten attention; writes ``output`` in place (tree_attention.py:552-667)."""
+    from .tree_cache import lookup_plan
+    nq, H, HKV, D = _check_qkvo(query_states, key_buffer, value_buffer, output)
+    block_q, block_q_cnts, block_q_offset = _i64(block_q), _i64(block_q_cnts), _i64(block_q_offset)
+    block_bitmasks, block_kv, block_lens = _i64(block_bitmasks), _i64(block_kv), _i64(block_lens)
+    n_partials, n_blocks = block_q.numel(), block_q_cnts.numel()
+    if plan is None:
+        meta = lookup_plan(block_q)
+        if meta is not None and meta.flat_plan is not None and meta.block_kv.data_ptr() == block_kv.data_ptr():
+            plan = meta.flat_plan
+    stream = torch.cuda.current_stream(query_states.device).cuda_stream
+    need = _lib.lib.deft_b200_flatten_workspace_bytes(nq, H, D, n_partials, n_blocks)
+    ws = _workspace(query_states.device, stream, need)
+    _lib.check(_lib.lib.deft_b200_flatten_fwd(
+        query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
+        key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1),
+        output.data_ptr(), output.stride(0), output.stride(1), nq, H, HKV, D, int(block_len),
+        block_q.data_ptr(), n_partials, block_q_cnts.data_ptr(), block_q_offset.data_ptr(), block_lens.data_ptr(),
+        n_blocks, block_bitmasks.data_ptr(), block_kv.data_ptr(),
+        C.byref(plan) if plan is not None else None, ws.data_ptr(), ws.numel(), stream))
+
+
+def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, value_buffer: torch.Tensor,
+                       output: torch.Tensor, KV_indices: torch.Tensor, KV_indices_offset: torch.Tensor,
+                       KV_len: torch.Tensor, KVMapQ_List: torch.Tensor, KVMapQ_List_Offset: torch.Tensor,
+                       KVMapQ_List_Len: torch.Tensor, plan: Optional[Plan] = None) -> None:
+    """DeFT-Node / Node-Chunk / Tree-Index attention; writes ``output`` in place (tree_attention.py:14-68)."""
+    from .tree_cache import lookup_plan
+    nq, H, HKV, D = _check_qkvo(query_states, key_buffer, value_buffer, output)
+    assert KV_indices.is_cuda and KV_indices.dtype in (torch.int64, torch.int32)
+    KV_indices = KV_indices if KV_indices.is_contiguous() else KV_indices.contiguous()
+    kv_off, kv_len = _i64(KV_indices_offset), _i64(KV_len)
+    node_q, q_off, q_len = _i64(KVMapQ_List), _i64(KVMapQ_List_Offset), _i64(KVMapQ_List_Len)
+    n_partials, n_entries = node_q.numel(), kv_off.numel()
+    # int64 node_kv holds exactly sum(kv_len) pages, which bounds the split of long entries; the int32
+    # tree-index table gives no such bound, and its entries are <= 128 tokens anyway -> no split
+    total_kv_bound = KV_indices.numel() if KV_indices.dtype == torch.int64 else 0
+    if plan is None:
+        meta = lookup_plan(node_q)
+        if meta is not None and meta.node_plan is not None and meta.node_kv.data_ptr() == KV_indices.data_ptr():
+            plan = meta.node_plan
+    stream = torch.cuda.current_stream(query_states.device).cuda_stream
+    need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, D, n_partials, n_entries, total_kv_bound)
+    ws = _workspace(query_states.device, stream, need)
+    _lib.check(_lib.lib.deft_b200_node_fwd(
+        query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
+        key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1),
+        output.data_ptr(), output.stride(0), output.stride(1), nq, H, HKV, D,
+        KV_indices.data_ptr(), KV_indices.element_size(), kv_off.data_ptr(), kv_len.data_ptr(), node_q.data_ptr(),
+        n_partials, q_off.data_ptr(), q_len.data_ptr(), n_entries, total_kv_bound,
+        C.byref(plan) if plan is not None else None, ws.data_ptr(), ws.numel(), stream))
+
+
+def kv_append(kv_layer: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, cache_loc: torch.Tensor) -> None:
+    """``key_buffer[cache_loc] = cache_k; value_buffer[cache_loc] = cache_v`` in one launch.
+
+    ``kv_layer`` is ``TokenToKVPool.kv_data[layer]`` ``[size, 2, HKV, D]`` (tree_cache.py:67-76).
+    """
+    if not (kv_layer.is_cuda and cache_k.is_cuda and cache_v.is_cuda and cache_loc.is_cuda):
+        raise _lib.DeftError("kv_append needs CUDA tensors (there is no CPU fallback)")
+    assert cache_loc.dtype == torch.int32 and cache_loc.is_contiguous()
+    k, v = kv_layer[:, 0], kv_layer[:, 1]
+    n, HKV, D = cache_k.shape
+    assert cache_v.shape == cache_k.shape and cache_k.stride() == cache_v.stride() and cache_k.stride(2) == 1
+    assert cache_loc.numel() == n and k.shape[1] == HKV and k.shape[2] == D
+    stream = torch.cuda.current_stream(kv_layer.device).cuda_stream
+    _lib.check(_lib.lib.deft_b200_kv_append(k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1),
+                                            cache_k.data_ptr(), cache_v.data_ptr(), cache_k.stride(0),
+                                            cache_k.stride(1), cache_loc.data_ptr(), n, HKV, D, stream))

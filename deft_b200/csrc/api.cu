@@ -1,0 +1,244 @@
+// C ABI of libdeft_b200.so (see include/deft_b200.h for the contract of every entry point).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace deft {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Carves the caller's workspace.  Layout (all 256-byte aligned):
+//   po [rows][H][D] f32 | plse [rows][H] f32 | items | groups | csr_off | csr_rows | cursor | counters
+struct Workspace {
+  float* po;
+  float* plse;
+  PlanBuffers pb;
+  size_t bytes;
+};
+
+Workspace carve(void* base, int64_t rows, int64_t items, int32_t nq, int32_t H, int32_t D, bool with_plan) {
+  Workspace w{};
+  size_t off = 0;
+  auto take = [&](size_t n) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += align_up(n);
+    return p;
+  };
+  w.po = static_cast<float*>(take((size_t)rows * H * D * sizeof(float)));
+  w.plse = static_cast<float*>(take((size_t)rows * H * sizeof(float)));
+  if (with_plan) {
+    w.pb.items = static_cast<deft_item_t*>(take((size_t)items * sizeof(deft_item_t)));
+    w.pb.groups = static_cast<deft_group_t*>(take((size_t)items * sizeof(deft_group_t)));
+    w.pb.csr_off = static_cast<int32_t*>(take((size_t)(nq + 1) * sizeof(int32_t)));
+    w.pb.csr_rows = static_cast<int32_t*>(take((size_t)rows * sizeof(int32_t)));
+    w.pb.cursor = static_cast<int32_t*>(take((size_t)(nq + 1) * sizeof(int32_t)));
+    w.pb.counters = static_cast<int32_t*>(take(16));
+  }
+  w.bytes = off;
+  return w;
+}
+
+inline int64_t node_items_bound(int64_t n_entries, int64_t total_kv_bound) {
+  return n_entries + (total_kv_bound > 0 ? total_kv_bound / kNodeSplit + 1 : 0);
+}
+inline int64_t node_rows_bound(int64_t n_partials, int64_t total_kv_bound) {
+  return n_partials + (total_kv_bound > 0 ? kMaxGroupQ * (total_kv_bound / kNodeSplit + 1) : 0);
+}
+
+int check_common(const void* q, const void* k, const void* v, const void* o, int32_t nq, int32_t H,
+                 int32_t HKV, int32_t D, int64_t q_row_stride, int64_t q_head_stride,
+                 int64_t kv_tok_stride, int64_t kv_head_stride, int64_t o_row_stride,
+                 int64_t o_head_stride) {
+  DEFT_CHECK_ARG(q && k && v && o, "null tensor pointer");
+  DEFT_CHECK_ARG(nq > 0 && H > 0 && HKV > 0 && H % HKV == 0, "bad head geometry nq=%d H=%d HKV=%d", nq, H, HKV);
+  // the reference asserts head_dim in {16, 32, 64, 128} (tree_attention.py:100,305,582)
+  DEFT_CHECK_ARG(D == 32 || D == 64 || D == 128, "head_dim %d not supported (32, 64, 128)", D);
+  DEFT_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) % 16 == 0,
+                 "q/k/v/o must be 16-byte aligned");
+  DEFT_CHECK_ARG((q_row_stride | q_head_stride | kv_tok_stride | kv_head_stride | o_row_stride | o_head_stride) % 8 == 0,
+                 "strides must be multiples of 8 elements (16 bytes)");
+  return DEFT_OK;
+}
+
+AttnParams base_params(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                       const void* v, int64_t kv_tok_stride, int64_t kv_head_stride, void* o,
+                       int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H, int32_t HKV,
+                       int32_t D) {
+  AttnParams p{};
+  p.q = static_cast<const __half*>(q);
+  p.k = static_cast<const __half*>(k);
+  p.v = static_cast<const __half*>(v);
+  p.o = static_cast<__half*>(o);
+  p.q_row_stride = q_row_stride; p.q_head_stride = q_head_stride;
+  p.kv_tok_stride = kv_tok_stride; p.kv_head_stride = kv_head_stride;
+  p.o_row_stride = o_row_stride; p.o_head_stride = o_head_stride;
+  p.nq = nq; p.H = H; p.HKV = HKV; p.D = D;
+  p.scale = 1.0f / sqrtf((float)D);  // recomputed from head_dim like the reference (tree_attention.py:104)
+  return p;
+}
+
+void use_plan(AttnParams& p, const deft_plan_t* plan) {
+  p.items = plan->items; p.groups = plan->groups;
+  p.csr_off = plan->csr_off; p.csr_rows = plan->csr_rows;
+  p.n_items = plan->n_items; p.n_items_dev = nullptr;
+}
+void use_plan(AttnParams& p, const PlanBuffers& pb, int64_t items_bound) {
+  p.items = pb.items; p.groups = pb.groups;
+  p.csr_off = pb.csr_off; p.csr_rows = pb.csr_rows;
+  p.n_items = (int32_t)items_bound; p.n_items_dev = pb.counters;
+}
+
+__global__ void kv_append_kernel(__half* k, __half* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                                 const __half* nk, const __half* nv, int64_t new_row_stride,
+                                 int64_t new_head_stride, const int32_t* loc, int n, int HKV, int CH) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  const int64_t total = (int64_t)n * HKV * CH;
+  if (i >= total) return;
+  const int ch = (int)(i % CH), h = (int)((i / CH) % HKV), r = (int)(i / ((int64_t)CH * HKV));
+  const int64_t src = (int64_t)r * new_row_stride + (int64_t)h * new_head_stride + ch * 8;
+  const int64_t dst = (int64_t)loc[r] * kv_tok_stride + (int64_t)h * kv_head_stride + ch * 8;
+  *reinterpret_cast<uint4*>(k + dst) = *reinterpret_cast<const uint4*>(nk + src);
+  *reinterpret_cast<uint4*>(v + dst) = *reinterpret_cast<const uint4*>(nv + src);
+}
+
+}  // namespace
+}  // namespace deft
+
+using namespace deft;
+
+extern "C" {
+
+int deft_b200_abi_version(void) { return DEFT_B200_ABI_VERSION; }
+const char* deft_b200_last_error(void) { return g_error; }
+
+size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
+                                         int64_t n_blocks) {
+  return carve(nullptr, n_partials, n_blocks, nq, H, D, true).bytes;
+}
+
+size_t deft_b200_node_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
+                                      int64_t n_entries, int64_t total_kv_bound) {
+  return carve(nullptr, node_rows_bound(n_partials, total_kv_bound),
+               node_items_bound(n_entries, total_kv_bound), nq, H, D, true).bytes;
+}
+
+int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                          const void* v, int64_t kv_tok_stride, int64_t kv_head_stride, void* o,
+                          int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
+                          int32_t HKV, int32_t D, int32_t block_len, const int64_t* block_q,
+                          int64_t n_partials, const int64_t* block_q_cnts,
+                          const int64_t* block_q_offset, const int64_t* block_lens, int64_t n_blocks,
+                          const int64_t* block_bitmasks, const int64_t* block_kv,
+                          const deft_plan_t* plan, void* workspace, size_t workspace_bytes,
+                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_common(q, k, v, o, nq, H, HKV, D, q_row_stride, q_head_stride, kv_tok_stride,
+                        kv_head_stride, o_row_stride, o_head_stride);
+  if (rc) return rc;
+  DEFT_CHECK_ARG(block_len == 128, "block_len must be 128 (got %d): the reference Flatten kernel hard-wires it", block_len);
+  DEFT_CHECK_ARG(block_q && block_q_cnts && block_q_offset && block_lens && block_bitmasks && block_kv,
+                 "null table pointer");
+  DEFT_CHECK_ARG(n_blocks > 0 && n_partials > 0, "empty tables");
+  DEFT_CHECK_ARG(workspace, "null workspace");
+  const int64_t rows = plan ? plan->n_part_rows : n_partials;
+  Workspace w = carve(workspace, rows, n_blocks, nq, H, D, plan == nullptr);
+  if (w.bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return DEFT_E_WORKSPACE;
+  }
+  AttnParams p = base_params(q, q_row_stride, q_head_stride, k, v, kv_tok_stride, kv_head_stride, o,
+                             o_row_stride, o_head_stride, nq, H, HKV, D);
+  p.kv_idx = block_kv; p.kv_idx_bytes = 8;
+  p.q_list = block_q; p.masks = block_bitmasks;
+  p.po = w.po; p.plse = w.plse;
+  if (plan) {
+    use_plan(p, plan);
+  } else {
+    rc = launch_plan_flatten(block_q_cnts, block_q_offset, block_lens, block_kv, block_q, n_blocks,
+                             block_len, nq, w.pb, stream);
+    if (rc) return rc;
+    use_plan(p, w.pb, n_blocks);
+  }
+  rc = launch_stage1_fma(p, stream);
+  if (rc) return rc;
+  return launch_stage2(p, stream);
+}
+
+int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                       const void* v, int64_t kv_tok_stride, int64_t kv_head_stride, void* o,
+                       int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
+                       int32_t HKV, int32_t D, const void* kv_indices, int32_t kv_index_bytes,
+                       const int64_t* kv_offset, const int64_t* kv_len, const int64_t* node_q,
+                       int64_t n_partials, const int64_t* q_offset, const int64_t* q_len,
+                       int64_t n_entries, int64_t total_kv_bound, const deft_plan_t* plan,
+                       void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_common(q, k, v, o, nq, H, HKV, D, q_row_stride, q_head_stride, kv_tok_stride,
+                        kv_head_stride, o_row_stride, o_head_stride);
+  if (rc) return rc;
+  DEFT_CHECK_ARG(kv_index_bytes == 8 || kv_index_bytes == 4, "kv_index_bytes must be 8 or 4");
+  DEFT_CHECK_ARG(kv_indices && kv_offset && kv_len && node_q && q_offset && q_len, "null table pointer");
+  DEFT_CHECK_ARG(n_entries > 0 && n_partials > 0, "empty tables");
+  DEFT_CHECK_ARG(workspace, "null workspace");
+  const int64_t rows = plan ? plan->n_part_rows : node_rows_bound(n_partials, total_kv_bound);
+  const int64_t items = node_items_bound(n_entries, total_kv_bound);
+  Workspace w = carve(workspace, rows, items, nq, H, D, plan == nullptr);
+  if (w.bytes > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return DEFT_E_WORKSPACE;
+  }
+  AttnParams p = base_params(q, q_row_stride, q_head_stride, k, v, kv_tok_stride, kv_head_stride, o,
+                             o_row_stride, o_head_stride, nq, H, HKV, D);
+  p.kv_idx = kv_indices; p.kv_idx_bytes = kv_index_bytes;
+  p.q_list = node_q; p.masks = nullptr;
+  p.po = w.po; p.plse = w.plse;
+  if (plan) {
+    use_plan(p, plan);
+  } else {
+    rc = launch_plan_node(kv_offset, kv_len, q_offset, q_len, node_q, n_entries,
+                          total_kv_bound > 0 ? kNodeSplit : 0, nq, w.pb, stream);
+    if (rc) return rc;
+    use_plan(p, w.pb, items);
+  }
+  rc = launch_stage1_fma(p, stream);
+  if (rc) return rc;
+  return launch_stage2(p, stream);
+}
+
+int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                        const void* new_k, const void* new_v, int64_t new_row_stride,
+                        int64_t new_head_stride, const int32_t* cache_loc, int32_t n, int32_t HKV,
+                        int32_t D, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEFT_CHECK_ARG(k && v && new_k && new_v && cache_loc, "null pointer");
+  DEFT_CHECK_ARG(n >= 0 && HKV > 0 && D > 0 && D % 8 == 0, "bad shape n=%d HKV=%d D=%d", n, HKV, D);
+  DEFT_CHECK_ARG(((uintptr_t)k | (uintptr_t)v | (uintptr_t)new_k | (uintptr_t)new_v) % 16 == 0,
+                 "buffers must be 16-byte aligned");
+  DEFT_CHECK_ARG((kv_tok_stride | kv_head_stride | new_row_stride | new_head_stride) % 8 == 0,
+                 "strides must be multiples of 8 elements");
+  if (n == 0) return DEFT_OK;
+  const int CH = D / 8;
+  const int64_t total = (int64_t)n * HKV * CH;
+  const int threads = 256;
+  kv_append_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
+      static_cast<__half*>(k), static_cast<__half*>(v), kv_tok_stride, kv_head_stride,
+      static_cast<const __half*>(new_k), static_cast<const __half*>(new_v), new_row_stride,
+      new_head_stride, cache_loc, n, HKV, CH);
+  DEFT_CUDA(cudaGetLastError());
+  return DEFT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+// Stage 2: tree-topology log-sum-exp combine of the stage-1 partials.
+//
+// Replaces DeFT_splitBynode_Triton_stage2 (DeFT/deft/layers/attention/tree_attention.py:297-416 with
+// kernels :420-445 and :485-546).  The reference scatters with atomics (zero-initialised atomic max,
+// fp32 atomic add of the weights, fp16 atomic add into the output, then o.div_(L)); here one warp
+// owns one (query, head), walks the query's partial rows through a CSR in ascending row order and
+// merges in fp32 with the true maximum, so the result is deterministic, needs no zeroed output and is
+// rounded to fp16 exactly once.
+#include "common.cuh"
+
+namespace deft {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) stage2_kernel(const AttnParams p) {
+  constexpr int DL = D / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (w >= (int64_t)p.nq * p.H) return;
+  const int q = (int)(w / p.H), h = (int)(w % p.H);
+  const int beg = p.csr_off[q], end = p.csr_off[q + 1];
+
+  float m = -INFINITY;
+  for (int i = beg + lane; i < end; i += 32) m = fmaxf(m, p.plse[(int64_t)p.csr_rows[i] * p.H + h]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+
+  float L = 0.f, acc[DL];
+#pragma unroll
+  for (int i = 0; i < DL; ++i) acc[i] = 0.f;
+  if (m > -INFINITY) {
+    for (int i = beg; i < end; ++i) {
+      const int64_t row = p.csr_rows[i];
+      const float wgt = __expf(p.plse[row * p.H + h] - m);
+      L += wgt;
+      const float* src = p.po + (row * p.H + h) * D + lane * DL;
+      if constexpr (DL == 4) {
+        const float4 x = *reinterpret_cast<const float4*>(src);
+        acc[0] = fmaf(wgt, x.x, acc[0]); acc[1] = fmaf(wgt, x.y, acc[1]);
+        acc[2] = fmaf(wgt, x.z, acc[2]); acc[3] = fmaf(wgt, x.w, acc[3]);
+      } else if constexpr (DL == 2) {
+        const float2 x = *reinterpret_cast<const float2*>(src);
+        acc[0] = fmaf(wgt, x.x, acc[0]); acc[1] = fmaf(wgt, x.y, acc[1]);
+      } else {
+        acc[0] = fmaf(wgt, src[0], acc[0]);
+      }
+    }
+  }
+  const float inv = L > 0.f ? 1.f / L : 0.f;
+  __half* dst = p.o + (int64_t)q * p.o_row_stride + (int64_t)h * p.o_head_stride + lane * DL;
+  if constexpr (DL == 4) {
+    __half2 a = __floats2half2_rn(acc[0] * inv, acc[1] * inv);
+    __half2 b = __floats2half2_rn(acc[2] * inv, acc[3] * inv);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a);
+    pk.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(dst) = pk;
+  } else if constexpr (DL == 2) {
+    *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(acc[0] * inv, acc[1] * inv);
+  } else {
+    dst[0] = __float2half_rn(acc[0] * inv);
+  }
+}
+
+template <int D>
+int launch_t(const AttnParams& p, cudaStream_t stream) {
+  const int64_t warps = (int64_t)p.nq * p.H;
+  const int64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
+  stage2_kernel<D><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  DEFT_CUDA(cudaGetLastError());
+  return DEFT_OK;
+}
+
+}  // namespace
+
+int launch_stage2(const AttnParams& p, cudaStream_t stream) {
+  if (p.nq <= 0) return DEFT_OK;
+  switch (p.D) {
+    case 32: return launch_t<32>(p, stream);
+    case 64: return launch_t<64>(p, stream);
+    case 128: return launch_t<128>(p, stream);
+  }
+  set_error("unsupported head_dim %d", p.D);
+  return DEFT_E_ARG;
+}
+
+}  // namespace deft

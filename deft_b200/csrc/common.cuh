@@ -1,0 +1,83 @@
+// Shared declarations of the libdeft_b200 translation units.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "deft_b200.h"
+
+namespace deft {
+
+void set_error(const char* fmt, ...);
+
+#define DEFT_CHECK_ARG(cond, ...)   \
+  do {                              \
+    if (!(cond)) {                  \
+      deft::set_error(__VA_ARGS__); \
+      return DEFT_E_ARG;            \
+    }                               \
+  } while (0)
+
+#define DEFT_CUDA(call)                                                              \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      deft::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                      __LINE__);                                                     \
+      return DEFT_E_CUDA;                                                            \
+    }                                                                                \
+  } while (0)
+
+constexpr int kMaxGroupQ = 32;     // queries per group (reference max_q_len / BLOCK_M, tree_cache.py:623)
+constexpr int kNodeSplit = 256;    // tokens per item when long Node entries are split on the device
+
+// Everything stage 1 / stage 2 need to know about one attention call.
+struct AttnParams {
+  const __half* q;
+  const __half* k;
+  const __half* v;
+  __half* o;
+  int64_t q_row_stride, q_head_stride;
+  int64_t kv_tok_stride, kv_head_stride;
+  int64_t o_row_stride, o_head_stride;
+  int32_t nq, H, HKV, D;
+  float scale;
+  // index tables
+  const void* kv_idx;     // int64 or int32 page ids
+  int32_t kv_idx_bytes;   // 8 or 4
+  const int64_t* q_list;  // query id per (group, row)
+  const int64_t* masks;   // per-token bitmask (bit r = row r of the group attends), may be null
+  // plan
+  const deft_item_t* items;
+  const deft_group_t* groups;
+  const int32_t* csr_off;
+  const int32_t* csr_rows;
+  const int32_t* n_items_dev;  // device-resident item count (device-built plans), or null
+  int32_t n_items;             // launch bound on the item count
+  // partial softmax buffers: po [rows][H][D] fp32, plse [rows][H] fp32
+  float* po;
+  float* plse;
+};
+
+// stage 1 (warp-FMA path) and stage 2, attn_fma.cu / combine.cu
+int launch_stage1_fma(const AttnParams& p, cudaStream_t stream);
+int launch_stage2(const AttnParams& p, cudaStream_t stream);
+
+// device-side plan derivation from the reference tables, plan.cu
+struct PlanBuffers {
+  deft_item_t* items;
+  deft_group_t* groups;
+  int32_t* csr_off;
+  int32_t* csr_rows;
+  int32_t* cursor;    // nq ints of scratch
+  int32_t* counters;  // [0] = n_items, [1] = n_part_rows
+};
+int launch_plan_flatten(const int64_t* block_q_cnts, const int64_t* block_q_offset,
+                        const int64_t* block_lens, const int64_t* block_kv, const int64_t* block_q,
+                        int64_t n_blocks, int32_t block_len, int32_t nq, const PlanBuffers& pb,
+                        cudaStream_t stream);
+int launch_plan_node(const int64_t* kv_offset, const int64_t* kv_len, const int64_t* q_offset,
+                     const int64_t* q_len, const int64_t* node_q, int64_t n_entries, int32_t split,
+                     int32_t nq, const PlanBuffers& pb, cudaStream_t stream);
+
+}  // namespace deft

@@ -1,0 +1,292 @@
+// Host metadata builder: KV-guided grouping + flattened-tree KV split, and the native work plan.
+//
+// Replaces TreeMetadata.from_tree_cache (DeFT/deft/tree_decoding/tree_cache.py:618-881) and
+// from_tree_cache_node (:883-1018).  The reference walks the tree in Python and uploads eleven
+// tensors one by one (2-7 ms per decode step in its own logs); this builder makes one pass in C++
+// and lays every table -- the twelve int64 reference tables, bit-identical, plus the item / group /
+// CSR plan of include/deft_b200.h -- into ONE packed buffer that the caller uploads with one copy.
+// No CUDA here: pure host code, re-entrant.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "deft_b200.h"
+
+namespace deft {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+using i64 = int64_t;
+using i32 = int32_t;
+
+struct Csr {
+  std::vector<i32> off, rows;
+};
+
+// q -> ascending partial rows, from the group list
+Csr make_csr(const std::vector<deft_group_t>& groups, const std::vector<i64>& q_list, i32 nq) {
+  Csr c;
+  c.off.assign((size_t)nq + 1, 0);
+  size_t total = 0;
+  for (const auto& g : groups)
+    for (i32 r = 0; r < g.q_cnt; ++r) {
+      const i64 q = q_list[(size_t)g.q_off + r];
+      if (q >= 0 && q < nq) { ++c.off[(size_t)q + 1]; ++total; }
+    }
+  for (i32 q = 0; q < nq; ++q) c.off[(size_t)q + 1] += c.off[(size_t)q];
+  c.rows.assign(total, 0);
+  std::vector<i32> cur(c.off.begin(), c.off.end() - 1);
+  for (const auto& g : groups)  // part_base grows with the group index, so rows come out ascending
+    for (i32 r = 0; r < g.q_cnt; ++r) {
+      const i64 q = q_list[(size_t)g.q_off + r];
+      if (q >= 0 && q < nq) c.rows[(size_t)cur[(size_t)q]++] = g.part_base + r;
+    }
+  for (i32 q = 0; q < nq; ++q) std::sort(c.rows.begin() + c.off[(size_t)q], c.rows.begin() + c.off[(size_t)q + 1]);
+  return c;
+}
+
+std::vector<i64> offsets_of(const std::vector<i64>& lens) {  // cat([0], cumsum(len)[:-1]), tree_cache.py:822-833
+  std::vector<i64> o(lens.size(), 0);
+  for (size_t i = 1; i < lens.size(); ++i) o[i] = o[i - 1] + lens[i - 1];
+  return o;
+}
+
+}  // namespace
+
+struct deft_tables {
+  std::vector<unsigned char> packed;
+  i64 dir[2 * DEFT_T_COUNT];
+  i64 scalars[6];
+};
+
+extern "C" {
+
+deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, const int64_t* kv_off,
+                                      const int64_t* kv, const int64_t* q_off, const int64_t* qs,
+                                      const int64_t* tix_row, int64_t tix_max_ctx,
+                                      int32_t query_num, int32_t block_len, int32_t max_q_len,
+                                      int32_t max_block_len, int32_t node_split) {
+  if (n_nodes <= 0 || !parent || !kv_off || !kv || !q_off || !qs) {
+    deft::set_error("build_tables: null or empty tree");
+    return nullptr;
+  }
+  if (block_len <= 0 || max_q_len <= 0 || max_q_len > 32 || query_num <= 0) {
+    deft::set_error("build_tables: need block_len > 0, 0 < max_q_len <= 32, query_num > 0");
+    return nullptr;
+  }
+  if (parent[0] != -1) {
+    deft::set_error("build_tables: node 0 must be the root (parent -1)");
+    return nullptr;
+  }
+  for (i32 i = 1; i < n_nodes; ++i)
+    if (parent[i] < 0 || parent[i] >= i) {
+      deft::set_error("build_tables: nodes must be in DFS pre-order (parent[%d] = %d)", i, parent[i]);
+      return nullptr;
+    }
+
+  std::vector<i64> node_q, node_kv, node_q_len, node_kv_len, node_kv_offset_ti;
+  std::vector<i64> block_q, block_q_cnts, block_kv, block_masks, block_lens;
+  std::vector<deft_item_t> f_items;
+  std::vector<deft_group_t> f_groups;
+  i64 total_kv_len = 0;
+
+  // open block (tree_cache.py:654-658)
+  std::vector<i64> seg_tokens;
+  std::vector<i64> seg_lens;
+  std::vector<std::vector<i64>> seg_qs;  // sorted query ids per segment
+  std::vector<i64> uni;                  // union, kept sorted + unique at close time
+
+  auto close_block = [&]() {  // pack_new_block, tree_cache.py:661-723
+    const i64 n_live = (i64)seg_tokens.size();
+    std::vector<i64> toks(seg_tokens);
+    std::vector<i64> lens(seg_lens);
+    size_t n_seg = seg_qs.size();
+    if (n_live < block_len) {
+      toks.resize((size_t)block_len, -1);
+      lens.push_back(block_len - n_live);
+      // the pad segment has an empty query set: handled by n_seg below
+    }
+    std::sort(uni.begin(), uni.end());
+    uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+    deft_item_t item{};
+    item.kv_off = (i64)block_lens.size() * block_len;
+    item.kv_len = (i32)n_live;
+    item.grp_off = (i32)f_groups.size();
+    for (size_t s0 = 0; s0 < uni.size(); s0 += (size_t)max_q_len) {
+      const size_t s1 = std::min(uni.size(), s0 + (size_t)max_q_len);
+      deft_group_t g{};
+      g.mask_off = (i64)block_lens.size() * block_len;
+      g.q_off = (i32)block_q.size();
+      g.q_cnt = (i32)(s1 - s0);
+      g.part_base = g.q_off;
+      f_groups.push_back(g);
+      block_q.insert(block_q.end(), uni.begin() + (long)s0, uni.begin() + (long)s1);
+      block_q_cnts.push_back((i64)(s1 - s0));
+      block_kv.insert(block_kv.end(), toks.begin(), toks.end());
+      block_lens.push_back(n_live);
+      for (size_t s = 0; s < lens.size(); ++s) {
+        i64 bits = 0;
+        if (s < n_seg)
+          for (i64 qv : seg_qs[s]) {
+            // position of qv inside the sub-list [s0, s1)
+            auto it = std::lower_bound(uni.begin() + (long)s0, uni.begin() + (long)s1, qv);
+            if (it != uni.begin() + (long)s1 && *it == qv) bits |= (i64)1 << (it - (uni.begin() + (long)s0));
+          }
+        block_masks.insert(block_masks.end(), (size_t)lens[s], bits);
+      }
+    }
+    item.n_grp = (i32)f_groups.size() - item.grp_off;
+    item.cost = item.kv_len * item.n_grp;
+    if (item.n_grp > 0) f_items.push_back(item);
+    seg_tokens.clear(); seg_lens.clear(); seg_qs.clear(); uni.clear();
+  };
+
+  std::vector<i64> kvs, q;
+  for (i32 n = 0; n < n_nodes; ++n) {  // pre-order visit == the reference's recursive dfs (:725-791)
+    const i64 k0 = kv_off[n], k1 = kv_off[n + 1], q0 = q_off[n], q1 = q_off[n + 1];
+    if (k1 < k0 || q1 <= q0) {
+      deft::set_error("build_tables: node %d has no attending query or a negative page count", n);
+      return nullptr;
+    }
+    kvs.assign(kv + k0, kv + k1);
+    const i64 n_kv = (i64)kvs.size();
+    q.assign(qs + q0, qs + q1);
+    std::sort(q.begin(), q.end());
+    for (i64 qv : q)
+      if (qv < 0 || qv >= query_num) {
+        deft::set_error("build_tables: node %d lists query %lld outside [0, %d)", n, (long long)qv, query_num);
+        return nullptr;
+      }
+    total_kv_len += n_kv;
+    if (max_block_len == -1 && n_kv == 0) {
+      // the reference raises here (range() step 0, tree_cache.py:746-748); report instead of crashing
+      deft::set_error("build_tables: node %d has no KV pages (call alloc() before building tables)", n);
+      return nullptr;
+    }
+    const i64 step = max_block_len == -1 ? n_kv : max_block_len;
+    if (!tix_row) std::sort(kvs.begin(), kvs.end());  // :736 (the tree-index table keeps page order)
+    for (size_t s0 = 0; s0 < q.size(); s0 += (size_t)max_q_len) {
+      const size_t s1 = std::min(q.size(), s0 + (size_t)max_q_len);
+      for (i64 c0 = 0; c0 < n_kv; c0 += step) {
+        const i64 c1 = std::min(n_kv, c0 + step);
+        node_q.insert(node_q.end(), q.begin() + (long)s0, q.begin() + (long)s1);
+        node_q_len.push_back((i64)(s1 - s0));
+        node_kv_len.push_back(c1 - c0);
+        if (tix_row) node_kv_offset_ti.push_back(tix_row[n] * tix_max_ctx + c0);  // tree_index_pool.py:47-49
+        else node_kv.insert(node_kv.end(), kvs.begin() + c0, kvs.begin() + c1);
+      }
+    }
+    if (tix_row) std::sort(kvs.begin(), kvs.end());
+    // flatten packing (:763-788)
+    i64 room = block_len - (i64)seg_tokens.size();
+    i64 done = 0;
+    while (done < n_kv) {
+      if (n_kv - done < room) {
+        seg_tokens.insert(seg_tokens.end(), kvs.begin() + done, kvs.end());
+        seg_lens.push_back(n_kv - done);
+        seg_qs.push_back(q);
+        uni.insert(uni.end(), q.begin(), q.end());
+        break;
+      }
+      seg_tokens.insert(seg_tokens.end(), kvs.begin() + done, kvs.begin() + done + room);
+      seg_lens.push_back(room);
+      seg_qs.push_back(q);
+      uni.insert(uni.end(), q.begin(), q.end());
+      close_block();
+      done += room;
+      room = block_len;
+    }
+  }
+  if (!seg_lens.empty()) close_block();  // :797-798
+
+  std::vector<i64> node_q_offset = offsets_of(node_q_len);
+  std::vector<i64> node_kv_offset = tix_row ? node_kv_offset_ti : offsets_of(node_kv_len);
+  std::vector<i64> block_q_offset = offsets_of(block_q_cnts);
+
+  // ---- Node plan: long entries are cut into node_split-token items
+  std::vector<deft_item_t> n_items;
+  std::vector<deft_group_t> n_groups;
+  i32 n_rows = 0;
+  for (size_t e = 0; e < node_q_len.size(); ++e) {
+    const i32 kn = (i32)node_kv_len[e], qn = (i32)node_q_len[e];
+    const i32 step = node_split > 0 ? node_split : std::max(kn, 1);
+    const i32 nch = std::max(1, (kn + step - 1) / step);
+    for (i32 j = 0; j < nch; ++j) {
+      deft_item_t it{};
+      it.kv_off = node_kv_offset[e] + (i64)j * step;
+      it.kv_len = std::max(0, std::min(step, kn - j * step));
+      it.grp_off = (i32)n_groups.size();
+      it.n_grp = 1;
+      it.cost = it.kv_len;
+      n_items.push_back(it);
+      deft_group_t g{};
+      g.mask_off = -1;
+      g.q_off = (i32)node_q_offset[e];
+      g.q_cnt = qn;
+      g.part_base = n_rows;
+      n_groups.push_back(g);
+      n_rows += qn;
+    }
+  }
+  Csr f_csr = make_csr(f_groups, block_q, query_num);
+  Csr n_csr = make_csr(n_groups, node_q, query_num);
+
+  // ---- pack
+  deft_tables_t* t = new (std::nothrow) deft_tables_t();
+  if (!t) {
+    deft::set_error("build_tables: out of memory");
+    return nullptr;
+  }
+  struct Src { const void* p; size_t n; size_t elem; };
+  const Src src[DEFT_T_COUNT] = {
+      {node_q.data(), node_q.size(), 8}, {node_kv.data(), node_kv.size(), 8},
+      {node_q_len.data(), node_q_len.size(), 8}, {node_kv_len.data(), node_kv_len.size(), 8},
+      {node_q_offset.data(), node_q_offset.size(), 8}, {node_kv_offset.data(), node_kv_offset.size(), 8},
+      {block_q.data(), block_q.size(), 8}, {block_q_cnts.data(), block_q_cnts.size(), 8},
+      {block_q_offset.data(), block_q_offset.size(), 8}, {block_masks.data(), block_masks.size(), 8},
+      {block_kv.data(), block_kv.size(), 8}, {block_lens.data(), block_lens.size(), 8},
+      {f_items.data(), f_items.size(), sizeof(deft_item_t)}, {f_groups.data(), f_groups.size(), sizeof(deft_group_t)},
+      {f_csr.off.data(), f_csr.off.size(), 4}, {f_csr.rows.data(), f_csr.rows.size(), 4},
+      {n_items.data(), n_items.size(), sizeof(deft_item_t)}, {n_groups.data(), n_groups.size(), sizeof(deft_group_t)},
+      {n_csr.off.data(), n_csr.off.size(), 4}, {n_csr.rows.data(), n_csr.rows.size(), 4},
+  };
+  size_t off = 0;
+  for (int i = 0; i < DEFT_T_COUNT; ++i) {
+    t->dir[2 * i] = (i64)off;
+    t->dir[2 * i + 1] = (i64)src[i].n;
+    off += (src[i].n * src[i].elem + 255) / 256 * 256;
+  }
+  t->packed.assign(std::max<size_t>(off, 256), 0);
+  for (int i = 0; i < DEFT_T_COUNT; ++i)
+    if (src[i].n) std::memcpy(t->packed.data() + t->dir[2 * i], src[i].p, src[i].n * src[i].elem);
+  t->scalars[0] = query_num;
+  t->scalars[1] = (i64)node_q_len.size();
+  t->scalars[2] = total_kv_len;
+  t->scalars[3] = block_len;
+  t->scalars[4] = (i64)block_q.size();
+  t->scalars[5] = n_rows;
+  return t;
+}
+
+const void* deft_b200_tables_data(const deft_tables_t* t) { return t ? t->packed.data() : nullptr; }
+size_t deft_b200_tables_bytes(const deft_tables_t* t) { return t ? t->packed.size() : 0; }
+
+int deft_b200_tables_directory(const deft_tables_t* t, int64_t* dir) {
+  if (!t || !dir) return DEFT_E_ARG;
+  std::memcpy(dir, t->dir, sizeof(t->dir));
+  return DEFT_OK;
+}
+
+int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out) {
+  if (!t || !out) return DEFT_E_ARG;
+  std::memcpy(out, t->scalars, sizeof(t->scalars));
+  return DEFT_OK;
+}
+
+void deft_b200_tables_free(deft_tables_t* t) { delete t; }
+
+}  // extern "C"

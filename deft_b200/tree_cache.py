@@ -1,0 +1,474 @@
+"""Decoding-tree state and the metadata that drives tree attention (host side).
+
+Mirrors, for the paged tree-attention path, the interface of the reference's
+``deft/tree_decoding/tree_cache.py``: ``TreeNode`` (:94-129), ``KVCacheUpdater`` (:53-91),
+``TreeCache`` (:147-584: ``init_prompt`` / ``new_node`` / ``alloc`` / ``merge_nodes`` /
+``reset_node_KV`` / ``branch`` / ``cut`` / ``add_ref`` / ``remove_ref``), the ``TreeMetadata``
+dataclass (:591-616) with ``from_tree_cache`` (:618-881) / ``from_tree_cache_node`` (:883-1018) and
+the module-level registry (:1021-1052).  Page ids, leaf order and every table are bit-identical to
+the reference's on the same sequence of operations (tests/test_tree_cache.py, tests/test_tables.py).
+
+What is different underneath:
+  * all bookkeeping is host-side; no ``.item()`` device round trips (the reference syncs once per
+    leaf per step in ``alloc``);
+  * ``from_tree_cache`` flattens the tree to arrays and calls the C++ builder
+    (``deft_b200_build_tables``), which returns the reference tables AND the native work plan in one
+    packed buffer that is uploaded with ONE host->device copy;
+  * ``KVCacheUpdater.update`` scatters K and V in one launch (``deft_b200_kv_append``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass, field
+from itertools import chain
+from typing import Any, Dict, List, Optional, Set
+
+import numpy as np
+import torch
+
+from . import _lib
+from .memory_pool import ReqToTokenPool, TokenToKVPool, TreeIndexPool
+
+BLOCK_CONFIG = {"BLOCK_LEN": 128, "MAX_BLOCK_LEN": -1}   # tree_cache.py:587
+TRAVERSAL_CONFIG = {"METHOD": "dfs"}
+NODE_SPLIT = 256   # tokens per work item when a Node entry is longer (csrc/common.cuh kNodeSplit)
+
+
+class KVCacheUpdater:
+    """Writes this step's K/V rows into the pages handed out by ``alloc`` / ``init_prompt``."""
+
+    def __init__(self, token_to_kv_pool: TokenToKVPool, cache_loc: torch.Tensor, is_prompt: bool) -> None:
+        self.use_paged_memory = True
+        self.token_to_kv_pool = token_to_kv_pool
+        self.cache_loc = cache_loc                     # int32, host
+        self.is_prompt = is_prompt
+        self._loc_dev: Optional[torch.Tensor] = None
+
+    def device_loc(self) -> torch.Tensor:
+        if self._loc_dev is None:
+            self._loc_dev = self.cache_loc.to(self.token_to_kv_pool.device, non_blocking=True)
+        return self._loc_dev
+
+    def update(self, layer_id: int, cache_k: torch.Tensor, cache_v: torch.Tensor) -> None:
+        from .attention import kv_append   # local import: attention imports this module
+        kv = self.token_to_kv_pool.kv_data[layer_id]
+        kv_append(kv, cache_k, cache_v, self.device_loc())
+
+
+class TreeNode:
+    def __init__(self, id: int, node_indices_id: Optional[int] = None,
+                 node_indices: Optional[torch.Tensor] = None) -> None:
+        self.id = id
+        self.children: Dict[int, "TreeNode"] = {}
+        self.token_ids: List[int] = []
+        self.positions: List[int] = []
+        self.position_offset = 0
+        self.kv_indices: List[int] = []
+        self.parent: Optional["TreeNode"] = None
+        self.refs: Set["TreeNode"] = set()
+        self.paused = False
+        self.node_indices_id = node_indices_id
+        self.node_indices = node_indices
+        self.cumulative_logprob = 0.0
+
+    def get_len(self) -> int:
+        return len(self.token_ids)
+
+    def append_token(self, token: int, logprob: Optional[float] = None) -> None:
+        self.positions.append(self.position_offset + len(self.token_ids))
+        self.token_ids.append(token)
+        if logprob is not None:
+            self.cumulative_logprob += logprob
+
+    def append_index(self, index: int) -> None:
+        self.kv_indices.append(index)
+        if self.node_indices is not None:
+            self.node_indices[len(self.kv_indices) - 1] = index
+
+
+class TreeCache:
+    """Tree topology + per-node page lists over a paged KV pool."""
+
+    def __init__(self, dtype: torch.dtype, head_num: int, head_dim: int, layer_num: int,
+                 req_to_token_pool: ReqToTokenPool, token_to_kv_pool: TokenToKVPool,
+                 tree_index_pool: Optional[TreeIndexPool] = None, use_paged_memory: bool = True,
+                 use_tree_index: bool = False) -> None:
+        if not use_paged_memory:
+            raise NotImplementedError("deft_b200 covers the paged tree-attention path only "
+                                      "(the unpaged modes are the reference's baselines)")
+        assert token_to_kv_pool is not None and req_to_token_pool is not None
+        if use_tree_index:
+            assert tree_index_pool is not None
+        self.node_cnt = 1
+        self.root: Optional[TreeNode] = None
+        self.nodes: Dict[int, TreeNode] = {}
+        self.leaves: Dict[int, TreeNode] = {}
+        self.leaf_to_req: Dict[int, int] = {}
+        self.paused_nodes: Set[int] = set()
+        self.leaf_to_q: Dict[int, int] = {}
+        self.req_to_token_pool = req_to_token_pool
+        self.token_to_kv_pool = token_to_kv_pool
+        self.tree_index_pool = tree_index_pool
+        self.use_paged_memory = True
+        self.use_tree_index = use_tree_index
+        self.layer_num = layer_num
+        self.deleted_token_num = 0
+
+    # ---- construction -------------------------------------------------------------------
+    def _take_index_row(self):
+        if not self.use_tree_index:
+            return None, None
+        rows = self.tree_index_pool.alloc(1)
+        assert rows is not None
+        rid = int(rows[0])
+        return rid, self.tree_index_pool.node_to_kv[rid]
+
+    def init_prompt(self, prompt_ids) -> KVCacheUpdater:
+        ids = prompt_ids.tolist() if hasattr(prompt_ids, "tolist") else list(prompt_ids)
+        n = len(ids)
+        rid, row = self._take_index_row()
+        root = TreeNode(0, rid, row)
+        root.token_ids = ids
+        root.positions = list(range(n))
+        self.root = root
+        self.nodes[0] = root
+        self.leaves[0] = root
+        self.add_ref(root)
+        req = self.req_to_token_pool.alloc(1)
+        assert req is not None
+        req_id = int(req[0])
+        self.leaf_to_req[0] = req_id
+        cache_loc = self.token_to_kv_pool.alloc(n)
+        assert cache_loc is not None
+        root.kv_indices = cache_loc.tolist()
+        self.req_to_token_pool.req_to_token[req_id, :n] = cache_loc
+        if row is not None:
+            row[:n] = cache_loc
+        return KVCacheUpdater(self.token_to_kv_pool, cache_loc, is_prompt=True)
+
+    def new_node(self, parent: TreeNode) -> TreeNode:
+        rid, row = self._take_index_row()
+        node = TreeNode(self.node_cnt, rid, row)
+        self.node_cnt += 1
+        node.parent = parent
+        node.position_offset = parent.position_offset + len(parent.positions)
+        parent.children[node.id] = node
+        self.nodes[node.id] = node
+        return node
+
+    def alloc(self) -> KVCacheUpdater:
+        """One new page per leaf, leaves in ascending id order (tree_cache.py:261-283)."""
+        leaves = sorted(self.leaves.values(), key=lambda x: x.id)
+        out_cache_loc = self.token_to_kv_pool.alloc(len(leaves))
+        assert out_cache_loc is not None
+        table = self.req_to_token_pool.req_to_token
+        for leaf, loc in zip(leaves, out_cache_loc.tolist()):
+            leaf.append_index(loc)
+            table[self.leaf_to_req[leaf.id], leaf.positions[-1]] = loc
+        return KVCacheUpdater(self.token_to_kv_pool, out_cache_loc, is_prompt=False)
+
+    # ---- mutation -------------------------------------------------------------------------
+    def merge_nodes(self, node_A: TreeNode, node_B: TreeNode, pruneB_flag: Optional[bool] = True) -> None:
+        """Append B's tokens and pages to A (speculative verification, tree_cache.py:300-327)."""
+        for token_id in node_B.token_ids:
+            # the reference appends the position twice (once here, once in append_token)
+            node_A.positions.append(node_A.position_offset + len(node_A.token_ids))
+            node_A.append_token(token=token_id)
+        for kv_idx in node_B.kv_indices:
+            node_A.append_index(index=kv_idx)
+        self.token_to_kv_pool.add_refs(node_B.kv_indices)
+        if pruneB_flag:
+            self.cut(node_B)
+
+    def reset_node_KV(self, node: TreeNode, diff: int) -> None:
+        self.token_to_kv_pool.free(node.kv_indices)
+        node.kv_indices = []
+        node.position_offset += diff
+        node.positions = [pos + diff for pos in node.positions]
+
+    def branch(self, node: TreeNode, branch_cnt: int) -> List[TreeNode]:
+        assert node.id in self.leaves
+        self.leaves.pop(node.id)
+        path_len = node.positions[-1] + 1
+        req = self.leaf_to_req.pop(node.id)
+        new_nodes: List[TreeNode] = []
+        for i in range(branch_cnt):
+            child = self.new_node(node)
+            new_nodes.append(child)
+            self.leaves[child.id] = child
+            if i == 0:
+                self.leaf_to_req[child.id] = req          # the first child inherits the parent's slot
+            else:
+                fresh = self.req_to_token_pool.alloc(1)
+                assert fresh is not None
+                fresh_id = int(fresh[0])
+                self.req_to_token_pool.copy(req, fresh_id, path_len)
+                self.leaf_to_req[child.id] = fresh_id
+        self.remove_ref(node)
+        for child in new_nodes:
+            self.add_ref(child)
+        return new_nodes
+
+    def cut(self, node: TreeNode, record_deleted: bool = False) -> List[TreeNode]:
+        assert len(node.children) == 0
+        assert node.id in self.leaves
+        self.leaves.pop(node.id)
+        self.remove_ref(node)
+        self.req_to_token_pool.free(self.leaf_to_req.pop(node.id))
+        assert len(node.refs) == 0
+        deleted: List[TreeNode] = []
+        cur: Optional[TreeNode] = node
+        while cur is not None and len(cur.refs) == 0:
+            deleted.append(self.nodes.pop(cur.id))
+            self.token_to_kv_pool.free(cur.kv_indices)
+            if self.use_tree_index:
+                assert cur.node_indices_id is not None
+                self.tree_index_pool.free(cur.node_indices_id)
+            parent = cur.parent
+            if parent is not None:
+                parent.children.pop(cur.id)
+            cur = parent
+        if record_deleted:
+            self.deleted_token_num += sum(len(d.token_ids) for d in deleted)
+        return deleted
+
+    def add_ref(self, node: TreeNode) -> None:
+        ref = node
+        cur: Optional[TreeNode] = node
+        while cur is not None:
+            cur.refs.add(ref)
+            cur = cur.parent
+
+    def remove_ref(self, node: TreeNode) -> None:
+        ref = node
+        cur: Optional[TreeNode] = node
+        while cur is not None:
+            cur.refs.remove(ref)
+            cur = cur.parent
+
+    def free(self) -> None:
+        self.root = None
+        self.nodes.clear()
+        self.leaves.clear()
+        self.node_cnt = 0
+
+    def get_tree_token_number(self) -> int:
+        return sum(len(n.token_ids) for n in self.nodes.values()) + self.deleted_token_num
+
+
+# ------------------------------------------------------------------------------------------------
+# metadata
+# ------------------------------------------------------------------------------------------------
+def flatten_tree(tree) -> Dict[str, Any]:
+    """Any ``TreeCache``-shaped object -> the flat arrays ``deft_b200_build_tables`` takes.
+
+    Nodes in DFS pre-order, children in dict (creation) order -- the visiting order of
+    tree_cache.py:725-791; queries = rank of each ref'd leaf by ascending leaf id (:650-652).
+    """
+    leaf_to_q = {leaf.id: i for i, leaf in enumerate(sorted(tree.leaves.values(), key=lambda x: x.id))}
+    parent: List[int] = []
+    kv_lists: List[List[int]] = []
+    q_lists: List[List[int]] = []
+    tix: List[int] = []
+    stack = [(tree.root, -1)]
+    while stack:
+        node, par = stack.pop()
+        if node.paused:
+            continue
+        me = len(parent)
+        parent.append(par)
+        kv_lists.append(node.kv_indices)
+        q_lists.append([leaf_to_q[r.id] for r in node.refs if not r.paused])
+        tix.append(-1 if node.node_indices_id is None else node.node_indices_id)
+        for child in reversed(list(node.children.values())):
+            stack.append((child, me))
+    n = len(parent)
+    kv_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in kv_lists], out=kv_off[1:])
+    q_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(x) for x in q_lists], out=q_off[1:])
+    kv = np.fromiter(chain.from_iterable(kv_lists), dtype=np.int64, count=int(kv_off[-1]))
+    qs = np.fromiter(chain.from_iterable(q_lists), dtype=np.int64, count=int(q_off[-1]))
+    return dict(parent=np.asarray(parent, dtype=np.int32), kv_off=kv_off, kv=kv, q_off=q_off, qs=qs,
+                tix=np.asarray(tix, dtype=np.int64), leaf_to_q=leaf_to_q)
+
+
+class _Staging:
+    """Ring of pinned host buffers for the one-copy table upload."""
+
+    def __init__(self, depth: int = 4) -> None:
+        self.bufs: List[Optional[torch.Tensor]] = [None] * depth
+        self.events: List[Optional[torch.cuda.Event]] = [None] * depth
+        self.i = 0
+
+    def upload(self, src: np.ndarray, device: torch.device) -> torch.Tensor:
+        n = src.nbytes
+        slot = self.i
+        self.i = (self.i + 1) % len(self.bufs)
+        if self.events[slot] is not None:
+            self.events[slot].synchronize()
+        buf = self.bufs[slot]
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1 << 20), dtype=torch.uint8, pin_memory=True)
+            self.bufs[slot] = buf
+        buf[:n].numpy()[:] = src
+        out = torch.empty(n, dtype=torch.uint8, device=device)
+        out.copy_(buf[:n], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[slot] = ev
+        return out
+
+
+_STAGING = _Staging()
+_PLAN_REGISTRY: Dict[int, "weakref.ReferenceType[TreeMetadata]"] = {}
+
+
+def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: int = -1,
+                      block_len: int = 128, tree_index_max_ctx: int = 0, node_split: int = NODE_SPLIT):
+    """Runs the C++ builder; returns (packed bytes as numpy uint8, directory, scalars)."""
+    def ptr(a: np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    query_num = len(flat["leaf_to_q"])
+    use_tix = tree_index_max_ctx > 0
+    h = _lib.lib.deft_b200_build_tables(len(flat["parent"]), ptr(flat["parent"]), ptr(flat["kv_off"]), ptr(flat["kv"]),
+                                        ptr(flat["q_off"]), ptr(flat["qs"]), ptr(flat["tix"]) if use_tix else None,
+                                        tree_index_max_ctx, query_num, block_len, max_q_len, max_block_len, node_split)
+    if not h:
+        raise _lib.DeftError(f"deft_b200_build_tables failed: {_lib.last_error()}")
+    try:
+        nbytes = _lib.lib.deft_b200_tables_bytes(h)
+        data = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(_lib.lib.deft_b200_tables_data(h))).copy()
+        directory = np.zeros(2 * _lib.T_COUNT, dtype=np.int64)
+        _lib.check(_lib.lib.deft_b200_tables_directory(h, ptr(directory)))
+        scalars = np.zeros(6, dtype=np.int64)
+        _lib.check(_lib.lib.deft_b200_tables_scalars(h, ptr(scalars)))
+    finally:
+        _lib.lib.deft_b200_tables_free(h)
+    return data, directory.reshape(-1, 2), scalars
+
+
+@dataclass
+class TreeMetadata:
+    """Field names and meanings of the reference dataclass (tree_cache.py:591-616)."""
+    query_num: int
+    node_num: int
+    total_kv_len: int
+    leaf_to_q: Dict[int, int]
+    node_q: torch.Tensor
+    node_kv: torch.Tensor
+    node_q_len: torch.Tensor
+    node_kv_len: torch.Tensor
+    node_q_offset: torch.Tensor
+    node_kv_offset: torch.Tensor
+    block_len: int
+    block_q: torch.Tensor
+    block_q_cnts: torch.Tensor
+    block_q_offset: torch.Tensor
+    block_bitmasks: torch.Tensor
+    block_kv: torch.Tensor
+    block_lens: torch.Tensor
+    # native extras (not in the reference): the packed device buffer and the two work plans
+    packed: Optional[torch.Tensor] = field(default=None, repr=False)
+    flat_plan: Optional[_lib.Plan] = field(default=None, repr=False)
+    node_plan: Optional[_lib.Plan] = field(default=None, repr=False)
+    host_tables: Optional[Dict[str, np.ndarray]] = field(default=None, repr=False)
+
+    @classmethod
+    def _assemble(cls, tree, flat, max_q_len: int, max_block_len: int, tree_index: bool) -> "TreeMetadata":
+        block_len = BLOCK_CONFIG["BLOCK_LEN"]
+        if max_block_len == -1:
+            max_block_len = BLOCK_CONFIG["MAX_BLOCK_LEN"]
+        max_ctx = tree.tree_index_pool.node_to_kv.shape[1] if tree_index else 0
+        data, directory, scalars = build_tables_host(flat, max_q_len, max_block_len, block_len, max_ctx)
+        pool = tree.token_to_kv_pool           # ours, or the reference's (which has no .device)
+        device = getattr(pool, "device", None) or pool.kv_data[0].device
+        on_gpu = device.type == "cuda"
+        packed = _STAGING.upload(data, device) if on_gpu else torch.from_numpy(data)
+
+        def view(i: int, dtype: torch.dtype, elem: int) -> torch.Tensor:
+            off, cnt = int(directory[i, 0]), int(directory[i, 1])
+            return packed[off: off + cnt * elem].view(dtype)
+
+        t = {name: view(i, torch.int64, 8) for i, name in enumerate(_lib.T_NAMES[:12])}
+        base = packed.data_ptr()
+
+        def plan(first: int, rows: int) -> _lib.Plan:
+            return _lib.Plan(items=base + int(directory[first, 0]), groups=base + int(directory[first + 1, 0]),
+                             csr_off=base + int(directory[first + 2, 0]), csr_rows=base + int(directory[first + 3, 0]),
+                             n_items=int(directory[first, 1]), n_groups=int(directory[first + 1, 1]),
+                             n_part_rows=rows, pad=0)
+
+        if tree_index:
+            null = torch.empty(0, dtype=torch.int64, device=device)
+            tix = tree.tree_index_pool
+            t["node_kv"] = (tix.device_table() if on_gpu and hasattr(tix, "device_table") else tix.node_to_kv).view(-1)
+            for k in ("block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv", "block_lens"):
+                t[k] = null
+        meta = cls(query_num=int(scalars[0]), node_num=int(scalars[1]), total_kv_len=int(scalars[2]),
+                   leaf_to_q=flat["leaf_to_q"], block_len=int(scalars[3]), packed=packed,
+                   flat_plan=None if tree_index else plan(12, int(scalars[4])), node_plan=plan(16, int(scalars[5])), **t)
+        if on_gpu:
+            register_plan(meta)
+        return meta
+
+    @classmethod
+    def from_tree_cache(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":
+        return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=False)
+
+    @classmethod
+    def from_tree_cache_node(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":
+        assert tree.use_tree_index and tree.tree_index_pool is not None
+        return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=True)
+
+
+def register_plan(meta: TreeMetadata) -> None:
+    """Lets the operator find the native plan from the table pointers it is called with."""
+    keys = [meta.node_q.data_ptr()]
+    if meta.flat_plan is not None:
+        keys.append(meta.block_q.data_ptr())
+    ref = weakref.ref(meta)
+    for k in keys:
+        _PLAN_REGISTRY[k] = ref
+    weakref.finalize(meta, lambda ks=tuple(keys), r=ref: [_PLAN_REGISTRY.pop(k, None) for k in ks
+                                                       if _PLAN_REGISTRY.get(k) is r])
+
+
+def lookup_plan(table: torch.Tensor) -> Optional[TreeMetadata]:
+    ref = _PLAN_REGISTRY.get(table.data_ptr())
+    return ref() if ref is not None else None
+
+
+GLOBAL_TREE_METADATA: Optional[TreeMetadata] = None
+GLOBAL_TREE_CACHE: Optional[TreeCache] = None
+
+
+def register_tree_metadata(tree_metadata: TreeMetadata) -> None:
+    global GLOBAL_TREE_METADATA
+    GLOBAL_TREE_METADATA = tree_metadata
+
+
+def unregister_tree_metadata() -> None:
+    global GLOBAL_TREE_METADATA
+    GLOBAL_TREE_METADATA = None
+
+
+def get_global_tree_metadata() -> TreeMetadata:
+    assert GLOBAL_TREE_METADATA is not None
+    return GLOBAL_TREE_METADATA
+
+
+def register_tree_cache(tree_cache: TreeCache) -> None:
+    global GLOBAL_TREE_CACHE
+    GLOBAL_TREE_CACHE = tree_cache
+
+
+def unregister_tree_cache() -> None:
+    global GLOBAL_TREE_CACHE
+    GLOBAL_TREE_CACHE = None
+
+
+def get_global_tree_cache() -> TreeCache:
+    assert GLOBAL_TREE_CACHE is not None
+    return GLOBAL_TREE_CACHE

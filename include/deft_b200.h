@@ -1,0 +1,172 @@
+/*
+ * deft_b200.h -- C ABI of libdeft_b200.so: B200 (sm_100a) tree-attention decode for DeFT.
+ *
+ * This is the drop-in boundary for the ONE path this repository accelerates: DeFT's decode-step
+ * tree attention (DeFT-Flatten / DeFT-Node / DeFT-Node-Chunk / Tree-Index) over its token-granular
+ * paged KV pool, plus the KV-guided-grouping metadata builder that drives it.  Every entry point
+ * names the reference interface it replaces (paths under LINs-lab/DeFT, DeFT/deft/...).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; device pointers are marked [dev], host pointers [host]
+ *   - all tensors are caller-owned and must outlive the (asynchronous) call
+ *   - launches go to the cudaStream_t passed as `void* stream` (0 = legacy default stream)
+ *   - return 0 on success, a negative DEFT_E_* code otherwise; deft_b200_last_error() gives text
+ *   - thread-compatible: no global mutable state besides a thread-local error string and
+ *     once-only cudaFuncSetAttribute calls
+ *   - activations / KV are IEEE fp16 (the reference hard-codes torch.float16, model_runner.py:271,336)
+ */
+#ifndef DEFT_B200_H_
+#define DEFT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEFT_B200_ABI_VERSION 1
+
+enum {
+  DEFT_OK = 0,
+  DEFT_E_ARG = -1,       /* bad argument (shape, alignment, null pointer) */
+  DEFT_E_WORKSPACE = -2, /* workspace too small */
+  DEFT_E_CUDA = -3,      /* a CUDA runtime call failed */
+  DEFT_E_TREE = -4       /* malformed tree handed to the metadata builder */
+};
+
+int deft_b200_abi_version(void);
+const char* deft_b200_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Work plan (device side).  One *item* = one KV token range of the table, attended by 1..n
+ * *groups* of <= 32 queries; a group row r stands for the 4 (= H/HKV) GQA heads of query
+ * q_list[q_off + r].  `part_base + r` is the partial-softmax row the group writes.
+ * The plan is either built on the host by deft_b200_build_tables() (and uploaded by the caller
+ * in one copy) or derived on the device from the reference tables by the *_fwd calls.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t kv_off;   /* first element of the KV index table this item reads */
+  int32_t kv_len;   /* tokens in the item (any length; tiled by 128 inside the kernel) */
+  int32_t grp_off;  /* first group */
+  int32_t n_grp;    /* number of groups sharing the KV range */
+  int32_t cost;     /* scheduling weight (tokens x rows); informational */
+} deft_item_t;
+
+typedef struct {
+  int64_t mask_off;  /* first element of the per-token bitmask table, -1 = no mask (all attend) */
+  int32_t q_off;     /* first element of the query list */
+  int32_t q_cnt;     /* 1..32 */
+  int32_t part_base; /* first partial row */
+  int32_t pad;
+} deft_group_t;
+
+typedef struct {
+  const deft_item_t* items;   /* [dev] */
+  const deft_group_t* groups; /* [dev] */
+  const int32_t* csr_off;     /* [dev] nq+1: partial rows of query q are csr_rows[csr_off[q]:csr_off[q+1]] */
+  const int32_t* csr_rows;    /* [dev] n_part_rows, ascending within a query (deterministic merge order) */
+  int32_t n_items;
+  int32_t n_groups;
+  int32_t n_part_rows;
+  int32_t pad;
+} deft_plan_t;
+
+/* ------------------------------------------------------------------------------------------
+ * DeFT-Flatten operator.
+ * Replaces tree_attention_subtree_fwd (layers/attention/tree_attention.py:552-667: stage-1 kernel2
+ * :860-976 + DeFT_splitBynode_Triton_stage2 :297-416).  Argument meaning is the reference's:
+ *   q  [nq, H, D] fp16, strides in elements (row stride 6144 for the fused-qkv view)
+ *   k/v[pool, HKV, D] fp16 views of kv_data[layer][:,0] / [:,1] (memory_pool.py:68-72)
+ *   o  [nq, H, D] fp16, fully overwritten (the reference requires it pre-zeroed; we do not)
+ *   block_q [n_partials], block_q_cnts/offset/lens [n_blocks], block_bitmasks/block_kv
+ *   [n_blocks*block_len] -- int64 device tables of TreeMetadata (tree_cache.py:591-616)
+ * block_len must be 128 (the reference kernel hard-wires BLOCK_N=128, tree_attention.py:655-657).
+ * `plan` may be NULL: the plan is then derived on the device inside `workspace`.
+ * ------------------------------------------------------------------------------------------ */
+size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
+                                         int64_t n_blocks);
+
+int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride,
+                          const void* k, const void* v, int64_t kv_tok_stride,
+                          int64_t kv_head_stride, void* o, int64_t o_row_stride,
+                          int64_t o_head_stride, int32_t nq, int32_t H, int32_t HKV, int32_t D,
+                          int32_t block_len, const int64_t* block_q, int64_t n_partials,
+                          const int64_t* block_q_cnts, const int64_t* block_q_offset,
+                          const int64_t* block_lens, int64_t n_blocks,
+                          const int64_t* block_bitmasks, const int64_t* block_kv,
+                          const deft_plan_t* plan, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DeFT-Node / Node-Chunk / Tree-Index operator.
+ * Replaces tree_attention_fwd (layers/attention/tree_attention.py:14-68: stage-1 :82-293 + stage 2).
+ *   kv_indices: node_kv, int64 -- or the int32 node->page table of tree-index mode
+ *               (tree_decoding/tree_index_pool.py:11-50); kv_index_bytes is 8 or 4
+ *   kv_offset/kv_len/q_offset/q_len [n_entries] int64; node_q [n_partials] int64
+ *   max_kv_len: upper bound of kv_len[] (sizes the split of long entries; e.g. the pool size)
+ * ------------------------------------------------------------------------------------------ */
+size_t deft_b200_node_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
+                                      int64_t n_entries, int64_t total_kv_bound);
+
+int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                       const void* v, int64_t kv_tok_stride, int64_t kv_head_stride, void* o,
+                       int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
+                       int32_t HKV, int32_t D, const void* kv_indices, int32_t kv_index_bytes,
+                       const int64_t* kv_offset, const int64_t* kv_len, const int64_t* node_q,
+                       int64_t n_partials, const int64_t* q_offset, const int64_t* q_len,
+                       int64_t n_entries, int64_t total_kv_bound, const deft_plan_t* plan,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * KV append.  Replaces KVCacheUpdater.update (tree_decoding/tree_cache.py:67-76):
+ *   key_buffer[cache_loc] = cache_k; value_buffer[cache_loc] = cache_v   in ONE launch.
+ *   new_k/new_v [n, HKV, D] fp16 (row stride in elements), cache_loc [n] int32.
+ * ------------------------------------------------------------------------------------------ */
+int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                        const void* new_k, const void* new_v, int64_t new_row_stride,
+                        int64_t new_head_stride, const int32_t* cache_loc, int32_t n, int32_t HKV,
+                        int32_t D, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Metadata builder (host only, no CUDA, thread-safe).
+ * Replaces TreeMetadata.from_tree_cache (tree_decoding/tree_cache.py:618-881) and
+ * from_tree_cache_node (:883-1018): KV-guided grouping + flattened-tree KV split.  Tables are
+ * bit-identical to the reference's; the work plan above is produced in the same pass.
+ *
+ * The tree is handed over as flat arrays, nodes in DFS pre-order with children in creation
+ * (dict insertion) order -- the order tree_cache.py:725-791 visits them:
+ *   parent[n]        index of the parent in this order, -1 for the root (node 0)
+ *   kv_off[n+1], kv  per-node page lists (node.kv_indices, any order; sorted inside, :736)
+ *   q_off[n+1], qs   per-node attending queries = rank by leaf id of node.refs (:650-652, :737)
+ *   tix_row[n]       tree-index mode only: node.node_indices_id, else NULL
+ * The result is one packed host buffer (upload with a single copy) + a directory.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  DEFT_T_NODE_Q = 0, DEFT_T_NODE_KV, DEFT_T_NODE_Q_LEN, DEFT_T_NODE_KV_LEN, DEFT_T_NODE_Q_OFFSET,
+  DEFT_T_NODE_KV_OFFSET, DEFT_T_BLOCK_Q, DEFT_T_BLOCK_Q_CNTS, DEFT_T_BLOCK_Q_OFFSET,
+  DEFT_T_BLOCK_BITMASKS, DEFT_T_BLOCK_KV, DEFT_T_BLOCK_LENS,          /* int64 reference tables */
+  DEFT_T_FLAT_ITEMS, DEFT_T_FLAT_GROUPS, DEFT_T_FLAT_CSR_OFF, DEFT_T_FLAT_CSR_ROWS, /* Flatten plan */
+  DEFT_T_NODE_ITEMS, DEFT_T_NODE_GROUPS, DEFT_T_NODE_CSR_OFF, DEFT_T_NODE_CSR_ROWS, /* Node plan */
+  DEFT_T_COUNT
+};
+
+typedef struct deft_tables deft_tables_t;
+
+deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, const int64_t* kv_off,
+                                      const int64_t* kv, const int64_t* q_off, const int64_t* qs,
+                                      const int64_t* tix_row, int64_t tix_max_ctx,
+                                      int32_t query_num, int32_t block_len, int32_t max_q_len,
+                                      int32_t max_block_len, int32_t node_split);
+const void* deft_b200_tables_data(const deft_tables_t* t);  /* packed host buffer */
+size_t deft_b200_tables_bytes(const deft_tables_t* t);
+/* dir[2*i] = byte offset of array i in the packed buffer, dir[2*i+1] = element count */
+int deft_b200_tables_directory(const deft_tables_t* t, int64_t* dir /* [2*DEFT_T_COUNT] */);
+/* scalars: {query_num, node_num, total_kv_len, block_len, flat_part_rows, node_part_rows} */
+int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [6] */);
+void deft_b200_tables_free(deft_tables_t* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFT_B200_H_ */

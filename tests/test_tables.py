@@ -1,0 +1,165 @@
+"""C++ metadata builder (deft_b200_build_tables) vs the reference's tables and the oracle.  CPU only."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import deft_oracle as orc
+from oracle.plain_tree import PlainNode, PlainTree, thaw
+from oracle.scenarios import SCENARIOS, TABLE_SCENARIOS
+
+from deft_b200 import _lib
+from deft_b200.tree_cache import build_tables_host, flatten_tree
+
+TABLE_KEYS = _lib.T_NAMES[:12]
+ITEM = np.dtype([("kv_off", "<i8"), ("kv_len", "<i4"), ("grp_off", "<i4"), ("n_grp", "<i4"), ("cost", "<i4")])
+GROUP = np.dtype([("mask_off", "<i8"), ("q_off", "<i4"), ("q_cnt", "<i4"), ("part_base", "<i4"), ("pad", "<i4")])
+
+
+def unpack(data, directory):
+    out = {}
+    for i, name in enumerate(_lib.T_NAMES):
+        off, cnt = int(directory[i, 0]), int(directory[i, 1])
+        dt = np.dtype("<i8") if i < 12 else (ITEM if name.endswith("items") else GROUP if name.endswith("groups") else np.dtype("<i4"))
+        out[name] = np.frombuffer(data, dtype=dt, count=cnt, offset=off)
+    return out
+
+
+def build(tree, mbl=-1, **kw):
+    data, directory, scalars = build_tables_host(flatten_tree(tree), max_block_len=mbl, **kw)
+    return unpack(data, directory), scalars
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    return z, thaw({k[5:]: z[k] for k in z.files if k.startswith("tree_")})
+
+
+def test_struct_sizes():
+    assert ITEM.itemsize == _lib.ITEM_BYTES and GROUP.itemsize == _lib.GROUP_BYTES
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS) + list(TABLE_SCENARIOS))
+def test_tables_match_reference_bit_exact(golden_dir, name):
+    z, tree = load(golden_dir, name)
+    for prefix, mbl in (("t_", -1), ("tc_", 128)):
+        t, scalars = build(tree, mbl)
+        for k in TABLE_KEYS:
+            assert np.array_equal(t[k], z[prefix + k]), (name, prefix, k)
+        assert scalars[:4].tolist() == z[prefix + "scalars"].tolist()
+
+
+def test_tree_index_tables_match_reference(golden_dir):
+    z, tree = load(golden_dir, "tree_index")
+    t, _ = build(tree, 128, tree_index_max_ctx=int(z["geom"][4]))
+    for k in ["node_q", "node_q_len", "node_q_offset", "node_kv_offset", "node_kv_len"]:
+        assert np.array_equal(t[k], z["ti_" + k]), k
+
+
+def check_plan(t, nq, kind):
+    """Structural invariants of the native plan."""
+    items, groups = t[f"{kind}_items"], t[f"{kind}_groups"]
+    off, rows = t[f"{kind}_csr_off"], t[f"{kind}_csr_rows"]
+    q_list = t["block_q"] if kind == "flat" else t["node_q"]
+    assert len(off) == nq + 1 and off[0] == 0 and off[-1] == len(rows)
+    # groups are covered by items exactly once, in order
+    assert items["grp_off"].tolist() == np.concatenate([[0], np.cumsum(items["n_grp"])[:-1]]).tolist()
+    assert int(items["n_grp"].sum()) == len(groups)
+    # every partial row appears exactly once in the CSR, under the right query, ascending per query
+    row_to_q = {}
+    for g in groups:
+        assert 1 <= g["q_cnt"] <= 32
+        for r in range(g["q_cnt"]):
+            row_to_q[int(g["part_base"]) + r] = int(q_list[g["q_off"] + r])
+    assert sorted(row_to_q) == sorted(rows.tolist()) and len(set(rows.tolist())) == len(rows)
+    for q in range(nq):
+        mine = rows[off[q]: off[q + 1]]
+        assert np.all(np.diff(mine) > 0)
+        assert all(row_to_q[int(r)] == q for r in mine)
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS) + list(TABLE_SCENARIOS))
+def test_plan_invariants(golden_dir, name):
+    z, tree = load(golden_dir, name)
+    for mbl in (-1, 128):
+        t, scalars = build(tree, mbl)
+        nq = int(scalars[0])
+        check_plan(t, nq, "flat")
+        check_plan(t, nq, "node")
+        # Flatten items = unique KV blocks: one item per distinct block start, all sub-blocks grouped
+        bk = t["block_kv"].reshape(-1, 128)
+        firsts = [0] + [b for b in range(1, len(bk)) if bk[b, 0] != bk[b - 1, 0]]
+        assert (t["flat_items"]["kv_off"] // 128).tolist() == firsts
+        assert t["flat_items"]["kv_len"].tolist() == t["block_lens"][firsts].tolist()
+        # Node items tile every entry's KV range with <= 256-token pieces
+        covered = sum(int(x) for x in t["node_items"]["kv_len"])
+        assert covered == int(t["node_kv_len"].sum())
+        assert int(t["node_items"]["kv_len"].max()) <= 256
+
+
+def random_tree(rng: random.Random) -> PlainTree:
+    """Random topology, ragged node lengths around the 128 edge, shuffled page ids, leaf ids != DFS order."""
+    t = PlainTree()
+    depth = rng.randint(0, 4)
+    ids = list(range(1, 4000))
+    rng.shuffle(ids)
+    root = PlainNode(0)
+    t.root = root
+    t.nodes[0] = root
+    frontier = [root]
+    for _ in range(depth):
+        nxt = []
+        for n in frontier:
+            if n is not root and rng.random() < 0.25:
+                continue
+            for _ in range(rng.choice([1, 2, 2, 3, 7, 40 if len(frontier) < 3 else 2])):
+                c = PlainNode(ids.pop())
+                c.parent = n
+                n.children[c.id] = c
+                t.nodes[c.id] = c
+                nxt.append(c)
+        frontier = nxt or frontier
+    pages = list(range(200000))
+    rng.shuffle(pages)
+    for n in t.nodes.values():
+        ln = rng.choice([1, 1, 2, 16, 127, 128, 129, 300, rng.randint(1, 700)])
+        n.kv_indices = [pages.pop() for _ in range(ln)]
+    for n in t.nodes.values():
+        if not n.children:
+            t.leaves[n.id] = n
+            cur = n
+            while cur is not None:
+                cur.refs.add(n)
+                cur = cur.parent
+    return t
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_trees_match_oracle(seed):
+    rng = random.Random(seed)
+    tree = random_tree(rng)
+    for mbl in (-1, 128):
+        t, scalars = build(tree, mbl)
+        want = orc.build_tables(tree, max_block_len=mbl)
+        for k in TABLE_KEYS:
+            assert np.array_equal(t[k], want[k]), (seed, mbl, k)
+        assert scalars[:4].tolist() == [want["query_num"], want["node_num"], want["total_kv_len"], 128]
+        check_plan(t, want["query_num"], "flat")
+        check_plan(t, want["query_num"], "node")
+
+
+def test_builder_rejects_malformed_trees():
+    tree = PlainTree()
+    root = PlainNode(0)
+    tree.root = root
+    tree.nodes[0] = root
+    tree.leaves[0] = root
+    root.refs.add(root)
+    root.kv_indices = []                 # the reference crashes on this (range step 0); we report
+    with pytest.raises(_lib.DeftError, match="no KV pages"):
+        build(tree)
+    root.kv_indices = [3, 1, 2]
+    t, scalars = build(tree)
+    assert t["node_kv"].tolist() == [1, 2, 3] and t["block_lens"].tolist() == [3]
+    assert t["block_kv"][:4].tolist() == [1, 2, 3, -1] and scalars[2] == 3

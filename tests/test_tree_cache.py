@@ -1,0 +1,105 @@
+"""deft_b200.TreeCache replays the scripted scenarios to the SAME pages / refs / tables as the reference.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.plain_tree import freeze
+from oracle.scenarios import SCENARIOS, TABLE_SCENARIOS, replay
+
+from deft_b200 import _lib
+from deft_b200.memory_pool import ReqToTokenPool, TokenToKVPool, TreeIndexPool
+from deft_b200.tree_cache import BLOCK_CONFIG, TreeCache, TreeMetadata
+
+TABLE_KEYS = _lib.T_NAMES[:12]
+
+
+def build(cfg):
+    H, HKV, D = cfg.get("H", 8), cfg.get("HKV", 1), cfg.get("D", 16)
+    r2t = ReqToTokenPool(size=128, max_context_len=cfg["max_ctx"], device="cpu")
+    kvp = TokenToKVPool(size=cfg["pool"], dtype=torch.float16, head_num=HKV, head_dim=D, layer_num=1, device="cpu")
+    tix = TreeIndexPool(size=64, max_context_len=cfg["max_ctx"], device="cpu") if cfg.get("tree_index") else None
+    tree = TreeCache(torch.float16, HKV, D, 1, r2t, kvp, tix, True, tix is not None)
+    replay(tree, cfg["script"], lambda n: torch.arange(1, n + 1, dtype=torch.int32))
+    return tree, r2t, kvp, tix
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS) + list(TABLE_SCENARIOS))
+def test_replay_is_bit_identical_to_reference(golden_dir, name):
+    cfg = {**SCENARIOS, **TABLE_SCENARIOS}[name]
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    tree, r2t, kvp, tix = build(cfg)
+    mine = freeze(tree)
+    for k, v in mine.items():
+        assert np.array_equal(v, z["tree_" + k]), (name, k)
+    if "mem_state" in z.files:
+        assert np.array_equal(kvp.mem_state.astype(np.int64), z["mem_state"])
+    if "req_to_token" in z.files and name != "spec_merge":
+        # compare the rows of live leaves (the reference's table is torch.empty elsewhere)
+        leaves = sorted(tree.leaves.values(), key=lambda x: x.id)
+        assert [tree.leaf_to_req[l.id] for l in leaves] == z["req_idx"].tolist()
+        for l, n in zip(leaves, z["seq_lens"].tolist()):
+            row = tree.leaf_to_req[l.id]
+            assert np.array_equal(r2t.req_to_token[row, :n].numpy(), z["req_to_token"][row, :n])
+    if tix is not None:
+        for n in tree.nodes.values():
+            ln = len(n.kv_indices)
+            assert np.array_equal(tix.node_to_kv[n.node_indices_id, :ln].numpy(), z["node_to_kv"][n.node_indices_id, :ln])
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS) + list(TABLE_SCENARIOS))
+def test_metadata_from_tree_cache(golden_dir, name):
+    cfg = {**SCENARIOS, **TABLE_SCENARIOS}[name]
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    tree, *_ = build(cfg)
+    for prefix, mbl in (("t_", -1), ("tc_", 128)):
+        BLOCK_CONFIG["MAX_BLOCK_LEN"] = mbl          # how the reference CLI selects node_chunk
+        try:
+            m = TreeMetadata.from_tree_cache(tree)
+        finally:
+            BLOCK_CONFIG["MAX_BLOCK_LEN"] = -1
+        for k in TABLE_KEYS:
+            got = getattr(m, k)
+            assert got.dtype == torch.int64
+            assert np.array_equal(got.numpy(), z[prefix + k]), (name, prefix, k)
+        q_num, node_num, total, blen = z[prefix + "scalars"].tolist()
+        assert (m.query_num, m.node_num, m.total_kv_len, m.block_len) == (q_num, node_num, total, blen)
+        assert sorted(m.leaf_to_q.items()) == [tuple(r) for r in z[prefix + "leaf_to_q"].tolist()]
+        assert m.flat_plan.n_part_rows == len(z[prefix + "block_q"]) and m.node_plan.n_items >= node_num
+
+
+def test_metadata_tree_index_mode(golden_dir):
+    z = np.load(os.path.join(golden_dir, "tree_index.npz"))
+    tree, *_ = build(SCENARIOS["tree_index"])
+    BLOCK_CONFIG["MAX_BLOCK_LEN"] = 128
+    try:
+        m = TreeMetadata.from_tree_cache_node(tree)
+    finally:
+        BLOCK_CONFIG["MAX_BLOCK_LEN"] = -1
+    for k in ["node_q", "node_q_len", "node_q_offset", "node_kv_offset", "node_kv_len"]:
+        assert np.array_equal(getattr(m, k).numpy(), z["ti_" + k]), k
+    assert m.node_kv.dtype == torch.int32 and m.block_q.numel() == 0 and m.flat_plan is None
+
+
+def test_pool_allocator_contract():
+    """First-free ascending allocation, refcounts, exhaustion -> None (memory_pool.py:74-108)."""
+    p = TokenToKVPool(size=8, dtype=torch.float16, head_num=1, head_dim=16, layer_num=2, device="cpu")
+    assert p.kv_data[0].shape == (8, 2, 1, 16) and p.get_key_buffer(1).stride() == (32, 16, 1)
+    a = p.alloc(3)
+    assert a.dtype == torch.int32 and a.tolist() == [0, 1, 2]
+    p.add_refs([1])
+    assert p.free(torch.tensor([0, 1])) == 1            # page 1 still referenced
+    assert p.alloc(2).tolist() == [0, 3] and p.used_size() == 4 and p.available_size() == 4
+    assert p.alloc(5) is None and p.alloc(4).tolist() == [4, 5, 6, 7]
+    p.clear()
+    assert p.available_size() == 8 and p.alloc_ct == 0
+    r = ReqToTokenPool(size=3, max_context_len=4, device="cpu")
+    assert r.alloc(2).tolist() == [0, 1] and r.alloc(2) is None
+    r.free(0)
+    assert r.alloc(1).tolist() == [0]
+
+
+def test_unpaged_mode_is_refused():
+    with pytest.raises(NotImplementedError):
+        TreeCache(torch.float16, 1, 16, 1, None, None, None, use_paged_memory=False)
