@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Decode-step tree-attention benchmark (BASELINE.json metric) for deft_b200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+
+A *step* is one decode step of the tree-attention path on a Llama-3-8B-geometry synthetic tree:
+32 layer-calls of DeFT-Flatten attention (stage 1 + stage 2), each layer over its OWN KV pool, so
+that the 32 pools (cfg2: 0.8 GB) cycle far beyond the 126 MB L2 between consecutive calls.
+
+* ``value``      tokens/s with everything resident in HBM; the step is one CUDA graph of the 64
+                 launches, timed with CUDA events on the launching stream, max over ranks.
+* ``e2e``        the same step through the public Python API with HOST buffers: C++ table builder +
+                 one-copy upload, host->device copy of the step's fused qkv activations (pinned),
+                 KV append, 32 x tree_attention_subtree_fwd, device->host read of the outputs.
+* ``roofline``   stage-1 kernel alone (graph of 32 stage-1 launches): algorithmic bytes / duration
+                 against MEASURED_PEAKS.json.
+* ``cpu_baseline`` / ``--impl reference``: the sequence-based (per-leaf, no prefix reuse) semantics
+                 of the reference on the host cores (oracle/seq_cpu.py); a bounded sample.
+
+With N > 1 (torchrun) every rank runs its own tree (trees shard with no collective on the data
+path); NCCL carries the barrier and the max-over-ranks reduction only.  scaling = weak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+LAYERS = 32
+METRIC = "decode_attention_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="flatten", choices=["flatten", "node", "node_chunk"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-reps", type=int, default=3)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int) -> None:
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_paths_and_inputs(workload: str, layers: int):
+    """Host copies of the synthetic inputs for the CPU baseline (same shapes, seeded)."""
+    from oracle import deft_oracle as orc
+    from deft_b200.workloads import build_tree
+    tree = build_tree(workload, layers=0, device="cpu")
+    paths = orc.leaf_paths(tree)
+    g = torch.Generator().manual_seed(0)
+    size = len(tree.token_to_kv_pool.mem_state)
+    kv_layers = [torch.randn(size, 2, 8, 128, generator=g, dtype=torch.float32).half() for _ in range(layers)]
+    q = torch.randn(len(paths), 32, 128, generator=g, dtype=torch.float32).half()
+    return q, kv_layers, paths
+
+
+def cpu_baseline(workload: str, reps: int):
+    from oracle.seq_cpu import time_layer_calls
+    q, kv_layers, paths = cpu_paths_and_inputs(workload, layers=2)
+    sec, threads = time_layer_calls(q, kv_layers, paths, reps=reps, warmup=1)
+    nq = len(paths)
+    return {"value": nq / (sec * LAYERS), "unit": UNIT, "cores": threads, "kind": "port",
+            "ms_per_layer_call": sec * 1e3,
+            "sample": f"{reps} layer-calls of {workload} (of the 32 a step has), sequence-based per-leaf attention "
+                      f"(oracle/seq_cpu.py, fp32 torch bmm, {threads} threads); step time = 32 x median layer-call"}
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's sequence-based path on the host cores (bounded sample per step)."""
+    if rank != 0:
+        return
+    from oracle.seq_cpu import time_layer_calls
+    from deft_b200.workloads import WORKLOADS
+    q, kv_layers, paths = cpu_paths_and_inputs(args.workload, layers=2)
+    steps = min(args.steps, 5)
+    warm = min(args.warmup, 1)
+    sec, threads = time_layer_calls(q, kv_layers, paths, reps=steps, warmup=warm)
+    nq = len(paths)
+    value = nq / (sec * LAYERS)
+    sample = (f"each step = 1 layer-call of {args.workload} sampled from the 32 (x32 extrapolated); "
+              f"{steps} timed / {warm} warm-up (capped from --steps {args.steps} --warmup {args.warmup})")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": sec * LAYERS * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][2]}", "layers": LAYERS,
+                       "path": "sequence-based per-leaf attention on host cores (reference has no CPU kernel; port)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the tree-attention path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import deft_b200
+    from deft_b200 import BLOCK_CONFIG, TreeMetadata, _lib
+    from deft_b200.workloads import WORKLOADS, algorithmic_bytes, build_tree
+
+    # ---- synthetic inputs: one tree per rank, 32 layer pools, random-normal fp16 -----------------
+    torch.manual_seed(1234 + rank)
+    tree = build_tree(args.workload, layers=LAYERS, device=dev)
+    kvp = tree.token_to_kv_pool
+    for l in range(LAYERS):
+        kvp.kv_data[l].normal_()
+    nq = len(tree.leaves)
+    H, HKV, D = 32, 8, 128
+    qkv = torch.randn(LAYERS, nq, (H + 2 * HKV) * D, dtype=torch.float16, device=dev)   # fused qkv, row stride 6144
+    out = torch.empty(LAYERS, nq, H, D, dtype=torch.float16, device=dev)
+    if args.mode == "node_chunk":
+        BLOCK_CONFIG["MAX_BLOCK_LEN"] = 128
+    meta = TreeMetadata.from_tree_cache(tree)
+
+    def q_of(buf, l):
+        return buf[l, :, : H * D].view(nq, H, D)
+
+    def attention(l, qbuf, m):
+        K, V = kvp.get_key_buffer(l), kvp.get_value_buffer(l)
+        if args.mode == "flatten":
+            deft_b200.tree_attention_subtree_fwd(q_of(qbuf, l), K, V, out[l], m.block_len, m.block_q, m.block_q_cnts,
+                                                 m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens)
+        else:
+            deft_b200.tree_attention_fwd(q_of(qbuf, l), K, V, out[l], m.node_kv, m.node_kv_offset, m.node_kv_len,
+                                         m.node_q, m.node_q_offset, m.node_q_len)
+
+    def step_resident():
+        for l in range(LAYERS):
+            attention(l, qkv, meta)
+
+    def capture(stages):
+        _lib.lib.deft_b200_set_stages(stages)
+        step_resident()                                  # sizes the workspace outside the capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step_resident()
+        _lib.lib.deft_b200_set_stages(7)
+        return g
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    warm = max(args.warmup, 3)
+    g_full, g_s1, g_s2 = capture(7), capture(2), capture(4)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_step = timed(g_full.replay, args.steps, warm)
+    clocks = sampler.stop() if sampler else None
+    ms_s1 = timed(g_s1.replay, args.steps, warm)
+    ms_s2 = timed(g_s2.replay, args.steps, warm)
+
+    # ---- end to end through the public API with host buffers -------------------------------------
+    host_qkv = torch.randn(LAYERS, nq, (H + 2 * HKV) * D, dtype=torch.float16).pin_memory()
+    host_out = torch.empty(LAYERS, nq, H, D, dtype=torch.float16).pin_memory()
+    dev_qkv = torch.empty_like(qkv)
+    leaves = sorted(tree.leaves.values(), key=lambda x: x.id)
+    host_loc = torch.tensor([leaf.kv_indices[-1] for leaf in leaves], dtype=torch.int32).pin_memory()
+    table_bytes = [0]
+
+    def step_e2e():
+        m = TreeMetadata.from_tree_cache(tree)           # C++ builder + one H2D copy of tables and plan
+        table_bytes[0] = m.packed.numel()
+        loc = host_loc.to(dev, non_blocking=True)        # this step's pages (one per leaf)
+        dev_qkv.copy_(host_qkv, non_blocking=True)       # this step's activations for the 32 layers
+        for l in range(LAYERS):
+            k_new = dev_qkv[l, :, H * D: (H + HKV) * D].view(nq, HKV, D)
+            v_new = dev_qkv[l, :, (H + HKV) * D:].view(nq, HKV, D)
+            deft_b200.kv_append(kvp.kv_data[l], k_new, v_new, loc)
+            attention(l, dev_qkv, m)
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the caller reads the result on the host
+
+    e2e_steps = max(3, min(args.steps, 20))
+    ms_e2e = timed(step_e2e, e2e_steps, 3)
+    h2d = host_qkv.numel() * 2 + table_bytes[0] + host_loc.numel() * 4
+    d2h = host_out.numel() * 2
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    alg = algorithmic_bytes(args.workload)
+    peak, peak_src = peaks()
+    s1_s = ms_s1 / LAYERS * 1e-3
+    achieved = alg / s1_s / 1e9
+    line = {
+        "metric": METRIC, "value": world * nq / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload][2]}", "mode": args.mode, "layers": LAYERS,
+                   "geometry": "H=32 HKV=8 D=128 fp16", "trees_per_gpu": 1, "queries_per_tree": nq,
+                   "l2": "32 distinct layer KV pools cycled per step (%.0f MB > 126 MB L2)" % (LAYERS * kvp.kv_data[0].numel() * 2 / 1e6),
+                   "timing": "CUDA graph of one step (64 launches), CUDA events, max over ranks"},
+        "us_per_layer_call": ms_step / LAYERS * 1e3,
+        "us_stage1": ms_s1 / LAYERS * 1e3, "us_stage2": ms_s2 / LAYERS * 1e3,
+        "clocks": clocks,
+        "e2e": {"value": world * nq / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "path": "TreeMetadata.from_tree_cache (C++ builder, 1 upload) + pinned H2D of fused qkv + kv_append + "
+                        "32 x tree_attention_subtree_fwd + D2H of outputs"},
+        "gpu_launches": args.steps * LAYERS * 2,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "stage1 (partial softmax over KV items)",
+                     "algorithmic_bytes_per_launch": alg, "us_per_launch": s1_s * 1e6, "peak_source": peak_src},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_reps)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

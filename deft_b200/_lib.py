@@ -40,6 +40,7 @@ def _load() -> C.CDLL:
     sig = {
         "deft_b200_abi_version": (C.c_int, []),
         "deft_b200_last_error": (C.c_char_p, []),
+        "deft_b200_set_stages": (None, [i32]),
         "deft_b200_flatten_workspace_bytes": (sz, [i32, i32, i32, i64, i64]),
         "deft_b200_flatten_fwd": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, i32, i32, i32, i32,
                                             i32, vp, i64, vp, vp, vp, i64, vp, vp, C.POINTER(Plan), vp, sz, vp]),
@@ -64,7 +65,7 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
-EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_flatten_workspace_bytes",
+EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_set_stages", "deft_b200_flatten_workspace_bytes",
            "deft_b200_flatten_fwd", "deft_b200_node_workspace_bytes", "deft_b200_node_fwd", "deft_b200_kv_append",
            "deft_b200_build_tables", "deft_b200_tables_data", "deft_b200_tables_bytes",
            "deft_b200_tables_directory", "deft_b200_tables_scalars", "deft_b200_tables_free"]

@@ -8,6 +8,7 @@
 namespace deft {
 
 static thread_local char g_error[512] = "";
+static thread_local int g_stages = DEFT_STAGE_PLAN | DEFT_STAGE_1 | DEFT_STAGE_2;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -101,6 +102,15 @@ void use_plan(AttnParams& p, const PlanBuffers& pb, int64_t items_bound) {
   p.n_items = (int32_t)items_bound; p.n_items_dev = pb.counters;
 }
 
+int run_stages(const AttnParams& p, cudaStream_t stream) {
+  if (g_stages & DEFT_STAGE_1) {
+    int rc = launch_stage1_fma(p, stream);
+    if (rc) return rc;
+  }
+  if (g_stages & DEFT_STAGE_2) return launch_stage2(p, stream);
+  return DEFT_OK;
+}
+
 __global__ void kv_append_kernel(__half* k, __half* v, int64_t kv_tok_stride, int64_t kv_head_stride,
                                  const __half* nk, const __half* nv, int64_t new_row_stride,
                                  int64_t new_head_stride, const int32_t* loc, int n, int HKV, int CH) {
@@ -123,6 +133,7 @@ extern "C" {
 
 int deft_b200_abi_version(void) { return DEFT_B200_ABI_VERSION; }
 const char* deft_b200_last_error(void) { return g_error; }
+void deft_b200_set_stages(int32_t mask) { g_stages = mask; }
 
 size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
                                          int64_t n_blocks) {
@@ -167,14 +178,14 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
   if (plan) {
     use_plan(p, plan);
   } else {
-    rc = launch_plan_flatten(block_q_cnts, block_q_offset, block_lens, block_kv, block_q, n_blocks,
-                             block_len, nq, w.pb, stream);
-    if (rc) return rc;
+    if (g_stages & DEFT_STAGE_PLAN) {
+      rc = launch_plan_flatten(block_q_cnts, block_q_offset, block_lens, block_kv, block_q, n_blocks,
+                               block_len, nq, w.pb, stream);
+      if (rc) return rc;
+    }
     use_plan(p, w.pb, n_blocks);
   }
-  rc = launch_stage1_fma(p, stream);
-  if (rc) return rc;
-  return launch_stage2(p, stream);
+  return run_stages(p, stream);
 }
 
 int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
@@ -208,14 +219,14 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
   if (plan) {
     use_plan(p, plan);
   } else {
-    rc = launch_plan_node(kv_offset, kv_len, q_offset, q_len, node_q, n_entries,
-                          total_kv_bound > 0 ? kNodeSplit : 0, nq, w.pb, stream);
-    if (rc) return rc;
+    if (g_stages & DEFT_STAGE_PLAN) {
+      rc = launch_plan_node(kv_offset, kv_len, q_offset, q_len, node_q, n_entries,
+                            total_kv_bound > 0 ? kNodeSplit : 0, nq, w.pb, stream);
+      if (rc) return rc;
+    }
     use_plan(p, w.pb, items);
   }
-  rc = launch_stage1_fma(p, stream);
-  if (rc) return rc;
-  return launch_stage2(p, stream);
+  return run_stages(p, stream);
 }
 
 int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head_stride,

@@ -38,6 +38,14 @@ enum {
 int deft_b200_abi_version(void);
 const char* deft_b200_last_error(void);
 
+/* Measurement hook (bench.py): which stages the *_fwd calls of THIS thread launch.
+ * bit 0 = device plan derivation, bit 1 = stage 1 (partial softmax), bit 2 = stage 2 (combine).
+ * Default 7.  Lets a kernel be timed alone, back to back, on the launching stream. */
+#define DEFT_STAGE_PLAN 1
+#define DEFT_STAGE_1 2
+#define DEFT_STAGE_2 4
+void deft_b200_set_stages(int32_t mask);
+
 /* ------------------------------------------------------------------------------------------
  * Work plan (device side).  One *item* = one KV token range of the table, attended by 1..n
  * *groups* of <= 32 queries; a group row r stands for the 4 (= H/HKV) GQA heads of query

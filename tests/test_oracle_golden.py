@@ -95,3 +95,16 @@ def test_exact_and_seq_semantics(golden_dir, name):
     t = {k: z["t_" + k] for k in TABLE_KEYS}
     mine = np.abs(orc.flatten_fwd(q, K, V, t, faithful_fp16=False).astype(np.float64) - exact).max()
     assert mine <= np.abs(z["o_flatten"].astype(np.float64) - exact).max() + 1e-4
+
+
+@pytest.mark.parametrize("name", ["toy_binary", "llama_flat8"])
+def test_torch_cpu_baseline_matches_oracle(golden_dir, name):
+    """The multi-threaded CPU baseline bench.py times computes what oracle.seq_attention computes."""
+    import torch
+    from oracle.seq_cpu import seq_attention_torch
+    z, tree = load(golden_dir, name)
+    paths = orc.leaf_paths(tree)
+    got = seq_attention_torch(torch.from_numpy(z["q"]), torch.from_numpy(z["kv_pool"]), paths).float().numpy()
+    want = orc.seq_attention(z["q"], z["kv_pool"][:, 0], z["kv_pool"][:, 1], paths).astype(np.float32)
+    assert np.abs(got - want).max() <= 1e-3
+    assert np.abs(got - z["o_seq"].astype(np.float32)).max() <= 1e-3
