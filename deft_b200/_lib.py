@@ -17,6 +17,7 @@ T_NAMES = ["node_q", "node_kv", "node_q_len", "node_kv_len", "node_q_offset", "n
            "flat_items", "flat_groups", "flat_csr_off", "flat_csr_rows",
            "node_items", "node_groups", "node_csr_off", "node_csr_rows"]
 T_COUNT = len(T_NAMES)
+STAGE1_AUTO, STAGE1_FMA, STAGE1_UMMA = 0, 1, 2
 ITEM_BYTES = 24
 GROUP_BYTES = 24
 
@@ -41,6 +42,8 @@ def _load() -> C.CDLL:
         "deft_b200_abi_version": (C.c_int, []),
         "deft_b200_last_error": (C.c_char_p, []),
         "deft_b200_set_stages": (None, [i32]),
+        "deft_b200_set_stage1_impl": (None, [i32]),
+        "deft_b200_set_debug_buffer": (None, [vp]),
         "deft_b200_flatten_workspace_bytes": (sz, [i32, i32, i32, i64, i64]),
         "deft_b200_flatten_fwd": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, i32, i32, i32, i32,
                                             i32, vp, i64, vp, vp, vp, i64, vp, vp, C.POINTER(Plan), vp, sz, vp]),
@@ -65,7 +68,8 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
-EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_set_stages", "deft_b200_flatten_workspace_bytes",
+EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_set_stages", "deft_b200_set_stage1_impl",
+           "deft_b200_set_debug_buffer", "deft_b200_flatten_workspace_bytes",
            "deft_b200_flatten_fwd", "deft_b200_node_workspace_bytes", "deft_b200_node_fwd", "deft_b200_kv_append",
            "deft_b200_build_tables", "deft_b200_tables_data", "deft_b200_tables_bytes",
            "deft_b200_tables_directory", "deft_b200_tables_scalars", "deft_b200_tables_free"]

@@ -9,6 +9,8 @@ namespace deft {
 
 static thread_local char g_error[512] = "";
 static thread_local int g_stages = DEFT_STAGE_PLAN | DEFT_STAGE_1 | DEFT_STAGE_2;
+static thread_local int g_stage1_impl = DEFT_STAGE1_AUTO;
+static thread_local float* g_debug = nullptr;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -104,7 +106,16 @@ void use_plan(AttnParams& p, const PlanBuffers& pb, int64_t items_bound) {
 
 int run_stages(const AttnParams& p, cudaStream_t stream) {
   if (g_stages & DEFT_STAGE_1) {
-    int rc = launch_stage1_fma(p, stream);
+    int rc;
+    if (g_stage1_impl == DEFT_STAGE1_FMA) {
+      rc = launch_stage1_fma(p, stream);
+    } else if (g_stage1_impl == DEFT_STAGE1_UMMA) {
+      AttnParams pd = p;
+      pd.dbg = g_debug;
+      rc = launch_stage1_umma(pd, stream);
+    } else {
+      rc = stage1_umma_supported(p) ? launch_stage1_umma(p, stream) : launch_stage1_fma(p, stream);
+    }
     if (rc) return rc;
   }
   if (g_stages & DEFT_STAGE_2) return launch_stage2(p, stream);
@@ -134,6 +145,8 @@ extern "C" {
 int deft_b200_abi_version(void) { return DEFT_B200_ABI_VERSION; }
 const char* deft_b200_last_error(void) { return g_error; }
 void deft_b200_set_stages(int32_t mask) { g_stages = mask; }
+void deft_b200_set_stage1_impl(int32_t impl) { g_stage1_impl = impl; }
+void deft_b200_set_debug_buffer(void* dev) { g_debug = static_cast<float*>(dev); }
 
 size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
                                          int64_t n_blocks) {

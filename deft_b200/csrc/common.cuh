@@ -57,11 +57,15 @@ struct AttnParams {
   // partial softmax buffers: po [rows][H][D] fp32, plse [rows][H] fp32
   float* po;
   float* plse;
+  float* dbg;  // debug dump of the tensor-core path (raw S and O of the first unit), normally null
 };
 
 // stage 1 (warp-FMA path) and stage 2, attn_fma.cu / combine.cu
 int launch_stage1_fma(const AttnParams& p, cudaStream_t stream);
 int launch_stage2(const AttnParams& p, cudaStream_t stream);
+// stage 1 (tcgen05 path), attn_umma.cu
+bool stage1_umma_supported(const AttnParams& p);
+int launch_stage1_umma(const AttnParams& p, cudaStream_t stream);
 
 // device-side plan derivation from the reference tables, plan.cu
 struct PlanBuffers {

@@ -46,6 +46,16 @@ const char* deft_b200_last_error(void);
 #define DEFT_STAGE_2 4
 void deft_b200_set_stages(int32_t mask);
 
+/* Stage-1 kernel selection of THIS thread.  AUTO: the tcgen05 tensor-core kernel when the geometry
+ * fits it (head_dim 64/128, H/HKV in {1,2,4}), else the warp-FMA kernel. */
+#define DEFT_STAGE1_AUTO 0
+#define DEFT_STAGE1_FMA 1
+#define DEFT_STAGE1_UMMA 2
+void deft_b200_set_stage1_impl(int32_t impl);
+/* Test hook: with DEFT_STAGE1_UMMA forced, the first work unit dumps its raw S [128][128] and
+ * O [128][D] accumulators (fp32) to this device buffer.  NULL (default) disables. */
+void deft_b200_set_debug_buffer(void* dev);
+
 /* ------------------------------------------------------------------------------------------
  * Work plan (device side).  One *item* = one KV token range of the table, attended by 1..n
  * *groups* of <= 32 queries; a group row r stands for the 4 (= H/HKV) GQA heads of query

@@ -1,0 +1,129 @@
+"""tcgen05 stage-1 kernel: accumulator-level checks (raw S and O of the first work unit) and parity of both
+stage-1 implementations.  Needs a B200."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import deft_oracle as orc
+from oracle.plain_tree import thaw
+from oracle.scenarios import SCENARIOS
+
+pytestmark = pytest.mark.gpu
+TABLE_KEYS = ["node_q", "node_kv", "node_q_len", "node_kv_len", "node_q_offset", "node_kv_offset",
+              "block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv", "block_lens"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture
+def force_impl():
+    from deft_b200 import _lib
+    def set_impl(i):
+        _lib.lib.deft_b200_set_stage1_impl(i)
+    yield set_impl
+    _lib.lib.deft_b200_set_stage1_impl(_lib.STAGE1_AUTO)
+    _lib.lib.deft_b200_set_debug_buffer(None)
+
+
+def flatten(z, dev, q, K, V):
+    import deft_b200
+    t = {k: torch.from_numpy(z["t_" + k]).to(dev) for k in TABLE_KEYS}
+    o = torch.full_like(q, float("nan"))
+    deft_b200.tree_attention_subtree_fwd(q, K, V, o, 128, t["block_q"], t["block_q_cnts"], t["block_q_offset"],
+                                         t["block_bitmasks"], t["block_kv"], t["block_lens"])
+    return o
+
+
+@pytest.mark.parametrize("name", ["llama_flat8", "toy_binary"])
+def test_accumulators_of_first_unit(golden_dir, dev, force_impl, name):
+    """S = Q K^T and O = P V of (item 0, kv-head 0, group 0) read back from TMEM, vs fp32 torch."""
+    from deft_b200 import _lib
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    H, HKV, D = z["geom"][:3].tolist()
+    G = H // HKV
+    q = torch.from_numpy(z["q"]).to(dev)
+    pool = torch.from_numpy(z["kv_pool"]).to(dev)
+    K, V = pool[:, 0], pool[:, 1]
+    dbg = torch.zeros(128 * 128 + 128 * D, dtype=torch.float32, device=dev)
+    force_impl(_lib.STAGE1_UMMA)
+    _lib.lib.deft_b200_set_debug_buffer(dbg.data_ptr())
+    o = flatten(z, dev, q, K, V)
+    torch.cuda.synchronize()
+    _lib.lib.deft_b200_set_debug_buffer(None)
+    S = dbg[: 128 * 128].view(128, 128).cpu()
+    O = dbg[128 * 128:].view(128, D).cpu()
+    cnt, ln = int(z["t_block_q_cnts"][0]), int(z["t_block_lens"][0])
+    qids = torch.from_numpy(z["t_block_q"][:cnt])
+    pages = torch.from_numpy(z["t_block_kv"][:ln])
+    bits = torch.from_numpy(z["t_block_bitmasks"][:ln])
+    qq = q.cpu().float()[qids][:, :G]                      # [cnt, G, D] heads of kv-head 0
+    kk = K.cpu().float()[pages][:, 0]                      # [ln, D]
+    vv = V.cpu().float()[pages][:, 0]
+    S_want = torch.einsum("cgd,nd->cgn", qq, kk).reshape(cnt * G, ln)
+    err_s = (S[: cnt * G, :ln] - S_want).abs().max().item()
+    print(f"{name}: max|S - QK^T| = {err_s:.3e} (|S| max {S_want.abs().max():.2f})")
+    assert err_s < 2e-2 * max(1.0, S_want.abs().max().item()), "QK^T through tcgen05 is wrong (descriptor / layout?)"
+    assert S[cnt * G:, :].abs().max().item() == 0.0, "rows past the group must be zero (zero-filled Q)"
+    assert ln == 128 or S[:, ln:].abs().max().item() == 0.0, "columns past the tile end must be zero (zero-filled K)"
+    allow = ((bits[None, :] >> torch.arange(cnt)[:, None]) & 1).bool().repeat_interleave(G, dim=0)
+    sc = S_want / D ** 0.5
+    sc = torch.where(allow, sc, torch.tensor(float("-inf")))
+    m = sc.max(dim=1, keepdim=True).values
+    P = torch.exp(sc - m)
+    O_want = P @ vv
+    err_o = (O[: cnt * G] - O_want).abs().max().item()
+    print(f"{name}: max|O - PV| = {err_o:.3e} (|O| max {O_want.abs().max():.2f})")
+    assert err_o < 2e-2 * max(1.0, O_want.abs().max().item()), "PV through tcgen05 is wrong (V / P descriptor?)"
+    want = z["o_flatten"].astype(np.float32)
+    assert np.allclose(o.float().cpu().numpy(), want, atol=1e-3, rtol=1e-2)
+
+
+@pytest.mark.parametrize("impl", ["fma", "umma"])
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_both_stage1_kernels_match_reference(golden_dir, dev, force_impl, name, impl):
+    import deft_b200
+    from deft_b200 import _lib
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    q = torch.from_numpy(z["q"]).to(dev)
+    pool = torch.from_numpy(z["kv_pool"]).to(dev)
+    K, V = pool[:, 0], pool[:, 1]
+    force_impl(_lib.STAGE1_FMA if impl == "fma" else _lib.STAGE1_UMMA)
+    o = flatten(z, dev, q, K, V)
+    assert np.allclose(o.float().cpu().numpy(), z["o_flatten"].astype(np.float32), atol=1e-3, rtol=1e-2)
+    for prefix, key in (("t_", "o_node"), ("tc_", "o_node_chunk")):
+        t = {k: torch.from_numpy(z[prefix + k]).to(dev) for k in TABLE_KEYS}
+        o = torch.full_like(q, float("nan"))
+        deft_b200.tree_attention_fwd(q, K, V, o, t["node_kv"], t["node_kv_offset"], t["node_kv_len"], t["node_q"],
+                                     t["node_q_offset"], t["node_q_len"])
+        got = o.float().cpu().numpy()
+        assert np.isfinite(got).all(), (impl, key)
+        assert np.allclose(got, z[key].astype(np.float32), atol=1e-3, rtol=1e-2), (impl, key, np.abs(got - z[key]).max())
+
+
+def test_kernels_agree_at_full_size(dev, force_impl):
+    """cfg2 at full size: tensor-core and warp-FMA stage 1 agree to fp16 rounding of P."""
+    from deft_b200 import TreeMetadata, _lib
+    import deft_b200
+    from deft_b200.workloads import build_tree
+    torch.manual_seed(1)
+    tree = build_tree("cfg2", layers=1, device=dev)
+    kvp = tree.token_to_kv_pool
+    kvp.kv_data[0].normal_()
+    K, V = kvp.get_key_buffer(0), kvp.get_value_buffer(0)
+    nq = len(tree.leaves)
+    q = torch.randn(nq, 48 * 128, dtype=torch.float16, device=dev)[:, : 32 * 128].view(nq, 32, 128)
+    m = TreeMetadata.from_tree_cache(tree)
+    outs = {}
+    for impl in (_lib.STAGE1_FMA, _lib.STAGE1_UMMA):
+        force_impl(impl)
+        o = torch.empty(nq, 32, 128, dtype=torch.float16, device=dev)
+        deft_b200.tree_attention_subtree_fwd(q, K, V, o, 128, m.block_q, m.block_q_cnts, m.block_q_offset,
+                                             m.block_bitmasks, m.block_kv, m.block_lens)
+        outs[impl] = o.float()
+    assert torch.allclose(outs[_lib.STAGE1_FMA], outs[_lib.STAGE1_UMMA], atol=1e-3, rtol=1e-2)
