@@ -11,21 +11,27 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdeft_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 T_NAMES = ["node_q", "node_kv", "node_q_len", "node_kv_len", "node_q_offset", "node_kv_offset",
            "block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv", "block_lens",
            "flat_items", "flat_groups", "flat_csr_off", "flat_csr_rows",
-           "node_items", "node_groups", "node_csr_off", "node_csr_rows"]
+           "node_items", "node_groups", "node_csr_off", "node_csr_rows",
+           "u_units", "u_csr_off", "u_csr_rows", "u_kv", "u_mask", "u_q", "u_job_off", "u_jobs"]
 T_COUNT = len(T_NAMES)
 STAGE1_AUTO, STAGE1_FMA, STAGE1_UMMA = 0, 1, 2
 ITEM_BYTES = 24
 GROUP_BYTES = 24
+UNIT_BYTES = 64
+N_SCALARS = 8
 
 
 class Plan(C.Structure):
     """``deft_plan_t``"""
     _fields_ = [("items", C.c_void_p), ("groups", C.c_void_p), ("csr_off", C.c_void_p), ("csr_rows", C.c_void_p),
-                ("n_items", C.c_int32), ("n_groups", C.c_int32), ("n_part_rows", C.c_int32), ("pad", C.c_int32)]
+                ("n_items", C.c_int32), ("n_groups", C.c_int32), ("n_part_rows", C.c_int32), ("n_units", C.c_int32),
+                ("units", C.c_void_p), ("u_csr_off", C.c_void_p), ("u_csr_rows", C.c_void_p), ("u_kv", C.c_void_p),
+                ("u_mask", C.c_void_p), ("u_q", C.c_void_p), ("u_job_off", C.c_void_p), ("u_jobs", C.c_void_p),
+                ("n_unit_slots", C.c_int32), ("n_ctas", C.c_int32), ("hkv", C.c_int32), ("pad", C.c_int32)]
 
 
 class DeftError(RuntimeError):
@@ -44,14 +50,14 @@ def _load() -> C.CDLL:
         "deft_b200_set_stages": (None, [i32]),
         "deft_b200_set_stage1_impl": (None, [i32]),
         "deft_b200_set_debug_buffer": (None, [vp]),
-        "deft_b200_flatten_workspace_bytes": (sz, [i32, i32, i32, i64, i64]),
+        "deft_b200_flatten_workspace_bytes": (sz, [i32, i32, i32, i32, i64, i64, C.POINTER(Plan)]),
         "deft_b200_flatten_fwd": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, i32, i32, i32, i32,
                                             i32, vp, i64, vp, vp, vp, i64, vp, vp, C.POINTER(Plan), vp, sz, vp]),
-        "deft_b200_node_workspace_bytes": (sz, [i32, i32, i32, i64, i64, i64]),
+        "deft_b200_node_workspace_bytes": (sz, [i32, i32, i32, i32, i64, i64, i64, C.POINTER(Plan)]),
         "deft_b200_node_fwd": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, i32, i32, i32, i32,
                                          vp, i32, vp, vp, vp, i64, vp, vp, i64, i64, C.POINTER(Plan), vp, sz, vp]),
         "deft_b200_kv_append": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, i64, vp, i32, i32, i32, vp]),
-        "deft_b200_build_tables": (vp, [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32]),
+        "deft_b200_build_tables": (vp, [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32]),
         "deft_b200_tables_data": (vp, [vp]),
         "deft_b200_tables_bytes": (sz, [vp]),
         "deft_b200_tables_directory": (C.c_int, [vp, vp]),

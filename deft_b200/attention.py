@@ -69,7 +69,8 @@ def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Ten
         if meta is not None and meta.flat_plan is not None and meta.block_kv.data_ptr() == block_kv.data_ptr():
             plan = meta.flat_plan
     stream = torch.cuda.current_stream(query_states.device).cuda_stream
-    need = _lib.lib.deft_b200_flatten_workspace_bytes(nq, H, D, n_partials, n_blocks)
+    need = _lib.lib.deft_b200_flatten_workspace_bytes(nq, H, HKV, D, n_partials, n_blocks,
+                                                      C.byref(plan) if plan is not None else None)
     ws = _workspace(query_states.device, stream, need)
     _lib.check(_lib.lib.deft_b200_flatten_fwd(
         query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
@@ -100,7 +101,8 @@ def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, val
         if meta is not None and meta.node_plan is not None and meta.node_kv.data_ptr() == KV_indices.data_ptr():
             plan = meta.node_plan
     stream = torch.cuda.current_stream(query_states.device).cuda_stream
-    need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, D, n_partials, n_entries, total_kv_bound)
+    need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, HKV, D, n_partials, n_entries, total_kv_bound,
+                                                   C.byref(plan) if plan is not None else None)
     ws = _workspace(query_states.device, stream, need)
     _lib.check(_lib.lib.deft_b200_node_fwd(
         query_states.data_ptr(), query_states.stride(0), query_states.stride(1),

@@ -23,16 +23,35 @@ namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// Which stage-1 kernel a call of this thread runs (the stage-2 kernel and the partial layout follow it).
+bool use_umma(int32_t H, int32_t HKV, int32_t D) {
+  if (g_stage1_impl == DEFT_STAGE1_FMA) return false;
+  AttnParams probe{};
+  probe.H = H; probe.HKV = HKV; probe.D = D;
+  return g_stage1_impl == DEFT_STAGE1_UMMA || stage1_umma_supported(probe);
+}
+
 // Carves the caller's workspace.  Layout (all 256-byte aligned):
-//   po [rows][H][D] f32 | plse [rows][H] f32 | items | groups | csr_off | csr_rows | cursor | counters
+//   tcgen05 path: po16 [slots*HKV][D/8][32G][8] f16 | plse16 [slots*HKV][32G] f32
+//   warp-FMA path: po [rows][H][D] f32 | plse [rows][H] f32
+//   device-derived plan: items | groups | units | csr_off | csr_rows | cursor | counters
 struct Workspace {
   float* po;
   float* plse;
+  __half* po16;
+  float* plse16;
   PlanBuffers pb;
   size_t bytes;
 };
 
-Workspace carve(void* base, int64_t rows, int64_t items, int32_t nq, int32_t H, int32_t D, bool with_plan) {
+struct Sizes {
+  int64_t fma_rows;     // partial rows of the warp-FMA layout
+  int64_t slots;        // unit slots (32 partial rows each) of the tile layout
+  int64_t groups;       // device plan: bound on items / groups / units
+  int64_t csr_entries;  // device plan: bound on sum of q_cnt over groups
+};
+
+Workspace carve(void* base, const Sizes& z, bool umma, bool with_plan, int32_t nq, int32_t H, int32_t HKV, int32_t D) {
   Workspace w{};
   size_t off = 0;
   auto take = [&](size_t n) {
@@ -40,13 +59,20 @@ Workspace carve(void* base, int64_t rows, int64_t items, int32_t nq, int32_t H, 
     off += align_up(n);
     return p;
   };
-  w.po = static_cast<float*>(take((size_t)rows * H * D * sizeof(float)));
-  w.plse = static_cast<float*>(take((size_t)rows * H * sizeof(float)));
+  if (umma) {
+    const size_t tile_rows = (size_t)kMaxGroupQ * (H / HKV);
+    w.po16 = static_cast<__half*>(take((size_t)z.slots * HKV * tile_rows * D * sizeof(__half)));
+    w.plse16 = static_cast<float*>(take((size_t)z.slots * HKV * tile_rows * sizeof(float)));
+  } else {
+    w.po = static_cast<float*>(take((size_t)z.fma_rows * H * D * sizeof(float)));
+    w.plse = static_cast<float*>(take((size_t)z.fma_rows * H * sizeof(float)));
+  }
   if (with_plan) {
-    w.pb.items = static_cast<deft_item_t*>(take((size_t)items * sizeof(deft_item_t)));
-    w.pb.groups = static_cast<deft_group_t*>(take((size_t)items * sizeof(deft_group_t)));
+    w.pb.items = static_cast<deft_item_t*>(take((size_t)z.groups * sizeof(deft_item_t)));
+    w.pb.groups = static_cast<deft_group_t*>(take((size_t)z.groups * sizeof(deft_group_t)));
+    w.pb.units = static_cast<deft_unit_t*>(take((size_t)z.groups * sizeof(deft_unit_t)));
     w.pb.csr_off = static_cast<int32_t*>(take((size_t)(nq + 1) * sizeof(int32_t)));
-    w.pb.csr_rows = static_cast<int32_t*>(take((size_t)rows * sizeof(int32_t)));
+    w.pb.csr_rows = static_cast<int32_t*>(take((size_t)z.csr_entries * sizeof(int32_t)));
     w.pb.cursor = static_cast<int32_t*>(take((size_t)(nq + 1) * sizeof(int32_t)));
     w.pb.counters = static_cast<int32_t*>(take(16));
   }
@@ -57,8 +83,18 @@ Workspace carve(void* base, int64_t rows, int64_t items, int32_t nq, int32_t H, 
 inline int64_t node_items_bound(int64_t n_entries, int64_t total_kv_bound) {
   return n_entries + (total_kv_bound > 0 ? total_kv_bound / kNodeSplit + 1 : 0);
 }
-inline int64_t node_rows_bound(int64_t n_partials, int64_t total_kv_bound) {
+inline int64_t node_csr_bound(int64_t n_partials, int64_t total_kv_bound) {
   return n_partials + (total_kv_bound > 0 ? kMaxGroupQ * (total_kv_bound / kNodeSplit + 1) : 0);
+}
+
+Sizes flatten_sizes(const deft_plan_t* plan, int64_t n_partials, int64_t n_blocks) {
+  if (plan) return Sizes{plan->n_part_rows, plan->n_unit_slots, 0, 0};
+  return Sizes{n_blocks * kMaxGroupQ, n_blocks, n_blocks, n_partials};
+}
+Sizes node_sizes(const deft_plan_t* plan, int64_t n_partials, int64_t n_entries, int64_t total_kv_bound) {
+  if (plan) return Sizes{plan->n_part_rows, plan->n_unit_slots, 0, 0};
+  const int64_t items = node_items_bound(n_entries, total_kv_bound);
+  return Sizes{items * kMaxGroupQ, items, items, node_csr_bound(n_partials, total_kv_bound)};
 }
 
 int check_common(const void* q, const void* k, const void* v, const void* o, int32_t nq, int32_t H,
@@ -93,32 +129,52 @@ AttnParams base_params(const void* q, int64_t q_row_stride, int64_t q_head_strid
   return p;
 }
 
-void use_plan(AttnParams& p, const deft_plan_t* plan) {
-  p.items = plan->items; p.groups = plan->groups;
-  p.csr_off = plan->csr_off; p.csr_rows = plan->csr_rows;
-  p.n_items = plan->n_items; p.n_items_dev = nullptr;
+// Host-built plan: the warp-FMA path reads the item/group layer (reference tables), the tcgen05 path
+// the unit layer (native 32-bit tables).
+int use_plan(AttnParams& p, const deft_plan_t* plan, bool umma) {
+  if (umma) {
+    DEFT_CHECK_ARG(plan->units && plan->u_csr_off && plan->u_csr_rows && plan->u_kv && plan->u_q,
+                   "plan has no unit layer (rebuild the tables with this library version)");
+    p.units = plan->units; p.n_units = plan->n_units; p.n_units_dev = nullptr;
+    p.u_kv = plan->u_kv; p.u_kv_bytes = 4;
+    p.u_mask = plan->u_mask; p.u_mask_bytes = 4;
+    p.u_q = plan->u_q; p.u_q_bytes = 4;
+    p.u_csr_off = plan->u_csr_off; p.u_csr_rows = plan->u_csr_rows;
+    if (plan->u_job_off && plan->u_jobs && plan->hkv == p.HKV && plan->n_ctas > 0) {
+      p.job_off = plan->u_job_off; p.jobs = plan->u_jobs; p.n_ctas = plan->n_ctas;
+    }
+  } else {
+    p.items = plan->items; p.groups = plan->groups;
+    p.csr_off = plan->csr_off; p.csr_rows = plan->csr_rows;
+    p.n_items = plan->n_items; p.n_items_dev = nullptr;
+  }
+  return DEFT_OK;
 }
-void use_plan(AttnParams& p, const PlanBuffers& pb, int64_t items_bound) {
+// Device-derived plan: both layers index the reference tables the call was given.
+void use_plan(AttnParams& p, const PlanBuffers& pb, int64_t bound) {
   p.items = pb.items; p.groups = pb.groups;
   p.csr_off = pb.csr_off; p.csr_rows = pb.csr_rows;
-  p.n_items = (int32_t)items_bound; p.n_items_dev = pb.counters;
+  p.n_items = (int32_t)bound; p.n_items_dev = pb.counters;
+  p.units = pb.units; p.n_units = (int32_t)bound; p.n_units_dev = pb.counters + 2;
+  p.u_kv = p.kv_idx; p.u_kv_bytes = p.kv_idx_bytes;
+  p.u_mask = p.masks; p.u_mask_bytes = 8;
+  p.u_q = p.q_list; p.u_q_bytes = 8;
+  p.u_csr_off = pb.csr_off; p.u_csr_rows = pb.csr_rows;
 }
 
-int run_stages(const AttnParams& p, cudaStream_t stream) {
+int run_stages(const AttnParams& p, bool umma, cudaStream_t stream) {
   if (g_stages & DEFT_STAGE_1) {
     int rc;
-    if (g_stage1_impl == DEFT_STAGE1_FMA) {
-      rc = launch_stage1_fma(p, stream);
-    } else if (g_stage1_impl == DEFT_STAGE1_UMMA) {
+    if (umma) {
       AttnParams pd = p;
       pd.dbg = g_debug;
       rc = launch_stage1_umma(pd, stream);
     } else {
-      rc = stage1_umma_supported(p) ? launch_stage1_umma(p, stream) : launch_stage1_fma(p, stream);
+      rc = launch_stage1_fma(p, stream);
     }
     if (rc) return rc;
   }
-  if (g_stages & DEFT_STAGE_2) return launch_stage2(p, stream);
+  if (g_stages & DEFT_STAGE_2) return umma ? launch_stage2_tiles(p, stream) : launch_stage2(p, stream);
   return DEFT_OK;
 }
 
@@ -148,15 +204,17 @@ void deft_b200_set_stages(int32_t mask) { g_stages = mask; }
 void deft_b200_set_stage1_impl(int32_t impl) { g_stage1_impl = impl; }
 void deft_b200_set_debug_buffer(void* dev) { g_debug = static_cast<float*>(dev); }
 
-size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
-                                         int64_t n_blocks) {
-  return carve(nullptr, n_partials, n_blocks, nq, H, D, true).bytes;
+size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_t D,
+                                         int64_t n_partials, int64_t n_blocks, const deft_plan_t* plan) {
+  if (HKV <= 0 || H % HKV) return 0;
+  return carve(nullptr, flatten_sizes(plan, n_partials, n_blocks), use_umma(H, HKV, D), plan == nullptr, nq, H, HKV, D).bytes;
 }
 
-size_t deft_b200_node_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
-                                      int64_t n_entries, int64_t total_kv_bound) {
-  return carve(nullptr, node_rows_bound(n_partials, total_kv_bound),
-               node_items_bound(n_entries, total_kv_bound), nq, H, D, true).bytes;
+size_t deft_b200_node_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_t D, int64_t n_partials,
+                                      int64_t n_entries, int64_t total_kv_bound, const deft_plan_t* plan) {
+  if (HKV <= 0 || H % HKV) return 0;
+  return carve(nullptr, node_sizes(plan, n_partials, n_entries, total_kv_bound), use_umma(H, HKV, D),
+               plan == nullptr, nq, H, HKV, D).bytes;
 }
 
 int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
@@ -177,8 +235,8 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
                  "null table pointer");
   DEFT_CHECK_ARG(n_blocks > 0 && n_partials > 0, "empty tables");
   DEFT_CHECK_ARG(workspace, "null workspace");
-  const int64_t rows = plan ? plan->n_part_rows : n_partials;
-  Workspace w = carve(workspace, rows, n_blocks, nq, H, D, plan == nullptr);
+  const bool umma = use_umma(H, HKV, D);
+  Workspace w = carve(workspace, flatten_sizes(plan, n_partials, n_blocks), umma, plan == nullptr, nq, H, HKV, D);
   if (w.bytes > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
     return DEFT_E_WORKSPACE;
@@ -187,9 +245,10 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
                              o_row_stride, o_head_stride, nq, H, HKV, D);
   p.kv_idx = block_kv; p.kv_idx_bytes = 8;
   p.q_list = block_q; p.masks = block_bitmasks;
-  p.po = w.po; p.plse = w.plse;
+  p.po = w.po; p.plse = w.plse; p.po16 = w.po16; p.plse16 = w.plse16;
   if (plan) {
-    use_plan(p, plan);
+    rc = use_plan(p, plan, umma);
+    if (rc) return rc;
   } else {
     if (g_stages & DEFT_STAGE_PLAN) {
       rc = launch_plan_flatten(block_q_cnts, block_q_offset, block_lens, block_kv, block_q, n_blocks,
@@ -198,7 +257,7 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
     }
     use_plan(p, w.pb, n_blocks);
   }
-  return run_stages(p, stream);
+  return run_stages(p, umma, stream);
 }
 
 int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
@@ -217,9 +276,10 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
   DEFT_CHECK_ARG(kv_indices && kv_offset && kv_len && node_q && q_offset && q_len, "null table pointer");
   DEFT_CHECK_ARG(n_entries > 0 && n_partials > 0, "empty tables");
   DEFT_CHECK_ARG(workspace, "null workspace");
-  const int64_t rows = plan ? plan->n_part_rows : node_rows_bound(n_partials, total_kv_bound);
+  const bool umma = use_umma(H, HKV, D);
   const int64_t items = node_items_bound(n_entries, total_kv_bound);
-  Workspace w = carve(workspace, rows, items, nq, H, D, plan == nullptr);
+  Workspace w = carve(workspace, node_sizes(plan, n_partials, n_entries, total_kv_bound), umma, plan == nullptr,
+                      nq, H, HKV, D);
   if (w.bytes > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
     return DEFT_E_WORKSPACE;
@@ -228,9 +288,10 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
                              o_row_stride, o_head_stride, nq, H, HKV, D);
   p.kv_idx = kv_indices; p.kv_idx_bytes = kv_index_bytes;
   p.q_list = node_q; p.masks = nullptr;
-  p.po = w.po; p.plse = w.plse;
+  p.po = w.po; p.plse = w.plse; p.po16 = w.po16; p.plse16 = w.plse16;
   if (plan) {
-    use_plan(p, plan);
+    rc = use_plan(p, plan, umma);
+    if (rc) return rc;
   } else {
     if (g_stages & DEFT_STAGE_PLAN) {
       rc = launch_plan_node(kv_offset, kv_len, q_offset, q_len, node_q, n_entries,
@@ -239,7 +300,7 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
     }
     use_plan(p, w.pb, items);
   }
-  return run_stages(p, stream);
+  return run_stages(p, umma, stream);
 }
 
 int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head_stride,

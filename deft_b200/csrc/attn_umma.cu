@@ -1,29 +1,44 @@
-// Stage 1, tensor-core path (sm_100a): tcgen05.mma with TMEM accumulators, persistent CTAs.
+// Stage 1, tensor-core path (sm_100a): tcgen05.mma with TMEM accumulators, warp-specialised
+// persistent CTAs walking the unit plan.
 //
-// One work unit = (item, kv-head).  A unit's KV tile (128 tokens x D, K and V) is gathered from the
-// token-granular paged pool ONCE into 128B-swizzled shared memory and serves every query group of
-// the item and all G = H/HKV query heads that share the kv-head: a group of <= 32 queries x G heads
-// is one M = 128 UMMA tile (row r = query r/G, head r%G).
+// One job = (unit, kv-head).  A unit is a chain of KV tiles (128 tokens x D, K and V) attended by one
+// or two *slots* of <= 32 queries; with G = H/HKV query heads per kv-head a slot is one M = 128 UMMA
+// tile (row r = query r/G, head r%G).  Each KV tile is gathered from the token-granular paged pool
+// ONCE into 128B-swizzled shared memory and serves both slots and all G heads:
 //
-//   S[128 x 128]  = Q[128 x D] . K^T          tcgen05.mma kind::f16, A/B K-major SW128 smem, D in TMEM
-//   P             = exp2(S*c - m), masked by the per-token bitmask     (4 softmax warps, row = TMEM lane)
-//   O[128 x D]   += P[128 x 128] . V          A = P (K-major smem), B = V (MN-major SW128 smem)
+//   S_s[128 x 128]  = Q_s[128 x D] . K^T        tcgen05.mma kind::f16, SS: A/B K-major SW128 smem -> TMEM
+//   P_s             = exp2(S_s*c - m_ref), masked by the per-token row bitmask; written back over S_s
+//                     in TMEM as packed fp16 (the A operand of the next MMA never touches smem)
+//   O_s[128 x D]   += P_s[128 x 128] . V        tcgen05.mma TS: A = P_s in TMEM, B = V (MN-major SW128 smem)
 //
-// Warp roles (192 threads): warps 0-3 softmax/epilogue (thread 0 also issues the MMAs), warps 4-5
-// producers (cp.async 16-byte gathers of paged KV rows, Q rows, masks -> mbarrier rings).
+// The chain is walked with an online softmax whose reference maximum m_ref is only raised when a tile
+// exceeds it by more than 2^8 (P stays <= 256 in fp16, O and l stay consistent), so the accumulator in
+// TMEM is almost never rescaled.  ONE partial (O/l as fp16, log-sum-exp as fp32) leaves the SM per
+// (job, slot); stage 2 (combine.cu) merges the partials of every query.
+//
+// Warp roles (384 threads, 1 CTA per SM, all 512 TMEM columns):
+//   warps 0-3   softmax + epilogue of slot 0 (thread = row = TMEM lane)
+//   warps 4-7   softmax + epilogue of slot 1; the two slots ping-pong on the tensor pipe:
+//               S_0(t) S_1(t) PV_0(t) | S_0(t+1) PV_1(t) S_1(t+1) PV_0(t+1) | ...
+//   warp  8     MMA issuer (one elected thread) and TMEM allocator
+//   warp  9/10  K / V producers: cp.async 16-byte gathers of paged rows into the swizzled stage ring
+//   warp  11    Q tiles (gathered per slot) and per-(tile, slot) mask words + "dense tile" flag
+// All hand-offs are mbarriers (cp.async arrive-on, tcgen05.commit, plain arrive); no __syncthreads in
+// the steady state.
+//
 // Reference semantics: DeFT/deft/layers/attention/tree_attention.py:860-976 (Flatten stage 1) and
-// :170-293 (Node stage 1); items longer than 128 tokens are walked tile by tile with online softmax.
+// :170-293 (Node stage 1).
 #include "common.cuh"
 
 namespace deft {
 namespace {
 
-constexpr int kTileN = 128;           // tokens per KV tile (= the reference's BLOCK_LEN)
-constexpr int kRows = 128;            // UMMA M
-constexpr int kComputeThreads = 128;  // warps 0-3
-constexpr int kProducerThreads = 64;  // warps 4-5
-constexpr int kThreads = kComputeThreads + kProducerThreads;
-constexpr int kKvStages = 2, kQStages = 2, kMaskStages = 2;
+constexpr int kTileN = 128;  // tokens per KV tile (= the reference's BLOCK_LEN)
+constexpr int kRows = 128;   // UMMA M
+constexpr int kThreads = 384;
+constexpr int kMmaWarp = 8, kKWarp = 9, kVWarp = 10, kQWarp = 11;
+constexpr int kKvStages = 2, kMaskStages = 2;
+constexpr float kRescaleLog2 = 8.f;  // raise m_ref only when a tile tops it by more than 2^8
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -45,8 +60,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a protocol bug becomes a launch failure (trap) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
   }
 }
 // arrives on `bar` when all cp.async of this thread issued so far have landed (counts as one arrival)
@@ -61,7 +79,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -71,10 +88,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 // D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
   asm volatile(
       "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p; }" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
 // arrives on `bar` when every tcgen05.mma issued so far by this thread has completed
@@ -104,7 +128,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -130,7 +171,7 @@ __host__ __device__ constexpr uint32_t instr_desc(int n, bool b_mn_major) {
 }
 
 // One operand tile in shared memory: [D/64 or 2 panels][128 rows][128 bytes], 16-byte chunks XOR-swizzled
-// by (row & 7) -- the canonical SWIZZLE_128B layout.  For K-major operands (Q, K, P) a row is an M/N
+// by (row & 7) -- the canonical SWIZZLE_128B layout.  For K-major operands (Q, K) a row is an M/N
 // index and a panel is 64 elements of the contraction dim; for the MN-major operand (V) a row is a
 // token (contraction index) and a panel is 64 elements of D.
 constexpr int kPanelBytes = kRows * 128;
@@ -138,38 +179,58 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk16) {
   return (uint32_t)((chunk16 >> 3) * kPanelBytes + row * 128 + (((chunk16 & 7) ^ (row & 7)) << 4));
 }
 
+// barrier indices
+enum : int {
+  K_FULL = 0, K_EMPTY = K_FULL + kKvStages, V_FULL = K_EMPTY + kKvStages, V_EMPTY = V_FULL + kKvStages,
+  Q_FULL = V_EMPTY + kKvStages, Q_EMPTY = Q_FULL + 2,
+  M_FULL = Q_EMPTY + 2,                    // [slot][stage]
+  M_EMPTY = M_FULL + 2 * kMaskStages,
+  S_FULL = M_EMPTY + 2 * kMaskStages,      // [slot]
+  P_FULL = S_FULL + 2, O_FULL = P_FULL + 2, O_EMPTY = O_FULL + 2,
+  kNumBars = O_EMPTY + 2
+};
+
 template <int D>
 struct Layout {
-  static constexpr int kOperandBytes = kRows * D * 2;  // Q, K or V tile
-  static constexpr int kPBytes = kRows * kTileN * 2;
-  static constexpr int kKv = 0;                                               // [stage][K|V]
-  static constexpr int kQ = kKv + kKvStages * 2 * kOperandBytes;              // [stage]
-  static constexpr int kP = kQ + kQStages * kOperandBytes;
-  static constexpr int kMask = kP + kPBytes;                                  // [stage][128] u32
-  static constexpr int kBars = kMask + kMaskStages * kTileN * 4;
-  static constexpr int kNumBars = 2 * kKvStages + 2 * kQStages + 2 * kMaskStages + 2;
+  static constexpr int kOperandBytes = kRows * D * 2;                      // Q, K or V tile
+  static constexpr int kK = 0;                                             // [stage]
+  static constexpr int kV = kK + kKvStages * kOperandBytes;                // [stage]
+  static constexpr int kQ = kV + kKvStages * kOperandBytes;                // [slot]
+  static constexpr int kMask = kQ + 2 * kOperandBytes;                     // [slot][stage][128] u32
+  static constexpr int kFlag = kMask + 2 * kMaskStages * kTileN * 4;       // [slot][stage] u32
+  static constexpr int kBars = kFlag + 2 * kMaskStages * 4;
   static constexpr int kTmemSlot = kBars + kNumBars * 8;
   static constexpr int kBytes = kTmemSlot + 16;
   static constexpr int kAlloc = kBytes + 1024;  // slack for the manual 1024-byte alignment
 };
 
-struct Ring {  // position in an mbarrier ring
-  int stage = 0;
-  uint32_t phase = 0;
-  template <int N>
-  __device__ __forceinline__ void next() {
-    if (++stage == N) {
-      stage = 0;
-      phase ^= 1;
+// The (unit, kv-head) jobs of one CTA: an explicit host-balanced list, or jobs c, c+grid, ...
+struct Jobs {
+  const int32_t* list;
+  int begin, end, stride;
+  __device__ __forceinline__ Jobs(const AttnParams& p) {
+    if (p.job_off != nullptr) {
+      list = p.jobs;
+      begin = (int)blockIdx.x < p.n_ctas ? p.job_off[blockIdx.x] : 0;
+      end = (int)blockIdx.x < p.n_ctas ? p.job_off[blockIdx.x + 1] : 0;
+      stride = 1;
+    } else {
+      list = nullptr;
+      const int n_units = p.n_units_dev ? *p.n_units_dev : p.n_units;
+      begin = blockIdx.x;
+      end = n_units * p.HKV;
+      stride = gridDim.x;
     }
   }
+  __device__ __forceinline__ int get(int i) const { return list ? list[i] : i; }
 };
 
 template <int D, int G>
 __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnParams p) {
   using L = Layout<D>;
-  constexpr int CH = D / 8;            // 16-byte chunks per row
-  constexpr int kTmemCols = 256;       // S: columns [0,128), O: columns [128,128+D)
+  constexpr int CH = D / 8;           // 16-byte chunks per row
+  constexpr int R = kMaxGroupQ * G;   // live rows of a full slot
+  constexpr uint32_t kTmemCols = 512; // S_0 [0,128) S_1 [128,256) O_0 [256,256+D) O_1 [384,384+D)
   constexpr uint32_t kIdescQK = instr_desc(kTileN, false);
   constexpr uint32_t kIdescPV = instr_desc(D, true);
 
@@ -178,275 +239,341 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
   unsigned char* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + L::kBars;
   auto bar = [&](int i) { return bars + 8u * i; };
-  // barrier indices
-  constexpr int KV_FULL = 0, KV_EMPTY = KV_FULL + kKvStages, Q_FULL = KV_EMPTY + kKvStages,
-                Q_EMPTY = Q_FULL + kQStages, M_FULL = Q_EMPTY + kQStages, M_EMPTY = M_FULL + kMaskStages,
-                S_FULL = M_EMPTY + kMaskStages, O_FULL = S_FULL + 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < kKvStages; ++s) { mbar_init(bar(KV_FULL + s), kProducerThreads); mbar_init(bar(KV_EMPTY + s), 1); }
-    for (int s = 0; s < kQStages; ++s) { mbar_init(bar(Q_FULL + s), kProducerThreads); mbar_init(bar(Q_EMPTY + s), 1); }
-    for (int s = 0; s < kMaskStages; ++s) { mbar_init(bar(M_FULL + s), kProducerThreads); mbar_init(bar(M_EMPTY + s), kComputeThreads); }
-    mbar_init(bar(S_FULL), 1);
-    mbar_init(bar(O_FULL), 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(bar(K_FULL + s), 32); mbar_init(bar(K_EMPTY + s), 1);
+      mbar_init(bar(V_FULL + s), 32); mbar_init(bar(V_EMPTY + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(Q_FULL + s), 32); mbar_init(bar(Q_EMPTY + s), 1);
+      for (int m = 0; m < kMaskStages; ++m) {
+        mbar_init(bar(M_FULL + s * kMaskStages + m), 32);
+        mbar_init(bar(M_EMPTY + s * kMaskStages + m), 128);
+      }
+      mbar_init(bar(S_FULL + s), 1); mbar_init(bar(P_FULL + s), 128);
+      mbar_init(bar(O_FULL + s), 1); mbar_init(bar(O_EMPTY + s), 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc(base + L::kTmemSlot, kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(base + L::kTmemSlot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gbase + L::kTmemSlot);
 
-  const int n_items = p.n_items_dev ? *p.n_items_dev : p.n_items;
-  const int n_units = n_items * p.HKV;
+  const Jobs jobs(p);
 
-  if (warp >= 4) {
-    // ============================== producers ==============================
-    const int pt = tid - kComputeThreads;  // 0..63
-    const int pw = warp - 4;               // 0: K, 1: V
-    Ring kv, qr, mr;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int item_id = u / p.HKV, hkv = u % p.HKV;
-      const deft_item_t item = p.items[item_id];
-      const int ntile = max(1, (item.kv_len + kTileN - 1) / kTileN);
-      for (int gi = 0; gi < item.n_grp; ++gi) {
-        const deft_group_t grp = p.groups[item.grp_off + gi];
-        // ---- Q tile of the group: row r = (query r / G, head r % G); rows past q_cnt*G are zero
-        {
-          mbar_wait(bar(Q_EMPTY + qr.stage), qr.phase ^ 1);
-          const int64_t my_q = lane < grp.q_cnt ? p.q_list[grp.q_off + lane] : 0;
-          const uint32_t qs = base + L::kQ + qr.stage * L::kOperandBytes;
-#pragma unroll 4
-          for (int i = 0; i < kRows * CH / kProducerThreads; ++i) {
-            const int c = pt + i * kProducerThreads;
-            const int r = c / CH, ch = c % CH;
-            const int qi = r / G, g = r % G;
-            const int64_t qid = __shfl_sync(0xffffffffu, my_q, qi & 31);
-            const bool ok = qi < grp.q_cnt;
-            const __half* src = p.q + qid * p.q_row_stride + (int64_t)(hkv * G + g) * p.q_head_stride + ch * 8;
-            cp_async_16(qs + tile_off(r, ch), ok ? src : p.q, ok ? 16u : 0u);
-          }
-          cp_async_arrive(bar(Q_FULL + qr.stage));
-          qr.next<kQStages>();
+  if (warp == kKWarp || warp == kVWarp) {
+    // ============================== K / V producers ==============================
+    const bool is_k = warp == kKWarp;
+    const __half* src_pool = is_k ? p.k : p.v;
+    const uint32_t dst_pool = base + (is_k ? L::kK : L::kV);
+    const int full0 = is_k ? K_FULL : V_FULL, empty0 = is_k ? K_EMPTY : V_EMPTY;
+    uint32_t cnt = 0;  // tiles produced
+    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+      const int job = jobs.get(ji);
+      const int hkv = job % p.HKV;
+      const deft_unit_t u = p.units[job / p.HKV];
+      const __half* src_base = src_pool + (int64_t)hkv * p.kv_head_stride;
+      for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
+        const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
+        const int st = cnt % kKvStages;
+        mbar_wait(bar(empty0 + st), ((cnt / kKvStages) & 1) ^ 1);
+        int64_t pg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = lane + 32 * j;
+          pg[j] = n < tlen ? load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + n) : 0;
         }
-        for (int t = 0; t < ntile; ++t) {
-          const int t0 = t * kTileN;
-          const int tlen = max(0, min(kTileN, item.kv_len - t0));
-          // ---- KV tile: loaded once per item when the item is a single tile, else once per (group, tile)
-          if (ntile > 1 || gi == 0) {
-            mbar_wait(bar(KV_EMPTY + kv.stage), kv.phase ^ 1);
-            int64_t pg[4];
+        const uint32_t dst_base = dst_pool + st * L::kOperandBytes;
+        constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int n = lane + 32 * j;
-              pg[j] = 0;
-              if (n < tlen) {
-                const int64_t e = item.kv_off + t0 + n;
-                pg[j] = p.kv_idx_bytes == 8 ? reinterpret_cast<const int64_t*>(p.kv_idx)[e]
-                                            : (int64_t) reinterpret_cast<const int32_t*>(p.kv_idx)[e];
-              }
-            }
-            const __half* src_base = (pw == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
-            const uint32_t dst_base = base + L::kKv + (kv.stage * 2 + pw) * L::kOperandBytes;
-            constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 4; ++j) {
 #pragma unroll 4
-              for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
-                const int n = j * 32 + i * TOK_PER_INSTR + lane / CH;
-                const int ch = lane % CH;
-                const int64_t page = __shfl_sync(0xffffffffu, pg[j], n & 31);
-                const bool ok = n < tlen;
-                cp_async_16(dst_base + tile_off(n, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
-              }
-            }
-            cp_async_arrive(bar(KV_FULL + kv.stage));
-            kv.next<kKvStages>();
+          for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
+            const int n = j * 32 + i * TOK_PER_INSTR + lane / CH;
+            const int ch = lane % CH;
+            const int64_t page = __shfl_sync(0xffffffffu, pg[j], n & 31);
+            const bool ok = n < tlen;
+            cp_async_16(dst_base + tile_off(n, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
           }
-          // ---- mask words of (group, tile): bit q = query q of the group attends; 0 past the tile end
-          {
-            mbar_wait(bar(M_EMPTY + mr.stage), mr.phase ^ 1);
-            uint32_t* ms = reinterpret_cast<uint32_t*>(gbase + L::kMask) + mr.stage * kTileN;
+        }
+        cp_async_arrive(bar(full0 + st));
+      }
+    }
+  } else if (warp == kQWarp) {
+    // ============================== Q tiles and mask words ==============================
+    uint32_t q_cnt[2] = {0, 0};  // jobs per slot
+    uint32_t m_cnt[2] = {0, 0};  // tiles per slot
+    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+      const int job = jobs.get(ji);
+      const int hkv = job % p.HKV;
+      const deft_unit_t u = p.units[job / p.HKV];
+      const int n_slots = u.q_cnt[1] > 0 ? 2 : 1;
+      for (int s = 0; s < n_slots; ++s) {
+        // Q tile of the slot: row r = (query r / G, head r % G); rows past q_cnt*G are zero
+        mbar_wait(bar(Q_EMPTY + s), (q_cnt[s] & 1) ^ 1);
+        const int64_t my_q = lane < u.q_cnt[s] ? load_index(p.u_q, p.u_q_bytes, u.q_off[s] + lane) : 0;
+        const uint32_t qs = base + L::kQ + s * L::kOperandBytes;
+#pragma unroll 4
+        for (int i = 0; i < kRows * CH / 32; ++i) {
+          const int c = lane + i * 32;
+          const int r = c / CH, ch = c % CH;
+          const int qi = r / G, g = r % G;
+          const int64_t qid = __shfl_sync(0xffffffffu, my_q, qi & 31);
+          const bool ok = qi < u.q_cnt[s];
+          const __half* src = p.q + qid * p.q_row_stride + (int64_t)(hkv * G + g) * p.q_head_stride + ch * 8;
+          cp_async_16(qs + tile_off(r, ch), ok ? src : p.q, ok ? 16u : 0u);
+        }
+        cp_async_arrive(bar(Q_FULL + s));
+        ++q_cnt[s];
+      }
+      for (int t = 0; t < u.n_tiles; ++t) {
+        const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
+        for (int s = 0; s < n_slots; ++s) {
+          const int st = m_cnt[s] % kMaskStages;
+          mbar_wait(bar(M_EMPTY + s * kMaskStages + st), ((m_cnt[s] / kMaskStages) & 1) ^ 1);
+          uint32_t* ms = reinterpret_cast<uint32_t*>(gbase + L::kMask) + (s * kMaskStages + st) * kTileN;
+          const uint32_t full = u.q_cnt[s] >= 32 ? 0xffffffffu : ((1u << u.q_cnt[s]) - 1u);
+          bool dense = tlen == kTileN;
 #pragma unroll
-            for (int j = 0; j < kTileN / kProducerThreads; ++j) {
-              const int n = pt + j * kProducerThreads;
-              uint32_t m = 0;
-              if (n < tlen) m = grp.mask_off >= 0 ? (uint32_t)p.masks[grp.mask_off + t0 + n] : 0xffffffffu;
-              ms[n] = m;
-            }
-            mbar_arrive(bar(M_FULL + mr.stage));
-            mr.next<kMaskStages>();
+          for (int j = 0; j < kTileN / 32; ++j) {
+            const int n = lane + 32 * j;
+            uint32_t m = 0;
+            if (n < tlen)
+              m = u.mask_off[s] >= 0
+                      ? (uint32_t)load_index(p.u_mask, p.u_mask_bytes, u.mask_off[s] + (int64_t)t * u.mask_tile_stride + n)
+                      : 0xffffffffu;
+            dense = dense && ((m & full) == full);
+            ms[n] = m;
           }
+          dense = __all_sync(0xffffffffu, dense);
+          if (lane == 0) reinterpret_cast<uint32_t*>(gbase + L::kFlag)[s * kMaskStages + st] = dense ? 1u : 0u;
+          mbar_arrive(bar(M_FULL + s * kMaskStages + st));
+          ++m_cnt[s];
         }
       }
     }
-  } else {
-    // ============================== softmax / MMA issue / epilogue ==============================
-    const int r = tid;             // my row == my TMEM lane
-    const int qi = r / G, g = r % G;
-    const uint32_t qbit = qi < 32 ? (1u << qi) : 0u;   // my query's bit in the per-token masks
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    const uint32_t t_s = t_lane, t_o = t_lane + 128;
-    const float c = p.scale * 1.4426950408889634f;  // scores are handled in the log2 domain
-    Ring kv, qr, mr;
-    uint32_t s_phase = 0, o_phase = 0;
-    const uint32_t p_smem = base + L::kP;
+  } else if (warp == kMmaWarp) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      uint32_t k_cnt = 0, v_cnt = 0;  // KV tiles consumed
+      uint32_t s_cnt[2] = {0, 0};     // tiles per slot (S_FULL / P_FULL / O_FULL phases)
+      uint32_t j_cnt[2] = {0, 0};     // jobs per slot (Q_FULL / O_EMPTY phases)
+      for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+        const int job = jobs.get(ji);
+        const deft_unit_t u = p.units[job / p.HKV];
+        const int n = u.n_tiles;
+        const bool has_b = u.q_cnt[1] > 0;
+        const uint32_t v_base = v_cnt;
+        const uint32_t s_base[2] = {s_cnt[0], s_cnt[1]};
 
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int item_id = u / p.HKV, hkv = u % p.HKV;
-      const deft_item_t item = p.items[item_id];
-      const int ntile = max(1, (item.kv_len + kTileN - 1) / kTileN);
-      for (int gi = 0; gi < item.n_grp; ++gi) {
-        const deft_group_t grp = p.groups[item.grp_off + gi];
-        float m_run = -INFINITY, l_run = 0.f;
-        for (int t = 0; t < ntile; ++t) {
-          const bool new_kv = ntile > 1 || gi == 0;
-          const bool last_kv_use = ntile > 1 || gi == item.n_grp - 1;
-          // after a single-tile item's first group the KV ring has already advanced: look one back
-          int kv_stage = kv.stage;
-          if (!new_kv) kv_stage = kv.stage == 0 ? kKvStages - 1 : kv.stage - 1;
-          const uint32_t k_smem = base + L::kKv + (kv_stage * 2 + 0) * L::kOperandBytes;
-          const uint32_t v_smem = base + L::kKv + (kv_stage * 2 + 1) * L::kOperandBytes;
-          const uint32_t q_smem = base + L::kQ + qr.stage * L::kOperandBytes;
-
-          // ---- S = Q K^T
-          if (tid == 0) {
-            if (t == 0) mbar_wait(bar(Q_FULL + qr.stage), qr.phase);
-            if (new_kv) mbar_wait(bar(KV_FULL + kv.stage), kv.phase);
-            fence_proxy_async();
-            tc_fence_after();
+        auto issue_s = [&](int s, int t, uint32_t k_smem) {
+          const uint32_t q_smem = base + L::kQ + s * L::kOperandBytes;
 #pragma unroll
-            for (int ks = 0; ks < D / 16; ++ks) {
-              const uint32_t koff = (ks >> 2) * kPanelBytes + (ks & 3) * 32;
-              umma_f16(tmem, smem_desc_sw128(q_smem + koff, 16, 1024), smem_desc_sw128(k_smem + koff, 16, 1024),
-                       kIdescQK, ks > 0);
-            }
-            umma_commit(bar(S_FULL));
-            if (t == ntile - 1) umma_commit(bar(Q_EMPTY + qr.stage));  // Q is only read by these MMAs
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t koff = (ks >> 2) * kPanelBytes + (ks & 3) * 32;
+            umma_ss(tmem + s * 128, smem_desc_sw128(q_smem + koff, 16, 1024), smem_desc_sw128(k_smem + koff, 16, 1024),
+                    kIdescQK, ks > 0);
           }
-          if (new_kv) kv.next<kKvStages>();
-
-          // ---- softmax of my row
-          mbar_wait(bar(M_FULL + mr.stage), mr.phase);
-          const uint32_t* ms = reinterpret_cast<const uint32_t*>(gbase + L::kMask) + mr.stage * kTileN;
-          mbar_wait(bar(S_FULL), s_phase);
-          s_phase ^= 1;
+          umma_commit(bar(S_FULL + s));
+          if (t == n - 1) umma_commit(bar(Q_EMPTY + s));  // Q is only read by these MMAs
+        };
+        auto issue_pv = [&](int s, int t) {
+          const uint32_t vi = v_base + t;
+          const int vst = vi % kKvStages;
+          if (s == 0) mbar_wait(bar(V_FULL + vst), (vi / kKvStages) & 1);
+          mbar_wait(bar(P_FULL + s), (s_base[s] + t) & 1);
+          if (t == 0) mbar_wait(bar(O_EMPTY + s), (j_cnt[s] & 1) ^ 1);
+          fence_proxy_async();
           tc_fence_after();
-          float v[32];
-          float m_tile = -INFINITY;
-          const bool dbg = p.dbg != nullptr && u == 0 && gi == 0 && t == 0;
-#pragma unroll 1
-          for (int cb = 0; cb < kTileN / 32; ++cb) {
-            tmem_ld32(t_s + cb * 32, v);
-            if (dbg)
-              for (int j = 0; j < 32; ++j) p.dbg[r * kTileN + cb * 32 + j] = v[j];
+          const uint32_t v_smem = base + L::kV + vst * L::kOperandBytes;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const uint4 mk = *reinterpret_cast<const uint4*>(ms + cb * 32 + j);
-              if (mk.x & qbit) m_tile = fmaxf(m_tile, v[j]);
-              if (mk.y & qbit) m_tile = fmaxf(m_tile, v[j + 1]);
-              if (mk.z & qbit) m_tile = fmaxf(m_tile, v[j + 2]);
-              if (mk.w & qbit) m_tile = fmaxf(m_tile, v[j + 3]);
-            }
-          }
-          m_tile *= c;  // c > 0
-          const float m_new = fmaxf(m_run, m_tile);
-          const float m_use = m_new == -INFINITY ? 0.f : m_new;
-          const float alpha = exp2f(m_run - m_use);  // 0 on the first live tile
-          if (t > 0) {
-            // previous P V has completed (o_full was waited below); rescale the running output
-            if (__any_sync(0xffffffffu, alpha != 1.f)) {
-#pragma unroll 1
-              for (int cb = 0; cb < D / 32; ++cb) {
-                tmem_ld32(t_o + cb * 32, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= alpha;
-                tmem_st32(t_o + cb * 32, v);
-              }
-            }
-          }
-          float psum = 0.f;
-#pragma unroll 1
-          for (int cb = 0; cb < kTileN / 32; ++cb) {
-            tmem_ld32(t_s + cb * 32, v);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const uint4 mk = *reinterpret_cast<const uint4*>(ms + cb * 32 + j);
-              v[j] = (mk.x & qbit) ? exp2f(fmaf(v[j], c, -m_use)) : 0.f;
-              v[j + 1] = (mk.y & qbit) ? exp2f(fmaf(v[j + 1], c, -m_use)) : 0.f;
-              v[j + 2] = (mk.z & qbit) ? exp2f(fmaf(v[j + 2], c, -m_use)) : 0.f;
-              v[j + 3] = (mk.w & qbit) ? exp2f(fmaf(v[j + 3], c, -m_use)) : 0.f;
-              psum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
-            }
-            // P row -> K-major SW128 tile: 4 chunks of 8 halves
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint4 pk;
-              __half2 h0 = __floats2half2_rn(v[q4 * 8 + 0], v[q4 * 8 + 1]);
-              __half2 h1 = __floats2half2_rn(v[q4 * 8 + 2], v[q4 * 8 + 3]);
-              __half2 h2 = __floats2half2_rn(v[q4 * 8 + 4], v[q4 * 8 + 5]);
-              __half2 h3 = __floats2half2_rn(v[q4 * 8 + 6], v[q4 * 8 + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              const uint32_t dst = p_smem + tile_off(r, cb * 4 + q4);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
-            }
-          }
-          l_run = l_run * alpha + psum;
-          m_run = m_new;
-          mbar_arrive(bar(M_EMPTY + mr.stage));
-          mr.next<kMaskStages>();
-          fence_proxy_async();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
-          tc_fence_before();    // my TMEM loads/stores are ordered before the MMAs issued after the barrier
-          compute_bar();
+          for (int ks = 0; ks < kTileN / 16; ++ks)
+            umma_ts(tmem + 256 + s * 128, tmem + s * 128 + ks * 8,
+                    smem_desc_sw128(v_smem + ks * 2048, kPanelBytes, 1024), kIdescPV, t > 0 || ks > 0);
+          umma_commit(bar(O_FULL + s));
+          if (s == 1 || !has_b) umma_commit(bar(V_EMPTY + vst));
+        };
 
-          // ---- O (+)= P V
-          if (tid == 0) {
-            tc_fence_after();
-#pragma unroll
-            for (int ks = 0; ks < kTileN / 16; ++ks) {
-              const uint32_t poff = (ks >> 2) * kPanelBytes + (ks & 3) * 32;
-              umma_f16(tmem + 128, smem_desc_sw128(p_smem + poff, 16, 1024),
-                       smem_desc_sw128(v_smem + ks * 2048, kPanelBytes, 1024), kIdescPV, t > 0 || ks > 0);
-            }
-            umma_commit(bar(O_FULL));
-            if (last_kv_use) umma_commit(bar(KV_EMPTY + kv_stage));
-          }
-          mbar_wait(bar(O_FULL), o_phase);
-          o_phase ^= 1;
+        for (int t = 0; t < n; ++t) {
+          const int kst = k_cnt % kKvStages;
+          mbar_wait(bar(K_FULL + kst), (k_cnt / kKvStages) & 1);
+          if (t == 0) mbar_wait(bar(Q_FULL + 0), j_cnt[0] & 1);
+          fence_proxy_async();
           tc_fence_after();
-        }
-        qr.next<kQStages>();
-
-        // ---- epilogue: po[row][h][:] = O / l, plse[row][h] = ln-domain log-sum-exp
-        const bool live = qi < grp.q_cnt;
-        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-        float* dst = p.po + (((int64_t)grp.part_base + qi) * p.H + hkv * G + g) * D;
-        float v[32];
-#pragma unroll 1
-        for (int cb = 0; cb < D / 32; ++cb) {
-          tmem_ld32(t_o + cb * 32, v);
-          if (p.dbg != nullptr && u == 0 && gi == 0)
-            for (int j = 0; j < 32; ++j) p.dbg[kRows * kTileN + r * D + cb * 32 + j] = v[j];
-          if (live) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst + cb * 32 + j) = make_float4(v[j] * inv, v[j + 1] * inv, v[j + 2] * inv, v[j + 3] * inv);
+          const uint32_t k_smem = base + L::kK + kst * L::kOperandBytes;
+          issue_s(0, t, k_smem);
+          if (has_b) {
+            if (t > 0) issue_pv(1, t - 1);
+            if (t == 0) {
+              mbar_wait(bar(Q_FULL + 1), j_cnt[1] & 1);
+              fence_proxy_async();
+            }
+            issue_s(1, t, k_smem);
           }
+          umma_commit(bar(K_EMPTY + kst));
+          ++k_cnt;
+          issue_pv(0, t);
         }
-        if (live)
-          p.plse[((int64_t)grp.part_base + qi) * p.H + hkv * G + g] =
-              l_run > 0.f ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
-        tc_fence_before();  // O is overwritten by the next group's first P V (issued after the next compute_bar)
+        if (has_b) issue_pv(1, n - 1);
+        v_cnt += n;
+        s_cnt[0] += n; ++j_cnt[0];
+        if (has_b) { s_cnt[1] += n; ++j_cnt[1]; }
       }
+    }
+    __syncwarp();
+  } else {
+    // ============================== softmax + epilogue (slot = warp / 4) ==============================
+    const int s = warp >> 2;
+    const int r = tid & 127;  // my row == my TMEM lane
+    const int qi = r / G, g = r % G;
+    const uint32_t qbit = qi < 32 ? (1u << qi) : 0u;  // my query's bit in the per-token masks
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_s = t_lane + s * 128, t_o = t_lane + 256 + s * 128;
+    const float c = p.scale * 1.4426950408889634f;  // scores are handled in the log2 domain
+    uint32_t s_cnt = 0, m_cnt = 0;
+    bool first_job = blockIdx.x == 0;
+
+    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+      const int job = jobs.get(ji);
+      const int hkv = job % p.HKV;
+      const deft_unit_t u = p.units[job / p.HKV];
+      if (s == 1 && u.q_cnt[1] == 0) continue;
+      const bool dbg = p.dbg != nullptr && first_job && s == 0;
+      first_job = false;
+      float m_ref = -INFINITY, l_run = 0.f;
+      float v[32];
+
+      for (int t = 0; t < u.n_tiles; ++t, ++s_cnt, ++m_cnt) {
+        const int mst = m_cnt % kMaskStages;
+        mbar_wait(bar(M_FULL + s * kMaskStages + mst), (m_cnt / kMaskStages) & 1);
+        const uint32_t* ms = reinterpret_cast<const uint32_t*>(gbase + L::kMask) + (s * kMaskStages + mst) * kTileN;
+        const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[s * kMaskStages + mst] != 0;
+        mbar_wait(bar(S_FULL + s), s_cnt & 1);
+        tc_fence_after();
+
+        // ---- pass 1: maximum of my row over the tile
+        float mt = -INFINITY;
+#pragma unroll 1
+        for (int cb = 0; cb < kTileN / 32; ++cb) {
+          tmem_ld32(t_s + cb * 32, v);
+          if (dbg && t == 0)
+            for (int j = 0; j < 32; ++j) p.dbg[r * kTileN + cb * 32 + j] = v[j];
+          if (dense) {
+            float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+            for (int j = 4; j < 32; j += 4) {
+              m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+            }
+            mt = fmaxf(mt, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(ms + cb * 32 + j);
+              if (mk.x & qbit) mt = fmaxf(mt, v[j]);
+              if (mk.y & qbit) mt = fmaxf(mt, v[j + 1]);
+              if (mk.z & qbit) mt = fmaxf(mt, v[j + 2]);
+              if (mk.w & qbit) mt = fmaxf(mt, v[j + 3]);
+            }
+          }
+        }
+        mt *= c;  // c > 0
+
+        // ---- lazily raised reference maximum; the accumulator is rescaled only when it moves
+        const bool raise = mt > m_ref + kRescaleLog2;  // also the first live tile (m_ref = -inf)
+        float alpha = 1.f;
+        if (raise) {
+          alpha = fast_exp2(m_ref - mt);  // 0 when m_ref = -inf
+          m_ref = mt;
+          l_run *= alpha;
+        }
+        if (t > 0 && __any_sync(0xffffffffu, raise)) {
+          mbar_wait(bar(O_FULL + s), (s_cnt - 1) & 1);  // P V of the previous tile has landed in O
+          tc_fence_after();
+#pragma unroll 1
+          for (int cb = 0; cb < D / 32; ++cb) {
+            tmem_ld32(t_o + cb * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= alpha;
+            tmem_st32(t_o + cb * 32, v);
+          }
+          tmem_wait_st();
+        }
+        const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+
+        // ---- pass 2: P = exp2(S*c - m_ref) -> fp16, written over S in TMEM (P chunk cb lands in
+        //      columns [16cb, 16cb+16), always behind the S columns still to be read)
+        float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll 1
+        for (int cb = 0; cb < kTileN / 32; ++cb) {
+          tmem_ld32(t_s + cb * 32, v);
+          if (dense) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              v[j] = fast_exp2(fmaf(v[j], c, -m_use));
+              v[j + 1] = fast_exp2(fmaf(v[j + 1], c, -m_use));
+              v[j + 2] = fast_exp2(fmaf(v[j + 2], c, -m_use));
+              v[j + 3] = fast_exp2(fmaf(v[j + 3], c, -m_use));
+              ps0 += v[j]; ps1 += v[j + 1]; ps2 += v[j + 2]; ps3 += v[j + 3];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const uint4 mk = *reinterpret_cast<const uint4*>(ms + cb * 32 + j);
+              v[j] = (mk.x & qbit) ? fast_exp2(fmaf(v[j], c, -m_use)) : 0.f;
+              v[j + 1] = (mk.y & qbit) ? fast_exp2(fmaf(v[j + 1], c, -m_use)) : 0.f;
+              v[j + 2] = (mk.z & qbit) ? fast_exp2(fmaf(v[j + 2], c, -m_use)) : 0.f;
+              v[j + 3] = (mk.w & qbit) ? fast_exp2(fmaf(v[j + 3], c, -m_use)) : 0.f;
+              ps0 += v[j]; ps1 += v[j + 1]; ps2 += v[j + 2]; ps3 += v[j + 3];
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+          tmem_st16(t_s + cb * 16, pk);
+        }
+        tmem_wait_st();
+        l_run += (ps0 + ps1) + (ps2 + ps3);
+        mbar_arrive(bar(M_EMPTY + s * kMaskStages + mst));
+        tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
+        mbar_arrive(bar(P_FULL + s));
+      }
+
+      // ---- epilogue: partial = O / l as fp16, log-sum-exp in the natural-log domain
+      mbar_wait(bar(O_FULL + s), (s_cnt - 1) & 1);
+      tc_fence_after();
+      const bool live = qi < u.q_cnt[s];
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      const int64_t tile = (int64_t)(u.part_base[s] >> 5) * p.HKV + hkv;
+      uint4* dst = reinterpret_cast<uint4*>(p.po16) + tile * (CH * R) + r;  // [chunk][row] of 16 bytes
+#pragma unroll 1
+      for (int cb = 0; cb < D / 32; ++cb) {
+        tmem_ld32(t_o + cb * 32, v);
+        if (dbg)
+          for (int j = 0; j < 32; ++j) p.dbg[kRows * kTileN + r * D + cb * 32 + j] = v[j];
+        if (live) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 pk;
+            pk.x = pack_half2(v[c4 * 8 + 0] * inv, v[c4 * 8 + 1] * inv);
+            pk.y = pack_half2(v[c4 * 8 + 2] * inv, v[c4 * 8 + 3] * inv);
+            pk.z = pack_half2(v[c4 * 8 + 4] * inv, v[c4 * 8 + 5] * inv);
+            pk.w = pack_half2(v[c4 * 8 + 6] * inv, v[c4 * 8 + 7] * inv);
+            dst[(cb * 4 + c4) * R] = pk;
+          }
+        }
+      }
+      if (live) p.plse16[tile * R + r] = l_run > 0.f ? (m_ref + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+      tc_fence_before();  // my reads of O are ordered before the next job's first P V (accumulate = 0)
+      mbar_arrive(bar(O_EMPTY + s));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 template <int D, int G>
@@ -461,8 +588,14 @@ int launch_t(const AttnParams& p, cudaStream_t stream) {
     DEFT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
-  const int units = p.n_items * p.HKV;
-  const int grid = units < num_sms ? units : num_sms;
+  int grid;
+  if (p.job_off != nullptr) {
+    grid = p.n_ctas;
+  } else {
+    const int64_t n_jobs = (int64_t)p.n_units * p.HKV;
+    grid = (int)(n_jobs < num_sms ? n_jobs : num_sms);
+  }
+  if (grid <= 0) return DEFT_OK;
   stage1_umma_kernel<D, G><<<grid, kThreads, L::kAlloc, stream>>>(p);
   DEFT_CUDA(cudaGetLastError());
   return DEFT_OK;
@@ -476,7 +609,7 @@ bool stage1_umma_supported(const AttnParams& p) {
 }
 
 int launch_stage1_umma(const AttnParams& p, cudaStream_t stream) {
-  if (p.n_items <= 0) return DEFT_OK;
+  if (p.n_units <= 0) return DEFT_OK;
   const int G = p.H / p.HKV;
 #define DEFT_CASE(DD, GG) \
   if (p.D == DD && G == GG) return launch_t<DD, GG>(p, stream);

@@ -64,6 +64,71 @@ __global__ void __launch_bounds__(kThreads) stage2_kernel(const AttnParams p) {
   }
 }
 
+// Same merge over the tile partials of the tcgen05 stage 1: po16 [slot tile][D/8 chunks][32*G rows][8]
+// fp16 and plse16 [slot tile][32*G] fp32, slot tile = (partial row / 32) * HKV + kv_head, row inside
+// the tile = (partial row % 32) * G + g.  One warp owns (query, kv-head, group of 32/G chunks): lane
+// = (g, chunk), so the G heads of a query read 16*G contiguous bytes per chunk and write whole
+// 128-byte lines of the output.
+template <int D, int G>
+__global__ void __launch_bounds__(kThreads) stage2_tiles_kernel(const AttnParams p) {
+  constexpr int CH = D / 8, CPW = 32 / G, NCG = (CH + CPW - 1) / CPW, R = kMaxGroupQ * G;
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (w >= (int64_t)p.nq * p.HKV * NCG) return;
+  const int cg = (int)(w % NCG), kvh = (int)((w / NCG) % p.HKV), q = (int)(w / ((int64_t)NCG * p.HKV));
+  const int g = lane % G, c = lane / G + cg * CPW;
+  const bool active = c < CH;
+  const int beg = p.u_csr_off[q], end = p.u_csr_off[q + 1];
+
+  float m = -INFINITY;
+  for (int i = beg; i < end; ++i) {
+    const int row = p.u_csr_rows[i];
+    m = fmaxf(m, p.plse16[((int64_t)(row >> 5) * p.HKV + kvh) * R + (row & 31) * G + g]);
+  }
+  float L = 0.f, acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (m > -INFINITY) {
+    const uint4* po = reinterpret_cast<const uint4*>(p.po16);
+#pragma unroll 4
+    for (int i = beg; i < end; ++i) {
+      const int row = p.u_csr_rows[i];
+      const int64_t tile = (int64_t)(row >> 5) * p.HKV + kvh;
+      const int rr = (row & 31) * G + g;
+      const float wgt = __expf(p.plse16[tile * R + rr] - m);
+      L += wgt;
+      if (active) {
+        const uint4 raw = po[(tile * CH + c) * R + rr];
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 x = __half22float2(h[j]);
+          acc[2 * j] = fmaf(wgt, x.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(wgt, x.y, acc[2 * j + 1]);
+        }
+      }
+    }
+  }
+  if (!active) return;
+  const float inv = L > 0.f ? 1.f / L : 0.f;
+  uint4 pk;
+  __half2 h0 = __floats2half2_rn(acc[0] * inv, acc[1] * inv), h1 = __floats2half2_rn(acc[2] * inv, acc[3] * inv);
+  __half2 h2 = __floats2half2_rn(acc[4] * inv, acc[5] * inv), h3 = __floats2half2_rn(acc[6] * inv, acc[7] * inv);
+  pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+  *reinterpret_cast<uint4*>(p.o + (int64_t)q * p.o_row_stride + (int64_t)(kvh * G + g) * p.o_head_stride + c * 8) = pk;
+}
+
+template <int D, int G>
+int launch_tiles_t(const AttnParams& p, cudaStream_t stream) {
+  constexpr int CH = D / 8, CPW = 32 / G, NCG = (CH + CPW - 1) / CPW;
+  const int64_t warps = (int64_t)p.nq * p.HKV * NCG;
+  const int64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
+  stage2_tiles_kernel<D, G><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
+  DEFT_CUDA(cudaGetLastError());
+  return DEFT_OK;
+}
+
 template <int D>
 int launch_t(const AttnParams& p, cudaStream_t stream) {
   const int64_t warps = (int64_t)p.nq * p.H;
@@ -83,6 +148,17 @@ int launch_stage2(const AttnParams& p, cudaStream_t stream) {
     case 128: return launch_t<128>(p, stream);
   }
   set_error("unsupported head_dim %d", p.D);
+  return DEFT_E_ARG;
+}
+
+int launch_stage2_tiles(const AttnParams& p, cudaStream_t stream) {
+  if (p.nq <= 0) return DEFT_OK;
+  const int G = p.H / p.HKV;
+#define DEFT_CASE(DD, GG) \
+  if (p.D == DD && G == GG) return launch_tiles_t<DD, GG>(p, stream);
+  DEFT_CASE(128, 4) DEFT_CASE(128, 2) DEFT_CASE(128, 1) DEFT_CASE(64, 4) DEFT_CASE(64, 2) DEFT_CASE(64, 1)
+#undef DEFT_CASE
+  set_error("tile combine does not cover head_dim %d / GQA group %d", p.D, G);
   return DEFT_E_ARG;
 }
 

@@ -28,6 +28,7 @@ void set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
+static_assert(sizeof(deft_unit_t) == 64, "deft_unit_t is part of the ABI: 64 bytes");
 constexpr int kMaxGroupQ = 32;     // queries per group (reference max_q_len / BLOCK_M, tree_cache.py:623)
 constexpr int kNodeSplit = 256;    // tokens per item when long Node entries are split on the device
 
@@ -58,14 +59,35 @@ struct AttnParams {
   float* po;
   float* plse;
   float* dbg;  // debug dump of the tensor-core path (raw S and O of the first unit), normally null
+  // ---- unit plan (tcgen05 path): tables may be the reference's (int64) or the builder's (32-bit)
+  const deft_unit_t* units;
+  const int32_t* n_units_dev;  // device-resident unit count (device-built plans), or null
+  int32_t n_units;             // launch bound on the unit count
+  const void* u_kv;    int32_t u_kv_bytes;    // page id per token slot
+  const void* u_mask;  int32_t u_mask_bytes;  // per-token row bitmask, may be null
+  const void* u_q;     int32_t u_q_bytes;     // query id per (slot, row)
+  const int32_t* u_csr_off;
+  const int32_t* u_csr_rows;
+  const int32_t* job_off;  // per-CTA job lists (host-balanced), or null: CTA c runs jobs c, c+grid, ...
+  const int32_t* jobs;
+  int32_t n_ctas;          // CTAs the job lists cover (grid size), 0 when job_off is null
+  // tile partials: po16 [slot tile][D/8][32*G rows][8] fp16, plse16 [slot tile][32*G] fp32,
+  // slot tile = (part_base / 32) * HKV + kv_head
+  __half* po16;
+  float* plse16;
 };
+
+__device__ __forceinline__ int64_t load_index(const void* p, int bytes, int64_t i) {
+  return bytes == 8 ? reinterpret_cast<const int64_t*>(p)[i] : (int64_t) reinterpret_cast<const int32_t*>(p)[i];
+}
 
 // stage 1 (warp-FMA path) and stage 2, attn_fma.cu / combine.cu
 int launch_stage1_fma(const AttnParams& p, cudaStream_t stream);
 int launch_stage2(const AttnParams& p, cudaStream_t stream);
-// stage 1 (tcgen05 path), attn_umma.cu
+// stage 1 (tcgen05 path) over the unit plan, attn_umma.cu; stage 2 over its tile partials, combine.cu
 bool stage1_umma_supported(const AttnParams& p);
 int launch_stage1_umma(const AttnParams& p, cudaStream_t stream);
+int launch_stage2_tiles(const AttnParams& p, cudaStream_t stream);
 
 // device-side plan derivation from the reference tables, plan.cu
 struct PlanBuffers {
@@ -74,7 +96,8 @@ struct PlanBuffers {
   int32_t* csr_off;
   int32_t* csr_rows;
   int32_t* cursor;    // nq ints of scratch
-  int32_t* counters;  // [0] = n_items, [1] = n_part_rows
+  int32_t* counters;  // [0] = n_items, [1] = n_part_rows, [2] = n_units
+  deft_unit_t* units; // one per (item, pair of groups)
 };
 int launch_plan_flatten(const int64_t* block_q_cnts, const int64_t* block_q_offset,
                         const int64_t* block_lens, const int64_t* block_kv, const int64_t* block_q,

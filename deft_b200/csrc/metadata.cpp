@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <cstring>
 #include <new>
+#include <queue>
+#include <utility>
 #include <vector>
 
 #include "deft_b200.h"
@@ -60,7 +62,7 @@ std::vector<i64> offsets_of(const std::vector<i64>& lens) {  // cat([0], cumsum(
 struct deft_tables {
   std::vector<unsigned char> packed;
   i64 dir[2 * DEFT_T_COUNT];
-  i64 scalars[6];
+  i64 scalars[8];
 };
 
 extern "C" {
@@ -69,7 +71,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
                                       const int64_t* kv, const int64_t* q_off, const int64_t* qs,
                                       const int64_t* tix_row, int64_t tix_max_ctx,
                                       int32_t query_num, int32_t block_len, int32_t max_q_len,
-                                      int32_t max_block_len, int32_t node_split) {
+                                      int32_t max_block_len, int32_t node_split, int32_t hkv,
+                                      int32_t n_ctas) {
   if (n_nodes <= 0 || !parent || !kv_off || !kv || !q_off || !qs) {
     deft::set_error("build_tables: null or empty tree");
     return nullptr;
@@ -94,6 +97,15 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<deft_group_t> f_groups;
   i64 total_kv_len = 0;
 
+  // native tiles (one per 128-token block, KV NOT duplicated per 32-query sub-block)
+  struct Tile {
+    i32 n_live;
+    std::vector<i64> uni;          // attending queries, ascending
+    std::vector<uint32_t> masks;   // [group][128]: bit r = r-th query of the group attends the token
+  };
+  std::vector<Tile> tiles;
+  std::vector<i32> u_kv;
+
   // open block (tree_cache.py:654-658)
   std::vector<i64> seg_tokens;
   std::vector<i64> seg_lens;
@@ -112,6 +124,10 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     }
     std::sort(uni.begin(), uni.end());
     uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+    Tile tile;
+    tile.n_live = (i32)n_live;
+    tile.uni = uni;
+    for (i64 tk : toks) u_kv.push_back(tk < 0 ? 0 : (i32)tk);
     deft_item_t item{};
     item.kv_off = (i64)block_lens.size() * block_len;
     item.kv_len = (i32)n_live;
@@ -137,8 +153,10 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
             if (it != uni.begin() + (long)s1 && *it == qv) bits |= (i64)1 << (it - (uni.begin() + (long)s0));
           }
         block_masks.insert(block_masks.end(), (size_t)lens[s], bits);
+        tile.masks.insert(tile.masks.end(), (size_t)lens[s], s < n_seg ? (uint32_t)bits : 0u);
       }
     }
+    tiles.push_back(std::move(tile));
     item.n_grp = (i32)f_groups.size() - item.grp_off;
     item.cost = item.kv_len * item.n_grp;
     if (item.n_grp > 0) f_items.push_back(item);
@@ -235,6 +253,168 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   Csr f_csr = make_csr(f_groups, block_q, query_num);
   Csr n_csr = make_csr(n_groups, node_q, query_num);
 
+  // ---- native unit plan (tcgen05 path).  Runs of consecutive tiles with the same attending query
+  // list become chains; every chain is cut into pieces and every pair of 32-query groups into a unit.
+  // The piece length and the (unit, kv-head) -> CTA assignment come from a longest-first balance
+  // over n_ctas CTAs with the cost model below (tile steps; calibrated on B200).
+  std::vector<deft_unit_t> units;
+  std::vector<i32> u_q, u_job_off, u_jobs;
+  std::vector<uint32_t> u_mask;
+  Csr u_csr;
+  u_csr.off.assign((size_t)query_num + 1, 0);
+  i32 n_unit_slots = 0;
+  if (block_len == 128 && !tiles.empty()) {
+    struct Run { size_t t0, n_tiles; i32 n_grp; i64 q_base, mask_base; std::vector<char> dense; /* [tile][group] */ };
+    std::vector<Run> runs;
+    for (size_t t = 0; t < tiles.size();) {
+      size_t e = t + 1;
+      while (e < tiles.size() && tiles[e].uni == tiles[t].uni) ++e;
+      Run r;
+      r.t0 = t; r.n_tiles = e - t;
+      const std::vector<i64>& uq = tiles[t].uni;
+      r.n_grp = (i32)((uq.size() + (size_t)max_q_len - 1) / (size_t)max_q_len);
+      r.q_base = (i64)u_q.size();
+      // one 32-entry row of the query table per group, so q_off = q_base + 32 * group
+      for (i32 k = 0; k < r.n_grp; ++k)
+        for (i32 j = 0; j < 32; ++j) {
+          const size_t idx = (size_t)k * (size_t)max_q_len + (size_t)j;
+          u_q.push_back(j < max_q_len && idx < uq.size() ? (i32)uq[idx] : 0);
+        }
+      r.mask_base = (i64)u_mask.size();
+      r.dense.assign((e - t) * (size_t)r.n_grp, 1);
+      for (size_t tt = t; tt < e; ++tt) {
+        const Tile& tl = tiles[tt];
+        u_mask.insert(u_mask.end(), tl.masks.begin(), tl.masks.end());
+        for (i32 k = 0; k < r.n_grp; ++k) {
+          const size_t cnt = std::min((size_t)max_q_len, uq.size() - (size_t)k * (size_t)max_q_len);
+          const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+          char& d = r.dense[(tt - t) * (size_t)r.n_grp + (size_t)k];
+          if (tl.n_live != 128) d = 0;
+          for (i32 n = 0; n < tl.n_live && d; ++n)
+            if ((tl.masks[(size_t)k * 128 + (size_t)n] & full) != full) d = 0;
+        }
+      }
+      runs.push_back(std::move(r));
+      t = e;
+    }
+
+    const i32 heads = hkv > 0 ? hkv : 1;
+    const i32 ctas = n_ctas > 0 ? n_ctas : 148;
+    auto unit_cost = [](size_t n_tiles, bool pair) { return 0.8 + (double)n_tiles * (pair ? 1.0 : 0.85); };
+    // pieces of a run for a given maximum piece length: (first tile, count), near-equal sizes
+    auto pieces_of = [](size_t n_tiles, size_t max_len, std::vector<std::pair<size_t, size_t>>& out) {
+      out.clear();
+      const size_t np = (n_tiles + max_len - 1) / max_len;
+      size_t t = 0;
+      for (size_t i = 0; i < np; ++i) {
+        const size_t len = n_tiles / np + (i < n_tiles % np ? 1 : 0);
+        out.emplace_back(t, len);
+        t += len;
+      }
+    };
+    size_t longest = 1;
+    for (const Run& r : runs) longest = std::max(longest, r.n_tiles);
+    std::vector<size_t> cand;
+    for (size_t l : {(size_t)1, (size_t)2, (size_t)3, (size_t)4, (size_t)6, (size_t)8, (size_t)12, (size_t)16,
+                     (size_t)24, (size_t)32, (size_t)48, (size_t)64, (size_t)96, (size_t)128})
+      if (l < longest) cand.push_back(l);
+    cand.push_back(longest);
+    std::vector<std::pair<size_t, size_t>> pcs;
+    auto makespan = [&](size_t max_len) {
+      std::vector<double> costs;
+      for (const Run& r : runs) {
+        pieces_of(r.n_tiles, max_len, pcs);
+        for (const auto& pc : pcs)
+          for (i32 k = 0; k < r.n_grp; k += 2)
+            for (i32 h = 0; h < heads; ++h) costs.push_back(unit_cost(pc.second, k + 1 < r.n_grp));
+      }
+      std::sort(costs.begin(), costs.end(), [](double a, double b) { return a > b; });
+      std::priority_queue<double, std::vector<double>, std::greater<double>> bins;
+      for (i32 c = 0; c < ctas; ++c) bins.push(0.0);
+      double worst = 0.0;
+      for (double c : costs) {
+        const double load = bins.top() + c;
+        bins.pop();
+        bins.push(load);
+        worst = std::max(worst, load);
+      }
+      return worst;
+    };
+    size_t best_len = cand.back();
+    double best = -1.0;
+    for (size_t l : cand) {  // ascending: ties go to the longer piece (fewer partials)
+      const double m = makespan(l);
+      if (best < 0.0 || m <= best + 1e-9) { best = m; best_len = l; }
+    }
+
+    std::vector<double> ucost;
+    for (const Run& r : runs) {
+      pieces_of(r.n_tiles, best_len, pcs);
+      const bool last_run_tile_short = tiles[r.t0 + r.n_tiles - 1].n_live != 128;
+      for (const auto& pc : pcs)
+        for (i32 k = 0; k < r.n_grp; k += 2) {
+          deft_unit_t u{};
+          u.kv_off = (i64)(r.t0 + pc.first) * 128;
+          u.kv_tile_stride = 128;
+          u.mask_tile_stride = r.n_grp * 128;
+          u.n_tiles = (i32)pc.second;
+          const bool has_last = pc.first + pc.second == r.n_tiles;
+          u.last_len = has_last && last_run_tile_short ? tiles[r.t0 + r.n_tiles - 1].n_live : 128;
+          const size_t nq_run = tiles[r.t0].uni.size();
+          for (i32 sl = 0; sl < 2; ++sl) {
+            const i32 kk = k + sl;
+            if (kk < r.n_grp) {
+              bool dense = true;  // every tile of the piece: all live rows attend all 128 tokens
+              for (size_t tt = pc.first; tt < pc.first + pc.second; ++tt) dense = dense && r.dense[tt * (size_t)r.n_grp + (size_t)kk];
+              u.mask_off[sl] = dense ? -1 : r.mask_base + ((i64)pc.first * r.n_grp + kk) * 128;
+              u.q_off[sl] = (i32)(r.q_base + 32 * kk);
+              u.q_cnt[sl] = (i32)std::min((size_t)max_q_len, nq_run - (size_t)kk * (size_t)max_q_len);
+              u.part_base[sl] = 32 * n_unit_slots++;
+            } else {
+              u.mask_off[sl] = -1;
+            }
+          }
+          units.push_back(u);
+          ucost.push_back(unit_cost(pc.second, k + 1 < r.n_grp));
+        }
+    }
+    // CSR: partial rows of every query, ascending
+    {
+      std::vector<std::vector<i32>> rows((size_t)query_num);
+      for (const deft_unit_t& u : units)
+        for (int sl = 0; sl < 2; ++sl)
+          for (i32 rr = 0; rr < u.q_cnt[sl]; ++rr) rows[(size_t)u_q[(size_t)u.q_off[sl] + (size_t)rr]].push_back(u.part_base[sl] + rr);
+      for (i32 qv = 0; qv < query_num; ++qv) {
+        std::sort(rows[(size_t)qv].begin(), rows[(size_t)qv].end());
+        u_csr.off[(size_t)qv + 1] = u_csr.off[(size_t)qv] + (i32)rows[(size_t)qv].size();
+        u_csr.rows.insert(u_csr.rows.end(), rows[(size_t)qv].begin(), rows[(size_t)qv].end());
+      }
+    }
+    // (unit, kv-head) jobs -> CTAs, longest first onto the least loaded CTA
+    if (hkv > 0) {
+      std::vector<i32> order(units.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = (i32)i;
+      std::stable_sort(order.begin(), order.end(), [&](i32 a, i32 b) { return ucost[(size_t)a] > ucost[(size_t)b]; });
+      using Bin = std::pair<double, i32>;
+      std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> bins;
+      for (i32 c = 0; c < ctas; ++c) bins.push({0.0, c});
+      std::vector<std::vector<i32>> per((size_t)ctas);
+      for (i32 ui : order)
+        for (i32 h = 0; h < hkv; ++h) {
+          Bin b = bins.top();
+          bins.pop();
+          per[(size_t)b.second].push_back(ui * hkv + h);
+          b.first += ucost[(size_t)ui];
+          bins.push(b);
+        }
+      u_job_off.push_back(0);
+      for (i32 c = 0; c < ctas; ++c) {
+        u_jobs.insert(u_jobs.end(), per[(size_t)c].begin(), per[(size_t)c].end());
+        u_job_off.push_back((i32)u_jobs.size());
+      }
+    }
+  }
+
   // ---- pack
   deft_tables_t* t = new (std::nothrow) deft_tables_t();
   if (!t) {
@@ -253,6 +433,9 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       {f_csr.off.data(), f_csr.off.size(), 4}, {f_csr.rows.data(), f_csr.rows.size(), 4},
       {n_items.data(), n_items.size(), sizeof(deft_item_t)}, {n_groups.data(), n_groups.size(), sizeof(deft_group_t)},
       {n_csr.off.data(), n_csr.off.size(), 4}, {n_csr.rows.data(), n_csr.rows.size(), 4},
+      {units.data(), units.size(), sizeof(deft_unit_t)}, {u_csr.off.data(), u_csr.off.size(), 4},
+      {u_csr.rows.data(), u_csr.rows.size(), 4}, {u_kv.data(), u_kv.size(), 4}, {u_mask.data(), u_mask.size(), 4},
+      {u_q.data(), u_q.size(), 4}, {u_job_off.data(), u_job_off.size(), 4}, {u_jobs.data(), u_jobs.size(), 4},
   };
   size_t off = 0;
   for (int i = 0; i < DEFT_T_COUNT; ++i) {
@@ -269,6 +452,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   t->scalars[3] = block_len;
   t->scalars[4] = (i64)block_q.size();
   t->scalars[5] = n_rows;
+  t->scalars[6] = n_unit_slots;
+  t->scalars[7] = u_job_off.empty() ? 0 : (i64)u_job_off.size() - 1;
   return t;
 }
 

@@ -118,6 +118,50 @@ __device__ void build_csr(const deft_group_t* groups, int n_groups, const int64_
   }
 }
 
+// Units of the tcgen05 path: one per (item, pair of groups); the item's KV range becomes a chain of
+// 128-token tiles, the pair's groups become the two slots.
+__device__ void build_units(const deft_item_t* items, const deft_group_t* groups, int n_items, const PlanBuffers& pb,
+                            int* warp_sums) {
+  const int tid = threadIdx.x;
+  int carry = 0;
+  for (int base = 0; base < n_items; base += kThreads) {
+    const int i = base + tid;
+    deft_item_t it{};
+    int np = 0;
+    if (i < n_items) {
+      it = items[i];
+      np = (it.n_grp + 1) / 2;
+    }
+    int total;
+    const int u0 = carry + block_excl_scan(np, warp_sums, total);
+    for (int k = 0; k < np; ++k) {
+      deft_unit_t u{};
+      u.kv_off = it.kv_off;
+      u.kv_tile_stride = 128;
+      u.mask_tile_stride = 128;
+      u.n_tiles = max(1, (it.kv_len + 127) / 128);
+      u.last_len = max(0, it.kv_len - (u.n_tiles - 1) * 128);
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int gi = 2 * k + s;
+        if (gi < it.n_grp) {
+          const deft_group_t g = groups[it.grp_off + gi];
+          u.mask_off[s] = g.mask_off;
+          u.q_off[s] = g.q_off;
+          u.q_cnt[s] = g.q_cnt;
+          u.part_base[s] = g.part_base;
+        } else {
+          u.mask_off[s] = -1;
+        }
+      }
+      pb.units[u0 + k] = u;
+    }
+    carry += total;
+    __syncthreads();
+  }
+  if (tid == 0) pb.counters[2] = carry;
+}
+
 __global__ void __launch_bounds__(kThreads) plan_flatten_kernel(
     const int64_t* __restrict__ block_q_cnts, const int64_t* __restrict__ block_q_offset,
     const int64_t* __restrict__ block_lens, const int64_t* __restrict__ block_kv,
@@ -146,7 +190,7 @@ __global__ void __launch_bounds__(kThreads) plan_flatten_kernel(
       g.mask_off = (int64_t)b * block_len;
       g.q_off = (int)block_q_offset[b];
       g.q_cnt = min((int)block_q_cnts[b], kMaxGroupQ);
-      g.part_base = g.q_off;
+      g.part_base = b * kMaxGroupQ;  // 32 partial rows per group: the tile-partial layout needs the alignment
       g.pad = 0;
       pb.groups[b] = g;
     }
@@ -163,6 +207,8 @@ __global__ void __launch_bounds__(kThreads) plan_flatten_kernel(
     pb.items[i].cost = pb.items[i].kv_len * ng;
   }
   __syncthreads();
+  build_units(pb.items, pb.groups, n_items, pb, warp_sums);
+  __syncthreads();
   build_csr(pb.groups, n_blocks, block_q, nq, pb, warp_sums);
 }
 
@@ -172,7 +218,7 @@ __global__ void __launch_bounds__(kThreads) plan_node_kernel(
     const int64_t* __restrict__ node_q, int n_entries, int split, int nq, PlanBuffers pb) {
   __shared__ int warp_sums[33];
   const int tid = threadIdx.x;
-  int carry_items = 0, carry_rows = 0;
+  int carry_items = 0;
   for (int base = 0; base < n_entries; base += kThreads) {
     const int e = base + tid;
     int nch = 0, qn = 0, kn = 0;
@@ -181,9 +227,8 @@ __global__ void __launch_bounds__(kThreads) plan_node_kernel(
       qn = min((int)q_len[e], kMaxGroupQ);
       nch = split > 0 ? max(1, (kn + split - 1) / split) : 1;
     }
-    int tot_i, tot_r;
+    int tot_i;
     const int ib = carry_items + block_excl_scan(nch, warp_sums, tot_i);
-    const int rb = carry_rows + block_excl_scan(nch * qn, warp_sums, tot_r);
     for (int j = 0; j < nch; ++j) {
       const int step = split > 0 ? split : kn;
       deft_item_t it;
@@ -197,15 +242,16 @@ __global__ void __launch_bounds__(kThreads) plan_node_kernel(
       g.mask_off = -1;
       g.q_off = (int)q_offset[e];
       g.q_cnt = qn;
-      g.part_base = rb + j * qn;
+      g.part_base = (ib + j) * kMaxGroupQ;
       g.pad = 0;
       pb.groups[ib + j] = g;
     }
     carry_items += tot_i;
-    carry_rows += tot_r;
     __syncthreads();
   }
   if (tid == 0) pb.counters[0] = carry_items;
+  __syncthreads();
+  build_units(pb.items, pb.groups, carry_items, pb, warp_sums);
   __syncthreads();
   build_csr(pb.groups, carry_items, node_q, nq, pb, warp_sums);
 }

@@ -325,8 +325,22 @@ _STAGING = _Staging()
 _PLAN_REGISTRY: Dict[int, "weakref.ReferenceType[TreeMetadata]"] = {}
 
 
+_SM_COUNT: Dict[int, int] = {}
+
+
+def sm_count(device: Optional[torch.device]) -> int:
+    """CTAs the native plan is balanced for: one per SM of the device that will run it (148 on B200)."""
+    if device is None or device.type != "cuda":
+        return 148
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
 def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: int = -1,
-                      block_len: int = 128, tree_index_max_ctx: int = 0, node_split: int = NODE_SPLIT):
+                      block_len: int = 128, tree_index_max_ctx: int = 0, node_split: int = NODE_SPLIT,
+                      hkv: int = 0, n_ctas: int = 148):
     """Runs the C++ builder; returns (packed bytes as numpy uint8, directory, scalars)."""
     def ptr(a: np.ndarray):
         return a.ctypes.data_as(C.c_void_p)
@@ -334,7 +348,8 @@ def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: 
     use_tix = tree_index_max_ctx > 0
     h = _lib.lib.deft_b200_build_tables(len(flat["parent"]), ptr(flat["parent"]), ptr(flat["kv_off"]), ptr(flat["kv"]),
                                         ptr(flat["q_off"]), ptr(flat["qs"]), ptr(flat["tix"]) if use_tix else None,
-                                        tree_index_max_ctx, query_num, block_len, max_q_len, max_block_len, node_split)
+                                        tree_index_max_ctx, query_num, block_len, max_q_len, max_block_len, node_split,
+                                        hkv, n_ctas)
     if not h:
         raise _lib.DeftError(f"deft_b200_build_tables failed: {_lib.last_error()}")
     try:
@@ -342,7 +357,7 @@ def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: 
         data = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(_lib.lib.deft_b200_tables_data(h))).copy()
         directory = np.zeros(2 * _lib.T_COUNT, dtype=np.int64)
         _lib.check(_lib.lib.deft_b200_tables_directory(h, ptr(directory)))
-        scalars = np.zeros(6, dtype=np.int64)
+        scalars = np.zeros(_lib.N_SCALARS, dtype=np.int64)
         _lib.check(_lib.lib.deft_b200_tables_scalars(h, ptr(scalars)))
     finally:
         _lib.lib.deft_b200_tables_free(h)
@@ -381,9 +396,11 @@ class TreeMetadata:
         if max_block_len == -1:
             max_block_len = BLOCK_CONFIG["MAX_BLOCK_LEN"]
         max_ctx = tree.tree_index_pool.node_to_kv.shape[1] if tree_index else 0
-        data, directory, scalars = build_tables_host(flat, max_q_len, max_block_len, block_len, max_ctx)
         pool = tree.token_to_kv_pool           # ours, or the reference's (which has no .device)
         device = getattr(pool, "device", None) or pool.kv_data[0].device
+        hkv = int(pool.kv_data[0].shape[2]) if len(pool.kv_data) else 0     # kv_data[l] is [size, 2, HKV, D]
+        data, directory, scalars = build_tables_host(flat, max_q_len, max_block_len, block_len, max_ctx,
+                                                     hkv=hkv, n_ctas=sm_count(device))
         on_gpu = device.type == "cuda"
         packed = _STAGING.upload(data, device) if on_gpu else torch.from_numpy(data)
 
@@ -394,11 +411,20 @@ class TreeMetadata:
         t = {name: view(i, torch.int64, 8) for i, name in enumerate(_lib.T_NAMES[:12])}
         base = packed.data_ptr()
 
+        U = _lib.T_NAMES.index("u_units")
+
+        def addr(i: int) -> Optional[int]:
+            return base + int(directory[i, 0]) if int(directory[i, 1]) > 0 else None
+
         def plan(first: int, rows: int) -> _lib.Plan:
+            """Item/group layer of one operator + the native unit layer (shared by both operators)."""
             return _lib.Plan(items=base + int(directory[first, 0]), groups=base + int(directory[first + 1, 0]),
                              csr_off=base + int(directory[first + 2, 0]), csr_rows=base + int(directory[first + 3, 0]),
                              n_items=int(directory[first, 1]), n_groups=int(directory[first + 1, 1]),
-                             n_part_rows=rows, pad=0)
+                             n_part_rows=rows, n_units=int(directory[U, 1]),
+                             units=addr(U), u_csr_off=addr(U + 1), u_csr_rows=addr(U + 2), u_kv=addr(U + 3),
+                             u_mask=addr(U + 4), u_q=addr(U + 5), u_job_off=addr(U + 6), u_jobs=addr(U + 7),
+                             n_unit_slots=int(scalars[6]), n_ctas=int(scalars[7]), hkv=hkv, pad=0)
 
         if tree_index:
             null = torch.empty(0, dtype=torch.int64, device=device)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DEFT_B200_ABI_VERSION 1
+#define DEFT_B200_ABI_VERSION 2
 
 enum {
   DEFT_OK = 0,
@@ -57,15 +57,23 @@ void deft_b200_set_stage1_impl(int32_t impl);
 void deft_b200_set_debug_buffer(void* dev);
 
 /* ------------------------------------------------------------------------------------------
- * Work plan (device side).  One *item* = one KV token range of the table, attended by 1..n
- * *groups* of <= 32 queries; a group row r stands for the 4 (= H/HKV) GQA heads of query
- * q_list[q_off + r].  `part_base + r` is the partial-softmax row the group writes.
- * The plan is either built on the host by deft_b200_build_tables() (and uploaded by the caller
- * in one copy) or derived on the device from the reference tables by the *_fwd calls.
+ * Work plan (device side).  Two layers:
+ *
+ * (1) items / groups over the REFERENCE tables (used by the warp-FMA stage 1).  One *item* = one KV
+ *     token range of the table, attended by 1..n *groups* of <= 32 queries; a group row r stands for
+ *     the G = H/HKV GQA heads of query q_list[q_off + r]; `part_base + r` is the partial row.
+ * (2) units (used by the tcgen05 stage 1).  One *unit* = a chain of n_tiles KV tiles (128 tokens
+ *     each, the last one possibly shorter) attended by one or two *slots* of <= 32 queries; the
+ *     kernel walks the chain with an online softmax and emits ONE partial per (unit, slot, kv-head).
+ *     `part_base[s]` is a multiple of 32; partial row = part_base[s] + r.  Units index either the
+ *     reference tables (device-derived plans) or the builder's compact native tables.
+ *
+ * The plan is either built on the host by deft_b200_build_tables() (and uploaded by the caller in
+ * one copy) or derived on the device from the reference tables by the *_fwd calls.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   int64_t kv_off;   /* first element of the KV index table this item reads */
-  int32_t kv_len;   /* tokens in the item (any length; tiled by 128 inside the kernel) */
+  int32_t kv_len;   /* tokens in the item (any length; tiled inside the kernel) */
   int32_t grp_off;  /* first group */
   int32_t n_grp;    /* number of groups sharing the KV range */
   int32_t cost;     /* scheduling weight (tokens x rows); informational */
@@ -80,13 +88,40 @@ typedef struct {
 } deft_group_t;
 
 typedef struct {
+  int64_t kv_off;           /* element of the KV index table holding token 0 of tile 0 */
+  int64_t mask_off[2];      /* element of the mask table for token 0 of tile 0, per slot; -1 = every
+                               live row attends every token of every tile (no table read) */
+  int32_t kv_tile_stride;   /* elements between consecutive tiles in the KV index table */
+  int32_t mask_tile_stride; /* elements between consecutive tiles in the mask table */
+  int32_t n_tiles;          /* >= 1 */
+  int32_t last_len;         /* tokens in the last tile, 1..128 (all other tiles hold 128) */
+  int32_t q_off[2];         /* first element of the query list, per slot */
+  int32_t q_cnt[2];         /* 1..32; q_cnt[1] == 0: single-slot unit */
+  int32_t part_base[2];     /* multiple of 32 */
+} deft_unit_t;              /* 64 bytes */
+
+typedef struct {
+  /* (1) item/group plan over the reference tables */
   const deft_item_t* items;   /* [dev] */
   const deft_group_t* groups; /* [dev] */
   const int32_t* csr_off;     /* [dev] nq+1: partial rows of query q are csr_rows[csr_off[q]:csr_off[q+1]] */
-  const int32_t* csr_rows;    /* [dev] n_part_rows, ascending within a query (deterministic merge order) */
+  const int32_t* csr_rows;    /* [dev] ascending within a query (deterministic merge order) */
   int32_t n_items;
   int32_t n_groups;
   int32_t n_part_rows;
+  int32_t n_units;
+  /* (2) unit plan over the native tables (all [dev]; NULL/0 when absent) */
+  const deft_unit_t* units;
+  const int32_t* u_csr_off;   /* nq+1 */
+  const int32_t* u_csr_rows;
+  const int32_t* u_kv;        /* page id per token slot, tiles of 128 */
+  const uint32_t* u_mask;     /* 128 words per (tile, slot): bit r = row r of the slot attends */
+  const int32_t* u_q;         /* query id per (slot, row) */
+  const int32_t* u_job_off;   /* n_ctas+1: CTA c runs jobs u_jobs[u_job_off[c]:u_job_off[c+1]] */
+  const int32_t* u_jobs;      /* job = unit * HKV + kv_head, balanced over CTAs by the builder */
+  int32_t n_unit_slots;       /* partial tiles per kv-head */
+  int32_t n_ctas;             /* CTAs the job lists were balanced for */
+  int32_t hkv;                /* kv-head count the job lists were built for */
   int32_t pad;
 } deft_plan_t;
 
@@ -101,9 +136,11 @@ typedef struct {
  *   [n_blocks*block_len] -- int64 device tables of TreeMetadata (tree_cache.py:591-616)
  * block_len must be 128 (the reference kernel hard-wires BLOCK_N=128, tree_attention.py:655-657).
  * `plan` may be NULL: the plan is then derived on the device inside `workspace`.
+ * The workspace size depends on the plan (pass the same `plan`, or NULL, to *_workspace_bytes).
  * ------------------------------------------------------------------------------------------ */
-size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
-                                         int64_t n_blocks);
+size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_t D,
+                                         int64_t n_partials, int64_t n_blocks,
+                                         const deft_plan_t* plan);
 
 int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride,
                           const void* k, const void* v, int64_t kv_tok_stride,
@@ -124,8 +161,9 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
  *   kv_offset/kv_len/q_offset/q_len [n_entries] int64; node_q [n_partials] int64
  *   max_kv_len: upper bound of kv_len[] (sizes the split of long entries; e.g. the pool size)
  * ------------------------------------------------------------------------------------------ */
-size_t deft_b200_node_workspace_bytes(int32_t nq, int32_t H, int32_t D, int64_t n_partials,
-                                      int64_t n_entries, int64_t total_kv_bound);
+size_t deft_b200_node_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_t D,
+                                      int64_t n_partials, int64_t n_entries, int64_t total_kv_bound,
+                                      const deft_plan_t* plan);
 
 int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
                        const void* v, int64_t kv_tok_stride, int64_t kv_head_stride, void* o,
@@ -158,6 +196,8 @@ int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head
  *   kv_off[n+1], kv  per-node page lists (node.kv_indices, any order; sorted inside, :736)
  *   q_off[n+1], qs   per-node attending queries = rank by leaf id of node.refs (:650-652, :737)
  *   tix_row[n]       tree-index mode only: node.node_indices_id, else NULL
+ * hkv / n_ctas: kv-head count and CTA count (SMs) the native unit plan is balanced for: the
+ * builder cuts long KV chains into pieces and assigns (unit, kv-head) jobs to CTAs (longest first).
  * The result is one packed host buffer (upload with a single copy) + a directory.
  * ------------------------------------------------------------------------------------------ */
 enum {
@@ -166,6 +206,8 @@ enum {
   DEFT_T_BLOCK_BITMASKS, DEFT_T_BLOCK_KV, DEFT_T_BLOCK_LENS,          /* int64 reference tables */
   DEFT_T_FLAT_ITEMS, DEFT_T_FLAT_GROUPS, DEFT_T_FLAT_CSR_OFF, DEFT_T_FLAT_CSR_ROWS, /* Flatten plan */
   DEFT_T_NODE_ITEMS, DEFT_T_NODE_GROUPS, DEFT_T_NODE_CSR_OFF, DEFT_T_NODE_CSR_ROWS, /* Node plan */
+  DEFT_T_U_UNITS, DEFT_T_U_CSR_OFF, DEFT_T_U_CSR_ROWS, DEFT_T_U_KV, DEFT_T_U_MASK, DEFT_T_U_Q,
+  DEFT_T_U_JOB_OFF, DEFT_T_U_JOBS,                                    /* native unit plan */
   DEFT_T_COUNT
 };
 
@@ -175,13 +217,15 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
                                       const int64_t* kv, const int64_t* q_off, const int64_t* qs,
                                       const int64_t* tix_row, int64_t tix_max_ctx,
                                       int32_t query_num, int32_t block_len, int32_t max_q_len,
-                                      int32_t max_block_len, int32_t node_split);
+                                      int32_t max_block_len, int32_t node_split, int32_t hkv,
+                                      int32_t n_ctas);
 const void* deft_b200_tables_data(const deft_tables_t* t);  /* packed host buffer */
 size_t deft_b200_tables_bytes(const deft_tables_t* t);
 /* dir[2*i] = byte offset of array i in the packed buffer, dir[2*i+1] = element count */
 int deft_b200_tables_directory(const deft_tables_t* t, int64_t* dir /* [2*DEFT_T_COUNT] */);
-/* scalars: {query_num, node_num, total_kv_len, block_len, flat_part_rows, node_part_rows} */
-int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [6] */);
+/* scalars: {query_num, node_num, total_kv_len, block_len, flat_part_rows, node_part_rows,
+ *           n_unit_slots, n_ctas} */
+int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [8] */);
 void deft_b200_tables_free(deft_tables_t* t);
 
 #ifdef __cplusplus

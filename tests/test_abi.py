@@ -27,7 +27,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_version_and_struct_layout():
     assert _lib.lib.deft_b200_abi_version() == _lib.ABI_VERSION
-    assert C.sizeof(_lib.Plan) == 48
+    assert C.sizeof(_lib.Plan) == 128      # deft_plan_t: item/group layer (48 bytes) + unit layer
 
 
 def test_argument_errors_are_reported_not_crashed():
@@ -39,13 +39,15 @@ def test_argument_errors_are_reported_not_crashed():
         _lib.check(rc)
     rc = _lib.lib.deft_b200_kv_append(None, None, 0, 0, None, None, 0, 0, None, 1, 8, 128, None)
     assert rc == -1
-    assert _lib.lib.deft_b200_build_tables(0, None, None, None, None, None, None, 0, 1, 128, 32, -1, 256) is None
+    assert _lib.lib.deft_b200_build_tables(0, None, None, None, None, None, None, 0, 1, 128, 32, -1, 256, 8, 148) is None
     assert "tree" in _lib.last_error()
 
 
 def test_workspace_size_is_monotone():
     f = _lib.lib.deft_b200_flatten_workspace_bytes
-    a, b = f(64, 32, 128, 2246, 81), f(64, 32, 128, 4492, 162)
-    assert b > a >= 2246 * 32 * 128 * 4
+    a, b = f(64, 32, 8, 128, 2246, 81, None), f(64, 32, 8, 128, 4492, 162, None)
+    assert b > a >= 81 * 8 * 128 * 128 * 2          # one fp16 partial tile per (block, kv-head) at least
     g = _lib.lib.deft_b200_node_workspace_bytes
-    assert g(64, 32, 128, 448, 128, 10208) > g(64, 32, 128, 448, 128, 0)
+    assert g(64, 32, 8, 128, 448, 128, 10208, None) > g(64, 32, 8, 128, 448, 128, 0, None)
+    # geometries the tcgen05 kernel does not cover size the fp32 row layout of the warp-FMA path
+    assert f(64, 32, 8, 32, 2246, 81, None) >= 81 * 32 * 32 * 32 * 4

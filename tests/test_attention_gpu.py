@@ -127,11 +127,15 @@ def test_own_metadata_host_plan(golden_dir, dev, name):
     o1 = run_flatten(q, K, V, t)                       # plan found through the registry
     assert_parity(o1, z["o_flatten"], exact, "flatten/host-plan")
     o2 = run_flatten(q, K, V, tables(z, "t_", dev))    # same tables, foreign copies -> device plan
-    assert torch.equal(o1, o2), "host-built and device-built plans must give identical results"
+    assert_parity(o2, z["o_flatten"], exact, "flatten/device-plan")
+    # the native plan chains tiles and splits differently from the per-block device plan: same maths, other rounding
+    assert torch.allclose(o1.float(), o2.float(), atol=5e-4, rtol=5e-3)
     assert torch.equal(o1, run_flatten(q, K, V, t)), "stage 2 must be deterministic"
+    assert torch.equal(o2, run_flatten(q, K, V, tables(z, "t_", dev))), "stage 2 must be deterministic (device plan)"
     n1 = run_node(q, K, V, t)
     assert_parity(n1, z["o_node"], exact, "node/host-plan")
-    assert torch.equal(n1, run_node(q, K, V, tables(z, "t_", dev)))
+    assert torch.equal(n1, o1), "with the native plan both operators run the same work list"
+    assert_parity(run_node(q, K, V, tables(z, "t_", dev)), z["o_node"], exact, "node/device-plan")
     BLOCK_CONFIG["MAX_BLOCK_LEN"] = 128
     try:
         mc = TreeMetadata.from_tree_cache(tree)

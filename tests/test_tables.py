@@ -15,13 +15,18 @@ from deft_b200.tree_cache import build_tables_host, flatten_tree
 TABLE_KEYS = _lib.T_NAMES[:12]
 ITEM = np.dtype([("kv_off", "<i8"), ("kv_len", "<i4"), ("grp_off", "<i4"), ("n_grp", "<i4"), ("cost", "<i4")])
 GROUP = np.dtype([("mask_off", "<i8"), ("q_off", "<i4"), ("q_cnt", "<i4"), ("part_base", "<i4"), ("pad", "<i4")])
+UNIT = np.dtype([("kv_off", "<i8"), ("mask_off", "<i8", (2,)), ("kv_tile_stride", "<i4"), ("mask_tile_stride", "<i4"),
+                 ("n_tiles", "<i4"), ("last_len", "<i4"), ("q_off", "<i4", (2,)), ("q_cnt", "<i4", (2,)),
+                 ("part_base", "<i4", (2,))])
 
 
 def unpack(data, directory):
     out = {}
     for i, name in enumerate(_lib.T_NAMES):
         off, cnt = int(directory[i, 0]), int(directory[i, 1])
-        dt = np.dtype("<i8") if i < 12 else (ITEM if name.endswith("items") else GROUP if name.endswith("groups") else np.dtype("<i4"))
+        dt = np.dtype("<i8") if i < 12 else (ITEM if name.endswith("items") else GROUP if name.endswith("groups")
+                                             else UNIT if name == "u_units" else np.dtype("<u4") if name == "u_mask"
+                                             else np.dtype("<i4"))
         out[name] = np.frombuffer(data, dtype=dt, count=cnt, offset=off)
     return out
 
@@ -37,7 +42,78 @@ def load(golden_dir, name):
 
 
 def test_struct_sizes():
-    assert ITEM.itemsize == _lib.ITEM_BYTES and GROUP.itemsize == _lib.GROUP_BYTES
+    assert ITEM.itemsize == _lib.ITEM_BYTES and GROUP.itemsize == _lib.GROUP_BYTES and UNIT.itemsize == _lib.UNIT_BYTES
+
+
+def check_unit_plan(t, scalars, tree, hkv, n_ctas):
+    """The native unit plan attends exactly the (query, page) pairs of the tree, each once; its CSR,
+    partial-row bases and per-CTA job lists are consistent."""
+    units, u_kv, u_mask, u_q = t["u_units"], t["u_kv"], t["u_mask"], t["u_q"]
+    nq = int(scalars[0])
+    paths = orc.leaf_paths(tree)
+    want = {(q, int(pg)) for q, path in enumerate(paths) for pg in path}
+    got = set()
+    bases = []
+    row_to_q = {}
+    for u in units:
+        assert u["n_tiles"] >= 1 and 1 <= u["last_len"] <= 128 and u["kv_tile_stride"] == 128
+        assert 1 <= u["q_cnt"][0] <= 32 and 0 <= u["q_cnt"][1] <= 32
+        for s in range(2):
+            cnt = int(u["q_cnt"][s])
+            if cnt == 0:
+                continue
+            assert u["part_base"][s] % 32 == 0
+            bases.append(int(u["part_base"][s]))
+            qs = u_q[u["q_off"][s]: u["q_off"][s] + cnt]
+            for r, q in enumerate(qs):
+                row_to_q[int(u["part_base"][s]) + r] = int(q)
+            for tile in range(int(u["n_tiles"])):
+                tlen = int(u["last_len"]) if tile == u["n_tiles"] - 1 else 128
+                pages = u_kv[u["kv_off"] + tile * 128: u["kv_off"] + tile * 128 + tlen]
+                if u["mask_off"][s] < 0:
+                    words = np.full(tlen, 0xffffffff, dtype=np.uint32)
+                else:
+                    m0 = int(u["mask_off"][s]) + tile * int(u["mask_tile_stride"])
+                    words = u_mask[m0: m0 + tlen]
+                for n in range(tlen):
+                    for r in range(cnt):
+                        if (int(words[n]) >> r) & 1:
+                            pair = (int(qs[r]), int(pages[n]))
+                            assert pair not in got, ("attended twice", pair)
+                            got.add(pair)
+    assert got == want
+    assert sorted(bases) == [32 * i for i in range(int(scalars[6]))]
+    off, rows = t["u_csr_off"], t["u_csr_rows"]
+    assert len(off) == nq + 1 and off[0] == 0 and off[-1] == len(rows)
+    assert sorted(rows.tolist()) == sorted(row_to_q)
+    for q in range(nq):
+        mine = rows[off[q]: off[q + 1]]
+        assert len(mine) >= 1 and np.all(np.diff(mine) > 0) and all(row_to_q[int(r)] == q for r in mine)
+    job_off, jobs = t["u_job_off"], t["u_jobs"]
+    assert int(scalars[7]) == n_ctas and len(job_off) == n_ctas + 1 and job_off[0] == 0 and job_off[-1] == len(jobs)
+    assert np.all(np.diff(job_off) >= 0)
+    assert sorted(jobs.tolist()) == list(range(len(units) * hkv)), "every (unit, kv-head) job exactly once"
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_unit_plan_covers_the_tree(golden_dir, name):
+    z, tree = load(golden_dir, name)
+    for mbl, hkv, n_ctas in ((-1, 2, 148), (128, 8, 16)):
+        t, scalars = build(tree, mbl, hkv=hkv, n_ctas=n_ctas)
+        check_unit_plan(t, scalars, tree, hkv, n_ctas)
+
+
+def test_unit_plan_cfg2_shape(golden_dir):
+    """cfg2: the 4096-token prompt is one chain of dense tiles cut into balanced pieces; 148 CTAs all get work."""
+    z, tree = load(golden_dir, "cfg2_tables")
+    t, scalars = build(tree, -1, hkv=8, n_ctas=148)
+    units = t["u_units"]
+    root = units[(units["q_cnt"][:, 0] == 32) & (units["q_cnt"][:, 1] == 32) & (units["kv_off"] < 4096)]
+    assert int(root["n_tiles"].sum()) == 32 and np.all(root["mask_off"] == -1), "root tiles: dense, no mask reads"
+    loads = np.diff(t["u_job_off"])
+    assert loads.min() >= 1 and loads.sum() == len(units) * 8
+    # far fewer partial rows than the reference's 2246 (one per (sub-block, query))
+    assert len(t["u_csr_rows"]) < 1400
 
 
 @pytest.mark.parametrize("name", list(SCENARIOS) + list(TABLE_SCENARIOS))
@@ -147,6 +223,9 @@ def test_random_trees_match_oracle(seed):
         assert scalars[:4].tolist() == [want["query_num"], want["node_num"], want["total_kv_len"], 128]
         check_plan(t, want["query_num"], "flat")
         check_plan(t, want["query_num"], "node")
+    if seed % 4 == 0:
+        t, scalars = build(tree, -1, hkv=2, n_ctas=7)
+        check_unit_plan(t, scalars, tree, 2, 7)
 
 
 def test_builder_rejects_malformed_trees():
