@@ -10,7 +10,14 @@ Only what the tree-attention path needs lives here:
 
 Importing the package loads the shared library and fails loudly if it is missing.
 """
-from . import _lib  # noqa: F401  (raises ImportError when libdeft_b200.so is absent)
+import sys as _sys
+
+if "deft_b200.build" in getattr(_sys, "orig_argv", []):      # `python -m deft_b200.build`: nothing to load yet
+    from . import build as _build
+    print(_build.build(force="--force" in _sys.argv, verbose="-v" in _sys.argv))
+    raise SystemExit(0)
+
+from . import _lib  # noqa: F401,E402  (raises ImportError when libdeft_b200.so is absent)
 from .attention import kv_append, tree_attention_fwd, tree_attention_subtree_fwd  # noqa: F401
 from .memory_pool import ReqToTokenPool, TokenToKVPool, TreeIndexPool  # noqa: F401
 from .tree_cache import (BLOCK_CONFIG, KVCacheUpdater, TreeCache, TreeMetadata, TreeNode,  # noqa: F401

@@ -97,11 +97,28 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<deft_group_t> f_groups;
   i64 total_kv_len = 0;
 
+  // ---- native plan, part 1: fixed query slots.  Queries are ranked in DFS LEAF order (the order the
+  // pre-order walk meets the childless nodes), so that every node's query set is a contiguous rank range;
+  // slot k holds ranks [32k, 32k+32).  A tile touches few slots and consecutive tiles touch the same ones.
+  std::vector<i32> rank_of((size_t)query_num, -1);
+  {
+    std::vector<char> has_child((size_t)n_nodes, 0);
+    for (i32 n = 1; n < n_nodes; ++n) has_child[(size_t)parent[n]] = 1;
+    i32 next = 0;
+    for (i32 n = 0; n < n_nodes; ++n)
+      if (!has_child[(size_t)n])
+        for (i64 i = q_off[n]; i < q_off[n + 1]; ++i) {
+          const i64 qv = qs[i];
+          if (qv >= 0 && qv < query_num && rank_of[(size_t)qv] < 0) rank_of[(size_t)qv] = next++;
+        }
+    for (i32 qv = 0; qv < query_num; ++qv)
+      if (rank_of[(size_t)qv] < 0) rank_of[(size_t)qv] = next++;
+  }
   // native tiles (one per 128-token block, KV NOT duplicated per 32-query sub-block)
   struct Tile {
     i32 n_live;
-    std::vector<i64> uni;          // attending queries, ascending
-    std::vector<uint32_t> masks;   // [group][128]: bit r = r-th query of the group attends the token
+    std::vector<i32> slots;        // query slots with at least one attending row, ascending
+    std::vector<uint32_t> masks;   // [touched slot][128]: bit r = rank 32*slot + r attends the token
   };
   std::vector<Tile> tiles;
   std::vector<i32> u_kv;
@@ -126,8 +143,22 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
     Tile tile;
     tile.n_live = (i32)n_live;
-    tile.uni = uni;
     for (i64 tk : toks) u_kv.push_back(tk < 0 ? 0 : (i32)tk);
+    for (i64 qv : uni) tile.slots.push_back(rank_of[(size_t)qv] / 32);
+    std::sort(tile.slots.begin(), tile.slots.end());
+    tile.slots.erase(std::unique(tile.slots.begin(), tile.slots.end()), tile.slots.end());
+    tile.masks.assign(tile.slots.size() * 128, 0u);
+    {
+      size_t tok = 0;
+      for (size_t sg = 0; sg < n_seg; ++sg) {
+        for (i64 qv : seg_qs[sg]) {
+          const i32 rk = rank_of[(size_t)qv];
+          const size_t si = (size_t)(std::lower_bound(tile.slots.begin(), tile.slots.end(), rk / 32) - tile.slots.begin());
+          for (i64 n = 0; n < seg_lens[sg]; ++n) tile.masks[si * 128 + tok + (size_t)n] |= 1u << (rk % 32);
+        }
+        tok += (size_t)seg_lens[sg];
+      }
+    }
     deft_item_t item{};
     item.kv_off = (i64)block_lens.size() * block_len;
     item.kv_len = (i32)n_live;
@@ -153,7 +184,6 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
             if (it != uni.begin() + (long)s1 && *it == qv) bits |= (i64)1 << (it - (uni.begin() + (long)s0));
           }
         block_masks.insert(block_masks.end(), (size_t)lens[s], bits);
-        tile.masks.insert(tile.masks.end(), (size_t)lens[s], s < n_seg ? (uint32_t)bits : 0u);
       }
     }
     tiles.push_back(std::move(tile));
@@ -253,10 +283,11 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   Csr f_csr = make_csr(f_groups, block_q, query_num);
   Csr n_csr = make_csr(n_groups, node_q, query_num);
 
-  // ---- native unit plan (tcgen05 path).  Runs of consecutive tiles with the same attending query
-  // list become chains; every chain is cut into pieces and every pair of 32-query groups into a unit.
-  // The piece length and the (unit, kv-head) -> CTA assignment come from a longest-first balance
-  // over n_ctas CTAs with the cost model below (tile steps; calibrated on B200).
+  // ---- native plan, part 2: units.  For every PAIR of slots, the tiles touching it form chains of
+  // consecutive tiles (the prompt plus the pair's own subtree are contiguous in DFS order); every chain
+  // is cut into pieces, one unit per piece.  All units of a pair share their Q tiles.  The piece length
+  // and the (unit, kv-head) -> CTA assignment come from a longest-first balance over n_ctas CTAs with
+  // the cost model below (tile steps; calibrated on B200).
   std::vector<deft_unit_t> units;
   std::vector<i32> u_q, u_job_off, u_jobs;
   std::vector<uint32_t> u_mask;
@@ -264,69 +295,61 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   u_csr.off.assign((size_t)query_num + 1, 0);
   i32 n_unit_slots = 0;
   if (block_len == 128 && !tiles.empty()) {
-    struct Run { size_t t0, n_tiles; i32 n_grp; i64 q_base, mask_base; std::vector<char> dense; /* [tile][group] */ };
-    std::vector<Run> runs;
-    for (size_t t = 0; t < tiles.size();) {
-      size_t e = t + 1;
-      while (e < tiles.size() && tiles[e].uni == tiles[t].uni) ++e;
-      Run r;
-      r.t0 = t; r.n_tiles = e - t;
-      const std::vector<i64>& uq = tiles[t].uni;
-      r.n_grp = (i32)((uq.size() + (size_t)max_q_len - 1) / (size_t)max_q_len);
-      r.q_base = (i64)u_q.size();
-      // one 32-entry row of the query table per group, so q_off = q_base + 32 * group
-      for (i32 k = 0; k < r.n_grp; ++k)
-        for (i32 j = 0; j < 32; ++j) {
-          const size_t idx = (size_t)k * (size_t)max_q_len + (size_t)j;
-          u_q.push_back(j < max_q_len && idx < uq.size() ? (i32)uq[idx] : 0);
-        }
-      r.mask_base = (i64)u_mask.size();
-      r.dense.assign((e - t) * (size_t)r.n_grp, 1);
-      for (size_t tt = t; tt < e; ++tt) {
-        const Tile& tl = tiles[tt];
-        u_mask.insert(u_mask.end(), tl.masks.begin(), tl.masks.end());
-        for (i32 k = 0; k < r.n_grp; ++k) {
-          const size_t cnt = std::min((size_t)max_q_len, uq.size() - (size_t)k * (size_t)max_q_len);
-          const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-          char& d = r.dense[(tt - t) * (size_t)r.n_grp + (size_t)k];
-          if (tl.n_live != 128) d = 0;
-          for (i32 n = 0; n < tl.n_live && d; ++n)
-            if ((tl.masks[(size_t)k * 128 + (size_t)n] & full) != full) d = 0;
+    const i32 n_slots = (query_num + 31) / 32, n_pairs = (n_slots + 1) / 2;
+    u_q.assign((size_t)n_slots * 32, 0);
+    for (i32 qv = 0; qv < query_num; ++qv) u_q[(size_t)rank_of[(size_t)qv]] = qv;
+    auto slot_cnt = [&](i32 sl) { return std::min(32, query_num - 32 * sl); };
+    auto tile_slot = [&](const Tile& tl, i32 sl) -> const uint32_t* {  // mask words of (tile, slot) or null
+      auto it = std::lower_bound(tl.slots.begin(), tl.slots.end(), sl);
+      return it != tl.slots.end() && *it == sl ? tl.masks.data() + (size_t)(it - tl.slots.begin()) * 128 : nullptr;
+    };
+
+    struct Chain { i32 pair; size_t t0, n_tiles; };
+    std::vector<Chain> chains;
+    for (i32 pr = 0; pr < n_pairs; ++pr) {
+      size_t run0 = 0, run_n = 0;
+      for (size_t t = 0; t <= tiles.size(); ++t) {
+        const bool hit = t < tiles.size() && (tile_slot(tiles[t], 2 * pr) || tile_slot(tiles[t], 2 * pr + 1));
+        if (hit) {
+          if (run_n == 0) run0 = t;
+          ++run_n;
+        } else if (run_n) {
+          chains.push_back({pr, run0, run_n});
+          run_n = 0;
         }
       }
-      runs.push_back(std::move(r));
-      t = e;
     }
 
     const i32 heads = hkv > 0 ? hkv : 1;
     const i32 ctas = n_ctas > 0 ? n_ctas : 148;
     auto unit_cost = [](size_t n_tiles, bool pair) { return 0.8 + (double)n_tiles * (pair ? 1.0 : 0.85); };
-    // pieces of a run for a given maximum piece length: (first tile, count), near-equal sizes
-    auto pieces_of = [](size_t n_tiles, size_t max_len, std::vector<std::pair<size_t, size_t>>& out) {
-      out.clear();
+    // pieces of a chain for a given maximum piece length: (first tile, count), near-equal sizes
+    std::vector<std::pair<size_t, size_t>> pcs;
+    auto pieces_of = [&](size_t n_tiles, size_t max_len) {
+      pcs.clear();
       const size_t np = (n_tiles + max_len - 1) / max_len;
       size_t t = 0;
       for (size_t i = 0; i < np; ++i) {
         const size_t len = n_tiles / np + (i < n_tiles % np ? 1 : 0);
-        out.emplace_back(t, len);
+        pcs.emplace_back(t, len);
         t += len;
       }
     };
     size_t longest = 1;
-    for (const Run& r : runs) longest = std::max(longest, r.n_tiles);
+    for (const Chain& c : chains) longest = std::max(longest, c.n_tiles);
     std::vector<size_t> cand;
-    for (size_t l : {(size_t)1, (size_t)2, (size_t)3, (size_t)4, (size_t)6, (size_t)8, (size_t)12, (size_t)16,
-                     (size_t)24, (size_t)32, (size_t)48, (size_t)64, (size_t)96, (size_t)128})
+    for (size_t l : {(size_t)1, (size_t)2, (size_t)3, (size_t)4, (size_t)5, (size_t)6, (size_t)8, (size_t)10,
+                     (size_t)12, (size_t)16, (size_t)20, (size_t)24, (size_t)32, (size_t)48, (size_t)64,
+                     (size_t)96, (size_t)128, (size_t)192, (size_t)256})
       if (l < longest) cand.push_back(l);
     cand.push_back(longest);
-    std::vector<std::pair<size_t, size_t>> pcs;
     auto makespan = [&](size_t max_len) {
       std::vector<double> costs;
-      for (const Run& r : runs) {
-        pieces_of(r.n_tiles, max_len, pcs);
+      for (const Chain& c : chains) {
+        pieces_of(c.n_tiles, max_len);
+        const bool pair = slot_cnt(2 * c.pair + 1) > 0;
         for (const auto& pc : pcs)
-          for (i32 k = 0; k < r.n_grp; k += 2)
-            for (i32 h = 0; h < heads; ++h) costs.push_back(unit_cost(pc.second, k + 1 < r.n_grp));
+          for (i32 h = 0; h < heads; ++h) costs.push_back(unit_cost(pc.second, pair));
       }
       std::sort(costs.begin(), costs.end(), [](double a, double b) { return a > b; });
       std::priority_queue<double, std::vector<double>, std::greater<double>> bins;
@@ -348,47 +371,62 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     }
 
     std::vector<double> ucost;
-    for (const Run& r : runs) {
-      pieces_of(r.n_tiles, best_len, pcs);
-      const bool last_run_tile_short = tiles[r.t0 + r.n_tiles - 1].n_live != 128;
-      for (const auto& pc : pcs)
-        for (i32 k = 0; k < r.n_grp; k += 2) {
-          deft_unit_t u{};
-          u.kv_off = (i64)(r.t0 + pc.first) * 128;
-          u.kv_tile_stride = 128;
-          u.mask_tile_stride = r.n_grp * 128;
-          u.n_tiles = (i32)pc.second;
-          const bool has_last = pc.first + pc.second == r.n_tiles;
-          u.last_len = has_last && last_run_tile_short ? tiles[r.t0 + r.n_tiles - 1].n_live : 128;
-          const size_t nq_run = tiles[r.t0].uni.size();
-          for (i32 sl = 0; sl < 2; ++sl) {
-            const i32 kk = k + sl;
-            if (kk < r.n_grp) {
-              bool dense = true;  // every tile of the piece: all live rows attend all 128 tokens
-              for (size_t tt = pc.first; tt < pc.first + pc.second; ++tt) dense = dense && r.dense[tt * (size_t)r.n_grp + (size_t)kk];
-              u.mask_off[sl] = dense ? -1 : r.mask_base + ((i64)pc.first * r.n_grp + kk) * 128;
-              u.q_off[sl] = (i32)(r.q_base + 32 * kk);
-              u.q_cnt[sl] = (i32)std::min((size_t)max_q_len, nq_run - (size_t)kk * (size_t)max_q_len);
-              u.part_base[sl] = 32 * n_unit_slots++;
-            } else {
-              u.mask_off[sl] = -1;
+    std::vector<std::vector<i32>> rows_of((size_t)query_num);  // CSR: partial rows of every query
+    for (const Chain& c : chains) {
+      pieces_of(c.n_tiles, best_len);
+      for (const auto& pc : pcs) {
+        const size_t ta = c.t0 + pc.first, tb = ta + pc.second;  // tiles [ta, tb)
+        // which slots of the pair have attending rows in this piece, and which rows
+        i32 live_slots[2];
+        uint32_t live_rows[2] = {0u, 0u};
+        int n_live_slots = 0;
+        for (int sl = 0; sl < 2; ++sl) {
+          const i32 slot = 2 * c.pair + sl;
+          uint32_t rows = 0;
+          for (size_t t = ta; t < tb; ++t)
+            if (const uint32_t* w = tile_slot(tiles[t], slot))
+              for (i32 n = 0; n < tiles[t].n_live; ++n) rows |= w[n];
+          if (rows) { live_slots[n_live_slots] = slot; live_rows[n_live_slots] = rows; ++n_live_slots; }
+        }
+        if (n_live_slots == 0) continue;
+        deft_unit_t u{};
+        u.kv_off = (i64)ta * 128;
+        u.kv_tile_stride = 128;
+        u.mask_tile_stride = n_live_slots * 128;
+        u.n_tiles = (i32)pc.second;
+        u.last_len = tiles[tb - 1].n_live;
+        const i64 mask_base = (i64)u_mask.size();
+        bool dense[2] = {true, true};
+        for (size_t t = ta; t < tb; ++t)
+          for (int k = 0; k < n_live_slots; ++k) {
+            const uint32_t* w = tile_slot(tiles[t], live_slots[k]);
+            const i32 cnt = slot_cnt(live_slots[k]);
+            const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+            if (tiles[t].n_live != 128) dense[k] = false;
+            for (i32 n = 0; n < 128; ++n) {
+              const uint32_t word = w && n < tiles[t].n_live ? w[n] : 0u;
+              u_mask.push_back(word);
+              if (n < tiles[t].n_live && (word & full) != full) dense[k] = false;
             }
           }
-          units.push_back(u);
-          ucost.push_back(unit_cost(pc.second, k + 1 < r.n_grp));
+        u.mask_off[1] = -1;
+        for (int k = 0; k < n_live_slots; ++k) {
+          u.mask_off[k] = dense[k] ? -1 : mask_base + (i64)k * 128;
+          u.q_off[k] = 32 * live_slots[k];
+          u.q_cnt[k] = slot_cnt(live_slots[k]);
+          u.part_base[k] = 32 * n_unit_slots++;
+          for (i32 rr = 0; rr < u.q_cnt[k]; ++rr)
+            if ((live_rows[k] >> rr) & 1u) rows_of[(size_t)u_q[(size_t)u.q_off[k] + (size_t)rr]].push_back(u.part_base[k] + rr);
         }
-    }
-    // CSR: partial rows of every query, ascending
-    {
-      std::vector<std::vector<i32>> rows((size_t)query_num);
-      for (const deft_unit_t& u : units)
-        for (int sl = 0; sl < 2; ++sl)
-          for (i32 rr = 0; rr < u.q_cnt[sl]; ++rr) rows[(size_t)u_q[(size_t)u.q_off[sl] + (size_t)rr]].push_back(u.part_base[sl] + rr);
-      for (i32 qv = 0; qv < query_num; ++qv) {
-        std::sort(rows[(size_t)qv].begin(), rows[(size_t)qv].end());
-        u_csr.off[(size_t)qv + 1] = u_csr.off[(size_t)qv] + (i32)rows[(size_t)qv].size();
-        u_csr.rows.insert(u_csr.rows.end(), rows[(size_t)qv].begin(), rows[(size_t)qv].end());
+        if (dense[0] && (n_live_slots < 2 || dense[1])) u_mask.resize((size_t)mask_base);  // nothing reads them
+        units.push_back(u);
+        ucost.push_back(unit_cost(pc.second, n_live_slots == 2));
       }
+    }
+    for (i32 qv = 0; qv < query_num; ++qv) {
+      std::sort(rows_of[(size_t)qv].begin(), rows_of[(size_t)qv].end());
+      u_csr.off[(size_t)qv + 1] = u_csr.off[(size_t)qv] + (i32)rows_of[(size_t)qv].size();
+      u_csr.rows.insert(u_csr.rows.end(), rows_of[(size_t)qv].begin(), rows_of[(size_t)qv].end());
     }
     // (unit, kv-head) jobs -> CTAs, longest first onto the least loaded CTA
     if (hkv > 0) {

@@ -55,6 +55,7 @@ def check_unit_plan(t, scalars, tree, hkv, n_ctas):
     got = set()
     bases = []
     row_to_q = {}
+    attending = set()       # partial rows with at least one attended token
     for u in units:
         assert u["n_tiles"] >= 1 and 1 <= u["last_len"] <= 128 and u["kv_tile_stride"] == 128
         assert 1 <= u["q_cnt"][0] <= 32 and 0 <= u["q_cnt"][1] <= 32
@@ -81,11 +82,12 @@ def check_unit_plan(t, scalars, tree, hkv, n_ctas):
                             pair = (int(qs[r]), int(pages[n]))
                             assert pair not in got, ("attended twice", pair)
                             got.add(pair)
+                            attending.add(int(u["part_base"][s]) + r)
     assert got == want
     assert sorted(bases) == [32 * i for i in range(int(scalars[6]))]
     off, rows = t["u_csr_off"], t["u_csr_rows"]
     assert len(off) == nq + 1 and off[0] == 0 and off[-1] == len(rows)
-    assert sorted(rows.tolist()) == sorted(row_to_q)
+    assert sorted(rows.tolist()) == sorted(attending), "the CSR lists exactly the partial rows that attend something"
     for q in range(nq):
         mine = rows[off[q]: off[q + 1]]
         assert len(mine) >= 1 and np.all(np.diff(mine) > 0) and all(row_to_q[int(r)] == q for r in mine)
@@ -108,10 +110,14 @@ def test_unit_plan_cfg2_shape(golden_dir):
     z, tree = load(golden_dir, "cfg2_tables")
     t, scalars = build(tree, -1, hkv=8, n_ctas=148)
     units = t["u_units"]
-    root = units[(units["q_cnt"][:, 0] == 32) & (units["q_cnt"][:, 1] == 32) & (units["kv_off"] < 4096)]
-    assert int(root["n_tiles"].sum()) == 32 and np.all(root["mask_off"] == -1), "root tiles: dense, no mask reads"
+    # 64 queries = one pair of slots: ONE chain of all 48 tiles (prompt + subtree), cut into pieces
+    assert np.all(units["q_cnt"][:, 0] == 32) and np.all(np.isin(units["q_cnt"][:, 1], (0, 32)))
+    assert int(units["n_tiles"].sum()) == 48
+    assert np.array_equal(np.sort(units["kv_off"]), np.cumsum(np.r_[0, units["n_tiles"][np.argsort(units["kv_off"])][:-1]]) * 128)
+    root = units[units["kv_off"] + units["n_tiles"] * 128 <= 4096]
+    assert len(root) > 0 and np.all(root["mask_off"] == -1), "prompt-only pieces: dense, no mask reads"
     loads = np.diff(t["u_job_off"])
-    assert loads.min() >= 1 and loads.sum() == len(units) * 8
+    assert loads.max() == 1 and loads.sum() == len(units) * 8, "cfg2 fits one job per CTA: no Q reload between jobs"
     # far fewer partial rows than the reference's 2246 (one per (sub-block, query))
     assert len(t["u_csr_rows"]) < 1400
 
