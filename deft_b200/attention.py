@@ -74,7 +74,7 @@ def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Ten
     ws = _workspace(query_states.device, stream, need)
     _lib.check(_lib.lib.deft_b200_flatten_fwd(
         query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
-        key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1),
+        key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1), key_buffer.shape[0],
         output.data_ptr(), output.stride(0), output.stride(1), nq, H, HKV, D, int(block_len),
         block_q.data_ptr(), n_partials, block_q_cnts.data_ptr(), block_q_offset.data_ptr(), block_lens.data_ptr(),
         n_blocks, block_bitmasks.data_ptr(), block_kv.data_ptr(),
@@ -106,7 +106,7 @@ def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, val
     ws = _workspace(query_states.device, stream, need)
     _lib.check(_lib.lib.deft_b200_node_fwd(
         query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
-        key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1),
+        key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1), key_buffer.shape[0],
         output.data_ptr(), output.stride(0), output.stride(1), nq, H, HKV, D,
         KV_indices.data_ptr(), KV_indices.element_size(), kv_off.data_ptr(), kv_len.data_ptr(), node_q.data_ptr(),
         n_partials, q_off.data_ptr(), q_len.data_ptr(), n_entries, total_kv_bound,

@@ -11,6 +11,8 @@ static thread_local char g_error[512] = "";
 static thread_local int g_stages = DEFT_STAGE_PLAN | DEFT_STAGE_1 | DEFT_STAGE_2;
 static thread_local int g_stage1_impl = DEFT_STAGE1_AUTO;
 static thread_local float* g_debug = nullptr;
+static thread_local int* g_trace = nullptr;
+static thread_local bool g_no_tma = false;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -22,6 +24,69 @@ void set_error(const char* fmt, ...) {
 namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- TMA tensor maps.  cuTensorMapEncodeTiled comes from the driver through the runtime (no -lcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// fp16 tensor [d2][d1][d0] with element strides s1, s2; box {64, b1, b2}; 128-byte swizzle.  Small
+// per-thread cache: a decode step calls with the same 32 layer pools over and over.
+struct MapKey {
+  const void* ptr; int64_t d0, d1, d2, s1, s2; int32_t b1, b2;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 && b1 == o.b1 && b2 == o.b2;
+  }
+};
+bool make_map(CUtensorMap* out, const MapKey& key) {
+  constexpr int kCache = 128;
+  struct Entry { MapKey key; CUtensorMap map; };
+  static thread_local Entry cache[kCache];
+  static thread_local int used = 0, next = 0;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].key == key) {
+      *out = cache[i].map;
+      return true;
+    }
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || key.d0 < 64 || key.d1 <= 0 || key.d2 <= 0) return false;
+  alignas(64) CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)key.d0, (cuuint64_t)key.d1, (cuuint64_t)key.d2};
+  const cuuint64_t strides[2] = {(cuuint64_t)key.s1 * 2, (cuuint64_t)key.s2 * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)key.b1, (cuuint32_t)key.b2};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(key.ptr), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  const int slot = used < kCache ? used++ : (next = (next + 1) % kCache);
+  cache[slot].key = key;
+  cache[slot].map = map;
+  *out = map;
+  return true;
+}
+
+void setup_tma(AttnParams& p, int64_t kv_pool_tokens) {
+  p.tma_kv = p.tma_q = 0;
+  if (g_no_tma) return;
+  const int G = p.H / p.HKV;
+  if (kv_pool_tokens > 0 && p.kv_head_stride >= p.D && p.kv_tok_stride >= p.D)
+    p.tma_kv = make_map(&p.tmap_k, MapKey{p.k, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 32}) &&
+               make_map(&p.tmap_v, MapKey{p.v, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 32});
+  if (p.q_head_stride >= p.D && p.q_row_stride >= p.D)
+    p.tma_q = make_map(&p.tmap_q, MapKey{p.q, p.D, p.H, p.nq, p.q_head_stride, p.q_row_stride, G, 32});
+}
 
 // Which stage-1 kernel a call of this thread runs (the stage-2 kernel and the partial layout follow it).
 bool use_umma(int32_t H, int32_t HKV, int32_t D) {
@@ -168,6 +233,7 @@ int run_stages(const AttnParams& p, bool umma, cudaStream_t stream) {
     if (umma) {
       AttnParams pd = p;
       pd.dbg = g_debug;
+      pd.trace = g_trace;
       rc = launch_stage1_umma(pd, stream);
     } else {
       rc = launch_stage1_fma(p, stream);
@@ -203,6 +269,8 @@ const char* deft_b200_last_error(void) { return g_error; }
 void deft_b200_set_stages(int32_t mask) { g_stages = mask; }
 void deft_b200_set_stage1_impl(int32_t impl) { g_stage1_impl = impl; }
 void deft_b200_set_debug_buffer(void* dev) { g_debug = static_cast<float*>(dev); }
+void deft_b200_set_trace_buffer(void* dev) { g_trace = static_cast<int*>(dev); }
+void deft_b200_set_tma(int32_t enabled) { g_no_tma = enabled == 0; }
 
 size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_t D,
                                          int64_t n_partials, int64_t n_blocks, const deft_plan_t* plan) {
@@ -218,7 +286,8 @@ size_t deft_b200_node_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_
 }
 
 int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
-                          const void* v, int64_t kv_tok_stride, int64_t kv_head_stride, void* o,
+                          const void* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                          int64_t kv_pool_tokens, void* o,
                           int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
                           int32_t HKV, int32_t D, int32_t block_len, const int64_t* block_q,
                           int64_t n_partials, const int64_t* block_q_cnts,
@@ -246,6 +315,7 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
   p.kv_idx = block_kv; p.kv_idx_bytes = 8;
   p.q_list = block_q; p.masks = block_bitmasks;
   p.po = w.po; p.plse = w.plse; p.po16 = w.po16; p.plse16 = w.plse16;
+  if (umma) setup_tma(p, kv_pool_tokens);
   if (plan) {
     rc = use_plan(p, plan, umma);
     if (rc) return rc;
@@ -261,7 +331,8 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
 }
 
 int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
-                       const void* v, int64_t kv_tok_stride, int64_t kv_head_stride, void* o,
+                       const void* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                       int64_t kv_pool_tokens, void* o,
                        int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
                        int32_t HKV, int32_t D, const void* kv_indices, int32_t kv_index_bytes,
                        const int64_t* kv_offset, const int64_t* kv_len, const int64_t* node_q,
@@ -289,6 +360,7 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
   p.kv_idx = kv_indices; p.kv_idx_bytes = kv_index_bytes;
   p.q_list = node_q; p.masks = nullptr;
   p.po = w.po; p.plse = w.plse; p.po16 = w.po16; p.plse16 = w.plse16;
+  if (umma) setup_tma(p, kv_pool_tokens);
   if (plan) {
     rc = use_plan(p, plan, umma);
     if (rc) return rc;

@@ -16,13 +16,19 @@
 // TMEM is almost never rescaled.  ONE partial (O/l as fp16, log-sum-exp as fp32) leaves the SM per
 // (job, slot); stage 2 (combine.cu) merges the partials of every query.
 //
-// Warp roles (384 threads, 1 CTA per SM, all 512 TMEM columns):
-//   warps 0-3   softmax + epilogue of slot 0 (thread = row = TMEM lane)
+// Warp roles (512 threads, 1 CTA per SM, all 512 TMEM columns):
+//   warps 0-3   softmax + epilogue of slot 0 (thread = row = TMEM lane; 200 registers via setmaxnreg:
+//               the whole 128-column S row is read from TMEM once and kept in registers)
 //   warps 4-7   softmax + epilogue of slot 1; the two slots ping-pong on the tensor pipe:
 //               S_0(t) S_1(t) PV_0(t) | S_0(t+1) PV_1(t) S_1(t+1) PV_0(t+1) | ...
 //   warp  8     MMA issuer (one elected thread) and TMEM allocator
-//   warp  9/10  K / V producers: cp.async 16-byte gathers of paged rows into the swizzled stage ring
-//   warp  11    Q tiles (gathered per slot) and per-(tile, slot) mask words + "dense tile" flag
+//   warp  9/10  Q tile of slot 0 / slot 1: one TMA box per 64-wide panel when the slot's query ids are
+//               consecutive, else cp.async 16-byte gathers
+//   warp  11    per-(tile, slot) row masks (token bitmask per query, transposed from the per-token
+//               words of the table) + "dense tile" flag
+//   warps 12-15 K / V producers: each warp owns 32 token rows of every tile -- one TMA box per panel
+//               when its 32 pages are consecutive (prompt), else cp.async 16-byte gathers (the in-flight
+//               depth of cp.async is per warp, hence four warps)
 // All hand-offs are mbarriers (cp.async arrive-on, tcgen05.commit, plain arrive); no __syncthreads in
 // the steady state.
 //
@@ -35,8 +41,9 @@ namespace {
 
 constexpr int kTileN = 128;  // tokens per KV tile (= the reference's BLOCK_LEN)
 constexpr int kRows = 128;   // UMMA M
-constexpr int kThreads = 384;
-constexpr int kMmaWarp = 8, kKWarp = 9, kVWarp = 10, kQWarp = 11;
+constexpr int kThreads = 512;  // 16 warps: 4 register-budget groups of 4 (setmaxnreg works per warpgroup)
+constexpr int kMmaWarp = 8, kQ0Warp = 9, kQ1Warp = 10, kMaskWarp = 11, kKvWarp0 = 12;  // 12-15: K/V producers
+constexpr int kSoftmaxRegs = 192, kProducerRegs = 64;  // 256 * 192 + 256 * 64 = 64 K registers
 constexpr int kKvStages = 2, kMaskStages = 2;
 constexpr float kRescaleLog2 = 8.f;  // raise m_ref only when a tile tops it by more than 2^8
 
@@ -75,7 +82,19 @@ __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA: one box of a 3-D tensor map -> shared memory (swizzled by the map), completes `bytes` on `bar`
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// NB: no fence.proxy.async on the consumer side.  Data staged by cp.async or TMA is handed over through
+// an mbarrier the MMA thread waits on; a proxy fence there also waits for every async-proxy copy still
+// in flight to this CTA (the NEXT tiles' loads), which serialised the tensor pipe behind the loads.
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -118,6 +137,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
   asm volatile(
@@ -129,19 +165,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; exp2(-inf) = 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 32 x 32 bit-matrix transpose across a warp: lane l holds row l; on return lane l holds column l
+// (bit b of the result = bit l of lane b's input).  Five butterfly stages of one shuffle each.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+#pragma unroll
+  for (int st = 0; st < 5; ++st) {
+    const int j = 16 >> st;
+    const uint32_t m = st == 0 ? 0x0000FFFFu : st == 1 ? 0x00FF00FFu : st == 2 ? 0x0F0F0F0Fu : st == 3 ? 0x33333333u : 0x55555555u;
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, x, j);
+    x = (lane & j) ? ((x & (m << j)) | ((other >> j) & m)) : ((x & m) | ((other & m) << j));
+  }
+  return x;
 }
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
@@ -179,6 +220,20 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk16) {
   return (uint32_t)((chunk16 >> 3) * kPanelBytes + row * 128 + (((chunk16 & 7) ^ (row & 7)) << 4));
 }
 
+// Optional per-CTA timeline (test/profiling hook, deft_b200_set_trace_buffer): trace[cta][event] =
+// SM cycles since the CTA started.  Events: see kTrace* below; per-tile events take 8 slots per tile.
+constexpr int kTraceSlots = 128;
+enum : int {
+  kTrStart = 0, kTrQIds = 1, kTrQ0Issued = 2, kTrQ1Issued = 3, kTrMask0 = 4, kTrKUnit = 5, kTrMmaQFull = 6, kTrEpiBegin = 7,
+  kTrEpiEnd = 8, kTrEnd = 9,
+  kTrTile0 = 16,  // + 8 * tile: K issued, K_FULL seen by MMA, S_FULL seen by softmax 0, pass 1 done, P_FULL arrive,
+                  //             P_FULL seen by MMA, V issued, (spare)
+};
+#define DEFT_TRACE(ev)                                                                          \
+  do {                                                                                          \
+    if (p.trace != nullptr && (ev) < kTraceSlots) p.trace[(int64_t)blockIdx.x * kTraceSlots + (ev)] = (int)(clock64() - t_start); \
+  } while (0)
+
 // barrier indices
 enum : int {
   K_FULL = 0, K_EMPTY = K_FULL + kKvStages, V_FULL = K_EMPTY + kKvStages, V_EMPTY = V_FULL + kKvStages,
@@ -187,7 +242,8 @@ enum : int {
   M_EMPTY = M_FULL + 2 * kMaskStages,
   S_FULL = M_EMPTY + 2 * kMaskStages,      // [slot]
   P_FULL = S_FULL + 2, O_FULL = P_FULL + 2, O_EMPTY = O_FULL + 2,
-  kNumBars = O_EMPTY + 2
+  ORDER = O_EMPTY + 2,                     // [slot]: the slot's turn on the exp (MUFU) section
+  kNumBars = ORDER + 2
 };
 
 template <int D>
@@ -226,7 +282,7 @@ struct Jobs {
 };
 
 template <int D, int G>
-__global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_constant__ AttnParams p) {
   using L = Layout<D>;
   constexpr int CH = D / 8;           // 16-byte chunks per row
   constexpr int R = kMaxGroupQ * G;   // live rows of a full slot
@@ -241,10 +297,11 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
   auto bar = [&](int i) { return bars + 8u * i; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long t_start = clock64();
   if (tid == 0) {
     for (int s = 0; s < kKvStages; ++s) {
-      mbar_init(bar(K_FULL + s), 32); mbar_init(bar(K_EMPTY + s), 1);
-      mbar_init(bar(V_FULL + s), 32); mbar_init(bar(V_EMPTY + s), 1);
+      mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 1);
+      mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(Q_FULL + s), 32); mbar_init(bar(Q_EMPTY + s), 1);
@@ -254,6 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
       }
       mbar_init(bar(S_FULL + s), 1); mbar_init(bar(P_FULL + s), 128);
       mbar_init(bar(O_FULL + s), 1); mbar_init(bar(O_EMPTY + s), 128);
+      mbar_init(bar(ORDER + s), 128);
     }
     fence_barrier_init();
   }
@@ -264,59 +322,94 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gbase + L::kTmemSlot);
 
   const Jobs jobs(p);
-
-  if (warp == kKWarp || warp == kVWarp) {
-    // ============================== K / V producers ==============================
-    const bool is_k = warp == kKWarp;
-    const __half* src_pool = is_k ? p.k : p.v;
-    const uint32_t dst_pool = base + (is_k ? L::kK : L::kV);
-    const int full0 = is_k ? K_FULL : V_FULL, empty0 = is_k ? K_EMPTY : V_EMPTY;
+  if (tid == 0) DEFT_TRACE(kTrStart);
+  if (warp >= 8) {
+  reg_dealloc<kProducerRegs>();  // warps 8-11 and 12-15: two whole warpgroups give registers away
+  if (warp >= kKvWarp0) {
+    // ============================== K / V producers: warp w owns token rows [32w, 32w+32) ==============================
+    const int w = warp - kKvWarp0;
     uint32_t cnt = 0;  // tiles produced
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
       const int job = jobs.get(ji);
       const int hkv = job % p.HKV;
       const deft_unit_t u = p.units[job / p.HKV];
-      const __half* src_base = src_pool + (int64_t)hkv * p.kv_head_stride;
+      if (w == 0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrKUnit);
+      const int n_mine = w * 32 + lane;  // my token row
+      auto page_of = [&](int t) -> int64_t {
+        const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
+        return t < u.n_tiles && n_mine < tlen ? load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + n_mine) : 0;
+      };
+      int64_t pg_next = page_of(0);
       for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
         const int st = cnt % kKvStages;
-        mbar_wait(bar(empty0 + st), ((cnt / kKvStages) & 1) ^ 1);
-        int64_t pg[4];
+        const uint32_t ph = ((cnt / kKvStages) & 1) ^ 1;
+        const int64_t pg = pg_next;
+        pg_next = page_of(t + 1);  // the next tile's page id is in flight while this tile is issued
+        // 32 consecutive pages of a full tile are ONE box of the pool's tensor map per 64-wide panel
+        const int64_t page0 = __shfl_sync(0xffffffffu, pg, 0);
+        const bool run = __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg == page0 + lane);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int n = lane + 32 * j;
-          pg[j] = n < tlen ? load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + n) : 0;
-        }
-        const uint32_t dst_base = dst_pool + st * L::kOperandBytes;
-        constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
+        for (int kv = 0; kv < 2; ++kv) {
+          const int full = (kv == 0 ? K_FULL : V_FULL) + st;
+          mbar_wait(bar((kv == 0 ? K_EMPTY : V_EMPTY) + st), ph);
+          const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
+          if (run) {
+            if (lane == 0) {
+              mbar_arrive_expect_tx(bar(full), 32 * D * 2);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+              for (int pn = 0; pn < D / 64; ++pn)
+                tma_load_3d(dst_base + pn * kPanelBytes + w * 32 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, bar(full), pn * 64,
+                            hkv, (int)page0);
+            } else {
+              mbar_arrive(bar(full));
+            }
+          } else {
+            const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
+            constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
 #pragma unroll 4
-          for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
-            const int n = j * 32 + i * TOK_PER_INSTR + lane / CH;
-            const int ch = lane % CH;
-            const int64_t page = __shfl_sync(0xffffffffu, pg[j], n & 31);
-            const bool ok = n < tlen;
-            cp_async_16(dst_base + tile_off(n, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
+            for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
+              const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside my 32
+              const int ch = lane % CH;
+              const int64_t page = __shfl_sync(0xffffffffu, pg, nl);
+              const bool ok = w * 32 + nl < tlen;
+              cp_async_16(dst_base + tile_off(w * 32 + nl, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
+            }
+            cp_async_arrive(bar(full));
           }
+          if (w == 0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
+          if (w > 0 && lane == 0 && ji == jobs.begin && t == 1 && kv == 0) DEFT_TRACE(9 + w);
         }
-        cp_async_arrive(bar(full0 + st));
       }
     }
-  } else if (warp == kQWarp) {
-    // ============================== Q tiles and mask words ==============================
-    uint32_t q_cnt[2] = {0, 0};  // jobs per slot
-    uint32_t m_cnt[2] = {0, 0};  // tiles per slot
+  } else if (warp == kQ0Warp || warp == kQ1Warp) {
+    // ============================== Q tile of one slot ==============================
+    const int s = warp == kQ0Warp ? 0 : 1;
+    uint32_t q_cnt = 0;  // jobs of this slot
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
       const int job = jobs.get(ji);
       const int hkv = job % p.HKV;
       const deft_unit_t u = p.units[job / p.HKV];
-      const int n_slots = u.q_cnt[1] > 0 ? 2 : 1;
-      for (int s = 0; s < n_slots; ++s) {
-        // Q tile of the slot: row r = (query r / G, head r % G); rows past q_cnt*G are zero
-        mbar_wait(bar(Q_EMPTY + s), (q_cnt[s] & 1) ^ 1);
-        const int64_t my_q = lane < u.q_cnt[s] ? load_index(p.u_q, p.u_q_bytes, u.q_off[s] + lane) : 0;
-        const uint32_t qs = base + L::kQ + s * L::kOperandBytes;
+      if (u.q_cnt[s] == 0) continue;
+      // row r = (query r / G, head r % G); rows past q_cnt*G are zero
+      const int64_t my_q = lane < u.q_cnt[s] ? load_index(p.u_q, p.u_q_bytes, u.q_off[s] + lane) : 0;
+      mbar_wait(bar(Q_EMPTY + s), (q_cnt & 1) ^ 1);
+      const uint32_t qs = base + L::kQ + s * L::kOperandBytes;
+      if (lane == 0 && ji == jobs.begin && s == 0 && my_q >= 0) DEFT_TRACE(kTrQIds);
+      // consecutive query ids: the slot's G heads x 32 queries are ONE box of q's tensor map per panel
+      // (rows past q_cnt then hold the next queries or zeros: finite, never stored)
+      const int64_t q0 = __shfl_sync(0xffffffffu, my_q, 0);
+      const bool run = p.tma_q != 0 && (lane >= u.q_cnt[s] || my_q == q0 + lane);
+      if (__all_sync(0xffffffffu, run)) {
+        if (lane == 0) {
+          mbar_arrive_expect_tx(bar(Q_FULL + s), R * D * 2);
+#pragma unroll
+          for (int pn = 0; pn < D / 64; ++pn)
+            tma_load_3d(qs + pn * kPanelBytes, &p.tmap_q, bar(Q_FULL + s), pn * 64, hkv * G, (int)q0);
+        } else {
+          mbar_arrive(bar(Q_FULL + s));
+        }
+      } else {
 #pragma unroll 4
         for (int i = 0; i < kRows * CH / 32; ++i) {
           const int c = lane + i * 32;
@@ -328,8 +421,17 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
           cp_async_16(qs + tile_off(r, ch), ok ? src : p.q, ok ? 16u : 0u);
         }
         cp_async_arrive(bar(Q_FULL + s));
-        ++q_cnt[s];
       }
+      if (lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrQ0Issued + s);
+      ++q_cnt;
+    }
+  } else if (warp == kMaskWarp) {
+    // ============================== mask words + dense flag per (tile, slot) ==============================
+    uint32_t m_cnt[2] = {0, 0};  // tiles per slot
+    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+      const int job = jobs.get(ji);
+      const deft_unit_t u = p.units[job / p.HKV];
+      const int n_slots = u.q_cnt[1] > 0 ? 2 : 1;
       for (int t = 0; t < u.n_tiles; ++t) {
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
         for (int s = 0; s < n_slots; ++s) {
@@ -337,21 +439,28 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
           mbar_wait(bar(M_EMPTY + s * kMaskStages + st), ((m_cnt[s] / kMaskStages) & 1) ^ 1);
           uint32_t* ms = reinterpret_cast<uint32_t*>(gbase + L::kMask) + (s * kMaskStages + st) * kTileN;
           const uint32_t full = u.q_cnt[s] >= 32 ? 0xffffffffu : ((1u << u.q_cnt[s]) - 1u);
+          // per-token words: bit r = row r of the slot attends token lane + 32j
+          uint32_t m[kTileN / 32];
           bool dense = tlen == kTileN;
 #pragma unroll
           for (int j = 0; j < kTileN / 32; ++j) {
             const int n = lane + 32 * j;
-            uint32_t m = 0;
+            m[j] = 0;
             if (n < tlen)
-              m = u.mask_off[s] >= 0
-                      ? (uint32_t)load_index(p.u_mask, p.u_mask_bytes, u.mask_off[s] + (int64_t)t * u.mask_tile_stride + n)
-                      : 0xffffffffu;
-            dense = dense && ((m & full) == full);
-            ms[n] = m;
+              m[j] = u.mask_off[s] >= 0
+                         ? (uint32_t)load_index(p.u_mask, p.u_mask_bytes, u.mask_off[s] + (int64_t)t * u.mask_tile_stride + n)
+                         : 0xffffffffu;
+            dense = dense && ((m[j] & full) == full);
           }
           dense = __all_sync(0xffffffffu, dense);
+          if (!dense) {
+            // transpose to row masks: lane = query, word j bit n = the query attends token 32j + n
+            *reinterpret_cast<uint4*>(ms + lane * 4) = make_uint4(warp_transpose32(m[0], lane), warp_transpose32(m[1], lane),
+                                                                  warp_transpose32(m[2], lane), warp_transpose32(m[3], lane));
+          }
           if (lane == 0) reinterpret_cast<uint32_t*>(gbase + L::kFlag)[s * kMaskStages + st] = dense ? 1u : 0u;
           mbar_arrive(bar(M_FULL + s * kMaskStages + st));
+          if (lane == 0 && ji == jobs.begin && t == 0 && s == 0) DEFT_TRACE(kTrMask0);
           ++m_cnt[s];
         }
       }
@@ -372,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
 
         auto issue_s = [&](int s, int t, uint32_t k_smem) {
           const uint32_t q_smem = base + L::kQ + s * L::kOperandBytes;
-#pragma unroll
+#pragma unroll 1
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint32_t koff = (ks >> 2) * kPanelBytes + (ks & 3) * 32;
             umma_ss(tmem + s * 128, smem_desc_sw128(q_smem + koff, 16, 1024), smem_desc_sw128(k_smem + koff, 16, 1024),
@@ -386,23 +495,25 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
           const int vst = vi % kKvStages;
           if (s == 0) mbar_wait(bar(V_FULL + vst), (vi / kKvStages) & 1);
           mbar_wait(bar(P_FULL + s), (s_base[s] + t) & 1);
+          if (ji == jobs.begin && s == 0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
           if (t == 0) mbar_wait(bar(O_EMPTY + s), (j_cnt[s] & 1) ^ 1);
-          fence_proxy_async();
           tc_fence_after();
           const uint32_t v_smem = base + L::kV + vst * L::kOperandBytes;
-#pragma unroll
+#pragma unroll 1
           for (int ks = 0; ks < kTileN / 16; ++ks)
             umma_ts(tmem + 256 + s * 128, tmem + s * 128 + ks * 8,
                     smem_desc_sw128(v_smem + ks * 2048, kPanelBytes, 1024), kIdescPV, t > 0 || ks > 0);
           umma_commit(bar(O_FULL + s));
           if (s == 1 || !has_b) umma_commit(bar(V_EMPTY + vst));
+          if (ji == jobs.begin && t == 0) DEFT_TRACE(s == 0 ? 13 : 15);
         };
 
         for (int t = 0; t < n; ++t) {
           const int kst = k_cnt % kKvStages;
           mbar_wait(bar(K_FULL + kst), (k_cnt / kKvStages) & 1);
+          if (ji == jobs.begin) DEFT_TRACE(kTrTile0 + 8 * t + 1);
           if (t == 0) mbar_wait(bar(Q_FULL + 0), j_cnt[0] & 1);
-          fence_proxy_async();
+          if (ji == jobs.begin && t == 0) DEFT_TRACE(kTrMmaQFull);
           tc_fence_after();
           const uint32_t k_smem = base + L::kK + kst * L::kOperandBytes;
           issue_s(0, t, k_smem);
@@ -410,9 +521,9 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
             if (t > 0) issue_pv(1, t - 1);
             if (t == 0) {
               mbar_wait(bar(Q_FULL + 1), j_cnt[1] & 1);
-              fence_proxy_async();
             }
             issue_s(1, t, k_smem);
+            if (ji == jobs.begin && t == 0) DEFT_TRACE(14);
           }
           umma_commit(bar(K_EMPTY + kst));
           ++k_cnt;
@@ -425,16 +536,18 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
       }
     }
     __syncwarp();
+  }
   } else {
+    reg_alloc<kSoftmaxRegs>();   // warps 0-3 and 4-7
     // ============================== softmax + epilogue (slot = warp / 4) ==============================
     const int s = warp >> 2;
     const int r = tid & 127;  // my row == my TMEM lane
-    const int qi = r / G, g = r % G;
-    const uint32_t qbit = qi < 32 ? (1u << qi) : 0u;  // my query's bit in the per-token masks
+    const int qi = r / G;
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t t_s = t_lane + s * 128, t_o = t_lane + 256 + s * 128;
     const float c = p.scale * 1.4426950408889634f;  // scores are handled in the log2 domain
     uint32_t s_cnt = 0, m_cnt = 0;
+    uint32_t ord_cnt = 0;  // tiles of two-slot jobs: the slots take turns on the exp section
     bool first_job = blockIdx.x == 0;
 
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
@@ -454,33 +567,34 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
         const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[s * kMaskStages + mst] != 0;
         mbar_wait(bar(S_FULL + s), s_cnt & 1);
         tc_fence_after();
+        const bool tr = ji == jobs.begin && tid == 0;
+        if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 2);
 
-        // ---- pass 1: maximum of my row over the tile
-        float mt = -INFINITY;
-#pragma unroll 1
-        for (int cb = 0; cb < kTileN / 32; ++cb) {
-          tmem_ld32(t_s + cb * 32, v);
-          if (dbg && t == 0)
-            for (int j = 0; j < 32; ++j) p.dbg[r * kTileN + cb * 32 + j] = v[j];
-          if (dense) {
-            float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+        // ---- the whole S row (128 columns) comes out of TMEM once and stays in registers
+        float sv[kTileN];
 #pragma unroll
-            for (int j = 4; j < 32; j += 4) {
-              m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
-            }
-            mt = fmaxf(mt, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-          } else {
+        for (int cb = 0; cb < kTileN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv + cb * 32);
+        tmem_wait_ld();
+        if (dbg && t == 0)
+          for (int j = 0; j < kTileN; ++j) p.dbg[r * kTileN + j] = sv[j];
+        if (!dense) {  // masked-out tokens score -inf: my query's token bitmask comes from the mask warp
+          const uint4 rm = qi < 32 ? *reinterpret_cast<const uint4*>(ms + qi * 4) : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t rw[4] = {rm.x, rm.y, rm.z, rm.w};
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const uint4 mk = *reinterpret_cast<const uint4*>(ms + cb * 32 + j);
-              if (mk.x & qbit) mt = fmaxf(mt, v[j]);
-              if (mk.y & qbit) mt = fmaxf(mt, v[j + 1]);
-              if (mk.z & qbit) mt = fmaxf(mt, v[j + 2]);
-              if (mk.w & qbit) mt = fmaxf(mt, v[j + 3]);
-            }
+          for (int j = 0; j < kTileN; ++j)
+            if (!((rw[j >> 5] >> (j & 31)) & 1u)) sv[j] = -INFINITY;
+        }
+        float mt;
+        {
+          float m0 = sv[0], m1 = sv[1], m2 = sv[2], m3 = sv[3];
+#pragma unroll
+          for (int j = 4; j < kTileN; j += 4) {
+            m0 = fmaxf(m0, sv[j]); m1 = fmaxf(m1, sv[j + 1]); m2 = fmaxf(m2, sv[j + 2]); m3 = fmaxf(m3, sv[j + 3]);
           }
+          mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         }
         mt *= c;  // c > 0
+        if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 3);
 
         // ---- lazily raised reference maximum; the accumulator is rescaled only when it moves
         const bool raise = mt > m_ref + kRescaleLog2;  // also the first live tile (m_ref = -inf)
@@ -504,47 +618,42 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
         }
         const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
 
-        // ---- pass 2: P = exp2(S*c - m_ref) -> fp16, written over S in TMEM (P chunk cb lands in
-        //      columns [16cb, 16cb+16), always behind the S columns still to be read)
+        // ---- P = exp2(S*c - m_ref) -> packed fp16, written over S in TMEM (columns [0, 64) of the slot).
+        // In a two-slot job the slots alternate on this MUFU-bound section (slot 0 first), which keeps them
+        // half a period apart: one exponentiates while the tensor pipe serves the other.
+        const bool ordered = u.q_cnt[1] > 0;
+        if (ordered) mbar_wait(bar(ORDER + s), s == 0 ? ((ord_cnt & 1) ^ 1) : (ord_cnt & 1));
         float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-#pragma unroll 1
-        for (int cb = 0; cb < kTileN / 32; ++cb) {
-          tmem_ld32(t_s + cb * 32, v);
-          if (dense) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              v[j] = fast_exp2(fmaf(v[j], c, -m_use));
-              v[j + 1] = fast_exp2(fmaf(v[j + 1], c, -m_use));
-              v[j + 2] = fast_exp2(fmaf(v[j + 2], c, -m_use));
-              v[j + 3] = fast_exp2(fmaf(v[j + 3], c, -m_use));
-              ps0 += v[j]; ps1 += v[j + 1]; ps2 += v[j + 2]; ps3 += v[j + 3];
-            }
-          } else {
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t pk[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const uint4 mk = *reinterpret_cast<const uint4*>(ms + cb * 32 + j);
-              v[j] = (mk.x & qbit) ? fast_exp2(fmaf(v[j], c, -m_use)) : 0.f;
-              v[j + 1] = (mk.y & qbit) ? fast_exp2(fmaf(v[j + 1], c, -m_use)) : 0.f;
-              v[j + 2] = (mk.z & qbit) ? fast_exp2(fmaf(v[j + 2], c, -m_use)) : 0.f;
-              v[j + 3] = (mk.w & qbit) ? fast_exp2(fmaf(v[j + 3], c, -m_use)) : 0.f;
-              ps0 += v[j]; ps1 += v[j + 1]; ps2 += v[j + 2]; ps3 += v[j + 3];
-            }
+          for (int j = 0; j < 64; j += 4) {
+            const int i = hf * 64 + j;
+            const float e0 = fast_exp2(fmaf(sv[i], c, -m_use)), e1 = fast_exp2(fmaf(sv[i + 1], c, -m_use));
+            const float e2 = fast_exp2(fmaf(sv[i + 2], c, -m_use)), e3 = fast_exp2(fmaf(sv[i + 3], c, -m_use));
+            ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
+            pk[j / 2] = pack_half2(e0, e1);
+            pk[j / 2 + 1] = pack_half2(e2, e3);
           }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_half2(v[2 * j], v[2 * j + 1]);
-          tmem_st16(t_s + cb * 16, pk);
+          tmem_st32(t_s + hf * 32, reinterpret_cast<const float*>(pk));
+        }
+        if (ordered) {
+          mbar_arrive(bar(ORDER + (s ^ 1)));
+          ++ord_cnt;
         }
         tmem_wait_st();
         l_run += (ps0 + ps1) + (ps2 + ps3);
         mbar_arrive(bar(M_EMPTY + s * kMaskStages + mst));
         tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
         mbar_arrive(bar(P_FULL + s));
+        if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 4);
       }
 
       // ---- epilogue: partial = O / l as fp16, log-sum-exp in the natural-log domain
       mbar_wait(bar(O_FULL + s), (s_cnt - 1) & 1);
       tc_fence_after();
+      if (ji == jobs.begin && tid == 0) DEFT_TRACE(kTrEpiBegin);
       const bool live = qi < u.q_cnt[s];
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       const int64_t tile = (int64_t)(u.part_base[s] >> 5) * p.HKV + hkv;
@@ -569,10 +678,12 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const AttnPara
       if (live) p.plse16[tile * R + r] = l_run > 0.f ? (m_ref + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
       tc_fence_before();  // my reads of O are ordered before the next job's first P V (accumulate = 0)
       mbar_arrive(bar(O_EMPTY + s));
+      if (ji == jobs.begin && tid == 0) DEFT_TRACE(kTrEpiEnd);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) DEFT_TRACE(kTrEnd);
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 

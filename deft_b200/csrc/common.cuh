@@ -1,5 +1,6 @@
 // Shared declarations of the libdeft_b200 translation units.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,6 +35,11 @@ constexpr int kNodeSplit = 256;    // tokens per item when long Node entries are
 
 // Everything stage 1 / stage 2 need to know about one attention call.
 struct AttnParams {
+  // TMA tensor maps (tcgen05 path), valid when the flags below are set:
+  //   tmap_k / tmap_v: [pool][HKV][D] fp16, box {64, 1, 32 pages}, 128B swizzle
+  //   tmap_q:          [nq][H][D]     fp16, box {64, G, 32 queries}, 128B swizzle
+  CUtensorMap tmap_k, tmap_v, tmap_q;
+  int32_t tma_kv, tma_q;
   const __half* q;
   const __half* k;
   const __half* v;
@@ -59,6 +65,7 @@ struct AttnParams {
   float* po;
   float* plse;
   float* dbg;  // debug dump of the tensor-core path (raw S and O of the first unit), normally null
+  int* trace;  // per-CTA timeline of the tensor-core path ([cta][128] SM cycles), normally null
   // ---- unit plan (tcgen05 path): tables may be the reference's (int64) or the builder's (32-bit)
   const deft_unit_t* units;
   const int32_t* n_units_dev;  // device-resident unit count (device-built plans), or null

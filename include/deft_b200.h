@@ -55,6 +55,12 @@ void deft_b200_set_stage1_impl(int32_t impl);
 /* Test hook: with DEFT_STAGE1_UMMA forced, the first work unit dumps its raw S [128][128] and
  * O [128][D] accumulators (fp32) to this device buffer.  NULL (default) disables. */
 void deft_b200_set_debug_buffer(void* dev);
+/* Profiling hook: the tcgen05 stage 1 records a per-CTA timeline ([n_ctas][128] int32, SM cycles since
+ * the CTA started; event ids in csrc/attn_umma.cu) into this device buffer.  NULL (default) disables. */
+void deft_b200_set_trace_buffer(void* dev);
+/* Test hook: 0 = never use TMA (every K/V/Q row is gathered with cp.async), 1 (default) = TMA for runs
+ * of 128 consecutive pages and for slots of consecutive query ids. */
+void deft_b200_set_tma(int32_t enabled);
 
 /* ------------------------------------------------------------------------------------------
  * Work plan (device side).  Two layers:
@@ -130,7 +136,9 @@ typedef struct {
  * Replaces tree_attention_subtree_fwd (layers/attention/tree_attention.py:552-667: stage-1 kernel2
  * :860-976 + DeFT_splitBynode_Triton_stage2 :297-416).  Argument meaning is the reference's:
  *   q  [nq, H, D] fp16, strides in elements (row stride 6144 for the fused-qkv view)
- *   k/v[pool, HKV, D] fp16 views of kv_data[layer][:,0] / [:,1] (memory_pool.py:68-72)
+ *   k/v[pool, HKV, D] fp16 views of kv_data[layer][:,0] / [:,1] (memory_pool.py:68-72);
+ *      kv_pool_tokens = pool size (pages): bounds the TMA tensor maps used for runs of consecutive
+ *      pages; 0 disables TMA (every page is then gathered with cp.async)
  *   o  [nq, H, D] fp16, fully overwritten (the reference requires it pre-zeroed; we do not)
  *   block_q [n_partials], block_q_cnts/offset/lens [n_blocks], block_bitmasks/block_kv
  *   [n_blocks*block_len] -- int64 device tables of TreeMetadata (tree_cache.py:591-616)
@@ -144,7 +152,7 @@ size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int
 
 int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride,
                           const void* k, const void* v, int64_t kv_tok_stride,
-                          int64_t kv_head_stride, void* o, int64_t o_row_stride,
+                          int64_t kv_head_stride, int64_t kv_pool_tokens, void* o, int64_t o_row_stride,
                           int64_t o_head_stride, int32_t nq, int32_t H, int32_t HKV, int32_t D,
                           int32_t block_len, const int64_t* block_q, int64_t n_partials,
                           const int64_t* block_q_cnts, const int64_t* block_q_offset,
@@ -166,7 +174,8 @@ size_t deft_b200_node_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_
                                       const deft_plan_t* plan);
 
 int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
-                       const void* v, int64_t kv_tok_stride, int64_t kv_head_stride, void* o,
+                       const void* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                       int64_t kv_pool_tokens, void* o,
                        int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
                        int32_t HKV, int32_t D, const void* kv_indices, int32_t kv_index_bytes,
                        const int64_t* kv_offset, const int64_t* kv_len, const int64_t* node_q,

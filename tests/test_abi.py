@@ -32,7 +32,7 @@ def test_abi_version_and_struct_layout():
 
 def test_argument_errors_are_reported_not_crashed():
     """Validation happens before any CUDA call, so this runs without a GPU."""
-    rc = _lib.lib.deft_b200_flatten_fwd(None, 0, 0, None, None, 0, 0, None, 0, 0, 1, 32, 8, 128, 128,
+    rc = _lib.lib.deft_b200_flatten_fwd(None, 0, 0, None, None, 0, 0, 0, None, 0, 0, 1, 32, 8, 128, 128,
                                         None, 1, None, None, None, 1, None, None, None, None, 0, None)
     assert rc == -1 and "null" in _lib.last_error()
     with pytest.raises(_lib.DeftError):

@@ -127,3 +127,32 @@ def test_kernels_agree_at_full_size(dev, force_impl):
                                              m.block_bitmasks, m.block_kv, m.block_lens)
         outs[impl] = o.float()
     assert torch.allclose(outs[_lib.STAGE1_FMA], outs[_lib.STAGE1_UMMA], atol=1e-3, rtol=1e-2)
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_tma_and_cp_async_paths_agree(dev, name):
+    """Runs of consecutive pages / query ids go through TMA boxes, everything else through cp.async gathers:
+    both stage the same bytes in the same swizzled layout, so the outputs are bit-identical."""
+    from deft_b200 import TreeMetadata, _lib
+    import deft_b200
+    from deft_b200.workloads import build_tree
+    torch.manual_seed(2)
+    tree = build_tree(name, layers=1, device=dev)
+    kvp = tree.token_to_kv_pool
+    kvp.kv_data[0].normal_()
+    K, V = kvp.get_key_buffer(0), kvp.get_value_buffer(0)
+    nq = len(tree.leaves)
+    q = torch.randn(nq, 48 * 128, dtype=torch.float16, device=dev)[:, : 32 * 128].view(nq, 32, 128)
+    m = TreeMetadata.from_tree_cache(tree)
+    outs = []
+    try:
+        for tma in (1, 0):
+            _lib.lib.deft_b200_set_tma(tma)
+            o = torch.full((nq, 32, 128), float("nan"), dtype=torch.float16, device=dev)
+            deft_b200.tree_attention_subtree_fwd(q, K, V, o, 128, m.block_q, m.block_q_cnts, m.block_q_offset,
+                                                 m.block_bitmasks, m.block_kv, m.block_lens)
+            outs.append(o)
+    finally:
+        _lib.lib.deft_b200_set_tma(1)
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1])

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Per-CTA timeline of the tcgen05 stage-1 kernel on a BASELINE workload (profiling aid, needs a B200).
+
+    python tools/trace_stage1.py [cfg2] [n_ctas_to_print]
+
+Uses the deft_b200_set_trace_buffer hook: every CTA records SM-cycle timestamps of its first job
+(event ids: csrc/attn_umma.cu kTr*).  Prints the events in microseconds at the nominal 1.965 GHz.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+
+import deft_b200
+from deft_b200 import TreeMetadata, _lib
+from deft_b200.workloads import build_tree
+
+NAMES = {0: "start", 1: "q_ids", 2: "q0_issued", 3: "q1_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
+         8: "epi_end", 9: "end", 10: "t1.k_issued_w1", 11: "t1.k_issued_w2", 12: "t1.k_issued_w3", 13: "mma_pv0(0)_issued",
+         14: "mma_s1(0)_issued", 15: "mma_pv1(0)_issued"}
+TILE = ["k_issued", "mma_k_full", "sm_s_full", "sm_pass1", "sm_p_arrive", "mma_p_full", "v_issued", "-"]
+
+
+def main():
+    wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+    show = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    dev = torch.device("cuda:0")
+    tree = build_tree(wl, layers=2, device=dev)
+    kvp = tree.token_to_kv_pool
+    for l in range(2):
+        kvp.kv_data[l].normal_()
+    nq = len(tree.leaves)
+    q = torch.randn(nq, 48 * 128, dtype=torch.float16, device=dev)[:, : 32 * 128].view(nq, 32, 128)
+    o = torch.empty(nq, 32, 128, dtype=torch.float16, device=dev)
+    m = TreeMetadata.from_tree_cache(tree)
+    trace = torch.full((256, 128), -1, dtype=torch.int32, device=dev)
+
+    def call(layer):
+        deft_b200.tree_attention_subtree_fwd(q, kvp.get_key_buffer(layer), kvp.get_value_buffer(layer), o, 128, m.block_q,
+                                             m.block_q_cnts, m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens)
+
+    for _ in range(3):
+        call(0)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush.zero_()                               # push the KV pool out of L2
+    call(1)                                     # warm the plan tables only (other layer)
+    torch.cuda.synchronize()
+    flush.zero_()
+    _lib.lib.deft_b200_set_trace_buffer(trace.data_ptr())
+    call(0)
+    torch.cuda.synchronize()
+    _lib.lib.deft_b200_set_trace_buffer(None)
+    t = trace.cpu().numpy()
+    ghz = 1.965
+    ends = t[:, 9]
+    active = [c for c in range(t.shape[0]) if ends[c] >= 0]
+    print(f"{wl}: {len(active)} CTAs traced; end (us): min {ends[active].min() / ghz / 1e3:.2f} "
+          f"max {ends[active].max() / ghz / 1e3:.2f} mean {ends[active].mean() / ghz / 1e3:.2f}")
+    order = sorted(active, key=lambda c: -ends[c])
+    for c in order[:show] + [order[len(order) // 2]] + order[-1:]:
+        print(f"--- CTA {c}")
+        ev = [(int(t[c, i]), NAMES[i]) for i in NAMES if t[c, i] >= 0]
+        for tile in range((128 - 16) // 8):
+            for k in range(8):
+                v = int(t[c, 16 + 8 * tile + k])
+                if v >= 0:
+                    ev.append((v, f"t{tile}.{TILE[k]}"))
+        for v, name in sorted(ev):
+            print(f"   {v / ghz / 1e3:8.2f} us  {name}")
+
+
+if __name__ == "__main__":
+    main()
