@@ -13,6 +13,7 @@ static thread_local int g_stage1_impl = DEFT_STAGE1_AUTO;
 static thread_local float* g_debug = nullptr;
 static thread_local int* g_trace = nullptr;
 static thread_local bool g_no_tma = false;
+static thread_local bool g_no_pdl = false;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -225,6 +226,7 @@ void use_plan(AttnParams& p, const PlanBuffers& pb, int64_t bound) {
   p.u_mask = p.masks; p.u_mask_bytes = 8;
   p.u_q = p.q_list; p.u_q_bytes = 8;
   p.u_csr_off = pb.csr_off; p.u_csr_rows = pb.csr_rows;
+  p.plan_fresh = 1;
 }
 
 int run_stages(const AttnParams& p, bool umma, cudaStream_t stream) {
@@ -271,6 +273,7 @@ void deft_b200_set_stage1_impl(int32_t impl) { g_stage1_impl = impl; }
 void deft_b200_set_debug_buffer(void* dev) { g_debug = static_cast<float*>(dev); }
 void deft_b200_set_trace_buffer(void* dev) { g_trace = static_cast<int*>(dev); }
 void deft_b200_set_tma(int32_t enabled) { g_no_tma = enabled == 0; }
+void deft_b200_set_pdl(int32_t enabled) { g_no_pdl = enabled == 0; }
 
 size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_t D,
                                          int64_t n_partials, int64_t n_blocks, const deft_plan_t* plan) {
@@ -316,6 +319,7 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
   p.q_list = block_q; p.masks = block_bitmasks;
   p.po = w.po; p.plse = w.plse; p.po16 = w.po16; p.plse16 = w.plse16;
   if (umma) setup_tma(p, kv_pool_tokens);
+  p.pdl = g_no_pdl ? 0 : 1;
   if (plan) {
     rc = use_plan(p, plan, umma);
     if (rc) return rc;
@@ -361,6 +365,7 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
   p.q_list = node_q; p.masks = nullptr;
   p.po = w.po; p.plse = w.plse; p.po16 = w.po16; p.plse16 = w.plse16;
   if (umma) setup_tma(p, kv_pool_tokens);
+  p.pdl = g_no_pdl ? 0 : 1;
   if (plan) {
     rc = use_plan(p, plan, umma);
     if (rc) return rc;

@@ -34,7 +34,7 @@
 //
 // Reference semantics: DeFT/deft/layers/attention/tree_attention.py:860-976 (Flatten stage 1) and
 // :170-293 (Node stage 1).
-#include "common.cuh"
+#include "combine.cuh"
 
 namespace deft {
 namespace {
@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long t_start = clock64();
+  griddep_launch_dependents();       // stage 2 may launch early: its CTAs wait for this grid to finish
+  if (p.plan_fresh) griddep_wait();  // the plan itself comes from the preceding (plan) kernel
   if (tid == 0) {
     for (int s = 0; s < kKvStages; ++s) {
       mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 1);
@@ -322,6 +324,9 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gbase + L::kTmemSlot);
 
   const Jobs jobs(p);
+  // Programmatic dependent launch: everything up to here (barrier init, TMEM allocation, job list) overlapped
+  // the tail of the preceding kernel; q, the KV pool and the partial workspace may still be in its hands.
+  griddep_wait();
   if (tid == 0) DEFT_TRACE(kTrStart);
   if (warp >= 8) {
   reg_dealloc<kProducerRegs>();  // warps 8-11 and 12-15: two whole warpgroups give registers away
@@ -707,8 +712,17 @@ int launch_t(const AttnParams& p, cudaStream_t stream) {
     grid = (int)(n_jobs < num_sms ? n_jobs : num_sms);
   }
   if (grid <= 0) return DEFT_OK;
-  stage1_umma_kernel<D, G><<<grid, kThreads, L::kAlloc, stream>>>(p);
-  DEFT_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L::kAlloc;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // launch early, wait inside (griddep_wait)
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  DEFT_CUDA(cudaLaunchKernelEx(&cfg, stage1_umma_kernel<D, G>, p));
   return DEFT_OK;
 }
 

@@ -6,7 +6,7 @@
 // owns one (query, head), walks the query's partial rows through a CSR in ascending row order and
 // merges in fp32 with the true maximum, so the result is deterministic, needs no zeroed output and is
 // rounded to fp16 exactly once.
-#include "common.cuh"
+#include "combine.cuh"
 
 namespace deft {
 namespace {
@@ -64,68 +64,30 @@ __global__ void __launch_bounds__(kThreads) stage2_kernel(const AttnParams p) {
   }
 }
 
-// Same merge over the tile partials of the tcgen05 stage 1: po16 [slot tile][D/8 chunks][32*G rows][8]
-// fp16 and plse16 [slot tile][32*G] fp32, slot tile = (partial row / 32) * HKV + kv_head, row inside
-// the tile = (partial row % 32) * G + g.  One warp owns (query, kv-head, group of 32/G chunks): lane
-// = (g, chunk), so the G heads of a query read 16*G contiguous bytes per chunk and write whole
-// 128-byte lines of the output.
+// Standalone merge of the tile partials of the tcgen05 stage 1 (one warp per item, combine.cuh).  Used
+// when the fused tail of the stage-1 kernel is disabled or cannot run (see attn_umma.cu).
 template <int D, int G>
 __global__ void __launch_bounds__(kThreads) stage2_tiles_kernel(const AttnParams p) {
-  constexpr int CH = D / 8, CPW = 32 / G, NCG = (CH + CPW - 1) / CPW, R = kMaxGroupQ * G;
-  const int lane = threadIdx.x & 31;
+  griddep_launch_dependents();  // the next kernel of the stream may start its own prologue
   const int64_t w = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  if (w >= (int64_t)p.nq * p.HKV * NCG) return;
-  const int cg = (int)(w % NCG), kvh = (int)((w / NCG) % p.HKV), q = (int)(w / ((int64_t)NCG * p.HKV));
-  const int g = lane % G, c = lane / G + cg * CPW;
-  const bool active = c < CH;
-  const int beg = p.u_csr_off[q], end = p.u_csr_off[q + 1];
-
-  float m = -INFINITY;
-  for (int i = beg; i < end; ++i) {
-    const int row = p.u_csr_rows[i];
-    m = fmaxf(m, p.plse16[((int64_t)(row >> 5) * p.HKV + kvh) * R + (row & 31) * G + g]);
-  }
-  float L = 0.f, acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  if (m > -INFINITY) {
-    const uint4* po = reinterpret_cast<const uint4*>(p.po16);
-#pragma unroll 4
-    for (int i = beg; i < end; ++i) {
-      const int row = p.u_csr_rows[i];
-      const int64_t tile = (int64_t)(row >> 5) * p.HKV + kvh;
-      const int rr = (row & 31) * G + g;
-      const float wgt = __expf(p.plse16[tile * R + rr] - m);
-      L += wgt;
-      if (active) {
-        const uint4 raw = po[(tile * CH + c) * R + rr];
-        const __half2* h = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 x = __half22float2(h[j]);
-          acc[2 * j] = fmaf(wgt, x.x, acc[2 * j]);
-          acc[2 * j + 1] = fmaf(wgt, x.y, acc[2 * j + 1]);
-        }
-      }
-    }
-  }
-  if (!active) return;
-  const float inv = L > 0.f ? 1.f / L : 0.f;
-  uint4 pk;
-  __half2 h0 = __floats2half2_rn(acc[0] * inv, acc[1] * inv), h1 = __floats2half2_rn(acc[2] * inv, acc[3] * inv);
-  __half2 h2 = __floats2half2_rn(acc[4] * inv, acc[5] * inv), h3 = __floats2half2_rn(acc[6] * inv, acc[7] * inv);
-  pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-  pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-  *reinterpret_cast<uint4*>(p.o + (int64_t)q * p.o_row_stride + (int64_t)(kvh * G + g) * p.o_head_stride + c * 8) = pk;
+  if (w >= (int64_t)p.nq * p.HKV * CombineShape<D, G>::NCG) return;
+  combine_tiles_item<D, G, true>(p, w, threadIdx.x & 31);
 }
 
 template <int D, int G>
 int launch_tiles_t(const AttnParams& p, cudaStream_t stream) {
-  constexpr int CH = D / 8, CPW = 32 / G, NCG = (CH + CPW - 1) / CPW;
-  const int64_t warps = (int64_t)p.nq * p.HKV * NCG;
+  const int64_t warps = (int64_t)p.nq * p.HKV * CombineShape<D, G>::NCG;
   const int64_t blocks = (warps + kThreads / 32 - 1) / (kThreads / 32);
-  stage2_tiles_kernel<D, G><<<(unsigned)blocks, kThreads, 0, stream>>>(p);
-  DEFT_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // launch early, wait inside (griddep_wait)
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  DEFT_CUDA(cudaLaunchKernelEx(&cfg, stage2_tiles_kernel<D, G>, p));
   return DEFT_OK;
 }
 

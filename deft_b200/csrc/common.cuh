@@ -82,6 +82,8 @@ struct AttnParams {
   // slot tile = (part_base / 32) * HKV + kv_head
   __half* po16;
   float* plse16;
+  int32_t pdl;         // launch the tcgen05-path kernels with programmatic stream serialization
+  int32_t plan_fresh;  // the unit plan was derived on the device by the preceding kernel of this call
 };
 
 __device__ __forceinline__ int64_t load_index(const void* p, int bytes, int64_t i) {

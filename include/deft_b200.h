@@ -61,6 +61,10 @@ void deft_b200_set_trace_buffer(void* dev);
 /* Test hook: 0 = never use TMA (every K/V/Q row is gathered with cp.async), 1 (default) = TMA for runs
  * of 128 consecutive pages and for slots of consecutive query ids. */
 void deft_b200_set_tma(int32_t enabled);
+/* Test hook: 0 = plain launches, 1 (default) = the tcgen05-path kernels are launched with programmatic
+ * stream serialization: each starts while its predecessor drains, does its dependency-free prologue
+ * (barriers, TMEM, plan tables) and only then waits for the predecessor (griddepcontrol.wait). */
+void deft_b200_set_pdl(int32_t enabled);
 
 /* ------------------------------------------------------------------------------------------
  * Work plan (device side).  Two layers:

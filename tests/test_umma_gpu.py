@@ -156,3 +156,40 @@ def test_tma_and_cp_async_paths_agree(dev, name):
         _lib.lib.deft_b200_set_tma(1)
     assert torch.isfinite(outs[0].float()).all()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_programmatic_dependent_launch_is_race_free(dev, name):
+    """Back-to-back calls sharing one workspace, with and without programmatic dependent launch: the kernels
+    overlap only their dependency-free prologues, so every call gives the bit-identical result."""
+    from deft_b200 import TreeMetadata, _lib
+    import deft_b200
+    from deft_b200.workloads import build_tree
+    torch.manual_seed(4)
+    tree = build_tree(name, layers=4, device=dev)
+    kvp = tree.token_to_kv_pool
+    for l in range(4):
+        kvp.kv_data[l].normal_()
+    nq = len(tree.leaves)
+    q = torch.randn(4, nq, 48 * 128, dtype=torch.float16, device=dev)
+    m = TreeMetadata.from_tree_cache(tree)
+
+    def run(pdl):
+        _lib.lib.deft_b200_set_pdl(pdl)
+        o = torch.full((12, nq, 32, 128), float("nan"), dtype=torch.float16, device=dev)
+        for i in range(12):                     # 12 calls in flight on one stream, 4 layer pools cycled
+            l = i % 4
+            deft_b200.tree_attention_subtree_fwd(q[l, :, : 32 * 128].view(nq, 32, 128), kvp.get_key_buffer(l),
+                                                 kvp.get_value_buffer(l), o[i], 128, m.block_q, m.block_q_cnts,
+                                                 m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens)
+        torch.cuda.synchronize()
+        return o
+
+    try:
+        a, b = run(1), run(0)
+    finally:
+        _lib.lib.deft_b200_set_pdl(1)
+    assert torch.isfinite(a.float()).all()
+    assert torch.equal(a, b)
+    for i in range(4, 12):
+        assert torch.equal(a[i], a[i - 4])
