@@ -173,6 +173,7 @@ def main():
 
     import deft_b200
     from deft_b200 import BLOCK_CONFIG, TreeMetadata, _lib
+    from deft_b200.sharding import max_over_ranks
     from deft_b200.workloads import WORKLOADS, algorithmic_bytes, build_tree
 
     # ---- synthetic inputs: one tree per rank, 32 layer pools, random-normal fp16 -----------------
@@ -230,12 +231,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps
+        return max_over_ranks(e0.elapsed_time(e1), dev) / steps
 
     warm = max(args.warmup, 3)
     g_full, g_s1, g_s2 = capture(7), capture(2), capture(4)
