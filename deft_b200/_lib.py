@@ -21,7 +21,7 @@ T_COUNT = len(T_NAMES)
 STAGE1_AUTO, STAGE1_FMA, STAGE1_UMMA = 0, 1, 2
 ITEM_BYTES = 24
 GROUP_BYTES = 24
-UNIT_BYTES = 64
+UNIT_BYTES = 80
 N_SCALARS = 8
 
 

@@ -340,8 +340,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       const deft_unit_t u = p.units[job / p.HKV];
       if (w == 0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrKUnit);
       const int n_mine = w * 32 + lane;  // my token row
+      const bool known_run = u.page0 >= 0 && p.tma_kv != 0;  // the builder's shortcut: no index-table read at all
       auto page_of = [&](int t) -> int64_t {
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
+        if (known_run) return (int64_t)u.page0 + t * kTileN + n_mine;
         return t < u.n_tiles && n_mine < tlen ? load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + n_mine) : 0;
       };
       int64_t pg_next = page_of(0);
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         pg_next = page_of(t + 1);  // the next tile's page id is in flight while this tile is issued
         // 32 consecutive pages of a full tile are ONE box of the pool's tensor map per 64-wide panel
         const int64_t page0 = __shfl_sync(0xffffffffu, pg, 0);
-        const bool run = __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg == page0 + lane);
+        const bool run = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg == page0 + lane);
 #pragma unroll
         for (int kv = 0; kv < 2; ++kv) {
           const int full = (kv == 0 ? K_FULL : V_FULL) + st;
@@ -397,7 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       const deft_unit_t u = p.units[job / p.HKV];
       if (u.q_cnt[s] == 0) continue;
       // row r = (query r / G, head r % G); rows past q_cnt*G are zero
-      const int64_t my_q = lane < u.q_cnt[s] ? load_index(p.u_q, p.u_q_bytes, u.q_off[s] + lane) : 0;
+      const bool known_run = u.q_id0[s] >= 0 && p.tma_q != 0;  // the builder's shortcut: no query-table read
+      const int64_t my_q = known_run ? (int64_t)u.q_id0[s] + lane
+                                     : (lane < u.q_cnt[s] ? load_index(p.u_q, p.u_q_bytes, u.q_off[s] + lane) : 0);
       mbar_wait(bar(Q_EMPTY + s), (q_cnt & 1) ^ 1);
       const uint32_t qs = base + L::kQ + s * L::kOperandBytes;
       if (lane == 0 && ji == jobs.begin && s == 0 && my_q >= 0) DEFT_TRACE(kTrQIds);
@@ -405,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       // (rows past q_cnt then hold the next queries or zeros: finite, never stored)
       const int64_t q0 = __shfl_sync(0xffffffffu, my_q, 0);
       const bool run = p.tma_q != 0 && (lane >= u.q_cnt[s] || my_q == q0 + lane);
-      if (__all_sync(0xffffffffu, run)) {
+      if (known_run || __all_sync(0xffffffffu, run)) {
         if (lane == 0) {
           mbar_arrive_expect_tx(bar(Q_FULL + s), R * D * 2);
 #pragma unroll
@@ -472,75 +476,83 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     }
   } else if (warp == kMmaWarp) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      uint32_t k_cnt = 0, v_cnt = 0;  // KV tiles consumed
-      uint32_t s_cnt[2] = {0, 0};     // tiles per slot (S_FULL / P_FULL / O_FULL phases)
-      uint32_t j_cnt[2] = {0, 0};     // jobs per slot (Q_FULL / O_EMPTY phases)
-      for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
-        const int job = jobs.get(ji);
-        const deft_unit_t u = p.units[job / p.HKV];
-        const int n = u.n_tiles;
-        const bool has_b = u.q_cnt[1] > 0;
-        const uint32_t v_base = v_cnt;
-        const uint32_t s_base[2] = {s_cnt[0], s_cnt[1]};
+    // The whole warp runs the (uniform) control flow and the waits; lane 0 alone executes the tcgen05.mma /
+    // tcgen05.commit instructions, so their operands live in uniform registers (a `lane == 0` branch around
+    // the loop made the compiler wrap every MMA in an ELECT loop and spill its descriptors).
+    const bool leader = lane == 0;
+    uint32_t k_cnt = 0, v_cnt = 0;         // KV tiles consumed
+    uint32_t s_cnt0 = 0, s_cnt1 = 0;       // tiles per slot (S_FULL / P_FULL / O_FULL phases)
+    uint32_t j_cnt0 = 0, j_cnt1 = 0;       // jobs per slot (Q_FULL / O_EMPTY phases)
+    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+      const int job = jobs.get(ji);
+      const deft_unit_t u = p.units[job / p.HKV];
+      const int n = u.n_tiles;
+      const bool has_b = u.q_cnt[1] > 0;
+      const bool tr0 = ji == jobs.begin && leader;
 
-        auto issue_s = [&](int s, int t, uint32_t k_smem) {
-          const uint32_t q_smem = base + L::kQ + s * L::kOperandBytes;
-#pragma unroll 1
+      // S_s = Q_s K^T.  Descriptors are built once per GEMM and advanced by compile-time constants (the
+      // start-address field holds bytes >> 4 and cannot carry out of its 14 bits inside 227 KB of smem).
+      auto issue_s = [&](const int s, int t, uint32_t k_smem) {
+        const uint64_t q_desc = smem_desc_sw128(base + L::kQ + s * L::kOperandBytes, 16, 1024);
+        const uint64_t k_desc = smem_desc_sw128(k_smem, 16, 1024);
+        if (leader) {
+#pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
-            const uint32_t koff = (ks >> 2) * kPanelBytes + (ks & 3) * 32;
-            umma_ss(tmem + s * 128, smem_desc_sw128(q_smem + koff, 16, 1024), smem_desc_sw128(k_smem + koff, 16, 1024),
-                    kIdescQK, ks > 0);
+            const uint64_t koff = (uint64_t)(((ks >> 2) * kPanelBytes + (ks & 3) * 32) >> 4);
+            umma_ss(tmem + s * 128, q_desc + koff, k_desc + koff, kIdescQK, ks > 0);
           }
           umma_commit(bar(S_FULL + s));
           if (t == n - 1) umma_commit(bar(Q_EMPTY + s));  // Q is only read by these MMAs
-        };
-        auto issue_pv = [&](int s, int t) {
-          const uint32_t vi = v_base + t;
-          const int vst = vi % kKvStages;
-          if (s == 0) mbar_wait(bar(V_FULL + vst), (vi / kKvStages) & 1);
-          mbar_wait(bar(P_FULL + s), (s_base[s] + t) & 1);
-          if (ji == jobs.begin && s == 0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
-          if (t == 0) mbar_wait(bar(O_EMPTY + s), (j_cnt[s] & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t v_smem = base + L::kV + vst * L::kOperandBytes;
-#pragma unroll 1
-          for (int ks = 0; ks < kTileN / 16; ++ks)
-            umma_ts(tmem + 256 + s * 128, tmem + s * 128 + ks * 8,
-                    smem_desc_sw128(v_smem + ks * 2048, kPanelBytes, 1024), kIdescPV, t > 0 || ks > 0);
+        }
+        __syncwarp();
+      };
+      // O_s (+)= P_s V, tile t of this job (vi = its position in the V ring)
+      auto issue_pv = [&](const int s, int t, uint32_t vi, uint32_t p_phase, uint32_t o_empty_phase) {
+        const int vst = vi % kKvStages;
+        if (s == 0) mbar_wait(bar(V_FULL + vst), (vi / kKvStages) & 1);
+        mbar_wait(bar(P_FULL + s), p_phase);
+        if (tr0 && s == 0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
+        if (t == 0) mbar_wait(bar(O_EMPTY + s), o_empty_phase);
+        tc_fence_after();
+        const uint64_t v_desc = smem_desc_sw128(base + L::kV + vst * L::kOperandBytes, kPanelBytes, 1024);
+        const uint32_t o_tmem = tmem + 256 + s * 128, p_tmem = tmem + s * 128;
+        if (leader) {
+          umma_ts(o_tmem, p_tmem, v_desc, kIdescPV, t > 0);
+#pragma unroll
+          for (int ks = 1; ks < kTileN / 16; ++ks)
+            umma_ts(o_tmem, p_tmem + ks * 8, v_desc + (uint64_t)((ks * 2048) >> 4), kIdescPV, true);
           umma_commit(bar(O_FULL + s));
           if (s == 1 || !has_b) umma_commit(bar(V_EMPTY + vst));
-          if (ji == jobs.begin && t == 0) DEFT_TRACE(s == 0 ? 13 : 15);
-        };
-
-        for (int t = 0; t < n; ++t) {
-          const int kst = k_cnt % kKvStages;
-          mbar_wait(bar(K_FULL + kst), (k_cnt / kKvStages) & 1);
-          if (ji == jobs.begin) DEFT_TRACE(kTrTile0 + 8 * t + 1);
-          if (t == 0) mbar_wait(bar(Q_FULL + 0), j_cnt[0] & 1);
-          if (ji == jobs.begin && t == 0) DEFT_TRACE(kTrMmaQFull);
-          tc_fence_after();
-          const uint32_t k_smem = base + L::kK + kst * L::kOperandBytes;
-          issue_s(0, t, k_smem);
-          if (has_b) {
-            if (t > 0) issue_pv(1, t - 1);
-            if (t == 0) {
-              mbar_wait(bar(Q_FULL + 1), j_cnt[1] & 1);
-            }
-            issue_s(1, t, k_smem);
-            if (ji == jobs.begin && t == 0) DEFT_TRACE(14);
-          }
-          umma_commit(bar(K_EMPTY + kst));
-          ++k_cnt;
-          issue_pv(0, t);
         }
-        if (has_b) issue_pv(1, n - 1);
-        v_cnt += n;
-        s_cnt[0] += n; ++j_cnt[0];
-        if (has_b) { s_cnt[1] += n; ++j_cnt[1]; }
+        __syncwarp();
+        if (tr0 && t == 0) DEFT_TRACE(s == 0 ? 13 : 15);
+      };
+
+      for (int t = 0; t < n; ++t) {
+        const int kst = k_cnt % kKvStages;
+        mbar_wait(bar(K_FULL + kst), (k_cnt / kKvStages) & 1);
+        if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 1);
+        if (t == 0) mbar_wait(bar(Q_FULL + 0), j_cnt0 & 1);
+        if (tr0 && t == 0) DEFT_TRACE(kTrMmaQFull);
+        tc_fence_after();
+        const uint32_t k_smem = base + L::kK + kst * L::kOperandBytes;
+        issue_s(0, t, k_smem);
+        if (has_b) {
+          if (t > 0) issue_pv(1, t - 1, v_cnt + t - 1, (s_cnt1 + t - 1) & 1, (j_cnt1 & 1) ^ 1);
+          if (t == 0) mbar_wait(bar(Q_FULL + 1), j_cnt1 & 1);
+          issue_s(1, t, k_smem);
+          if (tr0 && t == 0) DEFT_TRACE(14);
+        }
+        if (leader) umma_commit(bar(K_EMPTY + kst));
+        __syncwarp();
+        ++k_cnt;
+        issue_pv(0, t, v_cnt + t, (s_cnt0 + t) & 1, (j_cnt0 & 1) ^ 1);
       }
+      if (has_b) issue_pv(1, n - 1, v_cnt + n - 1, (s_cnt1 + n - 1) & 1, (j_cnt1 & 1) ^ 1);
+      v_cnt += n;
+      s_cnt0 += n; ++j_cnt0;
+      if (has_b) { s_cnt1 += n; ++j_cnt1; }
     }
-    __syncwarp();
   }
   } else {
     reg_alloc<kSoftmaxRegs>();   // warps 0-3 and 4-7
@@ -572,8 +584,9 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[s * kMaskStages + mst] != 0;
         mbar_wait(bar(S_FULL + s), s_cnt & 1);
         tc_fence_after();
-        const bool tr = ji == jobs.begin && tid == 0;
-        if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 2);
+        const bool tr = ji == jobs.begin && (tid & 127) == 0 && t < 5;
+        const int tr0 = kTrTile0 + (s == 0 ? 0 : 48) + 8 * t;  // slot 1 events sit 48 slots higher
+        if (tr) DEFT_TRACE(tr0 + 2);
 
         // ---- the whole S row (128 columns) comes out of TMEM once and stays in registers
         float sv[kTileN];
@@ -599,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         }
         mt *= c;  // c > 0
-        if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 3);
+        if (tr) DEFT_TRACE(tr0 + 3);
 
         // ---- lazily raised reference maximum; the accumulator is rescaled only when it moves
         const bool raise = mt > m_ref + kRescaleLog2;  // also the first live tile (m_ref = -inf)
@@ -628,6 +641,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         // half a period apart: one exponentiates while the tensor pipe serves the other.
         const bool ordered = u.q_cnt[1] > 0;
         if (ordered) mbar_wait(bar(ORDER + s), s == 0 ? ((ord_cnt & 1) ^ 1) : (ord_cnt & 1));
+        if (tr) DEFT_TRACE(tr0 + 7);
         float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -652,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         mbar_arrive(bar(M_EMPTY + s * kMaskStages + mst));
         tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
         mbar_arrive(bar(P_FULL + s));
-        if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 4);
+        if (tr) DEFT_TRACE(tr0 + 4);
       }
 
       // ---- epilogue: partial = O / l as fp16, log-sum-exp in the natural-log domain

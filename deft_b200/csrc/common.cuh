@@ -29,7 +29,7 @@ void set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
-static_assert(sizeof(deft_unit_t) == 64, "deft_unit_t is part of the ABI: 64 bytes");
+static_assert(sizeof(deft_unit_t) == 80, "deft_unit_t is part of the ABI: 80 bytes");
 constexpr int kMaxGroupQ = 32;     // queries per group (reference max_q_len / BLOCK_M, tree_cache.py:623)
 constexpr int kNodeSplit = 256;    // tokens per item when long Node entries are split on the device
 

@@ -410,11 +410,21 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
             }
           }
         u.mask_off[1] = -1;
+        u.q_id0[0] = u.q_id0[1] = -1;
+        {  // shortcut: all tiles full and on consecutive pages
+          const size_t k0 = ta * 128, k1 = tb * 128;
+          bool runp = tiles[tb - 1].n_live == 128;
+          for (size_t kk = k0 + 1; kk < k1 && runp; ++kk) runp = u_kv[kk] == u_kv[k0] + (i32)(kk - k0);
+          u.page0 = runp ? u_kv[k0] : -1;
+        }
         for (int k = 0; k < n_live_slots; ++k) {
           u.mask_off[k] = dense[k] ? -1 : mask_base + (i64)k * 128;
           u.q_off[k] = 32 * live_slots[k];
           u.q_cnt[k] = slot_cnt(live_slots[k]);
           u.part_base[k] = 32 * n_unit_slots++;
+          bool runq = true;  // shortcut: consecutive query ids
+          for (i32 rr = 1; rr < u.q_cnt[k] && runq; ++rr) runq = u_q[(size_t)u.q_off[k] + (size_t)rr] == u_q[(size_t)u.q_off[k]] + rr;
+          u.q_id0[k] = runq ? u_q[(size_t)u.q_off[k]] : -1;
           for (i32 rr = 0; rr < u.q_cnt[k]; ++rr)
             if ((live_rows[k] >> rr) & 1u) rows_of[(size_t)u_q[(size_t)u.q_off[k] + (size_t)rr]].push_back(u.part_base[k] + rr);
         }

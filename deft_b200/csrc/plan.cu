@@ -141,6 +141,8 @@ __device__ void build_units(const deft_item_t* items, const deft_group_t* groups
       u.mask_tile_stride = 128;
       u.n_tiles = max(1, (it.kv_len + 127) / 128);
       u.last_len = max(0, it.kv_len - (u.n_tiles - 1) * 128);
+      u.page0 = -1;
+      u.q_id0[0] = u.q_id0[1] = -1;
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         const int gi = 2 * k + s;

@@ -108,7 +108,13 @@ typedef struct {
   int32_t q_off[2];         /* first element of the query list, per slot */
   int32_t q_cnt[2];         /* 1..32; q_cnt[1] == 0: single-slot unit */
   int32_t part_base[2];     /* multiple of 32 */
-} deft_unit_t;              /* 64 bytes */
+  /* Shortcuts the builder fills in when it can (-1 otherwise): with them the kernel issues its TMA loads
+   * straight from the unit record, without the dependent reads of the index tables. */
+  int32_t page0;            /* >= 0: every tile is full and the unit's tokens sit on consecutive pages
+                               page0, page0 + 1, ... (the prompt) */
+  int32_t q_id0[2];         /* >= 0: the slot's queries have consecutive ids q_id0[s], q_id0[s] + 1, ... */
+  int32_t pad;
+} deft_unit_t;              /* 80 bytes */
 
 typedef struct {
   /* (1) item/group plan over the reference tables */

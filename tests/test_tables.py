@@ -17,7 +17,7 @@ ITEM = np.dtype([("kv_off", "<i8"), ("kv_len", "<i4"), ("grp_off", "<i4"), ("n_g
 GROUP = np.dtype([("mask_off", "<i8"), ("q_off", "<i4"), ("q_cnt", "<i4"), ("part_base", "<i4"), ("pad", "<i4")])
 UNIT = np.dtype([("kv_off", "<i8"), ("mask_off", "<i8", (2,)), ("kv_tile_stride", "<i4"), ("mask_tile_stride", "<i4"),
                  ("n_tiles", "<i4"), ("last_len", "<i4"), ("q_off", "<i4", (2,)), ("q_cnt", "<i4", (2,)),
-                 ("part_base", "<i4", (2,))])
+                 ("part_base", "<i4", (2,)), ("page0", "<i4"), ("q_id0", "<i4", (2,)), ("pad", "<i4")])
 
 
 def unpack(data, directory):
@@ -59,6 +59,10 @@ def check_unit_plan(t, scalars, tree, hkv, n_ctas):
     for u in units:
         assert u["n_tiles"] >= 1 and 1 <= u["last_len"] <= 128 and u["kv_tile_stride"] == 128
         assert 1 <= u["q_cnt"][0] <= 32 and 0 <= u["q_cnt"][1] <= 32
+        if u["page0"] >= 0:              # shortcut: full tiles on consecutive pages
+            n_tok = int(u["n_tiles"]) * 128
+            assert u["last_len"] == 128
+            assert u_kv[u["kv_off"]: u["kv_off"] + n_tok].tolist() == list(range(int(u["page0"]), int(u["page0"]) + n_tok))
         for s in range(2):
             cnt = int(u["q_cnt"][s])
             if cnt == 0:
@@ -66,6 +70,8 @@ def check_unit_plan(t, scalars, tree, hkv, n_ctas):
             assert u["part_base"][s] % 32 == 0
             bases.append(int(u["part_base"][s]))
             qs = u_q[u["q_off"][s]: u["q_off"][s] + cnt]
+            if u["q_id0"][s] >= 0:       # shortcut: consecutive query ids
+                assert qs.tolist() == list(range(int(u["q_id0"][s]), int(u["q_id0"][s]) + cnt))
             for r, q in enumerate(qs):
                 row_to_q[int(u["part_base"][s]) + r] = int(q)
             for tile in range(int(u["n_tiles"])):
@@ -116,6 +122,7 @@ def test_unit_plan_cfg2_shape(golden_dir):
     assert np.array_equal(np.sort(units["kv_off"]), np.cumsum(np.r_[0, units["n_tiles"][np.argsort(units["kv_off"])][:-1]]) * 128)
     root = units[units["kv_off"] + units["n_tiles"] * 128 <= 4096]
     assert len(root) > 0 and np.all(root["mask_off"] == -1), "prompt-only pieces: dense, no mask reads"
+    assert np.all(root["page0"] == root["kv_off"]) and np.all(units["q_id0"][:, 0] >= 0), "prompt pages and leaf ids are runs"
     loads = np.diff(t["u_job_off"])
     assert loads.max() == 1 and loads.sum() == len(units) * 8, "cfg2 fits one job per CTA: no Q reload between jobs"
     # far fewer partial rows than the reference's 2246 (one per (sub-block, query))

@@ -21,7 +21,7 @@ from deft_b200.workloads import build_tree
 NAMES = {0: "start", 1: "q_ids", 2: "q0_issued", 3: "q1_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
          8: "epi_end", 9: "end", 10: "t1.k_issued_w1", 11: "t1.k_issued_w2", 12: "t1.k_issued_w3", 13: "mma_pv0(0)_issued",
          14: "mma_s1(0)_issued", 15: "mma_pv1(0)_issued"}
-TILE = ["k_issued", "mma_k_full", "sm_s_full", "sm_pass1", "sm_p_arrive", "mma_p_full", "v_issued", "-"]
+TILE = ["k_issued", "mma_k_full", "sm_s_full", "sm_pass1", "sm_p_arrive", "mma_p_full", "v_issued", "sm_turn"]
 
 
 def main():
@@ -64,11 +64,14 @@ def main():
     for c in order[:show] + [order[len(order) // 2]] + order[-1:]:
         print(f"--- CTA {c}")
         ev = [(int(t[c, i]), NAMES[i]) for i in NAMES if t[c, i] >= 0]
-        for tile in range((128 - 16) // 8):
+        for tile in range(6):
             for k in range(8):
                 v = int(t[c, 16 + 8 * tile + k])
                 if v >= 0:
                     ev.append((v, f"t{tile}.{TILE[k]}"))
+                v = int(t[c, 64 + 8 * tile + k])
+                if v >= 0:
+                    ev.append((v, f"t{tile}.slot1.{TILE[k]}"))
         for v, name in sorted(ev):
             print(f"   {v / ghz / 1e3:8.2f} us  {name}")
 
