@@ -85,8 +85,11 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     deft::set_error("build_tables: node 0 must be the root (parent -1)");
     return nullptr;
   }
+  // Further nodes with parent -1 start further trees: a FOREST of independent decoding trees over one page
+  // pool (batched serving; the reference handles one tree per call).  The tables are what the reference's
+  // DFS would emit walking the trees one after the other.
   for (i32 i = 1; i < n_nodes; ++i)
-    if (parent[i] < 0 || parent[i] >= i) {
+    if (parent[i] < -1 || parent[i] >= i) {
       deft::set_error("build_tables: nodes must be in DFS pre-order (parent[%d] = %d)", i, parent[i]);
       return nullptr;
     }
@@ -103,7 +106,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<i32> rank_of((size_t)query_num, -1);
   {
     std::vector<char> has_child((size_t)n_nodes, 0);
-    for (i32 n = 1; n < n_nodes; ++n) has_child[(size_t)parent[n]] = 1;
+    for (i32 n = 1; n < n_nodes; ++n)
+      if (parent[n] >= 0) has_child[(size_t)parent[n]] = 1;
     i32 next = 0;
     for (i32 n = 0; n < n_nodes; ++n)
       if (!has_child[(size_t)n])

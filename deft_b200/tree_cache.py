@@ -294,6 +294,27 @@ def flatten_tree(tree) -> Dict[str, Any]:
                 tix=np.asarray(tix, dtype=np.int64), leaf_to_q=leaf_to_q)
 
 
+def flatten_forest(trees) -> Dict[str, Any]:
+    """Several independent trees over ONE page pool -> one set of flat arrays (batched decoding).
+
+    Trees are laid one after the other in DFS pre-order; the queries of tree ``t`` follow those of tree
+    ``t - 1`` (its leaves ranked by id, offset by the number of leaves before it).  The reference has no
+    batched mode (one tree per ``TreeMetadata``); this is the multi-tree extension SURVEY.md 8(d) cfg 5 asks for.
+    """
+    parts = [flatten_tree(t) for t in trees]
+    node_off = np.cumsum([0] + [len(p["parent"]) for p in parts])
+    q_base = np.cumsum([0] + [len(p["leaf_to_q"]) for p in parts])
+    parent = np.concatenate([np.where(p["parent"] >= 0, p["parent"] + node_off[i], -1) for i, p in enumerate(parts)])
+    kv = np.concatenate([p["kv"] for p in parts])
+    qs = np.concatenate([p["qs"] + q_base[i] for i, p in enumerate(parts)])
+    kv_off = np.concatenate([[0]] + [p["kv_off"][1:] + sum(len(x["kv"]) for x in parts[:i]) for i, p in enumerate(parts)])
+    q_off = np.concatenate([[0]] + [p["q_off"][1:] + sum(len(x["qs"]) for x in parts[:i]) for i, p in enumerate(parts)])
+    leaf_to_q = {(i, leaf): q + int(q_base[i]) for i, p in enumerate(parts) for leaf, q in p["leaf_to_q"].items()}
+    return dict(parent=parent.astype(np.int32), kv_off=kv_off.astype(np.int64), kv=kv.astype(np.int64),
+                q_off=q_off.astype(np.int64), qs=qs.astype(np.int64), tix=np.concatenate([p["tix"] for p in parts]),
+                leaf_to_q=leaf_to_q)
+
+
 class _Staging:
     """Ring of pinned host buffers for the one-copy table upload."""
 
@@ -442,6 +463,15 @@ class TreeMetadata:
     @classmethod
     def from_tree_cache(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":
         return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=False)
+
+    @classmethod
+    def from_forest(cls, trees, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":
+        """One metadata object (tables + native plan) for several trees sharing one KV pool: the operators
+        then attend the whole batch in one launch.  ``leaf_to_q`` is keyed by ``(tree index, leaf id)``."""
+        trees = list(trees)
+        assert trees and all(t.token_to_kv_pool is trees[0].token_to_kv_pool for t in trees), \
+            "the trees of a forest share one TokenToKVPool"
+        return cls._assemble(trees[0], flatten_forest(trees), max_q_len, max_block_len, tree_index=False)
 
     @classmethod
     def from_tree_cache_node(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":

@@ -59,6 +59,33 @@ def build_tree(name: str, layers: int, device="cuda", H: int = 32, HKV: int = 8,
     return tree
 
 
+def build_forest(name: str, n_trees: int, layers: int, device="cuda", H: int = 32, HKV: int = 8, D: int = 128,
+                 headroom: int = 64) -> List[TreeCache]:
+    """``n_trees`` independent trees of one workload over ONE page pool (BASELINE cfg 5: batched decoding).
+
+    Trees are grown one after the other, so tree ``t`` owns the pages ``[t * unique, (t + 1) * unique)`` with
+    the same relative layout as a stand-alone tree (prompt contiguous, decode pages strided by its leaves).
+    """
+    prompt, levels, _ = WORKLOADS[name]
+    size = unique_kv_tokens(name) * n_trees + headroom
+    r2t = ReqToTokenPool(size=max(2 * n_leaves(name) * n_trees, 8), max_context_len=prompt + sum(s for _, s in levels) + 8,
+                         device=device)
+    kvp = TokenToKVPool(size=size, dtype=torch.float16, head_num=HKV, head_dim=D, layer_num=layers, device=device)
+    trees = []
+    for _ in range(n_trees):
+        tree = TreeCache(torch.float16, HKV, D, layers, r2t, kvp, None, True, False)
+        tree.init_prompt(torch.arange(prompt, dtype=torch.int32))
+        for fan, steps in levels:
+            for leaf in sorted(tree.leaves.values(), key=lambda x: x.id):
+                tree.branch(leaf, fan)
+            for _ in range(steps):
+                for leaf in tree.leaves.values():
+                    leaf.append_token(7)
+                tree.alloc()
+        trees.append(tree)
+    return trees
+
+
 def algorithmic_bytes(name: str, H: int = 32, HKV: int = 8, D: int = 128) -> int:
     """Per layer-call: every unique KV token once (K and V) + Q read + O write."""
     return unique_kv_tokens(name) * 2 * HKV * D * 2 + 2 * n_leaves(name) * H * D * 2

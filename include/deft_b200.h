@@ -211,7 +211,9 @@ int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head
  *
  * The tree is handed over as flat arrays, nodes in DFS pre-order with children in creation
  * (dict insertion) order -- the order tree_cache.py:725-791 visits them:
- *   parent[n]        index of the parent in this order, -1 for the root (node 0)
+ *   parent[n]        index of the parent in this order, -1 for the root (node 0).  Further -1 entries start
+ *                    further trees: a forest of independent trees over one pool is built in one pass and
+ *                    attended in one launch (query ids and page ids are global to the forest)
  *   kv_off[n+1], kv  per-node page lists (node.kv_indices, any order; sorted inside, :736)
  *   q_off[n+1], qs   per-node attending queries = rank by leaf id of node.refs (:650-652, :737)
  *   tix_row[n]       tree-index mode only: node.node_indices_id, else NULL

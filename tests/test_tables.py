@@ -46,11 +46,12 @@ def test_struct_sizes():
 
 
 def check_unit_plan(t, scalars, tree, hkv, n_ctas):
-    """The native unit plan attends exactly the (query, page) pairs of the tree, each once; its CSR,
-    partial-row bases and per-CTA job lists are consistent."""
+    """The native unit plan attends exactly the (query, page) pairs of the tree (or of every tree of a
+    forest), each once; its CSR, partial-row bases and per-CTA job lists are consistent."""
     units, u_kv, u_mask, u_q = t["u_units"], t["u_kv"], t["u_mask"], t["u_q"]
     nq = int(scalars[0])
-    paths = orc.leaf_paths(tree)
+    paths = [p for tr in tree for p in orc.leaf_paths(tr)] if isinstance(tree, (list, tuple)) else orc.leaf_paths(tree)
+    assert len(paths) == nq
     want = {(q, int(pg)) for q, path in enumerate(paths) for pg in path}
     got = set()
     bases = []
@@ -109,6 +110,26 @@ def test_unit_plan_covers_the_tree(golden_dir, name):
     for mbl, hkv, n_ctas in ((-1, 2, 148), (128, 8, 16)):
         t, scalars = build(tree, mbl, hkv=hkv, n_ctas=n_ctas)
         check_unit_plan(t, scalars, tree, hkv, n_ctas)
+
+
+def test_forest_plan_covers_every_tree(golden_dir):
+    """Several independent trees in one set of tables (batched decoding): queries are numbered tree after tree,
+    every tree keeps exactly its own (query, page) pairs, nothing leaks across trees."""
+    from deft_b200.tree_cache import flatten_forest
+    trees = [load(golden_dir, n)[1] for n in ("toy_binary", "wide40", "single_seq", "ragged_cut")]
+    flat = flatten_forest(trees)
+    assert int((flat["parent"] == -1).sum()) == len(trees)
+    data, directory, scalars = build_tables_host(flat, hkv=2, n_ctas=148)
+    t = unpack(data, directory)
+    assert int(scalars[0]) == sum(len(tr.leaves) for tr in trees)
+    check_unit_plan(t, scalars, trees, 2, 148)
+    check_plan(t, int(scalars[0]), "flat")
+    check_plan(t, int(scalars[0]), "node")
+    # the Node tables of a forest are the trees' Node tables one after the other (queries offset)
+    singles = [build(tr)[0] for tr in trees]
+    assert t["node_kv"].tolist() == [int(x) for s1 in singles for x in s1["node_kv"]]
+    q_base = np.cumsum([0] + [len(tr.leaves) for tr in trees])
+    assert t["node_q"].tolist() == [int(x) + int(q_base[i]) for i, s1 in enumerate(singles) for x in s1["node_q"]]
 
 
 def test_unit_plan_cfg2_shape(golden_dir):
