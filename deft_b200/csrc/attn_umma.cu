@@ -21,8 +21,10 @@
 //               the whole 128-column S row is read from TMEM once and kept in registers)
 //   warps 4-7   softmax + epilogue of slot 1; the two slots ping-pong on the tensor pipe:
 //               S_0(t) S_1(t) PV_0(t) | S_0(t+1) PV_1(t) S_1(t+1) PV_0(t+1) | ...
-//   warp  8     MMA issuer (one elected thread) and TMEM allocator
-//   warp  9/10  Q tile of slot 0 / slot 1: one TMA box per 64-wide panel when the slot's query ids are
+//   warp  8/9   MMA issuer of slot 0 / slot 1 (one elected thread each; warp 8 also owns the TMEM allocation).
+//               One issuer per slot: a single thread's issue stream (~110 cycles per MMA with its waits and
+//               commits) was the serial bottleneck of a two-slot step
+//   warp  10    Q tiles of both slots: one TMA box per 64-wide panel when a slot's query ids are
 //               consecutive, else cp.async 16-byte gathers
 //   warp  11    per-(tile, slot) row masks (token bitmask per query, transposed from the per-token
 //               words of the table) + "dense tile" flag
@@ -42,7 +44,7 @@ namespace {
 constexpr int kTileN = 128;  // tokens per KV tile (= the reference's BLOCK_LEN)
 constexpr int kRows = 128;   // UMMA M
 constexpr int kThreads = 512;  // 16 warps: 4 register-budget groups of 4 (setmaxnreg works per warpgroup)
-constexpr int kMmaWarp = 8, kQ0Warp = 9, kQ1Warp = 10, kMaskWarp = 11, kKvWarp0 = 12;  // 12-15: K/V producers
+constexpr int kMmaWarp0 = 8, kMmaWarp1 = 9, kQWarp = 10, kMaskWarp = 11, kKvWarp0 = 12;  // 12-15: K/V producers
 constexpr int kSoftmaxRegs = 192, kProducerRegs = 64;  // 256 * 192 + 256 * 64 = 64 K registers
 constexpr int kKvStages = 2, kMaskStages = 2;
 constexpr float kRescaleLog2 = 8.f;  // raise m_ref only when a tile tops it by more than 2^8
@@ -302,8 +304,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   if (p.plan_fresh) griddep_wait();  // the plan itself comes from the preceding (plan) kernel
   if (tid == 0) {
     for (int s = 0; s < kKvStages; ++s) {
-      mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 1);
-      mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 1);
+      mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 2);  // one commit per slot issuer
+      mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 2);  // (slot 0's commits twice in a one-slot job)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(Q_FULL + s), 32); mbar_init(bar(Q_EMPTY + s), 1);
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(base + L::kTmemSlot, kTmemCols);
+  if (warp == kMmaWarp0) tmem_alloc(base + L::kTmemSlot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -389,15 +391,17 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == kQ0Warp || warp == kQ1Warp) {
-    // ============================== Q tile of one slot ==============================
-    const int s = warp == kQ0Warp ? 0 : 1;
-    uint32_t q_cnt = 0;  // jobs of this slot
+  } else if (warp == kQWarp) {
+    // ============================== Q tiles of both slots ==============================
+    uint32_t q_cnts[2] = {0, 0};  // jobs per slot
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
       const int job = jobs.get(ji);
       const int hkv = job % p.HKV;
       const deft_unit_t u = p.units[job / p.HKV];
+#pragma unroll
+     for (int s = 0; s < 2; ++s) {
       if (u.q_cnt[s] == 0) continue;
+      uint32_t& q_cnt = q_cnts[s];
       // row r = (query r / G, head r % G); rows past q_cnt*G are zero
       const bool known_run = u.q_id0[s] >= 0 && p.tma_q != 0;  // the builder's shortcut: no query-table read
       const int64_t my_q = known_run ? (int64_t)u.q_id0[s] + lane
@@ -433,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       }
       if (lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrQ0Issued + s);
       ++q_cnt;
+     }
     }
   } else if (warp == kMaskWarp) {
     // ============================== mask words + dense flag per (tile, slot) ==============================
@@ -474,84 +479,90 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == kMmaWarp) {
-    // ============================== MMA issuer ==============================
+  } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {
+    // ============================== MMA issuer of one slot ==============================
     // The whole warp runs the (uniform) control flow and the waits; lane 0 alone executes the tcgen05.mma /
-    // tcgen05.commit instructions, so their operands live in uniform registers (a `lane == 0` branch around
-    // the loop made the compiler wrap every MMA in an ELECT loop and spill its descriptors).
+    // tcgen05.commit instructions.  Per tile:  S_s(t) = Q_s K(t)^T,  then  O_s (+)= P_s(t) V(t)  once the
+    // slot's softmax warps have written P_s(t) over S_s(t); S_s(t+1) follows in the same in-order stream.
+    const int s = warp == kMmaWarp0 ? 0 : 1;
     const bool leader = lane == 0;
-    uint32_t k_cnt = 0, v_cnt = 0;         // KV tiles consumed
-    uint32_t s_cnt0 = 0, s_cnt1 = 0;       // tiles per slot (S_FULL / P_FULL / O_FULL phases)
-    uint32_t j_cnt0 = 0, j_cnt1 = 0;       // jobs per slot (Q_FULL / O_EMPTY phases)
+    const uint32_t s_tmem = tmem + s * 128, o_tmem = tmem + 256 + s * 128;
+    const uint64_t q_desc = smem_desc_sw128(base + L::kQ + s * L::kOperandBytes, 16, 1024);
+    uint32_t kv_cnt = 0;  // KV tiles consumed (ring position; every job advances both slots' issuers alike)
+    uint32_t s_cnt = 0;   // tiles of this slot (S_FULL / P_FULL / O_FULL phases)
+    uint32_t j_cnt = 0;   // jobs of this slot (Q_FULL / O_EMPTY phases)
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
       const int job = jobs.get(ji);
       const deft_unit_t u = p.units[job / p.HKV];
       const int n = u.n_tiles;
       const bool has_b = u.q_cnt[1] > 0;
-      const bool tr0 = ji == jobs.begin && leader;
-
-      // S_s = Q_s K^T.  Descriptors are built once per GEMM and advanced by compile-time constants (the
-      // start-address field holds bytes >> 4 and cannot carry out of its 14 bits inside 227 KB of smem).
-      auto issue_s = [&](const int s, int t, uint32_t k_smem) {
-        const uint64_t q_desc = smem_desc_sw128(base + L::kQ + s * L::kOperandBytes, 16, 1024);
-        const uint64_t k_desc = smem_desc_sw128(k_smem, 16, 1024);
+      if (s == 1 && !has_b) {  // one-slot job: slot 0's issuer signs off the KV stages for both
+        kv_cnt += n;
+        continue;
+      }
+      const bool tr0 = ji == jobs.begin && leader && s == 0;
+      // S_s(t): descriptors advance by compile-time constants (the start-address field holds bytes >> 4 and
+      // cannot carry out of its 14 bits inside 227 KB of shared memory).
+      auto issue_s = [&](int t) {
+        const uint32_t c = kv_cnt + t;
+        const int st = c % kKvStages;
+        mbar_wait(bar(K_FULL + st), (c / kKvStages) & 1);
+        if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 1);
+        if (t == 0) mbar_wait(bar(Q_FULL + s), j_cnt & 1);
+        if (tr0 && t == 0) DEFT_TRACE(kTrMmaQFull);
+        tc_fence_after();
+        const uint64_t k_desc = smem_desc_sw128(base + L::kK + st * L::kOperandBytes, 16, 1024);
         if (leader) {
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
             const uint64_t koff = (uint64_t)(((ks >> 2) * kPanelBytes + (ks & 3) * 32) >> 4);
-            umma_ss(tmem + s * 128, q_desc + koff, k_desc + koff, kIdescQK, ks > 0);
+            umma_ss(s_tmem, q_desc + koff, k_desc + koff, kIdescQK, ks > 0);
           }
-          umma_commit(bar(S_FULL + s));
-          if (t == n - 1) umma_commit(bar(Q_EMPTY + s));  // Q is only read by these MMAs
         }
-        __syncwarp();
       };
-      // O_s (+)= P_s V, tile t of this job (vi = its position in the V ring)
-      auto issue_pv = [&](const int s, int t, uint32_t vi, uint32_t p_phase, uint32_t o_empty_phase) {
-        const int vst = vi % kKvStages;
-        if (s == 0) mbar_wait(bar(V_FULL + vst), (vi / kKvStages) & 1);
-        mbar_wait(bar(P_FULL + s), p_phase);
-        if (tr0 && s == 0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
-        if (t == 0) mbar_wait(bar(O_EMPTY + s), o_empty_phase);
-        tc_fence_after();
-        const uint64_t v_desc = smem_desc_sw128(base + L::kV + vst * L::kOperandBytes, kPanelBytes, 1024);
-        const uint32_t o_tmem = tmem + 256 + s * 128, p_tmem = tmem + s * 128;
+      auto commit_s = [&](int t) {  // S_s(t) is readable; K(t) and, after the last tile, Q_s are free
+        const int st = (kv_cnt + t) % kKvStages;
         if (leader) {
-          umma_ts(o_tmem, p_tmem, v_desc, kIdescPV, t > 0);
+          umma_commit(bar(S_FULL + s));
+          umma_commit(bar(K_EMPTY + st));
+          if (!has_b) umma_commit(bar(K_EMPTY + st));
+          if (t == n - 1) umma_commit(bar(Q_EMPTY + s));
+        }
+      };
+      issue_s(0);
+      commit_s(0);
+      __syncwarp();
+      for (int t = 0; t < n; ++t) {
+        // ---- O_s (+)= P_s(t) V(t), then straight on to S_s(t+1): the commits (each covers every MMA
+        // issued before it) come after both, off the softmax -> P V -> S -> softmax critical path
+        const uint32_t c = kv_cnt + t;
+        const int st = c % kKvStages;
+        mbar_wait(bar(V_FULL + st), (c / kKvStages) & 1);
+        mbar_wait(bar(P_FULL + s), (s_cnt + t) & 1);
+        if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
+        if (t == 0) mbar_wait(bar(O_EMPTY + s), (j_cnt & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t v_desc = smem_desc_sw128(base + L::kV + st * L::kOperandBytes, kPanelBytes, 1024);
+        if (leader) {
+          umma_ts(o_tmem, s_tmem, v_desc, kIdescPV, t > 0);
 #pragma unroll
           for (int ks = 1; ks < kTileN / 16; ++ks)
-            umma_ts(o_tmem, p_tmem + ks * 8, v_desc + (uint64_t)((ks * 2048) >> 4), kIdescPV, true);
+            umma_ts(o_tmem, s_tmem + ks * 8, v_desc + (uint64_t)((ks * 2048) >> 4), kIdescPV, true);
+        }
+        if (t + 1 < n) {
+          issue_s(t + 1);
+          commit_s(t + 1);
+        }
+        if (leader) {
           umma_commit(bar(O_FULL + s));
-          if (s == 1 || !has_b) umma_commit(bar(V_EMPTY + vst));
+          umma_commit(bar(V_EMPTY + st));
+          if (!has_b) umma_commit(bar(V_EMPTY + st));
         }
         __syncwarp();
-        if (tr0 && t == 0) DEFT_TRACE(s == 0 ? 13 : 15);
-      };
-
-      for (int t = 0; t < n; ++t) {
-        const int kst = k_cnt % kKvStages;
-        mbar_wait(bar(K_FULL + kst), (k_cnt / kKvStages) & 1);
-        if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 1);
-        if (t == 0) mbar_wait(bar(Q_FULL + 0), j_cnt0 & 1);
-        if (tr0 && t == 0) DEFT_TRACE(kTrMmaQFull);
-        tc_fence_after();
-        const uint32_t k_smem = base + L::kK + kst * L::kOperandBytes;
-        issue_s(0, t, k_smem);
-        if (has_b) {
-          if (t > 0) issue_pv(1, t - 1, v_cnt + t - 1, (s_cnt1 + t - 1) & 1, (j_cnt1 & 1) ^ 1);
-          if (t == 0) mbar_wait(bar(Q_FULL + 1), j_cnt1 & 1);
-          issue_s(1, t, k_smem);
-          if (tr0 && t == 0) DEFT_TRACE(14);
-        }
-        if (leader) umma_commit(bar(K_EMPTY + kst));
-        __syncwarp();
-        ++k_cnt;
-        issue_pv(0, t, v_cnt + t, (s_cnt0 + t) & 1, (j_cnt0 & 1) ^ 1);
       }
-      if (has_b) issue_pv(1, n - 1, v_cnt + n - 1, (s_cnt1 + n - 1) & 1, (j_cnt1 & 1) ^ 1);
-      v_cnt += n;
-      s_cnt0 += n; ++j_cnt0;
-      if (has_b) { s_cnt1 += n; ++j_cnt1; }
+      kv_cnt += n;
+      s_cnt += n;
+      ++j_cnt;
     }
   }
   } else {
@@ -703,7 +714,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   if (tid == 0) DEFT_TRACE(kTrEnd);
-  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp0) tmem_dealloc(tmem, kTmemCols);
 }
 
 template <int D, int G>

@@ -19,7 +19,7 @@ from deft_b200 import TreeMetadata, _lib
 from deft_b200.workloads import build_tree
 
 NAMES = {0: "start", 1: "q_ids", 2: "q0_issued", 3: "q1_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
-         8: "epi_end", 9: "end", 10: "t1.k_issued_w1", 11: "t1.k_issued_w2", 12: "t1.k_issued_w3", 13: "mma_pv0(0)_issued",
+         8: "epi_end", 9: "end", 10: "mma_pv0(1)_begin", 11: "mma_pv0(1)_mmas_issued", 12: "mma_pv0(1)_committed", 13: "mma_pv0(0)_issued",
          14: "mma_s1(0)_issued", 15: "mma_pv1(0)_issued"}
 TILE = ["k_issued", "mma_k_full", "sm_s_full", "sm_pass1", "sm_p_arrive", "mma_p_full", "v_issued", "sm_turn"]
 
