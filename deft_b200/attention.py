@@ -18,6 +18,16 @@ from . import _lib
 from ._lib import Plan
 
 _SUPPORTED_HEAD_DIMS = (32, 64, 128)
+
+try:                                      # raw handle of the current stream without building a Stream object
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:                    # pragma: no cover - older / newer torch: public (slower) API
+    def _raw_stream(index: int) -> int:
+        return torch.cuda.current_stream(index).cuda_stream
+
+
+def _current_stream(t: torch.Tensor) -> int:
+    return _raw_stream(t.device.index if t.device.index is not None else torch.cuda.current_device())
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
@@ -53,32 +63,48 @@ def _i64(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _flat_tables(block_q, block_q_cnts, block_q_offset, block_bitmasks, block_kv, block_lens, plan):
+    """Pointers and counts of the Flatten tables + the plan to use; cached on the TreeMetadata that owns them
+    (the tables of a decode step are immutable and shared by the 32 layer-calls of the step)."""
+    from .tree_cache import lookup_plan
+    meta = lookup_plan(block_q)
+    owned = meta is not None and meta.flat_plan is not None and meta.block_kv.data_ptr() == block_kv.data_ptr()
+    if owned and plan is None:
+        cached = meta.__dict__.get("_flat_call")
+        if cached is not None:
+            return cached
+    bq, bc, bo = _i64(block_q), _i64(block_q_cnts), _i64(block_q_offset)
+    bm, bk, bl = _i64(block_bitmasks), _i64(block_kv), _i64(block_lens)
+    use = plan if plan is not None else (meta.flat_plan if owned else None)
+    args = (bq.data_ptr(), bq.numel(), bc.data_ptr(), bo.data_ptr(), bl.data_ptr(), bc.numel(), bm.data_ptr(),
+            bk.data_ptr(), C.byref(use) if use is not None else None, {}, (bq, bc, bo, bm, bk, bl, use))
+    if owned and plan is None:
+        meta.__dict__["_flat_call"] = args
+    return args
+
+
 def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, value_buffer: torch.Tensor,
                                output: torch.Tensor, block_len: int, block_q: torch.Tensor,
                                block_q_cnts: torch.Tensor, block_q_offset: torch.Tensor,
                                block_bitmasks: torch.Tensor, block_kv: torch.Tensor, block_lens: torch.Tensor,
                                plan: Optional[Plan] = None) -> None:
     """DeFT-Flatten attention; writes ``output`` in place (tree_attention.py:552-667)."""
-    from .tree_cache import lookup_plan
     nq, H, HKV, D = _check_qkvo(query_states, key_buffer, value_buffer, output)
-    block_q, block_q_cnts, block_q_offset = _i64(block_q), _i64(block_q_cnts), _i64(block_q_offset)
-    block_bitmasks, block_kv, block_lens = _i64(block_bitmasks), _i64(block_kv), _i64(block_lens)
-    n_partials, n_blocks = block_q.numel(), block_q_cnts.numel()
-    if plan is None:
-        meta = lookup_plan(block_q)
-        if meta is not None and meta.flat_plan is not None and meta.block_kv.data_ptr() == block_kv.data_ptr():
-            plan = meta.flat_plan
-    stream = torch.cuda.current_stream(query_states.device).cuda_stream
-    need = _lib.lib.deft_b200_flatten_workspace_bytes(nq, H, HKV, D, n_partials, n_blocks,
-                                                      C.byref(plan) if plan is not None else None)
+    (p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, ws_need, _keep) = _flat_tables(
+        block_q, block_q_cnts, block_q_offset, block_bitmasks, block_kv, block_lens, plan)
+    stream = _current_stream(query_states)
+    geom = (nq, H, HKV, D)
+    need = ws_need.get(geom)
+    if need is None:
+        need = ws_need[geom] = _lib.lib.deft_b200_flatten_workspace_bytes(nq, H, HKV, D, n_partials, n_blocks, plan_ref)
     ws = _workspace(query_states.device, stream, need)
-    _lib.check(_lib.lib.deft_b200_flatten_fwd(
-        query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
-        key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1), key_buffer.shape[0],
-        output.data_ptr(), output.stride(0), output.stride(1), nq, H, HKV, D, int(block_len),
-        block_q.data_ptr(), n_partials, block_q_cnts.data_ptr(), block_q_offset.data_ptr(), block_lens.data_ptr(),
-        n_blocks, block_bitmasks.data_ptr(), block_kv.data_ptr(),
-        C.byref(plan) if plan is not None else None, ws.data_ptr(), ws.numel(), stream))
+    qs, ks, os_ = query_states.stride(), key_buffer.stride(), output.stride()
+    rc = _lib.lib.deft_b200_flatten_fwd(
+        query_states.data_ptr(), qs[0], qs[1], key_buffer.data_ptr(), value_buffer.data_ptr(), ks[0], ks[1],
+        key_buffer.shape[0], output.data_ptr(), os_[0], os_[1], nq, H, HKV, D, int(block_len),
+        p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, ws.data_ptr(), ws.numel(), stream)
+    if rc:
+        _lib.check(rc)
 
 
 def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, value_buffer: torch.Tensor,
@@ -100,7 +126,7 @@ def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, val
         meta = lookup_plan(node_q)
         if meta is not None and meta.node_plan is not None and meta.node_kv.data_ptr() == KV_indices.data_ptr():
             plan = meta.node_plan
-    stream = torch.cuda.current_stream(query_states.device).cuda_stream
+    stream = _current_stream(query_states)
     need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, HKV, D, n_partials, n_entries, total_kv_bound,
                                                    C.byref(plan) if plan is not None else None)
     ws = _workspace(query_states.device, stream, need)
@@ -121,11 +147,14 @@ def kv_append(kv_layer: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tens
     if not (kv_layer.is_cuda and cache_k.is_cuda and cache_v.is_cuda and cache_loc.is_cuda):
         raise _lib.DeftError("kv_append needs CUDA tensors (there is no CPU fallback)")
     assert cache_loc.dtype == torch.int32 and cache_loc.is_contiguous()
-    k, v = kv_layer[:, 0], kv_layer[:, 1]
+    assert kv_layer.dtype == torch.float16 and cache_k.dtype == torch.float16 and cache_v.dtype == torch.float16
     n, HKV, D = cache_k.shape
-    assert cache_v.shape == cache_k.shape and cache_k.stride() == cache_v.stride() and cache_k.stride(2) == 1
-    assert cache_loc.numel() == n and k.shape[1] == HKV and k.shape[2] == D
-    stream = torch.cuda.current_stream(kv_layer.device).cuda_stream
-    _lib.check(_lib.lib.deft_b200_kv_append(k.data_ptr(), v.data_ptr(), k.stride(0), k.stride(1),
-                                            cache_k.data_ptr(), cache_v.data_ptr(), cache_k.stride(0),
-                                            cache_k.stride(1), cache_loc.data_ptr(), n, HKV, D, stream))
+    ks, ls = cache_k.stride(), kv_layer.stride()          # K view = kv_layer[:, 0], V view = kv_layer[:, 1]
+    assert cache_v.shape == cache_k.shape and ks == cache_v.stride() and ks[2] == 1 and ls[3] == 1
+    assert cache_loc.numel() == n and kv_layer.shape[1] == 2 and kv_layer.shape[2] == HKV and kv_layer.shape[3] == D
+    stream = _current_stream(kv_layer)
+    k_ptr = kv_layer.data_ptr()
+    rc = _lib.lib.deft_b200_kv_append(k_ptr, k_ptr + ls[1] * 2, ls[0], ls[2], cache_k.data_ptr(), cache_v.data_ptr(),
+                                      ks[0], ks[1], cache_loc.data_ptr(), n, HKV, D, stream)
+    if rc:
+        _lib.check(rc)

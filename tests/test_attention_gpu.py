@@ -229,6 +229,35 @@ def test_baseline_configs_full_size(dev, name):
     assert torch.allclose(o_half.float() * 2, outs["flatten"].float(), atol=2e-3, rtol=1e-2)
 
 
+def test_forest_batch_in_one_launch(dev):
+    """BASELINE cfg 5 shape, scaled: several independent trees over ONE page pool attended by one call.  Every
+    query sees exactly its own tree (per-leaf check), and the result equals the trees run one at a time."""
+    from deft_b200 import TreeMetadata
+    from deft_b200.workloads import build_forest
+    torch.manual_seed(5)
+    trees = build_forest("cfg3", 3, layers=1, device=dev) + []
+    kvp = trees[0].token_to_kv_pool
+    kvp.kv_data[0].normal_()
+    K, V = kvp.get_key_buffer(0), kvp.get_value_buffer(0)
+    m = TreeMetadata.from_forest(trees)
+    nq = m.query_num
+    assert nq == sum(len(t.leaves) for t in trees) == 192
+    q = torch.randn(nq, 48 * 128, dtype=torch.float16, device=dev)[:, : 32 * 128].view(nq, 32, 128)
+    t = {k: getattr(m, k) for k in TABLE_KEYS}
+    got = run_flatten(q, K, V, t)
+    paths = [p for tr in trees for p in orc.leaf_paths(tr)]
+    want = per_leaf_reference(q, K, V, paths)
+    assert torch.allclose(got.float(), want, atol=ATOL, rtol=RTOL), (got.float() - want).abs().max().item()
+    assert torch.equal(got, run_node(q, K, V, t))
+    off = 0
+    for tr in trees:                                     # one tree at a time, same pool
+        mt = TreeMetadata.from_tree_cache(tr)
+        n = len(tr.leaves)
+        one = run_flatten(q[off: off + n], K, V, {k: getattr(mt, k) for k in TABLE_KEYS})
+        assert torch.allclose(one.float(), got[off: off + n].float(), atol=5e-4, rtol=5e-3)
+        off += n
+
+
 def test_argument_errors(dev):
     import deft_b200
     q = torch.zeros(2, 8, 48, dtype=torch.float16, device=dev)      # head_dim 48: unsupported, like the reference
