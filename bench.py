@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="flatten", choices=["flatten", "node", "node_chunk"])
+    ap.add_argument("--mode", default="flatten", choices=["flatten", "node", "node_chunk", "seq"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--trees-per-gpu", type=int, default=1,
@@ -105,6 +105,14 @@ class ClockSampler:
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _path(leaf):
+    nodes = []
+    while leaf is not None:
+        nodes.append(leaf)
+        leaf = leaf.parent
+    return nodes[::-1]
 
 
 def cpu_paths_and_inputs(workload: str, layers: int):
@@ -200,9 +208,22 @@ def main():
     def q_of(buf, l):
         return buf[l, :, : H * D].view(nq, H, D)
 
+    if args.mode == "seq":     # Radix / sequence-based baseline ON OUR KERNELS: every leaf re-reads its whole path
+        r2t = trees[0].req_to_token_pool
+        sleaves = [leaf for t in trees for leaf in sorted(t.leaves.values(), key=lambda x: x.id)]
+        req_idx = torch.tensor([t.leaf_to_req[leaf.id] for t in trees for leaf in sorted(t.leaves.values(), key=lambda x: x.id)],
+                               dtype=torch.int32, device=dev)
+        seq_len_host = [sum(len(n.kv_indices) for n in _path(leaf)) for leaf in sleaves]
+        seq_lens = torch.tensor(seq_len_host, dtype=torch.int32, device=dev)
+        start_loc = torch.zeros_like(seq_lens)
+        r2t_dev = r2t.device_table() if hasattr(r2t, "device_table") else r2t.req_to_token
+
     def attention(l, qbuf, m):
         K, V = kvp.get_key_buffer(l), kvp.get_value_buffer(l)
-        if args.mode == "flatten":
+        if args.mode == "seq":
+            deft_b200.token_attention_fwd(q_of(qbuf, l), K, V, out[l], r2t_dev, req_idx, start_loc, seq_lens,
+                                          max(seq_len_host), None, sum(seq_len_host))
+        elif args.mode == "flatten":
             deft_b200.tree_attention_subtree_fwd(q_of(qbuf, l), K, V, out[l], m.block_len, m.block_q, m.block_q_cnts,
                                                  m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens)
         else:

@@ -139,6 +139,44 @@ def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, val
         C.byref(plan) if plan is not None else None, ws.data_ptr(), ws.numel(), stream))
 
 
+_SEQ_CONST: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def token_attention_fwd(q: torch.Tensor, k_buffer: torch.Tensor, v_buffer: torch.Tensor, o: torch.Tensor,
+                        req_to_token: torch.Tensor, b_req_idx: torch.Tensor, b_start_loc: torch.Tensor,
+                        b_seq_len: torch.Tensor, max_len_in_batch: int, other_kv_index=None,
+                        total_num_tokens=None, att_m=None) -> None:
+    """Sequence-based decode attention (Radix Attention / ``--mode seq --mem paged``), reference signature of
+    ``deft/layers/attention/token_attention.py:297-335``: query ``i`` attends the first ``b_seq_len[i]`` pages of
+    row ``b_req_idx[i]`` of ``req_to_token``, independently of every other query (no prefix sharing).
+
+    Runs on the same sm_100a kernels as the tree operators: every query is one entry of a Node-style table whose
+    KV list is its row of the page table (int32, read in place); the tables are a few device-side index ops, no
+    host synchronisation.  ``b_start_loc``, ``other_kv_index``, ``total_num_tokens`` and ``att_m`` (the
+    reference's logits scratch) are accepted and unused.
+    """
+    nq, H, HKV, D = _check_qkvo(q, k_buffer, v_buffer, o)
+    assert req_to_token.is_cuda and req_to_token.dtype == torch.int32 and req_to_token.stride(1) == 1
+    assert b_req_idx.numel() == nq and b_seq_len.numel() == nq
+    dev_idx = q.device.index if q.device.index is not None else torch.cuda.current_device()
+    const = _SEQ_CONST.get((nq, dev_idx))
+    if const is None:
+        const = _SEQ_CONST[(nq, dev_idx)] = (torch.arange(nq, dtype=torch.int64, device=q.device),
+                                             torch.ones(nq, dtype=torch.int64, device=q.device))
+    ids, ones = const
+    kv_off = b_req_idx.to(torch.int64) * req_to_token.stride(0)
+    kv_len = b_seq_len.to(torch.int64)
+    total_kv_bound = nq * int(max_len_in_batch)       # long sequences are cut into 256-token items on the device
+    stream = _current_stream(q)
+    need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, HKV, D, nq, nq, total_kv_bound, None)
+    ws = _workspace(q.device, stream, need)
+    _lib.check(_lib.lib.deft_b200_node_fwd(
+        q.data_ptr(), q.stride(0), q.stride(1), k_buffer.data_ptr(), v_buffer.data_ptr(), k_buffer.stride(0),
+        k_buffer.stride(1), k_buffer.shape[0], o.data_ptr(), o.stride(0), o.stride(1), nq, H, HKV, D,
+        req_to_token.data_ptr(), 4, kv_off.data_ptr(), kv_len.data_ptr(), ids.data_ptr(), nq, ids.data_ptr(),
+        ones.data_ptr(), nq, total_kv_bound, None, ws.data_ptr(), ws.numel(), stream))
+
+
 def kv_append(kv_layer: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, cache_loc: torch.Tensor) -> None:
     """``key_buffer[cache_loc] = cache_k; value_buffer[cache_loc] = cache_v`` in one launch.
 

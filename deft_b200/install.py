@@ -32,6 +32,7 @@ def install(metadata: bool = True) -> None:
         da = importlib.import_module("deft.layers.attention.deft_attention")
         _swap(da, "tree_attention_fwd", attention.tree_attention_fwd)
         _swap(da, "tree_attention_subtree_fwd", attention.tree_attention_subtree_fwd)
+        _swap(da, "token_attention_fwd", attention.token_attention_fwd)       # Radix / seq mode (:174)
     except Exception:  # pragma: no cover - import of the caller failed; direct users are still patched
         pass
     if metadata:

@@ -229,6 +229,23 @@ def test_baseline_configs_full_size(dev, name):
     assert torch.allclose(o_half.float() * 2, outs["flatten"].float(), atol=2e-3, rtol=1e-2)
 
 
+@pytest.mark.parametrize("name", [n for n in SCENARIOS if n != "spec_merge"])
+def test_sequence_mode_matches_reference(golden_dir, dev, name):
+    """Radix / seq mode (token_attention_fwd, token_attention.py:297-335) through the same kernels: every leaf
+    attends its own row of req_to_token; compared with the reference's Triton output and fp64 per-leaf attention."""
+    import deft_b200
+    z, tree = load(golden_dir, name)
+    q, K, V = device_inputs(z, dev)
+    r2t = torch.from_numpy(z["req_to_token"]).to(dev)
+    req_idx = torch.from_numpy(z["req_idx"]).to(dev)
+    seq_lens = torch.from_numpy(z["seq_lens"]).to(dev)
+    o = garbage_like(q)
+    deft_b200.token_attention_fwd(q, K, V, o, r2t, req_idx, torch.zeros_like(seq_lens), seq_lens,
+                                  int(z["seq_lens"].max()), None, int(z["seq_lens"].sum()))
+    exact = orc.exact_attention(z["q"], z["kv_pool"][:, 0], z["kv_pool"][:, 1], orc.leaf_paths(tree))
+    assert_parity(o, z["o_seq"], exact, "seq")
+
+
 def test_forest_batch_in_one_launch(dev):
     """BASELINE cfg 5 shape, scaled: several independent trees over ONE page pool attended by one call.  Every
     query sees exactly its own tree (per-leaf check), and the result equals the trees run one at a time."""
