@@ -14,6 +14,7 @@ static thread_local float* g_debug = nullptr;
 static thread_local int* g_trace = nullptr;
 static thread_local bool g_no_tma = false;
 static thread_local bool g_no_pdl = false;
+static thread_local bool g_no_gather4 = false;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -61,13 +62,14 @@ bool make_map(CUtensorMap* out, const MapKey& key) {
       return true;
     }
   EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn || key.d0 < 64 || key.d1 <= 0 || key.d2 <= 0) return false;
+  const bool two_d = key.d2 == 0 && key.b2 == 0;  // [d1][d0], box {64, b1}
+  if (!fn || key.d0 < 64 || key.d1 <= 0 || (!two_d && key.d2 <= 0)) return false;
   alignas(64) CUtensorMap map;
   const cuuint64_t dims[3] = {(cuuint64_t)key.d0, (cuuint64_t)key.d1, (cuuint64_t)key.d2};
   const cuuint64_t strides[2] = {(cuuint64_t)key.s1 * 2, (cuuint64_t)key.s2 * 2};
   const cuuint32_t box[3] = {64, (cuuint32_t)key.b1, (cuuint32_t)key.b2};
   const cuuint32_t estr[3] = {1, 1, 1};
-  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(key.ptr), dims, strides, box, estr,
+  if (fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, two_d ? 2 : 3, const_cast<void*>(key.ptr), dims, strides, box, estr,
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
@@ -79,12 +81,22 @@ bool make_map(CUtensorMap* out, const MapKey& key) {
 }
 
 void setup_tma(AttnParams& p, int64_t kv_pool_tokens) {
-  p.tma_kv = p.tma_q = 0;
+  p.tma_kv = p.tma_q = p.tma_gather = 0;
   if (g_no_tma) return;
   const int G = p.H / p.HKV;
-  if (kv_pool_tokens > 0 && p.kv_head_stride >= p.D && p.kv_tok_stride >= p.D)
+  if (kv_pool_tokens > 0 && p.kv_head_stride >= p.D && p.kv_tok_stride >= p.D) {
     p.tma_kv = make_map(&p.tmap_k, MapKey{p.k, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 32}) &&
                make_map(&p.tmap_v, MapKey{p.v, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 32});
+    // gather4 view: head rows at a constant pitch (the token stride must be a whole number of head strides)
+    const int64_t ratio = p.kv_tok_stride / p.kv_head_stride;
+    const int64_t rows = (kv_pool_tokens - 1) * ratio + p.HKV;
+    if (!g_no_gather4 && p.tma_kv && ratio * p.kv_head_stride == p.kv_tok_stride && ratio >= p.HKV && rows < (1ll << 31)) {
+      p.kv_row_ratio = (int32_t)ratio;
+      p.kv_rows = (int32_t)rows;
+      p.tma_gather = make_map(&p.tmap_kg, MapKey{p.k, p.D, rows, 0, p.kv_head_stride, 0, 1, 0}) &&
+                     make_map(&p.tmap_vg, MapKey{p.v, p.D, rows, 0, p.kv_head_stride, 0, 1, 0});
+    }
+  }
   if (p.q_head_stride >= p.D && p.q_row_stride >= p.D)
     p.tma_q = make_map(&p.tmap_q, MapKey{p.q, p.D, p.H, p.nq, p.q_head_stride, p.q_row_stride, G, 32});
 }
@@ -274,6 +286,7 @@ void deft_b200_set_debug_buffer(void* dev) { g_debug = static_cast<float*>(dev);
 void deft_b200_set_trace_buffer(void* dev) { g_trace = static_cast<int*>(dev); }
 void deft_b200_set_tma(int32_t enabled) { g_no_tma = enabled == 0; }
 void deft_b200_set_pdl(int32_t enabled) { g_no_pdl = enabled == 0; }
+void deft_b200_set_gather4(int32_t enabled) { g_no_gather4 = enabled == 0; }
 
 size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_t D,
                                          int64_t n_partials, int64_t n_blocks, const deft_plan_t* plan) {

@@ -42,12 +42,13 @@ namespace deft {
 namespace {
 
 constexpr int kTileN = 128;  // tokens per KV tile (= the reference's BLOCK_LEN)
+constexpr int kHalfN = 64;   // ... worked by the tensor pipe and the softmax warps in two halves
 constexpr int kRows = 128;   // UMMA M
 constexpr int kThreads = 512;  // 16 warps: 4 register-budget groups of 4 (setmaxnreg works per warpgroup)
 constexpr int kMmaWarp0 = 8, kMmaWarp1 = 9, kQWarp = 10, kMaskWarp = 11, kKvWarp0 = 12;  // 12-15: K/V producers
 constexpr int kSoftmaxRegs = 192, kProducerRegs = 64;  // 256 * 192 + 256 * 64 = 64 K registers
 constexpr int kKvStages = 2, kMaskStages = 2;
-constexpr float kRescaleLog2 = 8.f;  // raise m_ref only when a tile tops it by more than 2^8
+constexpr float kRescaleLog2 = 14.f;  // raise m_ref only when a half tile tops it by more than 2^14 (P stays < 2^15 in fp16)
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -70,9 +71,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a launch failure (trap) instead of a hung GPU.
+// kSleepNs > 0: the waiting warp backs off between polls -- the producer / issuer warps share their SM
+// sub-partition's issue slots with a softmax warp and must not spin in them.
+template <int kSleepNs = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (kSleepNs > 0) __nanosleep(kSleepNs);
     if (++spins > (1u << 26)) __trap();
   }
 }
@@ -92,6 +97,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// TMA tile::gather4: four arbitrary rows of a 2-D tensor map (box {64, 1}) -> four consecutive 128-byte rows of
+// shared memory (swizzled by the map), completes 4 x 128 bytes on `bar`; rows outside the tensor read as zeros
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int r0, int r1, int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
       : "memory");
 }
 // NB: no fence.proxy.async on the consumer side.  Data staged by cp.async or TMA is handed over through
@@ -242,9 +258,13 @@ enum : int {
   Q_FULL = V_EMPTY + kKvStages, Q_EMPTY = Q_FULL + 2,
   M_FULL = Q_EMPTY + 2,                    // [slot][stage]
   M_EMPTY = M_FULL + 2 * kMaskStages,
-  S_FULL = M_EMPTY + 2 * kMaskStages,      // [slot]
-  P_FULL = S_FULL + 2, O_FULL = P_FULL + 2, O_EMPTY = O_FULL + 2,
-  ORDER = O_EMPTY + 2,                     // [slot]: the slot's turn on the exp (MUFU) section
+  S_FULL = M_EMPTY + 2 * kMaskStages,      // [slot]: S of one tile is in TMEM
+  P_FULL = S_FULL + 2,                     // [slot][half]: P of one 64-token half has been written over S
+  O_FULL = P_FULL + 4,                     // [slot]: one phase per tile (P V of the whole tile has landed in O)
+  O_DONE = O_FULL + 2,                     // [slot]: one phase per job (the last P V has landed: O is complete)
+  O_EMPTY = O_DONE + 2,                    // [slot]
+  PVA_DONE = O_EMPTY + 2,                  // [slot]: one phase per tile (P V of the tile's first half has landed in O)
+  ORDER = PVA_DONE + 2,                    // [slot]: the slot's turn on the exp (MUFU) section
   kNumBars = ORDER + 2
 };
 
@@ -301,6 +321,11 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long t_start = clock64();
   griddep_launch_dependents();       // stage 2 may launch early: its CTAs wait for this grid to finish
+  if (tid == 32) {  // the first TMA of a map otherwise pays the fetch of its 128-byte descriptor
+    if (p.tma_kv) { prefetch_tensormap(&p.tmap_k); prefetch_tensormap(&p.tmap_v); }
+    if (p.tma_gather) { prefetch_tensormap(&p.tmap_kg); prefetch_tensormap(&p.tmap_vg); }
+    if (p.tma_q) prefetch_tensormap(&p.tmap_q);
+  }
   if (p.plan_fresh) griddep_wait();  // the plan itself comes from the preceding (plan) kernel
   if (tid == 0) {
     for (int s = 0; s < kKvStages; ++s) {
@@ -313,9 +338,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         mbar_init(bar(M_FULL + s * kMaskStages + m), 32);
         mbar_init(bar(M_EMPTY + s * kMaskStages + m), 128);
       }
-      mbar_init(bar(S_FULL + s), 1); mbar_init(bar(P_FULL + s), 128);
-      mbar_init(bar(O_FULL + s), 1); mbar_init(bar(O_EMPTY + s), 128);
-      mbar_init(bar(ORDER + s), 128);
+      mbar_init(bar(S_FULL + s), 1);
+      for (int h = 0; h < 2; ++h) mbar_init(bar(P_FULL + 2 * s + h), 128);
+      mbar_init(bar(O_FULL + s), 1); mbar_init(bar(O_DONE + s), 1); mbar_init(bar(O_EMPTY + s), 128);
+      mbar_init(bar(PVA_DONE + s), 1); mbar_init(bar(ORDER + s), 128);
     }
     fence_barrier_init();
   }
@@ -361,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
 #pragma unroll
         for (int kv = 0; kv < 2; ++kv) {
           const int full = (kv == 0 ? K_FULL : V_FULL) + st;
-          mbar_wait(bar((kv == 0 ? K_EMPTY : V_EMPTY) + st), ph);
+          mbar_wait<64>(bar((kv == 0 ? K_EMPTY : V_EMPTY) + st), ph);
           const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
           if (run) {
             if (lane == 0) {
@@ -373,6 +399,19 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
             } else {
               mbar_arrive(bar(full));
             }
+          } else if (p.tma_gather != 0) {
+            // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of my 32 with one gather4 per panel;
+            // rows past the tile's length name a row outside the map and arrive as zeros
+            constexpr int NP = D / 64;
+            const int g = lane / NP, pn = lane % NP;
+            const int my_row = n_mine < tlen ? (int)pg * p.kv_row_ratio + hkv : p.kv_rows;
+            const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
+            const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
+            if (lane == 0) mbar_arrive_expect_tx(bar(full), 32 * D * 2);
+            else mbar_arrive(bar(full));
+            if (lane < 8 * NP)
+              tma_gather4(dst_base + pn * kPanelBytes + (w * 32 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, bar(full), pn * 64,
+                          r0, r1, r2, r3);
           } else {
             const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
             constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
@@ -387,7 +426,6 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
             cp_async_arrive(bar(full));
           }
           if (w == 0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
-          if (w > 0 && lane == 0 && ji == jobs.begin && t == 1 && kv == 0) DEFT_TRACE(9 + w);
         }
       }
     }
@@ -406,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       const bool known_run = u.q_id0[s] >= 0 && p.tma_q != 0;  // the builder's shortcut: no query-table read
       const int64_t my_q = known_run ? (int64_t)u.q_id0[s] + lane
                                      : (lane < u.q_cnt[s] ? load_index(p.u_q, p.u_q_bytes, u.q_off[s] + lane) : 0);
-      mbar_wait(bar(Q_EMPTY + s), (q_cnt & 1) ^ 1);
+      mbar_wait<64>(bar(Q_EMPTY + s), (q_cnt & 1) ^ 1);
       const uint32_t qs = base + L::kQ + s * L::kOperandBytes;
       if (lane == 0 && ji == jobs.begin && s == 0 && my_q >= 0) DEFT_TRACE(kTrQIds);
       // consecutive query ids: the slot's G heads x 32 queries are ONE box of q's tensor map per panel
@@ -450,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
         for (int s = 0; s < n_slots; ++s) {
           const int st = m_cnt[s] % kMaskStages;
-          mbar_wait(bar(M_EMPTY + s * kMaskStages + st), ((m_cnt[s] / kMaskStages) & 1) ^ 1);
+          mbar_wait<64>(bar(M_EMPTY + s * kMaskStages + st), ((m_cnt[s] / kMaskStages) & 1) ^ 1);
           uint32_t* ms = reinterpret_cast<uint32_t*>(gbase + L::kMask) + (s * kMaskStages + st) * kTileN;
           const uint32_t full = u.q_cnt[s] >= 32 ? 0xffffffffu : ((1u << u.q_cnt[s]) - 1u);
           // per-token words: bit r = row r of the slot attends token lane + 32j
@@ -482,8 +520,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {
     // ============================== MMA issuer of one slot ==============================
     // The whole warp runs the (uniform) control flow and the waits; lane 0 alone executes the tcgen05.mma /
-    // tcgen05.commit instructions.  Per tile:  S_s(t) = Q_s K(t)^T,  then  O_s (+)= P_s(t) V(t)  once the
-    // slot's softmax warps have written P_s(t) over S_s(t); S_s(t+1) follows in the same in-order stream.
+    // tcgen05.commit instructions.  Per tile:  S_s(t) = Q_s K(t)^T (N = 128: SS MMAs are bound by the 128 B/clk
+    // of shared memory, so narrower ones cost more per token), then O_s (+)= P_s(t) V(t) in two 64-token halves,
+    // each as soon as the softmax warps have written that half of P over S (the second half's exponentials
+    // overlap the first half's MMAs), then straight on to S_s(t+1) in the same in-order stream.
     const int s = warp == kMmaWarp0 ? 0 : 1;
     const bool leader = lane == 0;
     const uint32_t s_tmem = tmem + s * 128, o_tmem = tmem + 256 + s * 128;
@@ -506,9 +546,9 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       auto issue_s = [&](int t) {
         const uint32_t c = kv_cnt + t;
         const int st = c % kKvStages;
-        mbar_wait(bar(K_FULL + st), (c / kKvStages) & 1);
+        mbar_wait<20>(bar(K_FULL + st), (c / kKvStages) & 1);
         if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 1);
-        if (t == 0) mbar_wait(bar(Q_FULL + s), j_cnt & 1);
+        if (t == 0) mbar_wait<20>(bar(Q_FULL + s), j_cnt & 1);
         if (tr0 && t == 0) DEFT_TRACE(kTrMmaQFull);
         tc_fence_after();
         const uint64_t k_desc = smem_desc_sw128(base + L::kK + st * L::kOperandBytes, 16, 1024);
@@ -518,45 +558,41 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
             const uint64_t koff = (uint64_t)(((ks >> 2) * kPanelBytes + (ks & 3) * 32) >> 4);
             umma_ss(s_tmem, q_desc + koff, k_desc + koff, kIdescQK, ks > 0);
           }
-        }
-      };
-      auto commit_s = [&](int t) {  // S_s(t) is readable; K(t) and, after the last tile, Q_s are free
-        const int st = (kv_cnt + t) % kKvStages;
-        if (leader) {
           umma_commit(bar(S_FULL + s));
-          umma_commit(bar(K_EMPTY + st));
+          umma_commit(bar(K_EMPTY + st));  // K(t) and, after the last tile, Q_s are free
           if (!has_b) umma_commit(bar(K_EMPTY + st));
           if (t == n - 1) umma_commit(bar(Q_EMPTY + s));
         }
       };
       issue_s(0);
-      commit_s(0);
       __syncwarp();
       for (int t = 0; t < n; ++t) {
-        // ---- O_s (+)= P_s(t) V(t), then straight on to S_s(t+1): the commits (each covers every MMA
-        // issued before it) come after both, off the softmax -> P V -> S -> softmax critical path
         const uint32_t c = kv_cnt + t;
         const int st = c % kKvStages;
-        mbar_wait(bar(V_FULL + st), (c / kKvStages) & 1);
-        mbar_wait(bar(P_FULL + s), (s_cnt + t) & 1);
-        if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
-        if (t == 0) mbar_wait(bar(O_EMPTY + s), (j_cnt & 1) ^ 1);
-        tc_fence_after();
+        mbar_wait<20>(bar(V_FULL + st), (c / kKvStages) & 1);
         const uint64_t v_desc = smem_desc_sw128(base + L::kV + st * L::kOperandBytes, kPanelBytes, 1024);
-        if (leader) {
-          umma_ts(o_tmem, s_tmem, v_desc, kIdescPV, t > 0);
 #pragma unroll
-          for (int ks = 1; ks < kTileN / 16; ++ks)
-            umma_ts(o_tmem, s_tmem + ks * 8, v_desc + (uint64_t)((ks * 2048) >> 4), kIdescPV, true);
+        for (int h = 0; h < 2; ++h) {
+          // ---- O_s (+)= P_s(t)[:, 64h .. 64h+64) V(t)[64h .. 64h+64)
+          mbar_wait<20>(bar(P_FULL + 2 * s + h), (s_cnt + t) & 1);
+          if (tr0 && h == 0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
+          if (t == 0 && h == 0) mbar_wait<20>(bar(O_EMPTY + s), (j_cnt & 1) ^ 1);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < kHalfN / 16; ++ks)
+              umma_ts(o_tmem, s_tmem + h * (kHalfN / 2) + ks * 8, v_desc + (uint64_t)(((h * kHalfN + ks * 16) * 128) >> 4), kIdescPV,
+                      t > 0 || h > 0 || ks > 0);
+            if (h == 0) umma_commit(bar(PVA_DONE + s));
+            if (tr0 && t == 1) DEFT_TRACE(14 + h);
+          }
         }
-        if (t + 1 < n) {
-          issue_s(t + 1);
-          commit_s(t + 1);
-        }
-        if (leader) {
+        if (t + 1 < n) issue_s(t + 1);
+        if (leader) {  // the commits (each covers every MMA issued before it) come after S(t+1), off the critical path
           umma_commit(bar(O_FULL + s));
           umma_commit(bar(V_EMPTY + st));
           if (!has_b) umma_commit(bar(V_EMPTY + st));
+          if (t == n - 1) umma_commit(bar(O_DONE + s));
         }
         __syncwarp();
       }
@@ -574,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t t_s = t_lane + s * 128, t_o = t_lane + 256 + s * 128;
     const float c = p.scale * 1.4426950408889634f;  // scores are handled in the log2 domain
-    uint32_t s_cnt = 0, m_cnt = 0;
+    uint32_t s_cnt = 0, m_cnt = 0, j_cnt = 0;
     uint32_t ord_cnt = 0;  // tiles of two-slot jobs: the slots take turns on the exp section
     bool first_job = blockIdx.x == 0;
 
@@ -586,128 +622,155 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       const bool dbg = p.dbg != nullptr && first_job && s == 0;
       first_job = false;
       float m_ref = -INFINITY, l_run = 0.f;
-      float v[32];
 
       for (int t = 0; t < u.n_tiles; ++t, ++s_cnt, ++m_cnt) {
         const int mst = m_cnt % kMaskStages;
-        mbar_wait(bar(M_FULL + s * kMaskStages + mst), (m_cnt / kMaskStages) & 1);
+        mbar_wait<32>(bar(M_FULL + s * kMaskStages + mst), (m_cnt / kMaskStages) & 1);
         const uint32_t* ms = reinterpret_cast<const uint32_t*>(gbase + L::kMask) + (s * kMaskStages + mst) * kTileN;
         const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[s * kMaskStages + mst] != 0;
-        mbar_wait(bar(S_FULL + s), s_cnt & 1);
-        tc_fence_after();
         const bool tr = ji == jobs.begin && (tid & 127) == 0 && t < 5;
         const int tr0 = kTrTile0 + (s == 0 ? 0 : 48) + 8 * t;  // slot 1 events sit 48 slots higher
+        const bool trf = tr && s == 0 && t == 1;
+        mbar_wait<32>(bar(S_FULL + s), s_cnt & 1);
+        tc_fence_after();
         if (tr) DEFT_TRACE(tr0 + 2);
 
-        // ---- the whole S row (128 columns) comes out of TMEM once and stays in registers
-        float sv[kTileN];
-#pragma unroll
-        for (int cb = 0; cb < kTileN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv + cb * 32);
-        tmem_wait_ld();
-        if (dbg && t == 0)
-          for (int j = 0; j < kTileN; ++j) p.dbg[r * kTileN + j] = sv[j];
-        if (!dense) {  // masked-out tokens score -inf: my query's token bitmask comes from the mask warp
-          const uint4 rm = qi < 32 ? *reinterpret_cast<const uint4*>(ms + qi * 4) : make_uint4(0u, 0u, 0u, 0u);
-          const uint32_t rw[4] = {rm.x, rm.y, rm.z, rm.w};
-#pragma unroll
-          for (int j = 0; j < kTileN; ++j)
-            if (!((rw[j >> 5] >> (j & 31)) & 1u)) sv[j] = -INFINITY;
-        }
-        float mt;
-        {
-          float m0 = sv[0], m1 = sv[1], m2 = sv[2], m3 = sv[3];
-#pragma unroll
-          for (int j = 4; j < kTileN; j += 4) {
-            m0 = fmaxf(m0, sv[j]); m1 = fmaxf(m1, sv[j + 1]); m2 = fmaxf(m2, sv[j + 2]); m3 = fmaxf(m3, sv[j + 3]);
-          }
-          mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        }
-        mt *= c;  // c > 0
-        if (tr) DEFT_TRACE(tr0 + 3);
-
-        // ---- lazily raised reference maximum; the accumulator is rescaled only when it moves
-        const bool raise = mt > m_ref + kRescaleLog2;  // also the first live tile (m_ref = -inf)
-        float alpha = 1.f;
-        if (raise) {
-          alpha = fast_exp2(m_ref - mt);  // 0 when m_ref = -inf
-          m_ref = mt;
-          l_run *= alpha;
-        }
-        if (t > 0 && __any_sync(0xffffffffu, raise)) {
-          mbar_wait(bar(O_FULL + s), (s_cnt - 1) & 1);  // P V of the previous tile has landed in O
-          tc_fence_after();
-#pragma unroll 1
-          for (int cb = 0; cb < D / 32; ++cb) {
-            tmem_ld32(t_o + cb * 32, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= alpha;
-            tmem_st32(t_o + cb * 32, v);
-          }
-          tmem_wait_st();
-        }
-        const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
-
-        // ---- P = exp2(S*c - m_ref) -> packed fp16, written over S in TMEM (columns [0, 64) of the slot).
-        // In a two-slot job the slots alternate on this MUFU-bound section (slot 0 first), which keeps them
-        // half a period apart: one exponentiates while the tensor pipe serves the other.
+        // In a two-slot job the slots alternate on the exp section (slot 0 first), which keeps them half a
+        // period apart: one exponentiates while the tensor pipe serves the other.
         const bool ordered = u.q_cnt[1] > 0;
-        if (ordered) mbar_wait(bar(ORDER + s), s == 0 ? ((ord_cnt & 1) ^ 1) : (ord_cnt & 1));
-        if (tr) DEFT_TRACE(tr0 + 7);
-        float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+
+        // ---- P = exp2(S*c - m_ref) -> packed fp16, written over S in TMEM (columns [0, 64) of the slot), worked
+        // and handed to the tensor pipe in two 64-token halves: the first half's P V runs under the second
+        // half's exponentials.
+        // Reference maximum m_ref: the first half tile of a job sets it to its exact row maximum.  Every later
+        // half is exponentiated against the m_ref it finds (no dependent max -> exp chain): its own maximum is
+        // tracked inside the MUFU-bound loop, and only if it tops m_ref by more than 2^14 (P would leave fp16)
+        // is m_ref raised, the accumulator rescaled and the half redone.
+        float sv[2][kHalfN];  // my row of S, one 64-column half at a time: out of TMEM once, kept in registers
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t pk[32];
+        for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv[0] + cb * 32);
 #pragma unroll
-          for (int j = 0; j < 64; j += 4) {
-            const int i = hf * 64 + j;
-            const float e0 = fast_exp2(fmaf(sv[i], c, -m_use)), e1 = fast_exp2(fmaf(sv[i + 1], c, -m_use));
-            const float e2 = fast_exp2(fmaf(sv[i + 2], c, -m_use)), e3 = fast_exp2(fmaf(sv[i + 3], c, -m_use));
-            ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
-            pk[j / 2] = pack_half2(e0, e1);
-            pk[j / 2 + 1] = pack_half2(e2, e3);
+        for (int h = 0; h < 2; ++h) {
+          tmem_wait_ld();
+          if (trf && h == 0) DEFT_TRACE(10);
+          if (dbg && t == 0)
+            for (int j = 0; j < kHalfN; ++j) p.dbg[r * kTileN + h * kHalfN + j] = sv[h][j];
+          if (!dense) {  // masked-out tokens score -inf: my query's token bitmask comes from the mask warp
+            const uint2 rm = qi < 32 ? *reinterpret_cast<const uint2*>(ms + qi * 4 + h * 2) : make_uint2(0u, 0u);
+            const uint32_t rw[2] = {rm.x, rm.y};
+#pragma unroll
+            for (int j = 0; j < kHalfN; ++j)
+              if (!((rw[j >> 5] >> (j & 31)) & 1u)) sv[h][j] = -INFINITY;
           }
-          tmem_st32(t_s + hf * 32, reinterpret_cast<const float*>(pk));
+          if (h == 1) mbar_arrive(bar(M_EMPTY + s * kMaskStages + mst));
+          auto half_max = [&]() {
+            float m0 = sv[h][0], m1 = sv[h][1], m2 = sv[h][2], m3 = sv[h][3];
+#pragma unroll
+            for (int j = 4; j < kHalfN; j += 4) {
+              m0 = fmaxf(m0, sv[h][j]); m1 = fmaxf(m1, sv[h][j + 1]); m2 = fmaxf(m2, sv[h][j + 2]); m3 = fmaxf(m3, sv[h][j + 3]);
+            }
+            return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;  // c > 0; -inf when the row attends nothing here
+          };
+          if (t == 0 && h == 0) m_ref = half_max();
+          if (h == 0) {
+            if (tr) DEFT_TRACE(tr0 + 3);
+            if (ordered) mbar_wait<32>(bar(ORDER + s), s == 0 ? ((ord_cnt & 1) ^ 1) : (ord_cnt & 1));
+            if (trf) DEFT_TRACE(11);
+          }
+          uint32_t pk[kHalfN / 2];
+          float hsum;
+          bool redo;
+          do {
+            const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < kHalfN; j += 4) {
+              const float e0 = fast_exp2(fmaf(sv[h][j], c, -m_use)), e1 = fast_exp2(fmaf(sv[h][j + 1], c, -m_use));
+              const float e2 = fast_exp2(fmaf(sv[h][j + 2], c, -m_use)), e3 = fast_exp2(fmaf(sv[h][j + 3], c, -m_use));
+              ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
+              pk[j / 2] = pack_half2(e0, e1);
+              pk[j / 2 + 1] = pack_half2(e2, e3);
+            }
+            hsum = (ps0 + ps1) + (ps2 + ps3);
+            // every P >= 0, so a half-row sum below 2^15 proves that no P left fp16's range; a row that had seen
+            // nothing yet (m_ref = -inf) takes the slow path at its first live token.  (!(x < y) also catches NaN.)
+            const bool over = !(hsum < 32768.f) || (m_ref == -INFINITY && hsum > 0.f);
+            redo = __any_sync(0xffffffffu, over);
+            if (redo) {
+              float alpha = 1.f;
+              if (over) {
+                const float hmax = half_max();
+                alpha = fast_exp2(m_ref - hmax);  // 0 when m_ref = -inf
+                m_ref = hmax;
+                l_run *= alpha;
+              }
+              if (t > 0 || h > 0) {
+                // every P V issued so far has landed in O: the previous tile's, or this tile's first half
+                if (h == 0) mbar_wait(bar(O_FULL + s), (s_cnt - 1) & 1);
+                else mbar_wait(bar(PVA_DONE + s), s_cnt & 1);
+                tc_fence_after();
+                float* ov = reinterpret_cast<float*>(pk);  // P is recomputed: its registers carry O meanwhile
+#pragma unroll 1
+                for (int cb = 0; cb < D / 32; ++cb) {
+                  tmem_ld32(t_o + cb * 32, ov);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) ov[j] *= alpha;
+                  tmem_st32(t_o + cb * 32, ov);
+                }
+                tmem_wait_st();
+              }
+            }
+          } while (redo);
+          l_run += hsum;
+          if (h == 0) {  // the second half of S is on its way out of TMEM while the first half of P goes in
+#pragma unroll
+            for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + kHalfN + cb * 32, sv[1] + cb * 32);
+          } else if (ordered) {
+            mbar_arrive(bar(ORDER + (s ^ 1)));  // the MUFU-bound part of my turn is over
+            ++ord_cnt;
+          }
+          if (trf && h == 0) DEFT_TRACE(12);
+          tmem_st32(t_s + h * (kHalfN / 2), reinterpret_cast<const float*>(pk));
+          tmem_wait_st();
+          if (trf && h == 0) DEFT_TRACE(13);
+          tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
+          mbar_arrive(bar(P_FULL + 2 * s + h));
+          if (tr) DEFT_TRACE(tr0 + (h == 0 ? 4 : 7));
         }
-        if (ordered) {
-          mbar_arrive(bar(ORDER + (s ^ 1)));
-          ++ord_cnt;
-        }
-        tmem_wait_st();
-        l_run += (ps0 + ps1) + (ps2 + ps3);
-        mbar_arrive(bar(M_EMPTY + s * kMaskStages + mst));
-        tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
-        mbar_arrive(bar(P_FULL + s));
-        if (tr) DEFT_TRACE(tr0 + 4);
       }
 
       // ---- epilogue: partial = O / l as fp16, log-sum-exp in the natural-log domain
-      mbar_wait(bar(O_FULL + s), (s_cnt - 1) & 1);
+      // (not O_FULL: a thread that is two of its phases behind would read the parity of an older phase)
+      mbar_wait(bar(O_DONE + s), j_cnt & 1);
+      ++j_cnt;
       tc_fence_after();
       if (ji == jobs.begin && tid == 0) DEFT_TRACE(kTrEpiBegin);
       const bool live = qi < u.q_cnt[s];
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       const int64_t tile = (int64_t)(u.part_base[s] >> 5) * p.HKV + hkv;
       uint4* dst = reinterpret_cast<uint4*>(p.po16) + tile * (CH * R) + r;  // [chunk][row] of 16 bytes
-#pragma unroll 1
-      for (int cb = 0; cb < D / 32; ++cb) {
-        tmem_ld32(t_o + cb * 32, v);
+      {
+        float ov[D];  // the whole O row in one round trip to TMEM, then O(1) arrives as soon as it is in registers
+#pragma unroll
+        for (int cb = 0; cb < D / 32; ++cb) tmem_ld32_nowait(t_o + cb * 32, ov + cb * 32);
+        tmem_wait_ld();
+        tc_fence_before();  // my reads of O are ordered before the next job's first P V (accumulate = 0)
+        mbar_arrive(bar(O_EMPTY + s));
         if (dbg)
-          for (int j = 0; j < 32; ++j) p.dbg[kRows * kTileN + r * D + cb * 32 + j] = v[j];
+          for (int j = 0; j < D; ++j) p.dbg[kRows * kTileN + r * D + j] = ov[j];
         if (live) {
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
+          for (int c8 = 0; c8 < D / 8; ++c8) {
             uint4 pk;
-            pk.x = pack_half2(v[c4 * 8 + 0] * inv, v[c4 * 8 + 1] * inv);
-            pk.y = pack_half2(v[c4 * 8 + 2] * inv, v[c4 * 8 + 3] * inv);
-            pk.z = pack_half2(v[c4 * 8 + 4] * inv, v[c4 * 8 + 5] * inv);
-            pk.w = pack_half2(v[c4 * 8 + 6] * inv, v[c4 * 8 + 7] * inv);
-            dst[(cb * 4 + c4) * R] = pk;
+            pk.x = pack_half2(ov[c8 * 8 + 0] * inv, ov[c8 * 8 + 1] * inv);
+            pk.y = pack_half2(ov[c8 * 8 + 2] * inv, ov[c8 * 8 + 3] * inv);
+            pk.z = pack_half2(ov[c8 * 8 + 4] * inv, ov[c8 * 8 + 5] * inv);
+            pk.w = pack_half2(ov[c8 * 8 + 6] * inv, ov[c8 * 8 + 7] * inv);
+            dst[c8 * R] = pk;
           }
         }
       }
       if (live) p.plse16[tile * R + r] = l_run > 0.f ? (m_ref + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
-      tc_fence_before();  // my reads of O are ordered before the next job's first P V (accumulate = 0)
-      mbar_arrive(bar(O_EMPTY + s));
       if (ji == jobs.begin && tid == 0) DEFT_TRACE(kTrEpiEnd);
     }
   }

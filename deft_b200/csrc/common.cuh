@@ -38,8 +38,12 @@ struct AttnParams {
   // TMA tensor maps (tcgen05 path), valid when the flags below are set:
   //   tmap_k / tmap_v: [pool][HKV][D] fp16, box {64, 1, 32 pages}, 128B swizzle
   //   tmap_q:          [nq][H][D]     fp16, box {64, G, 32 queries}, 128B swizzle
-  CUtensorMap tmap_k, tmap_v, tmap_q;
-  int32_t tma_kv, tma_q;
+  //   tmap_kg / tmap_vg: the same pool as a 2-D matrix of head rows [pool * row_ratio][D], box {64, 1}: the
+  //                    tile::gather4 form (four arbitrary rows per instruction) for pages that are not consecutive;
+  //                    row of (page, kv-head) = page * kv_row_ratio + kv-head, rows >= kv_rows read as zeros
+  CUtensorMap tmap_k, tmap_v, tmap_q, tmap_kg, tmap_vg;
+  int32_t tma_kv, tma_q, tma_gather;
+  int32_t kv_row_ratio, kv_rows;
   const __half* q;
   const __half* k;
   const __half* v;

@@ -65,6 +65,10 @@ void deft_b200_set_tma(int32_t enabled);
  * stream serialization: each starts while its predecessor drains, does its dependency-free prologue
  * (barriers, TMEM, plan tables) and only then waits for the predecessor (griddepcontrol.wait). */
 void deft_b200_set_pdl(int32_t enabled);
+/* Test hook: 0 = pages that are not consecutive are gathered with cp.async (16-byte copies), 1 (default) =
+ * with TMA tile::gather4 (four K or V rows per instruction) when the pool's token stride is a whole
+ * number of head strides. */
+void deft_b200_set_gather4(int32_t enabled);
 
 /* ------------------------------------------------------------------------------------------
  * Work plan (device side).  Two layers:

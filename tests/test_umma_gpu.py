@@ -1,5 +1,6 @@
 """tcgen05 stage-1 kernel: accumulator-level checks (raw S and O of the first work unit) and parity of both
 stage-1 implementations.  Needs a B200."""
+import math
 import os
 
 import numpy as np
@@ -74,7 +75,15 @@ def test_accumulators_of_first_unit(golden_dir, dev, force_impl, name):
     allow = ((bits[None, :] >> torch.arange(cnt)[:, None]) & 1).bool().repeat_interleave(G, dim=0)
     sc = S_want / D ** 0.5
     sc = torch.where(allow, sc, torch.tensor(float("-inf")))
-    m = sc.max(dim=1, keepdim=True).values
+    # the kernel's reference maximum: the first 64-token half's row maximum, raised to the second half's only
+    # if that half's exponentials would sum past 2^15 against it (attn_umma.cu) or the first half was all masked
+    m_a = sc[:, :64].max(dim=1, keepdim=True).values
+    if ln > 64:
+        m_b = sc[:, 64:].max(dim=1, keepdim=True).values
+        sum_b = torch.exp2((sc[:, 64:] - torch.where(torch.isinf(m_a), torch.zeros_like(m_a), m_a)) * math.log2(math.e)).sum(dim=1, keepdim=True)
+        m = torch.where((sum_b >= 32768) | (torch.isinf(m_a) & (sum_b > 0)), m_b, m_a)
+    else:
+        m = m_a
     P = torch.exp(sc - m)
     O_want = P @ vv
     err_o = (O[: cnt * G] - O_want).abs().max().item()
@@ -131,8 +140,9 @@ def test_kernels_agree_at_full_size(dev, force_impl):
 
 @pytest.mark.parametrize("name", ["cfg2", "cfg3"])
 def test_tma_and_cp_async_paths_agree(dev, name):
-    """Runs of consecutive pages / query ids go through TMA boxes, everything else through cp.async gathers:
-    both stage the same bytes in the same swizzled layout, so the outputs are bit-identical."""
+    """Runs of consecutive pages / query ids go through TMA boxes, scattered pages through TMA gather4 (four rows
+    per instruction) or, with that switched off, cp.async gathers: all stage the same bytes in the same swizzled
+    layout, so the outputs are bit-identical."""
     from deft_b200 import TreeMetadata, _lib
     import deft_b200
     from deft_b200.workloads import build_tree
@@ -146,16 +156,19 @@ def test_tma_and_cp_async_paths_agree(dev, name):
     m = TreeMetadata.from_tree_cache(tree)
     outs = []
     try:
-        for tma in (1, 0):
+        for tma, g4 in ((1, 1), (1, 0), (0, 0)):
             _lib.lib.deft_b200_set_tma(tma)
+            _lib.lib.deft_b200_set_gather4(g4)
             o = torch.full((nq, 32, 128), float("nan"), dtype=torch.float16, device=dev)
             deft_b200.tree_attention_subtree_fwd(q, K, V, o, 128, m.block_q, m.block_q_cnts, m.block_q_offset,
                                                  m.block_bitmasks, m.block_kv, m.block_lens)
             outs.append(o)
     finally:
         _lib.lib.deft_b200_set_tma(1)
+        _lib.lib.deft_b200_set_gather4(1)
     assert torch.isfinite(outs[0].float()).all()
     assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], outs[2])
 
 
 @pytest.mark.parametrize("name", ["cfg1", "cfg2"])

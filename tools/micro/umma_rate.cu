@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int iters)
   if (threadIdx.x == 0) {
     const uint64_t a = desc_sw128(base, 16, 1024), b = desc_sw128(base + 32768, 16, 1024);
     const uint64_t bv = desc_sw128(base + 32768, 16384, 1024);
-    constexpr uint32_t id = MODE == 1 ? idesc(256, false) : MODE == 2 ? idesc(128, true) : idesc(128, false);
+    constexpr uint32_t id = MODE == 1 ? idesc(256, false) : MODE == 2 ? idesc(128, true) : MODE == 4 ? idesc(64, false) : MODE == 5 ? idesc(32, false) : idesc(128, false);
     t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -92,6 +92,9 @@ int main() {
     run<3>("SS M128 N128 K16 (new acc / 8)", grid, 64);
     run<1>("SS M128 N256 K16", grid, 64);
     run<2>("TS M128 N128 K16 (B MN-major)", grid, 64);
+    run<4>("SS M128 N64 K16", grid, 64);
+    run<5>("SS M128 N32 K16", grid, 64);
+    run<4>("SS M128 N64 K16, 8 MMAs only", grid, 1);
     run<0>("SS M128 N128 K16, 8 MMAs only", grid, 1);
     run<2>("TS M128 N128 K16, 8 MMAs only", grid, 1);
   }

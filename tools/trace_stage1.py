@@ -19,9 +19,9 @@ from deft_b200 import TreeMetadata, _lib
 from deft_b200.workloads import build_tree
 
 NAMES = {0: "start", 1: "q_ids", 2: "q0_issued", 3: "q1_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
-         8: "epi_end", 9: "end", 10: "mma_pv0(1)_begin", 11: "mma_pv0(1)_mmas_issued", 12: "mma_pv0(1)_committed", 13: "mma_pv0(0)_issued",
-         14: "mma_s1(0)_issued", 15: "mma_pv1(0)_issued"}
-TILE = ["k_issued", "mma_k_full", "sm_s_full", "sm_pass1", "sm_p_arrive", "mma_p_full", "v_issued", "sm_turn"]
+         8: "epi_end", 9: "end", 10: "t1.ld_done", 11: "t1.max_raise_done", 12: "t1a.exp_done", 13: "t1a.st_done",
+         14: "t1.mma_pva_issued", 15: "t1.mma_pvb_issued"}
+TILE = ["k_issued", "mma_k_full", "sm_s_full", "sm_max", "sm_pa_arrive", "mma_pa_full", "v_issued", "sm_pb_arrive"]
 
 
 def main():
@@ -47,9 +47,8 @@ def main():
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     flush.zero_()                               # push the KV pool out of L2
-    call(1)                                     # warm the plan tables only (other layer)
-    torch.cuda.synchronize()
-    flush.zero_()
+    call(1)                                     # plan tables warm in L2 (as inside a decode step: 32 layers share
+    torch.cuda.synchronize()                    # them), layer 0's KV stays cold
     _lib.lib.deft_b200_set_trace_buffer(trace.data_ptr())
     call(0)
     torch.cuda.synchronize()
