@@ -45,10 +45,10 @@ constexpr int kTileN = 128;  // tokens per KV tile (= the reference's BLOCK_LEN)
 constexpr int kHalfN = 64;   // ... worked by the tensor pipe and the softmax warps in two halves
 constexpr int kRows = 128;   // UMMA M
 constexpr int kThreads = 512;  // 16 warps: 4 register-budget groups of 4 (setmaxnreg works per warpgroup)
-constexpr int kMmaWarp0 = 8, kMmaWarp1 = 9, kQWarp = 10, kMaskWarp = 11, kKvWarp0 = 12;  // 12-15: K/V producers
-constexpr int kSoftmaxRegs = 192, kProducerRegs = 64;  // 256 * 192 + 256 * 64 = 64 K registers
-constexpr int kKvStages = 2, kMaskStages = 2;
-constexpr float kRescaleLog2 = 14.f;  // raise m_ref only when a half tile tops it by more than 2^14 (P stays < 2^15 in fp16)
+constexpr int kMmaWarp = 8, kQWarp = 9, kMaskWarp = 10, kPvWarp = 11, kKvWarp0 = 12;  // 12, 13: K producers; 14, 15: V
+constexpr int kSoftmaxRegs = 160, kProducerRegs = 96;  // 256 * 160 + 256 * 96 = 64 K registers
+constexpr int kKStages = 3, kVStages = 2, kMaskStages = 2;
+constexpr int kSBufs = 3;  // S tiles in TMEM: O [0, 128) + 3 x 128 columns = all 512
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -65,6 +65,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking poll (try_wait may suspend the warp for a while; a loop polling two barriers must not)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
@@ -88,6 +98,9 @@ __device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
 // 16-byte global->shared copy; src_bytes = 0 zero-fills
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {  // no arrival
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
@@ -254,35 +267,39 @@ enum : int {
 
 // barrier indices
 enum : int {
-  K_FULL = 0, K_EMPTY = K_FULL + kKvStages, V_FULL = K_EMPTY + kKvStages, V_EMPTY = V_FULL + kKvStages,
-  Q_FULL = V_EMPTY + kKvStages, Q_EMPTY = Q_FULL + 2,
-  M_FULL = Q_EMPTY + 2,                    // [slot][stage]
-  M_EMPTY = M_FULL + 2 * kMaskStages,
-  S_FULL = M_EMPTY + 2 * kMaskStages,      // [slot]: S of one tile is in TMEM
-  P_FULL = S_FULL + 2,                     // [slot][half]: P of one 64-token half has been written over S
-  O_FULL = P_FULL + 4,                     // [slot]: one phase per tile (P V of the whole tile has landed in O)
-  O_DONE = O_FULL + 2,                     // [slot]: one phase per job (the last P V has landed: O is complete)
-  O_EMPTY = O_DONE + 2,                    // [slot]
-  PVA_DONE = O_EMPTY + 2,                  // [slot]: one phase per tile (P V of the tile's first half has landed in O)
-  ORDER = PVA_DONE + 2,                    // [slot]: the slot's turn on the exp (MUFU) section
-  kNumBars = ORDER + 2
+  K_FULL = 0, K_EMPTY = K_FULL + kKStages, V_FULL = K_EMPTY + kKStages, V_EMPTY = V_FULL + kVStages,
+  Q_FULL = V_EMPTY + kVStages, Q_EMPTY = Q_FULL + 1,
+  M_FULL = Q_EMPTY + 1,                    // [stage]
+  M_EMPTY = M_FULL + kMaskStages,
+  S_FULL = M_EMPTY + kMaskStages,          // [S buffer]: S of one tile is in TMEM
+  P_FULL = S_FULL + kSBufs,                // [S buffer][half]: P of one 64-token half has been written over S
+  S_FREE = P_FULL + 2 * kSBufs,            // [S buffer]: P V of the buffer's tile has completed
+  PV_DONE = S_FREE + kSBufs,               // one phase per tile: P V of the tile has landed in O
+  O_DONE = PV_DONE + 1,                    // one phase per job: the last P V has landed, O is complete
+  O_EMPTY = O_DONE + 1,                    // one phase per job: the epilogue has read O
+  kNumBars = O_EMPTY + 1
 };
 
 template <int D>
 struct Layout {
   static constexpr int kOperandBytes = kRows * D * 2;                      // Q, K or V tile
-  static constexpr int kK = 0;                                             // [stage]
-  static constexpr int kV = kK + kKvStages * kOperandBytes;                // [stage]
-  static constexpr int kQ = kV + kKvStages * kOperandBytes;                // [slot]
-  static constexpr int kMask = kQ + 2 * kOperandBytes;                     // [slot][stage][128] u32
-  static constexpr int kFlag = kMask + 2 * kMaskStages * kTileN * 4;       // [slot][stage] u32
-  static constexpr int kBars = kFlag + 2 * kMaskStages * 4;
+  static constexpr int kQ = 0;
+  static constexpr int kK = kQ + kOperandBytes;                            // [stage]
+  static constexpr int kV = kK + kKStages * kOperandBytes;                 // [stage]
+  static constexpr int kMask = kV + kVStages * kOperandBytes;              // [stage][128] u32
+  static constexpr int kFlag = kMask + kMaskStages * kTileN * 4;           // [stage] u32
+  static constexpr int kPvCnt = kFlag + 16;                                // u32: tiles whose P V the issuer has seen complete
+  static constexpr int kXchg = kPvCnt + 16;                                 // [tile parity][round parity][half][128] f32
+  static constexpr int kBars = kXchg + 2 * 2 * 2 * kRows * 4;
   static constexpr int kTmemSlot = kBars + kNumBars * 8;
   static constexpr int kBytes = kTmemSlot + 16;
   static constexpr int kAlloc = kBytes + 1024;  // slack for the manual 1024-byte alignment
 };
 
-// The (unit, kv-head) jobs of one CTA: an explicit host-balanced list, or jobs c, c+grid, ...
+// The jobs of one CTA.  job = ((unit * HKV + kv-head) << 1) | slot of the unit's pair: one CTA works ONE
+// slot (<= 32 queries x G heads = one M = 128 accumulator) over the unit's chain of KV tiles; the two
+// slots of a pair are separate jobs, on different SMs when the balance allows (their K/V tile reads meet
+// in L2).  Either an explicit host-balanced list, or jobs c, c + grid, ...
 struct Jobs {
   const int32_t* list;
   int begin, end, stride;
@@ -296,19 +313,24 @@ struct Jobs {
       list = nullptr;
       const int n_units = p.n_units_dev ? *p.n_units_dev : p.n_units;
       begin = blockIdx.x;
-      end = n_units * p.HKV;
+      end = n_units * p.HKV * 2;
       stride = gridDim.x;
     }
   }
   __device__ __forceinline__ int get(int i) const { return list ? list[i] : i; }
 };
 
+// pair of warps w, w + 4 (the two threads of a row sit in them): named barrier 1 + (w & 3)
+__device__ __forceinline__ void pair_sync(int warp) {
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+}
+
 template <int D, int G>
 __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_constant__ AttnParams p) {
   using L = Layout<D>;
   constexpr int CH = D / 8;           // 16-byte chunks per row
   constexpr int R = kMaxGroupQ * G;   // live rows of a full slot
-  constexpr uint32_t kTmemCols = 512; // S_0 [0,128) S_1 [128,256) O_0 [256,256+D) O_1 [384,384+D)
+  constexpr uint32_t kTmemCols = 512; // O [0, D)   S_0 [128, 256)   S_1 [256, 384)   S_2 [384, 512)
   constexpr uint32_t kIdescQK = instr_desc(kTileN, false);
   constexpr uint32_t kIdescPV = instr_desc(D, true);
 
@@ -328,24 +350,19 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   }
   if (p.plan_fresh) griddep_wait();  // the plan itself comes from the preceding (plan) kernel
   if (tid == 0) {
-    for (int s = 0; s < kKvStages; ++s) {
-      mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 2);  // one commit per slot issuer
-      mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 2);  // (slot 0's commits twice in a one-slot job)
+    for (int s = 0; s < kKStages; ++s) { mbar_init(bar(K_FULL + s), 64); mbar_init(bar(K_EMPTY + s), 1); }
+    for (int s = 0; s < kVStages; ++s) { mbar_init(bar(V_FULL + s), 64); mbar_init(bar(V_EMPTY + s), 1); }
+    mbar_init(bar(Q_FULL), 32); mbar_init(bar(Q_EMPTY), 1);
+    for (int m = 0; m < kMaskStages; ++m) { mbar_init(bar(M_FULL + m), 32); mbar_init(bar(M_EMPTY + m), 256); }
+    for (int b = 0; b < kSBufs; ++b) {
+      mbar_init(bar(S_FULL + b), 1); mbar_init(bar(S_FREE + b), 1);
+      for (int h = 0; h < 2; ++h) mbar_init(bar(P_FULL + 2 * b + h), 128);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar(Q_FULL + s), 32); mbar_init(bar(Q_EMPTY + s), 1);
-      for (int m = 0; m < kMaskStages; ++m) {
-        mbar_init(bar(M_FULL + s * kMaskStages + m), 32);
-        mbar_init(bar(M_EMPTY + s * kMaskStages + m), 128);
-      }
-      mbar_init(bar(S_FULL + s), 1);
-      for (int h = 0; h < 2; ++h) mbar_init(bar(P_FULL + 2 * s + h), 128);
-      mbar_init(bar(O_FULL + s), 1); mbar_init(bar(O_DONE + s), 1); mbar_init(bar(O_EMPTY + s), 128);
-      mbar_init(bar(PVA_DONE + s), 1); mbar_init(bar(ORDER + s), 128);
-    }
+    mbar_init(bar(PV_DONE), 1); mbar_init(bar(O_DONE), 1); mbar_init(bar(O_EMPTY), 256);
+    *reinterpret_cast<volatile uint32_t*>(gbase + L::kPvCnt) = 0u;
     fence_barrier_init();
   }
-  if (warp == kMmaWarp0) tmem_alloc(base + L::kTmemSlot, kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(base + L::kTmemSlot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -356,109 +373,129 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   // the tail of the preceding kernel; q, the KV pool and the partial workspace may still be in its hands.
   griddep_wait();
   if (tid == 0) DEFT_TRACE(kTrStart);
+  // job -> (unit, kv-head, slot); a pair's second slot may be empty (then the job is nobody's)
+  auto decode = [&](int job, deft_unit_t& u, int& hkv, int& k) -> bool {
+    k = job & 1;
+    hkv = (job >> 1) % p.HKV;
+    u = p.units[(job >> 1) / p.HKV];
+    return (k == 0 ? u.q_cnt[0] : u.q_cnt[1]) > 0;
+  };
   if (warp >= 8) {
-  reg_dealloc<kProducerRegs>();  // warps 8-11 and 12-15: two whole warpgroups give registers away
+  reg_dealloc<kProducerRegs>();  // warps 8-15: two whole warpgroups give registers away
   if (warp >= kKvWarp0) {
-    // ============================== K / V producers: warp w owns token rows [32w, 32w+32) ==============================
-    const int w = warp - kKvWarp0;
+    // ============================== K / V producers ==============================
+    // warps 12, 13: K rows [0, 64) / [64, 128) of every tile; warps 14, 15: V likewise.  K and V run on
+    // rings of their own (K is released as soon as S is done, a tile earlier than V).
+    const int kv = (warp - kKvWarp0) >> 1, w = (warp - kKvWarp0) & 1;
+    const int stages = kv == 0 ? kKStages : kVStages;
+    const int FULL = kv == 0 ? K_FULL : V_FULL, EMPTY = kv == 0 ? K_EMPTY : V_EMPTY;
     uint32_t cnt = 0;  // tiles produced
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
-      const int job = jobs.get(ji);
-      const int hkv = job % p.HKV;
-      const deft_unit_t u = p.units[job / p.HKV];
-      if (w == 0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrKUnit);
-      const int n_mine = w * 32 + lane;  // my token row
+      deft_unit_t u; int hkv, k;
+      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      if (warp == kKvWarp0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrKUnit);
       const bool known_run = u.page0 >= 0 && p.tma_kv != 0;  // the builder's shortcut: no index-table read at all
-      auto page_of = [&](int t) -> int64_t {
+      auto page_of = [&](int t, int row) -> int {  // page of token `row` of tile t (0 past the end)
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
-        if (known_run) return (int64_t)u.page0 + t * kTileN + n_mine;
-        return t < u.n_tiles && n_mine < tlen ? load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + n_mine) : 0;
+        if (known_run) return u.page0 + t * kTileN + row;
+        return t < u.n_tiles && row < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row) : 0;
       };
-      int64_t pg_next = page_of(0);
+      int pg_next[2] = {page_of(0, w * 64 + lane), page_of(0, w * 64 + 32 + lane)};
       for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
-        const int st = cnt % kKvStages;
-        const uint32_t ph = ((cnt / kKvStages) & 1) ^ 1;
-        const int64_t pg = pg_next;
-        pg_next = page_of(t + 1);  // the next tile's page id is in flight while this tile is issued
+        const int st = cnt % stages;
+        const uint32_t ph = ((cnt / stages) & 1) ^ 1;
+        const int pg[2] = {pg_next[0], pg_next[1]};
+        pg_next[0] = page_of(t + 1, w * 64 + lane);  // the next tile's page ids are in flight while this tile is issued
+        pg_next[1] = page_of(t + 1, w * 64 + 32 + lane);
+        const bool trp = kv == 0 && w == 0 && lane == 0 && ji == jobs.begin && t < 6;
+        if (trp) DEFT_TRACE(64 + 8 * t + 0);
+        mbar_wait<64>(bar(EMPTY + st), ph);
+        if (trp) DEFT_TRACE(64 + 8 * t + 1);
+        const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
+        const uint32_t full = bar(FULL + st);
         // 32 consecutive pages of a full tile are ONE box of the pool's tensor map per 64-wide panel
-        const int64_t page0 = __shfl_sync(0xffffffffu, pg, 0);
-        const bool run = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg == page0 + lane);
+        bool run[2];
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv) {
-          const int full = (kv == 0 ? K_FULL : V_FULL) + st;
-          mbar_wait<64>(bar((kv == 0 ? K_EMPTY : V_EMPTY) + st), ph);
-          const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
-          if (run) {
+        for (int hh = 0; hh < 2; ++hh) {
+          const int page0 = __shfl_sync(0xffffffffu, pg[hh], 0);
+          run[hh] = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg[hh] == page0 + lane);
+        }
+        const bool async_tx = p.tma_kv != 0 && (p.tma_gather != 0 || (run[0] && run[1]));
+        if (async_tx) {  // TMA only: one thread announces the warp's 64 rows, the copies complete them
+          if (lane == 0) mbar_arrive_expect_tx(full, 64 * D * 2);
+          else mbar_arrive(full);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row0 = w * 64 + hh * 32;  // my 32 rows of this pass
+          if (run[hh]) {
+            const int page0 = __shfl_sync(0xffffffffu, pg[hh], 0);
+            if (!async_tx && lane == 0) mbar_expect_tx(full, 32 * D * 2);  // (my arrival comes with the cp.async ones below)
             if (lane == 0) {
-              mbar_arrive_expect_tx(bar(full), 32 * D * 2);
 #pragma unroll
               for (int pn = 0; pn < D / 64; ++pn)
-                tma_load_3d(dst_base + pn * kPanelBytes + w * 32 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, bar(full), pn * 64,
-                            hkv, (int)page0);
-            } else {
-              mbar_arrive(bar(full));
+                tma_load_3d(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0);
             }
           } else if (p.tma_gather != 0) {
-            // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of my 32 with one gather4 per panel;
-            // rows past the tile's length name a row outside the map and arrive as zeros
+            // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of these 32 with one gather4 per
+            // panel; rows past the tile's length name a row outside the map and arrive as zeros
             constexpr int NP = D / 64;
             const int g = lane / NP, pn = lane % NP;
-            const int my_row = n_mine < tlen ? (int)pg * p.kv_row_ratio + hkv : p.kv_rows;
+            const int my_row = row0 + lane < tlen ? pg[hh] * p.kv_row_ratio + hkv : p.kv_rows;
             const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
             const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
-            if (lane == 0) mbar_arrive_expect_tx(bar(full), 32 * D * 2);
-            else mbar_arrive(bar(full));
             if (lane < 8 * NP)
-              tma_gather4(dst_base + pn * kPanelBytes + (w * 32 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, bar(full), pn * 64,
+              tma_gather4(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
                           r0, r1, r2, r3);
           } else {
             const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
             constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
 #pragma unroll 4
             for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
-              const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside my 32
+              const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside these 32
               const int ch = lane % CH;
-              const int64_t page = __shfl_sync(0xffffffffu, pg, nl);
-              const bool ok = w * 32 + nl < tlen;
-              cp_async_16(dst_base + tile_off(w * 32 + nl, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
+              const int64_t page = __shfl_sync(0xffffffffu, pg[hh], nl);
+              const bool ok = row0 + nl < tlen;
+              cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
             }
-            cp_async_arrive(bar(full));
           }
-          if (w == 0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
         }
+        if (!async_tx) {
+          // every lane arrives once: when all its cp.async have landed (none issued: immediately), and the
+          // TMA boxes of a mixed tile complete their bytes on the same barrier
+          cp_async_arrive(full);
+        }
+        if (w == 0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
       }
     }
   } else if (warp == kQWarp) {
-    // ============================== Q tiles of both slots ==============================
-    uint32_t q_cnts[2] = {0, 0};  // jobs per slot
+    // ============================== Q tile of the job's slot ==============================
+    uint32_t q_cnt = 0;  // jobs
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
-      const int job = jobs.get(ji);
-      const int hkv = job % p.HKV;
-      const deft_unit_t u = p.units[job / p.HKV];
-#pragma unroll
-     for (int s = 0; s < 2; ++s) {
-      if (u.q_cnt[s] == 0) continue;
-      uint32_t& q_cnt = q_cnts[s];
+      deft_unit_t u; int hkv, k;
+      if (!decode(jobs.get(ji), u, hkv, k)) continue;
       // row r = (query r / G, head r % G); rows past q_cnt*G are zero
-      const bool known_run = u.q_id0[s] >= 0 && p.tma_q != 0;  // the builder's shortcut: no query-table read
-      const int64_t my_q = known_run ? (int64_t)u.q_id0[s] + lane
-                                     : (lane < u.q_cnt[s] ? load_index(p.u_q, p.u_q_bytes, u.q_off[s] + lane) : 0);
-      mbar_wait<64>(bar(Q_EMPTY + s), (q_cnt & 1) ^ 1);
-      const uint32_t qs = base + L::kQ + s * L::kOperandBytes;
-      if (lane == 0 && ji == jobs.begin && s == 0 && my_q >= 0) DEFT_TRACE(kTrQIds);
+      const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
+      const int q_id0 = k == 0 ? u.q_id0[0] : u.q_id0[1];
+      const int q_off = k == 0 ? u.q_off[0] : u.q_off[1];
+      const bool known_run = q_id0 >= 0 && p.tma_q != 0;  // the builder's shortcut: no query-table read
+      const int64_t my_q = known_run ? (int64_t)q_id0 + lane : (lane < n_q ? load_index(p.u_q, p.u_q_bytes, q_off + lane) : 0);
+      mbar_wait<64>(bar(Q_EMPTY), (q_cnt & 1) ^ 1);
+      const uint32_t qs = base + L::kQ;
+      if (lane == 0 && ji == jobs.begin && my_q >= 0) DEFT_TRACE(kTrQIds);
       // consecutive query ids: the slot's G heads x 32 queries are ONE box of q's tensor map per panel
       // (rows past q_cnt then hold the next queries or zeros: finite, never stored)
       const int64_t q0 = __shfl_sync(0xffffffffu, my_q, 0);
-      const bool run = p.tma_q != 0 && (lane >= u.q_cnt[s] || my_q == q0 + lane);
+      const bool run = p.tma_q != 0 && (lane >= n_q || my_q == q0 + lane);
       if (known_run || __all_sync(0xffffffffu, run)) {
         if (lane == 0) {
-          mbar_arrive_expect_tx(bar(Q_FULL + s), R * D * 2);
+          mbar_arrive_expect_tx(bar(Q_FULL), R * D * 2);
 #pragma unroll
           for (int pn = 0; pn < D / 64; ++pn)
-            tma_load_3d(qs + pn * kPanelBytes, &p.tmap_q, bar(Q_FULL + s), pn * 64, hkv * G, (int)q0);
+            tma_load_3d(qs + pn * kPanelBytes, &p.tmap_q, bar(Q_FULL), pn * 64, hkv * G, (int)q0);
         } else {
-          mbar_arrive(bar(Q_FULL + s));
+          mbar_arrive(bar(Q_FULL));
         }
       } else {
 #pragma unroll 4
@@ -467,90 +504,76 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           const int r = c / CH, ch = c % CH;
           const int qi = r / G, g = r % G;
           const int64_t qid = __shfl_sync(0xffffffffu, my_q, qi & 31);
-          const bool ok = qi < u.q_cnt[s];
+          const bool ok = qi < n_q;
           const __half* src = p.q + qid * p.q_row_stride + (int64_t)(hkv * G + g) * p.q_head_stride + ch * 8;
           cp_async_16(qs + tile_off(r, ch), ok ? src : p.q, ok ? 16u : 0u);
         }
-        cp_async_arrive(bar(Q_FULL + s));
+        cp_async_arrive(bar(Q_FULL));
       }
-      if (lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrQ0Issued + s);
+      if (lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrQ0Issued);
       ++q_cnt;
-     }
     }
   } else if (warp == kMaskWarp) {
-    // ============================== mask words + dense flag per (tile, slot) ==============================
-    uint32_t m_cnt[2] = {0, 0};  // tiles per slot
+    // ============================== mask words + dense flag per tile ==============================
+    uint32_t m_cnt = 0;  // tiles
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
-      const int job = jobs.get(ji);
-      const deft_unit_t u = p.units[job / p.HKV];
-      const int n_slots = u.q_cnt[1] > 0 ? 2 : 1;
-      for (int t = 0; t < u.n_tiles; ++t) {
+      deft_unit_t u; int hkv, k;
+      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
+      const int64_t mask_off = k == 0 ? u.mask_off[0] : u.mask_off[1];
+      const uint32_t fullw = n_q >= 32 ? 0xffffffffu : ((1u << n_q) - 1u);
+      for (int t = 0; t < u.n_tiles; ++t, ++m_cnt) {
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
-        for (int s = 0; s < n_slots; ++s) {
-          const int st = m_cnt[s] % kMaskStages;
-          mbar_wait<64>(bar(M_EMPTY + s * kMaskStages + st), ((m_cnt[s] / kMaskStages) & 1) ^ 1);
-          uint32_t* ms = reinterpret_cast<uint32_t*>(gbase + L::kMask) + (s * kMaskStages + st) * kTileN;
-          const uint32_t full = u.q_cnt[s] >= 32 ? 0xffffffffu : ((1u << u.q_cnt[s]) - 1u);
-          // per-token words: bit r = row r of the slot attends token lane + 32j
-          uint32_t m[kTileN / 32];
-          bool dense = tlen == kTileN;
+        const int st = m_cnt % kMaskStages;
+        // per-token words: bit r = row r of the slot attends token lane + 32j (loaded ahead of the wait)
+        uint32_t m[kTileN / 32];
+        bool dense = tlen == kTileN;
 #pragma unroll
-          for (int j = 0; j < kTileN / 32; ++j) {
-            const int n = lane + 32 * j;
-            m[j] = 0;
-            if (n < tlen)
-              m[j] = u.mask_off[s] >= 0
-                         ? (uint32_t)load_index(p.u_mask, p.u_mask_bytes, u.mask_off[s] + (int64_t)t * u.mask_tile_stride + n)
-                         : 0xffffffffu;
-            dense = dense && ((m[j] & full) == full);
-          }
-          dense = __all_sync(0xffffffffu, dense);
-          if (!dense) {
-            // transpose to row masks: lane = query, word j bit n = the query attends token 32j + n
-            *reinterpret_cast<uint4*>(ms + lane * 4) = make_uint4(warp_transpose32(m[0], lane), warp_transpose32(m[1], lane),
-                                                                  warp_transpose32(m[2], lane), warp_transpose32(m[3], lane));
-          }
-          if (lane == 0) reinterpret_cast<uint32_t*>(gbase + L::kFlag)[s * kMaskStages + st] = dense ? 1u : 0u;
-          mbar_arrive(bar(M_FULL + s * kMaskStages + st));
-          if (lane == 0 && ji == jobs.begin && t == 0 && s == 0) DEFT_TRACE(kTrMask0);
-          ++m_cnt[s];
+        for (int j = 0; j < kTileN / 32; ++j) {
+          const int n = lane + 32 * j;
+          m[j] = 0;
+          if (n < tlen)
+            m[j] = mask_off >= 0 ? (uint32_t)load_index(p.u_mask, p.u_mask_bytes, mask_off + (int64_t)t * u.mask_tile_stride + n)
+                                 : 0xffffffffu;
+          dense = dense && ((m[j] & fullw) == fullw);
         }
+        dense = __all_sync(0xffffffffu, dense);
+        mbar_wait<64>(bar(M_EMPTY + st), ((m_cnt / kMaskStages) & 1) ^ 1);
+        uint32_t* ms = reinterpret_cast<uint32_t*>(gbase + L::kMask) + st * kTileN;
+        if (!dense) {
+          // transpose to row masks: lane = query, word j bit n = the query attends token 32j + n
+          *reinterpret_cast<uint4*>(ms + lane * 4) = make_uint4(warp_transpose32(m[0], lane), warp_transpose32(m[1], lane),
+                                                                warp_transpose32(m[2], lane), warp_transpose32(m[3], lane));
+        }
+        if (lane == 0) reinterpret_cast<uint32_t*>(gbase + L::kFlag)[st] = dense ? 1u : 0u;
+        mbar_arrive(bar(M_FULL + st));
+        if (lane == 0 && ji == jobs.begin && t == 0) DEFT_TRACE(kTrMask0);
       }
     }
-  } else if (warp == kMmaWarp0 || warp == kMmaWarp1) {
-    // ============================== MMA issuer of one slot ==============================
+  } else if (warp == kMmaWarp) {
+    // ============================== S issuer ==============================
     // The whole warp runs the (uniform) control flow and the waits; lane 0 alone executes the tcgen05.mma /
-    // tcgen05.commit instructions.  Per tile:  S_s(t) = Q_s K(t)^T (N = 128: SS MMAs are bound by the 128 B/clk
-    // of shared memory, so narrower ones cost more per token), then O_s (+)= P_s(t) V(t) in two 64-token halves,
-    // each as soon as the softmax warps have written that half of P over S (the second half's exponentials
-    // overlap the first half's MMAs), then straight on to S_s(t+1) in the same in-order stream.
-    const int s = warp == kMmaWarp0 ? 0 : 1;
+    // tcgen05.commit instructions.  S is triple-buffered in TMEM: S(t) = Q K(t)^T is issued as soon as K(t) has
+    // landed and P V of tile t - 3 (the buffer's previous tenant) has completed, i.e. up to two tiles ahead of
+    // the softmax warps, which therefore never wait for the tensor pipe in the steady state.
     const bool leader = lane == 0;
-    const uint32_t s_tmem = tmem + s * 128, o_tmem = tmem + 256 + s * 128;
-    const uint64_t q_desc = smem_desc_sw128(base + L::kQ + s * L::kOperandBytes, 16, 1024);
-    uint32_t kv_cnt = 0;  // KV tiles consumed (ring position; every job advances both slots' issuers alike)
-    uint32_t s_cnt = 0;   // tiles of this slot (S_FULL / P_FULL / O_FULL phases)
-    uint32_t j_cnt = 0;   // jobs of this slot (Q_FULL / O_EMPTY phases)
+    const uint64_t q_desc = smem_desc_sw128(base + L::kQ, 16, 1024);
+    uint32_t k_cnt = 0, g0 = 0, j_cnt = 0;  // K tiles consumed (ring position), tiles of earlier jobs, jobs
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
-      const int job = jobs.get(ji);
-      const deft_unit_t u = p.units[job / p.HKV];
+      deft_unit_t u; int hkv, k;
+      if (!decode(jobs.get(ji), u, hkv, k)) continue;
       const int n = u.n_tiles;
-      const bool has_b = u.q_cnt[1] > 0;
-      if (s == 1 && !has_b) {  // one-slot job: slot 0's issuer signs off the KV stages for both
-        kv_cnt += n;
-        continue;
-      }
-      const bool tr0 = ji == jobs.begin && leader && s == 0;
-      // S_s(t): descriptors advance by compile-time constants (the start-address field holds bytes >> 4 and
-      // cannot carry out of its 14 bits inside 227 KB of shared memory).
-      auto issue_s = [&](int t) {
-        const uint32_t c = kv_cnt + t;
-        const int st = c % kKvStages;
-        mbar_wait<20>(bar(K_FULL + st), (c / kKvStages) & 1);
-        if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 1);
-        if (t == 0) mbar_wait<20>(bar(Q_FULL + s), j_cnt & 1);
-        if (tr0 && t == 0) DEFT_TRACE(kTrMmaQFull);
+      const bool tr0 = ji == jobs.begin && leader;
+      mbar_wait(bar(Q_FULL), j_cnt & 1);
+      if (tr0) DEFT_TRACE(kTrMmaQFull);
+      for (int t = 0; t < n; ++t) {
+        const uint32_t gt = g0 + t, c = k_cnt + t;
+        const int sb = gt % kSBufs, st = c % kKStages;
+        if (gt >= (uint32_t)kSBufs) mbar_wait(bar(S_FREE + sb), (gt / kSBufs - 1) & 1);
+        mbar_wait(bar(K_FULL + st), (c / kKStages) & 1);
         tc_fence_after();
+        if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 1);
+        const uint32_t s_tmem = tmem + 128 + sb * 128;
         const uint64_t k_desc = smem_desc_sw128(base + L::kK + st * L::kOperandBytes, 16, 1024);
         if (leader) {
 #pragma unroll
@@ -558,226 +581,246 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
             const uint64_t koff = (uint64_t)(((ks >> 2) * kPanelBytes + (ks & 3) * 32) >> 4);
             umma_ss(s_tmem, q_desc + koff, k_desc + koff, kIdescQK, ks > 0);
           }
-          umma_commit(bar(S_FULL + s));
-          umma_commit(bar(K_EMPTY + st));  // K(t) and, after the last tile, Q_s are free
-          if (!has_b) umma_commit(bar(K_EMPTY + st));
-          if (t == n - 1) umma_commit(bar(Q_EMPTY + s));
-        }
-      };
-      issue_s(0);
-      __syncwarp();
-      for (int t = 0; t < n; ++t) {
-        const uint32_t c = kv_cnt + t;
-        const int st = c % kKvStages;
-        mbar_wait<20>(bar(V_FULL + st), (c / kKvStages) & 1);
-        const uint64_t v_desc = smem_desc_sw128(base + L::kV + st * L::kOperandBytes, kPanelBytes, 1024);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          // ---- O_s (+)= P_s(t)[:, 64h .. 64h+64) V(t)[64h .. 64h+64)
-          mbar_wait<20>(bar(P_FULL + 2 * s + h), (s_cnt + t) & 1);
-          if (tr0 && h == 0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
-          if (t == 0 && h == 0) mbar_wait<20>(bar(O_EMPTY + s), (j_cnt & 1) ^ 1);
-          tc_fence_after();
-          if (leader) {
-#pragma unroll
-            for (int ks = 0; ks < kHalfN / 16; ++ks)
-              umma_ts(o_tmem, s_tmem + h * (kHalfN / 2) + ks * 8, v_desc + (uint64_t)(((h * kHalfN + ks * 16) * 128) >> 4), kIdescPV,
-                      t > 0 || h > 0 || ks > 0);
-            if (h == 0) umma_commit(bar(PVA_DONE + s));
-            if (tr0 && t == 1) DEFT_TRACE(14 + h);
-          }
-        }
-        if (t + 1 < n) issue_s(t + 1);
-        if (leader) {  // the commits (each covers every MMA issued before it) come after S(t+1), off the critical path
-          umma_commit(bar(O_FULL + s));
-          umma_commit(bar(V_EMPTY + st));
-          if (!has_b) umma_commit(bar(V_EMPTY + st));
-          if (t == n - 1) umma_commit(bar(O_DONE + s));
+          umma_commit(bar(S_FULL + sb));
+          umma_commit(bar(K_EMPTY + st));  // K(t) and, after the last tile, Q are free
+          if (t == n - 1) umma_commit(bar(Q_EMPTY));
         }
         __syncwarp();
       }
-      kv_cnt += n;
-      s_cnt += n;
+      k_cnt += n;
+      g0 += n;
+      ++j_cnt;
+    }
+  } else if (warp == kPvWarp) {
+    // ============================== P V issuer ==============================
+    // O (+)= P(t) V(t) in two 64-token halves, each as soon as the softmax warps have written that half of P
+    // over S(t).  After a tile's MMAs and commits this warp sees the tile's PV_DONE phase through and publishes
+    // the count of completed tiles (the softmax warps' rare rescale path reads it: a parity wait is sound only
+    // one phase ahead of what is known complete, and only this warp sees every phase).
+    const bool leader = lane == 0;
+    const uint32_t o_tmem = tmem;
+    uint32_t v_cnt = 0, g0 = 0, j_cnt = 0;
+    volatile uint32_t* pv_cnt = reinterpret_cast<volatile uint32_t*>(gbase + L::kPvCnt);
+    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+      deft_unit_t u; int hkv, k;
+      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      const int n = u.n_tiles;
+      const bool tr0 = ji == jobs.begin && leader;
+      for (int t = 0; t < n; ++t) {
+        const uint32_t gt = g0 + t, c = v_cnt + t;
+        const int buf = gt % kSBufs, st = c % kVStages;
+        mbar_wait(bar(V_FULL + st), (c / kVStages) & 1);
+        if (t == 0) mbar_wait(bar(O_EMPTY), (j_cnt & 1) ^ 1);
+        const uint64_t v_desc = smem_desc_sw128(base + L::kV + st * L::kOperandBytes, kPanelBytes, 1024);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(bar(P_FULL + 2 * buf + half), (gt / kSBufs) & 1);
+          tc_fence_after();
+          if (tr0 && half == 0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
+          const uint32_t p_tmem = tmem + 128 + buf * 128 + half * kHalfN;  // P_a: columns [0, 32), P_b: [64, 96) of S
+          if (leader) {
+#pragma unroll
+            for (int ks = 0; ks < kHalfN / 16; ++ks)
+              umma_ts(o_tmem, p_tmem + ks * 8, v_desc + (uint64_t)(((half * kHalfN + ks * 16) * 128) >> 4), kIdescPV,
+                      t > 0 || half > 0 || ks > 0);
+          }
+        }
+        if (leader) {
+          umma_commit(bar(PV_DONE));
+          umma_commit(bar(V_EMPTY + st));
+          umma_commit(bar(S_FREE + buf));
+          if (t == n - 1) umma_commit(bar(O_DONE));
+        }
+        __syncwarp();
+        mbar_wait(bar(PV_DONE), gt & 1);
+        if (leader) *pv_cnt = gt + 1;
+      }
+      v_cnt += n;
+      g0 += n;
       ++j_cnt;
     }
   }
   } else {
-    reg_alloc<kSoftmaxRegs>();   // warps 0-3 and 4-7
-    // ============================== softmax + epilogue (slot = warp / 4) ==============================
-    const int s = warp >> 2;
+    reg_alloc<kSoftmaxRegs>();   // warps 0-7
+    // ============================== softmax + epilogue ==============================
+    // Two threads per row: warp w < 4 takes columns [0, 64) of every S tile, warp w + 4 columns [64, 128) of
+    // the same 32 rows (the same TMEM lanes).  They agree on the row's reference maximum through shared
+    // memory and a named barrier of the two warps, once per tile.
+    const int h = warp >> 2;
     const int r = tid & 127;  // my row == my TMEM lane
     const int qi = r / G;
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t t_s = t_lane + s * 128, t_o = t_lane + 256 + s * 128;
+    const uint32_t t_o = t_lane + h * (D / 2);  // my half of the O row
     const float c = p.scale * 1.4426950408889634f;  // scores are handled in the log2 domain
-    uint32_t s_cnt = 0, m_cnt = 0, j_cnt = 0;
-    uint32_t ord_cnt = 0;  // tiles of two-slot jobs: the slots take turns on the exp section
+    float* xchg = reinterpret_cast<float*>(gbase + L::kXchg);
+    uint32_t g0 = 0, j_cnt = 0;
     bool first_job = blockIdx.x == 0;
 
     for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
-      const int job = jobs.get(ji);
-      const int hkv = job % p.HKV;
-      const deft_unit_t u = p.units[job / p.HKV];
-      if (s == 1 && u.q_cnt[1] == 0) continue;
-      const bool dbg = p.dbg != nullptr && first_job && s == 0;
+      deft_unit_t u; int hkv, k;
+      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
+      const int part_base = k == 0 ? u.part_base[0] : u.part_base[1];
+      const bool dbg = p.dbg != nullptr && first_job;
       first_job = false;
       float m_ref = -INFINITY, l_run = 0.f;
 
-      for (int t = 0; t < u.n_tiles; ++t, ++s_cnt, ++m_cnt) {
-        const int mst = m_cnt % kMaskStages;
-        mbar_wait<32>(bar(M_FULL + s * kMaskStages + mst), (m_cnt / kMaskStages) & 1);
-        const uint32_t* ms = reinterpret_cast<const uint32_t*>(gbase + L::kMask) + (s * kMaskStages + mst) * kTileN;
-        const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[s * kMaskStages + mst] != 0;
+      for (int t = 0; t < u.n_tiles; ++t) {
+        const uint32_t gt = g0 + t;
+        const int buf = gt % kSBufs;
+        const int mst = gt % kMaskStages;
+        mbar_wait<32>(bar(M_FULL + mst), (gt / kMaskStages) & 1);
+        const uint32_t* ms = reinterpret_cast<const uint32_t*>(gbase + L::kMask) + mst * kTileN;
+        const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[mst] != 0;
         const bool tr = ji == jobs.begin && (tid & 127) == 0 && t < 5;
-        const int tr0 = kTrTile0 + (s == 0 ? 0 : 48) + 8 * t;  // slot 1 events sit 48 slots higher
-        const bool trf = tr && s == 0 && t == 1;
-        mbar_wait<32>(bar(S_FULL + s), s_cnt & 1);
+        const int tr0 = kTrTile0 + (h == 0 ? 0 : 48) + 8 * t;  // the second half's events sit 48 slots higher
+        mbar_wait<32>(bar(S_FULL + buf), (gt / kSBufs) & 1);
         tc_fence_after();
         if (tr) DEFT_TRACE(tr0 + 2);
 
-        // In a two-slot job the slots alternate on the exp section (slot 0 first), which keeps them half a
-        // period apart: one exponentiates while the tensor pipe serves the other.
-        const bool ordered = u.q_cnt[1] > 0;
-
-        // ---- P = exp2(S*c - m_ref) -> packed fp16, written over S in TMEM (columns [0, 64) of the slot), worked
-        // and handed to the tensor pipe in two 64-token halves: the first half's P V runs under the second
-        // half's exponentials.
-        // Reference maximum m_ref: the first half tile of a job sets it to its exact row maximum.  Every later
-        // half is exponentiated against the m_ref it finds (no dependent max -> exp chain): its own maximum is
-        // tracked inside the MUFU-bound loop, and only if it tops m_ref by more than 2^14 (P would leave fp16)
-        // is m_ref raised, the accumulator rescaled and the half redone.
-        float sv[2][kHalfN];  // my row of S, one 64-column half at a time: out of TMEM once, kept in registers
+        // ---- my half of the S row (64 columns) comes out of TMEM once and stays in registers
+        const uint32_t t_s = t_lane + 128 + buf * 128 + h * kHalfN;
+        float sv[kHalfN];
 #pragma unroll
-        for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv[0] + cb * 32);
+        for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv + cb * 32);
+        tmem_wait_ld();
+        if (dbg && t == 0)
+          for (int j = 0; j < kHalfN; ++j) p.dbg[r * kTileN + h * kHalfN + j] = sv[j];
+        if (!dense) {  // masked-out tokens score -inf: my query's token bitmask comes from the mask warp
+          const uint2 rm = qi < 32 ? *reinterpret_cast<const uint2*>(ms + qi * 4 + h * 2) : make_uint2(0u, 0u);
+          const uint32_t rw[2] = {rm.x, rm.y};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          tmem_wait_ld();
-          if (trf && h == 0) DEFT_TRACE(10);
-          if (dbg && t == 0)
-            for (int j = 0; j < kHalfN; ++j) p.dbg[r * kTileN + h * kHalfN + j] = sv[h][j];
-          if (!dense) {  // masked-out tokens score -inf: my query's token bitmask comes from the mask warp
-            const uint2 rm = qi < 32 ? *reinterpret_cast<const uint2*>(ms + qi * 4 + h * 2) : make_uint2(0u, 0u);
-            const uint32_t rw[2] = {rm.x, rm.y};
-#pragma unroll
-            for (int j = 0; j < kHalfN; ++j)
-              if (!((rw[j >> 5] >> (j & 31)) & 1u)) sv[h][j] = -INFINITY;
-          }
-          if (h == 1) mbar_arrive(bar(M_EMPTY + s * kMaskStages + mst));
-          auto half_max = [&]() {
-            float m0 = sv[h][0], m1 = sv[h][1], m2 = sv[h][2], m3 = sv[h][3];
-#pragma unroll
-            for (int j = 4; j < kHalfN; j += 4) {
-              m0 = fmaxf(m0, sv[h][j]); m1 = fmaxf(m1, sv[h][j + 1]); m2 = fmaxf(m2, sv[h][j + 2]); m3 = fmaxf(m3, sv[h][j + 3]);
-            }
-            return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;  // c > 0; -inf when the row attends nothing here
-          };
-          if (t == 0 && h == 0) m_ref = half_max();
-          if (h == 0) {
-            if (tr) DEFT_TRACE(tr0 + 3);
-            if (ordered) mbar_wait<32>(bar(ORDER + s), s == 0 ? ((ord_cnt & 1) ^ 1) : (ord_cnt & 1));
-            if (trf) DEFT_TRACE(11);
-          }
-          uint32_t pk[kHalfN / 2];
-          float hsum;
-          bool redo;
-          do {
-            const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
-            float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < kHalfN; j += 4) {
-              const float e0 = fast_exp2(fmaf(sv[h][j], c, -m_use)), e1 = fast_exp2(fmaf(sv[h][j + 1], c, -m_use));
-              const float e2 = fast_exp2(fmaf(sv[h][j + 2], c, -m_use)), e3 = fast_exp2(fmaf(sv[h][j + 3], c, -m_use));
-              ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
-              pk[j / 2] = pack_half2(e0, e1);
-              pk[j / 2 + 1] = pack_half2(e2, e3);
-            }
-            hsum = (ps0 + ps1) + (ps2 + ps3);
-            // every P >= 0, so a half-row sum below 2^15 proves that no P left fp16's range; a row that had seen
-            // nothing yet (m_ref = -inf) takes the slow path at its first live token.  (!(x < y) also catches NaN.)
-            const bool over = !(hsum < 32768.f) || (m_ref == -INFINITY && hsum > 0.f);
-            redo = __any_sync(0xffffffffu, over);
-            if (redo) {
-              float alpha = 1.f;
-              if (over) {
-                const float hmax = half_max();
-                alpha = fast_exp2(m_ref - hmax);  // 0 when m_ref = -inf
-                m_ref = hmax;
-                l_run *= alpha;
-              }
-              if (t > 0 || h > 0) {
-                // every P V issued so far has landed in O: the previous tile's, or this tile's first half
-                if (h == 0) mbar_wait(bar(O_FULL + s), (s_cnt - 1) & 1);
-                else mbar_wait(bar(PVA_DONE + s), s_cnt & 1);
-                tc_fence_after();
-                float* ov = reinterpret_cast<float*>(pk);  // P is recomputed: its registers carry O meanwhile
-#pragma unroll 1
-                for (int cb = 0; cb < D / 32; ++cb) {
-                  tmem_ld32(t_o + cb * 32, ov);
-#pragma unroll
-                  for (int j = 0; j < 32; ++j) ov[j] *= alpha;
-                  tmem_st32(t_o + cb * 32, ov);
-                }
-                tmem_wait_st();
-              }
-            }
-          } while (redo);
-          l_run += hsum;
-          if (h == 0) {  // the second half of S is on its way out of TMEM while the first half of P goes in
-#pragma unroll
-            for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + kHalfN + cb * 32, sv[1] + cb * 32);
-          } else if (ordered) {
-            mbar_arrive(bar(ORDER + (s ^ 1)));  // the MUFU-bound part of my turn is over
-            ++ord_cnt;
-          }
-          if (trf && h == 0) DEFT_TRACE(12);
-          tmem_st32(t_s + h * (kHalfN / 2), reinterpret_cast<const float*>(pk));
-          tmem_wait_st();
-          if (trf && h == 0) DEFT_TRACE(13);
-          tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
-          mbar_arrive(bar(P_FULL + 2 * s + h));
-          if (tr) DEFT_TRACE(tr0 + (h == 0 ? 4 : 7));
+          for (int j = 0; j < kHalfN; ++j)
+            if (!((rw[j >> 5] >> (j & 31)) & 1u)) sv[j] = -INFINITY;
         }
+        mbar_arrive(bar(M_EMPTY + mst));
+        auto half_max = [&]() {
+          float m0 = sv[0], m1 = sv[1], m2 = sv[2], m3 = sv[3];
+#pragma unroll
+          for (int j = 4; j < kHalfN; j += 4) {
+            m0 = fmaxf(m0, sv[j]); m1 = fmaxf(m1, sv[j + 1]); m2 = fmaxf(m2, sv[j + 2]); m3 = fmaxf(m3, sv[j + 3]);
+          }
+          return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;  // c > 0; -inf when the row attends nothing here
+        };
+        // ---- reference maximum m_ref (shared by the row's two threads).  The first tile of a job sets it to
+        // the exact row maximum.  Every later tile is exponentiated against the m_ref it finds (no dependent
+        // max -> exp chain); only if a half row's exponentials sum past 2^15 (a P might leave fp16) does its
+        // thread ask for a raise, and then both threads rescale their half of O and redo the tile.
+        int round = 0;
+        float* xq = xchg + (gt & 1) * (4 * kRows);  // [round parity][half][row]
+        if (t == 0) {
+          xq[h * kRows + r] = half_max();
+          pair_sync(warp);
+          m_ref = fmaxf(xq[r], xq[kRows + r]);
+          round = 1;
+        }
+        if (tr) DEFT_TRACE(tr0 + 3);
+        uint32_t pk[kHalfN / 2];
+        float hsum;
+        bool redo;
+        do {
+          const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+          float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < kHalfN; j += 4) {
+            const float e0 = fast_exp2(fmaf(sv[j], c, -m_use)), e1 = fast_exp2(fmaf(sv[j + 1], c, -m_use));
+            const float e2 = fast_exp2(fmaf(sv[j + 2], c, -m_use)), e3 = fast_exp2(fmaf(sv[j + 3], c, -m_use));
+            ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
+            pk[j / 2] = pack_half2(e0, e1);
+            pk[j / 2 + 1] = pack_half2(e2, e3);
+          }
+          hsum = (ps0 + ps1) + (ps2 + ps3);
+          // every P >= 0, so a half-row sum below 2^15 proves that no P left fp16's range; a row that had seen
+          // nothing yet (m_ref = -inf) asks at its first live token.  (!(x < y) also catches NaN.)
+          const bool over = !(hsum < 32768.f) || (m_ref == -INFINITY && hsum > 0.f);
+          float* xr = xq + (round & 1) * (2 * kRows);
+          xr[h * kRows + r] = over ? half_max() : -INFINITY;
+          pair_sync(warp);
+          const float rq = fmaxf(xr[r], xr[kRows + r]);  // the row's request, seen alike by its two threads
+          ++round;
+          redo = __any_sync(0xffffffffu, rq > -INFINITY);  // alike in the two warps: they hold the same rows
+          if (redo) {
+            float alpha = 1.f;
+            if (rq > -INFINITY) {
+              alpha = fast_exp2(m_ref - rq);  // 0 when m_ref = -inf
+              m_ref = rq;
+              l_run *= alpha;
+            }
+            if (t > 0) {
+              // P V of the previous tile has landed in O (this tile's waits on my P): the issuer warp follows
+              // the PV_DONE phases and publishes how many tiles are complete
+              {
+                volatile uint32_t* pv_cnt = reinterpret_cast<volatile uint32_t*>(gbase + L::kPvCnt);
+                uint32_t spins = 0;
+                while (*pv_cnt < gt) {
+                  __nanosleep(64);
+                  if (++spins > (1u << 24)) __trap();
+                }
+              }
+              tc_fence_after();
+              float* ov = reinterpret_cast<float*>(pk);  // P is recomputed: its registers carry O meanwhile
+#pragma unroll 1
+              for (int cb = 0; cb < D / 64; ++cb) {
+                tmem_ld32(t_o + cb * 32, ov);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ov[j] *= alpha;
+                tmem_st32(t_o + cb * 32, ov);
+              }
+              tmem_wait_st();
+            }
+          }
+        } while (redo);
+        l_run += hsum;
+        tmem_st32(t_s, reinterpret_cast<const float*>(pk));  // P_a over columns [0, 32) of S, P_b over [64, 96)
+        tmem_wait_st();
+        tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
+        mbar_arrive(bar(P_FULL + 2 * buf + h));
+        if (tr) DEFT_TRACE(tr0 + 4);
       }
+      g0 += u.n_tiles;
 
       // ---- epilogue: partial = O / l as fp16, log-sum-exp in the natural-log domain
-      // (not O_FULL: a thread that is two of its phases behind would read the parity of an older phase)
-      mbar_wait(bar(O_DONE + s), j_cnt & 1);
+      float* xq = xchg + (g0 & 1) * (4 * kRows) + 2 * kRows;  // a slot no tile of this parity is using right now
+      xq[h * kRows + r] = l_run;
+      mbar_wait(bar(O_DONE), j_cnt & 1);
       ++j_cnt;
       tc_fence_after();
+      pair_sync(warp);
+      const float l_row = xq[r] + xq[kRows + r];
       if (ji == jobs.begin && tid == 0) DEFT_TRACE(kTrEpiBegin);
-      const bool live = qi < u.q_cnt[s];
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      const int64_t tile = (int64_t)(u.part_base[s] >> 5) * p.HKV + hkv;
+      const bool live = qi < n_q;
+      const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
+      const int64_t tile = (int64_t)(part_base >> 5) * p.HKV + hkv;
       uint4* dst = reinterpret_cast<uint4*>(p.po16) + tile * (CH * R) + r;  // [chunk][row] of 16 bytes
       {
-        float ov[D];  // the whole O row in one round trip to TMEM, then O(1) arrives as soon as it is in registers
+        float ov[D / 2];  // my half of the O row in one round trip to TMEM
 #pragma unroll
-        for (int cb = 0; cb < D / 32; ++cb) tmem_ld32_nowait(t_o + cb * 32, ov + cb * 32);
+        for (int cb = 0; cb < D / 64; ++cb) tmem_ld32_nowait(t_o + cb * 32, ov + cb * 32);
         tmem_wait_ld();
         tc_fence_before();  // my reads of O are ordered before the next job's first P V (accumulate = 0)
-        mbar_arrive(bar(O_EMPTY + s));
+        mbar_arrive(bar(O_EMPTY));
         if (dbg)
-          for (int j = 0; j < D; ++j) p.dbg[kRows * kTileN + r * D + j] = ov[j];
+          for (int j = 0; j < D / 2; ++j) p.dbg[kRows * kTileN + r * D + h * (D / 2) + j] = ov[j];
         if (live) {
 #pragma unroll
-          for (int c8 = 0; c8 < D / 8; ++c8) {
-            uint4 pk;
-            pk.x = pack_half2(ov[c8 * 8 + 0] * inv, ov[c8 * 8 + 1] * inv);
-            pk.y = pack_half2(ov[c8 * 8 + 2] * inv, ov[c8 * 8 + 3] * inv);
-            pk.z = pack_half2(ov[c8 * 8 + 4] * inv, ov[c8 * 8 + 5] * inv);
-            pk.w = pack_half2(ov[c8 * 8 + 6] * inv, ov[c8 * 8 + 7] * inv);
-            dst[c8 * R] = pk;
+          for (int c8 = 0; c8 < D / 16; ++c8) {
+            uint4 o4;
+            o4.x = pack_half2(ov[c8 * 8 + 0] * inv, ov[c8 * 8 + 1] * inv);
+            o4.y = pack_half2(ov[c8 * 8 + 2] * inv, ov[c8 * 8 + 3] * inv);
+            o4.z = pack_half2(ov[c8 * 8 + 4] * inv, ov[c8 * 8 + 5] * inv);
+            o4.w = pack_half2(ov[c8 * 8 + 6] * inv, ov[c8 * 8 + 7] * inv);
+            dst[(h * (D / 16) + c8) * R] = o4;
           }
         }
       }
-      if (live) p.plse16[tile * R + r] = l_run > 0.f ? (m_ref + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+      if (live && h == 0) p.plse16[tile * R + r] = l_row > 0.f ? (m_ref + log2f(l_row)) * 0.6931471805599453f : -INFINITY;
       if (ji == jobs.begin && tid == 0) DEFT_TRACE(kTrEpiEnd);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (tid == 0) DEFT_TRACE(kTrEnd);
-  if (warp == kMmaWarp0) tmem_dealloc(tmem, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 }
 
 template <int D, int G>
@@ -796,7 +839,7 @@ int launch_t(const AttnParams& p, cudaStream_t stream) {
   if (p.job_off != nullptr) {
     grid = p.n_ctas;
   } else {
-    const int64_t n_jobs = (int64_t)p.n_units * p.HKV;
+    const int64_t n_jobs = (int64_t)p.n_units * p.HKV * 2;
     grid = (int)(n_jobs < num_sms ? n_jobs : num_sms);
   }
   if (grid <= 0) return DEFT_OK;

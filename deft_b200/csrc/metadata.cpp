@@ -7,6 +7,7 @@
 // CSR plan of include/deft_b200.h -- into ONE packed buffer that the caller uploads with one copy.
 // No CUDA here: pure host code, re-entrant.
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <new>
@@ -326,34 +327,58 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
 
     const i32 heads = hkv > 0 ? hkv : 1;
     const i32 ctas = n_ctas > 0 ? n_ctas : 148;
-    auto unit_cost = [](size_t n_tiles, bool pair) { return 0.8 + (double)n_tiles * (pair ? 1.0 : 0.85); };
-    // pieces of a chain for a given maximum piece length: (first tile, count), near-equal sizes
+    // one job = one SLOT of a unit on one kv-head (the kernel works one M = 128 accumulator per CTA).  Costs in
+    // tile steps (calibrated on B200): a tile whose 128 pages are consecutive arrives as TMA boxes, a tile of
+    // scattered pages is gathered row by row and is bound by that (~1.5x); the constant is a job's start-up
+    // + epilogue.
+    std::vector<double> tile_cost(tiles.size());
+    for (size_t t = 0; t < tiles.size(); ++t) {
+      bool runp = tiles[t].n_live == 128;
+      for (size_t kk = t * 128 + 1; kk < (t + 1) * 128 && runp; ++kk) runp = u_kv[kk] == u_kv[t * 128] + (i32)(kk - t * 128);
+      tile_cost[t] = runp ? 1.0 : 1.5;
+    }
+    const double kJobConst = 2.0;
+    // pieces of a chain for a given maximum piece cost: (first tile, count), near-equal costs
     std::vector<std::pair<size_t, size_t>> pcs;
-    auto pieces_of = [&](size_t n_tiles, size_t max_len) {
+    std::vector<double> pcs_cost;
+    auto pieces_of = [&](const Chain& c, double max_cost) {
       pcs.clear();
-      const size_t np = (n_tiles + max_len - 1) / max_len;
+      pcs_cost.clear();
+      double total = 0.0;
+      for (size_t t = 0; t < c.n_tiles; ++t) total += tile_cost[c.t0 + t];
+      const size_t np = std::max<size_t>(1, (size_t)std::ceil(total / max_cost - 1e-9));
       size_t t = 0;
-      for (size_t i = 0; i < np; ++i) {
-        const size_t len = n_tiles / np + (i < n_tiles % np ? 1 : 0);
-        pcs.emplace_back(t, len);
-        t += len;
+      double done = 0.0;
+      for (size_t i = 0; i < np && t < c.n_tiles; ++i) {
+        const double goal = total * (double)(i + 1) / (double)np;
+        const size_t t_begin = t;
+        double acc = 0.0;
+        while (t < c.n_tiles && (t == t_begin || i + 1 == np || done + acc + 0.5 * tile_cost[c.t0 + t] <= goal)) {
+          acc += tile_cost[c.t0 + t];
+          ++t;
+        }
+        done += acc;
+        pcs.emplace_back(t_begin, t - t_begin);
+        pcs_cost.push_back(acc);
       }
     };
-    size_t longest = 1;
-    for (const Chain& c : chains) longest = std::max(longest, c.n_tiles);
-    std::vector<size_t> cand;
-    for (size_t l : {(size_t)1, (size_t)2, (size_t)3, (size_t)4, (size_t)5, (size_t)6, (size_t)8, (size_t)10,
-                     (size_t)12, (size_t)16, (size_t)20, (size_t)24, (size_t)32, (size_t)48, (size_t)64,
-                     (size_t)96, (size_t)128, (size_t)192, (size_t)256})
+    double longest = 1.0;
+    for (const Chain& c : chains) {
+      double total = 0.0;
+      for (size_t t = 0; t < c.n_tiles; ++t) total += tile_cost[c.t0 + t];
+      longest = std::max(longest, total);
+    }
+    std::vector<double> cand;
+    for (double l : {1.5, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 10.0, 12.0, 16.0, 20.0, 24.0, 32.0, 48.0, 64.0, 96.0, 128.0, 192.0, 256.0})
       if (l < longest) cand.push_back(l);
     cand.push_back(longest);
-    auto makespan = [&](size_t max_len) {
+    auto makespan = [&](double max_cost) {
       std::vector<double> costs;
       for (const Chain& c : chains) {
-        pieces_of(c.n_tiles, max_len);
+        pieces_of(c, max_cost);
         const bool pair = slot_cnt(2 * c.pair + 1) > 0;
-        for (const auto& pc : pcs)
-          for (i32 h = 0; h < heads; ++h) costs.push_back(unit_cost(pc.second, pair));
+        for (double pc : pcs_cost)
+          for (i32 h = 0; h < heads * (pair ? 2 : 1); ++h) costs.push_back(kJobConst + pc);
       }
       std::sort(costs.begin(), costs.end(), [](double a, double b) { return a > b; });
       std::priority_queue<double, std::vector<double>, std::greater<double>> bins;
@@ -367,9 +392,9 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
       return worst;
     };
-    size_t best_len = cand.back();
+    double best_len = cand.back();
     double best = -1.0;
-    for (size_t l : cand) {  // ascending: ties go to the longer piece (fewer partials)
+    for (double l : cand) {  // ascending: ties go to the longer piece (fewer partials)
       const double m = makespan(l);
       if (best < 0.0 || m <= best + 1e-9) { best = m; best_len = l; }
     }
@@ -377,8 +402,11 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     std::vector<double> ucost;
     std::vector<std::vector<i32>> rows_of((size_t)query_num);  // CSR: partial rows of every query
     for (const Chain& c : chains) {
-      pieces_of(c.n_tiles, best_len);
-      for (const auto& pc : pcs) {
+      pieces_of(c, best_len);
+      const std::vector<std::pair<size_t, size_t>> chain_pcs = pcs;
+      const std::vector<double> chain_cost = pcs_cost;
+      for (size_t pi = 0; pi < chain_pcs.size(); ++pi) {
+        const auto& pc = chain_pcs[pi];
         const size_t ta = c.t0 + pc.first, tb = ta + pc.second;  // tiles [ta, tb)
         // which slots of the pair have attending rows in this piece, and which rows
         i32 live_slots[2];
@@ -434,7 +462,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         }
         if (dense[0] && (n_live_slots < 2 || dense[1])) u_mask.resize((size_t)mask_base);  // nothing reads them
         units.push_back(u);
-        ucost.push_back(unit_cost(pc.second, n_live_slots == 2));
+        ucost.push_back(kJobConst + chain_cost[pi]);
       }
     }
     for (i32 qv = 0; qv < query_num; ++qv) {
@@ -442,7 +470,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       u_csr.off[(size_t)qv + 1] = u_csr.off[(size_t)qv] + (i32)rows_of[(size_t)qv].size();
       u_csr.rows.insert(u_csr.rows.end(), rows_of[(size_t)qv].begin(), rows_of[(size_t)qv].end());
     }
-    // (unit, kv-head) jobs -> CTAs, longest first onto the least loaded CTA
+    // (unit, kv-head, slot) jobs -> CTAs, longest first onto the least loaded CTA; job = ((unit * hkv + head) << 1) | slot
     if (hkv > 0) {
       std::vector<i32> order(units.size());
       for (size_t i = 0; i < order.size(); ++i) order[i] = (i32)i;
@@ -452,13 +480,15 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       for (i32 c = 0; c < ctas; ++c) bins.push({0.0, c});
       std::vector<std::vector<i32>> per((size_t)ctas);
       for (i32 ui : order)
-        for (i32 h = 0; h < hkv; ++h) {
-          Bin b = bins.top();
-          bins.pop();
-          per[(size_t)b.second].push_back(ui * hkv + h);
-          b.first += ucost[(size_t)ui];
-          bins.push(b);
-        }
+        for (i32 h = 0; h < hkv; ++h)
+          for (i32 k = 0; k < 2; ++k) {
+            if (units[(size_t)ui].q_cnt[k] <= 0) continue;
+            Bin b = bins.top();
+            bins.pop();
+            per[(size_t)b.second].push_back(((ui * hkv + h) << 1) | k);
+            b.first += ucost[(size_t)ui];
+            bins.push(b);
+          }
       u_job_off.push_back(0);
       for (i32 c = 0; c < ctas; ++c) {
         u_jobs.insert(u_jobs.end(), per[(size_t)c].begin(), per[(size_t)c].end());

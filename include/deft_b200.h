@@ -138,7 +138,8 @@ typedef struct {
   const uint32_t* u_mask;     /* 128 words per (tile, slot): bit r = row r of the slot attends */
   const int32_t* u_q;         /* query id per (slot, row) */
   const int32_t* u_job_off;   /* n_ctas+1: CTA c runs jobs u_jobs[u_job_off[c]:u_job_off[c+1]] */
-  const int32_t* u_jobs;      /* job = unit * HKV + kv_head, balanced over CTAs by the builder */
+  const int32_t* u_jobs;      /* job = ((unit * HKV + kv_head) << 1) | slot of the pair: one CTA works one slot
+                                 of a unit on one kv-head; balanced over CTAs by the builder */
   int32_t n_unit_slots;       /* partial tiles per kv-head */
   int32_t n_ctas;             /* CTAs the job lists were balanced for */
   int32_t hkv;                /* kv-head count the job lists were built for */

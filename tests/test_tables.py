@@ -101,7 +101,8 @@ def check_unit_plan(t, scalars, tree, hkv, n_ctas):
     job_off, jobs = t["u_job_off"], t["u_jobs"]
     assert int(scalars[7]) == n_ctas and len(job_off) == n_ctas + 1 and job_off[0] == 0 and job_off[-1] == len(jobs)
     assert np.all(np.diff(job_off) >= 0)
-    assert sorted(jobs.tolist()) == list(range(len(units) * hkv)), "every (unit, kv-head) job exactly once"
+    want_jobs = [((ui * hkv + h) << 1) | k for ui, u in enumerate(units) for h in range(hkv) for k in range(2) if u["q_cnt"][k] > 0]
+    assert sorted(jobs.tolist()) == sorted(want_jobs), "every (unit, kv-head, live slot) job exactly once"
 
 
 @pytest.mark.parametrize("name", list(SCENARIOS))
@@ -145,7 +146,8 @@ def test_unit_plan_cfg2_shape(golden_dir):
     assert len(root) > 0 and np.all(root["mask_off"] == -1), "prompt-only pieces: dense, no mask reads"
     assert np.all(root["page0"] == root["kv_off"]) and np.all(units["q_id0"][:, 0] >= 0), "prompt pages and leaf ids are runs"
     loads = np.diff(t["u_job_off"])
-    assert loads.max() == 1 and loads.sum() == len(units) * 8, "cfg2 fits one job per CTA: no Q reload between jobs"
+    n_jobs = 8 * int((units["q_cnt"] > 0).sum())           # one job per (unit, kv-head, live slot)
+    assert loads.max() == 1 and loads.sum() == n_jobs, "cfg2 fits one job per CTA: no Q reload between jobs"
     # far fewer partial rows than the reference's 2246 (one per (sub-block, query))
     assert len(t["u_csr_rows"]) < 1400
 

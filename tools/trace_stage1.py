@@ -18,16 +18,17 @@ import deft_b200
 from deft_b200 import TreeMetadata, _lib
 from deft_b200.workloads import build_tree
 
-NAMES = {0: "start", 1: "q_ids", 2: "q0_issued", 3: "q1_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
-         8: "epi_end", 9: "end", 10: "t1.ld_done", 11: "t1.max_raise_done", 12: "t1a.exp_done", 13: "t1a.st_done",
-         14: "t1.mma_pva_issued", 15: "t1.mma_pvb_issued"}
-TILE = ["k_issued", "mma_k_full", "sm_s_full", "sm_max", "sm_pa_arrive", "mma_pa_full", "v_issued", "sm_pb_arrive"]
+NAMES = {0: "start", 1: "q_ids", 2: "q_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
+         8: "epi_end", 9: "end"}
+TILE = ["k_issued", "mma_k_full(S issued)", "sm_s_full", "sm_ready", "sm_p_arrive", "mma_pa_full", "v_issued", "k_landed"]
 
 
 def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
     show = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     dev = torch.device("cuda:0")
+    if os.environ.get("DEFT_NO_GATHER4"):
+        _lib.lib.deft_b200_set_gather4(0)
     tree = build_tree(wl, layers=2, device=dev)
     kvp = tree.token_to_kv_pool
     for l in range(2):
@@ -70,7 +71,7 @@ def main():
                     ev.append((v, f"t{tile}.{TILE[k]}"))
                 v = int(t[c, 64 + 8 * tile + k])
                 if v >= 0:
-                    ev.append((v, f"t{tile}.slot1.{TILE[k]}"))
+                    ev.append((v, f"t{tile}.halfb.{TILE[k]}" if k not in (0, 1) else f"t{tile}.{('k_loop_top', 'k_empty_seen')[k]}"))
         for v, name in sorted(ev):
             print(f"   {v / ghz / 1e3:8.2f} us  {name}")
 
