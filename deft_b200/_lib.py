@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdeft_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 T_NAMES = ["node_q", "node_kv", "node_q_len", "node_kv_len", "node_q_offset", "node_kv_offset",
            "block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv", "block_lens",
            "flat_items", "flat_groups", "flat_csr_off", "flat_csr_rows",
@@ -22,6 +22,7 @@ STAGE1_AUTO, STAGE1_FMA, STAGE1_UMMA = 0, 1, 2
 ITEM_BYTES = 24
 GROUP_BYTES = 24
 UNIT_BYTES = 80
+JOB_BYTES = 96
 N_SCALARS = 8
 
 

@@ -44,9 +44,11 @@ namespace {
 constexpr int kTileN = 128;  // tokens per KV tile (= the reference's BLOCK_LEN)
 constexpr int kHalfN = 64;   // ... worked by the tensor pipe and the softmax warps in two halves
 constexpr int kRows = 128;   // UMMA M
-constexpr int kThreads = 512;  // 16 warps: 4 register-budget groups of 4 (setmaxnreg works per warpgroup)
-constexpr int kMmaWarp = 8, kQWarp = 9, kMaskWarp = 10, kPvWarp = 11, kKvWarp0 = 12;  // 12, 13: K producers; 14, 15: V
-constexpr int kSoftmaxRegs = 160, kProducerRegs = 96;  // 256 * 160 + 256 * 96 = 64 K registers
+constexpr int kThreads = 640;  // 20 warps: 5 register-budget groups of 4 (setmaxnreg works per warpgroup)
+constexpr int kMmaWarp = 8, kQWarp = 9, kMaskWarp = 10, kPvWarp = 11, kKvWarp0 = 12;  // 12-15: K producers; 16-19: V
+// a gathering warp is bound by its copies in flight (~8 x 512 bytes against the memory latency), so scattered
+// pages want many producer warps: four per operand, 32 rows each
+constexpr int kSoftmaxRegs = 152, kProducerRegs = 56;  // 256 * 152 + 384 * 56 <= 64 K registers (launch: 96 each)
 constexpr int kKStages = 3, kVStages = 2, kMaskStages = 2;
 constexpr int kSBufs = 3;  // S tiles in TMEM: O [0, 128) + 3 x 128 columns = all 512
 
@@ -299,25 +301,43 @@ struct Layout {
 // The jobs of one CTA.  job = ((unit * HKV + kv-head) << 1) | slot of the unit's pair: one CTA works ONE
 // slot (<= 32 queries x G heads = one M = 128 accumulator) over the unit's chain of KV tiles; the two
 // slots of a pair are separate jobs, on different SMs when the balance allows (their K/V tile reads meet
-// in L2).  Either an explicit host-balanced list, or jobs c, c + grid, ...
+// in L2).  Either the host-balanced record lists (deft_job_t: the CTA's first record sits at [blockIdx.x]
+// and carries its unit, so a CTA starts from ONE load), or jobs c, c + grid, ... over the unit table.
 struct Jobs {
-  const int32_t* list;
-  int begin, end, stride;
+  const deft_job_t* recs;  // null: strided over the unit table
+  int n, next;
   __device__ __forceinline__ Jobs(const AttnParams& p) {
     if (p.job_off != nullptr) {
-      list = p.jobs;
-      begin = (int)blockIdx.x < p.n_ctas ? p.job_off[blockIdx.x] : 0;
-      end = (int)blockIdx.x < p.n_ctas ? p.job_off[blockIdx.x + 1] : 0;
-      stride = 1;
+      recs = p.jobs;
+      n = next = 0;
+      if ((int)blockIdx.x < p.n_ctas) {
+        const int4 hdr = *reinterpret_cast<const int4*>(recs + blockIdx.x);
+        n = hdr.x >= 0 ? hdr.y : 0;
+        next = hdr.z;
+      }
     } else {
-      list = nullptr;
+      recs = nullptr;
       const int n_units = p.n_units_dev ? *p.n_units_dev : p.n_units;
-      begin = blockIdx.x;
-      end = n_units * p.HKV * 2;
-      stride = gridDim.x;
+      const int total = n_units * p.HKV * 2;
+      n = (int)blockIdx.x < total ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      next = 0;
     }
   }
-  __device__ __forceinline__ int get(int i) const { return list ? list[i] : i; }
+  // i-th job of this CTA -> (unit, kv-head, slot); a pair's second slot may be empty (then the job is nobody's)
+  __device__ __forceinline__ bool get(const AttnParams& p, int i, deft_unit_t& u, int& hkv, int& k) const {
+    int job;
+    if (recs != nullptr) {
+      const deft_job_t* r = i == 0 ? recs + blockIdx.x : recs + next + (i - 1);
+      job = r->job;
+      u = r->unit;
+    } else {
+      job = (int)blockIdx.x + i * (int)gridDim.x;
+      u = p.units[(job >> 1) / p.HKV];
+    }
+    k = job & 1;
+    hkv = (job >> 1) % p.HKV;
+    return (k == 0 ? u.q_cnt[0] : u.q_cnt[1]) > 0;
+  }
 };
 
 // pair of warps w, w + 4 (the two threads of a row sit in them): named barrier 1 + (w & 3)
@@ -350,8 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   }
   if (p.plan_fresh) griddep_wait();  // the plan itself comes from the preceding (plan) kernel
   if (tid == 0) {
-    for (int s = 0; s < kKStages; ++s) { mbar_init(bar(K_FULL + s), 64); mbar_init(bar(K_EMPTY + s), 1); }
-    for (int s = 0; s < kVStages; ++s) { mbar_init(bar(V_FULL + s), 64); mbar_init(bar(V_EMPTY + s), 1); }
+    for (int s = 0; s < kKStages; ++s) { mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 1); }
+    for (int s = 0; s < kVStages; ++s) { mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 1); }
     mbar_init(bar(Q_FULL), 32); mbar_init(bar(Q_EMPTY), 1);
     for (int m = 0; m < kMaskStages; ++m) { mbar_init(bar(M_FULL + m), 32); mbar_init(bar(M_EMPTY + m), 256); }
     for (int b = 0; b < kSBufs; ++b) {
@@ -373,108 +393,87 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   // the tail of the preceding kernel; q, the KV pool and the partial workspace may still be in its hands.
   griddep_wait();
   if (tid == 0) DEFT_TRACE(kTrStart);
-  // job -> (unit, kv-head, slot); a pair's second slot may be empty (then the job is nobody's)
-  auto decode = [&](int job, deft_unit_t& u, int& hkv, int& k) -> bool {
-    k = job & 1;
-    hkv = (job >> 1) % p.HKV;
-    u = p.units[(job >> 1) / p.HKV];
-    return (k == 0 ? u.q_cnt[0] : u.q_cnt[1]) > 0;
-  };
   if (warp >= 8) {
-  reg_dealloc<kProducerRegs>();  // warps 8-15: two whole warpgroups give registers away
+  reg_dealloc<kProducerRegs>();  // warps 8-19: three whole warpgroups give registers away
   if (warp >= kKvWarp0) {
     // ============================== K / V producers ==============================
-    // warps 12, 13: K rows [0, 64) / [64, 128) of every tile; warps 14, 15: V likewise.  K and V run on
-    // rings of their own (K is released as soon as S is done, a tile earlier than V).
-    const int kv = (warp - kKvWarp0) >> 1, w = (warp - kKvWarp0) & 1;
+    // warps 12-15: K rows [32w, 32w + 32) of every tile; warps 16-19: V likewise.  K and V run on rings of their
+    // own (K is released as soon as S is done, a tile earlier than V).
+    const int kv = (warp - kKvWarp0) >> 2, w = (warp - kKvWarp0) & 3;
     const int stages = kv == 0 ? kKStages : kVStages;
     const int FULL = kv == 0 ? K_FULL : V_FULL, EMPTY = kv == 0 ? K_EMPTY : V_EMPTY;
+    const int row0 = w * 32;  // my 32 rows
     uint32_t cnt = 0;  // tiles produced
-    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+    for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k;
-      if (!decode(jobs.get(ji), u, hkv, k)) continue;
-      if (warp == kKvWarp0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrKUnit);
+      if (!jobs.get(p, ji, u, hkv, k)) continue;
+      if (warp == kKvWarp0 && lane == 0 && ji == 0) DEFT_TRACE(kTrKUnit);
       const bool known_run = u.page0 >= 0 && p.tma_kv != 0;  // the builder's shortcut: no index-table read at all
-      auto page_of = [&](int t, int row) -> int {  // page of token `row` of tile t (0 past the end)
+      auto page_of = [&](int t) -> int {  // page of my row of tile t (0 past the end)
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
-        if (known_run) return u.page0 + t * kTileN + row;
-        return t < u.n_tiles && row < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row) : 0;
+        if (known_run) return u.page0 + t * kTileN + row0 + lane;
+        return t < u.n_tiles && row0 + lane < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row0 + lane) : 0;
       };
-      int pg_next[2] = {page_of(0, w * 64 + lane), page_of(0, w * 64 + 32 + lane)};
+      int pg_next = page_of(0);
       for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
         const int st = cnt % stages;
         const uint32_t ph = ((cnt / stages) & 1) ^ 1;
-        const int pg[2] = {pg_next[0], pg_next[1]};
-        pg_next[0] = page_of(t + 1, w * 64 + lane);  // the next tile's page ids are in flight while this tile is issued
-        pg_next[1] = page_of(t + 1, w * 64 + 32 + lane);
-        const bool trp = kv == 0 && w == 0 && lane == 0 && ji == jobs.begin && t < 6;
+        const int pg = pg_next;
+        pg_next = page_of(t + 1);  // the next tile's page ids are in flight while this tile is issued
+        const bool trp = kv == 0 && w == 0 && lane == 0 && ji == 0 && t < 6;
         if (trp) DEFT_TRACE(64 + 8 * t + 0);
         mbar_wait<64>(bar(EMPTY + st), ph);
         if (trp) DEFT_TRACE(64 + 8 * t + 1);
         const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
         const uint32_t full = bar(FULL + st);
         // 32 consecutive pages of a full tile are ONE box of the pool's tensor map per 64-wide panel
-        bool run[2];
+        const int page0 = __shfl_sync(0xffffffffu, pg, 0);
+        const bool run = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg == page0 + lane);
+        if (run) {
+          if (lane == 0) {
+            mbar_arrive_expect_tx(full, 32 * D * 2);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int page0 = __shfl_sync(0xffffffffu, pg[hh], 0);
-          run[hh] = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg[hh] == page0 + lane);
-        }
-        const bool async_tx = p.tma_kv != 0 && (p.tma_gather != 0 || (run[0] && run[1]));
-        if (async_tx) {  // TMA only: one thread announces the warp's 64 rows, the copies complete them
-          if (lane == 0) mbar_arrive_expect_tx(full, 64 * D * 2);
-          else mbar_arrive(full);
-        }
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int row0 = w * 64 + hh * 32;  // my 32 rows of this pass
-          if (run[hh]) {
-            const int page0 = __shfl_sync(0xffffffffu, pg[hh], 0);
-            if (!async_tx && lane == 0) mbar_expect_tx(full, 32 * D * 2);  // (my arrival comes with the cp.async ones below)
-            if (lane == 0) {
-#pragma unroll
-              for (int pn = 0; pn < D / 64; ++pn)
-                tma_load_3d(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0);
-            }
-          } else if (p.tma_gather != 0) {
-            // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of these 32 with one gather4 per
-            // panel; rows past the tile's length name a row outside the map and arrive as zeros
-            constexpr int NP = D / 64;
-            const int g = lane / NP, pn = lane % NP;
-            const int my_row = row0 + lane < tlen ? pg[hh] * p.kv_row_ratio + hkv : p.kv_rows;
-            const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
-            const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
-            if (lane < 8 * NP)
-              tma_gather4(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
-                          r0, r1, r2, r3);
+            for (int pn = 0; pn < D / 64; ++pn)
+              tma_load_3d(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0);
           } else {
-            const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
-            constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
-#pragma unroll 4
-            for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
-              const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside these 32
-              const int ch = lane % CH;
-              const int64_t page = __shfl_sync(0xffffffffu, pg[hh], nl);
-              const bool ok = row0 + nl < tlen;
-              cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
-            }
+            mbar_arrive(full);
           }
-        }
-        if (!async_tx) {
-          // every lane arrives once: when all its cp.async have landed (none issued: immediately), and the
-          // TMA boxes of a mixed tile complete their bytes on the same barrier
+        } else if (p.tma_gather != 0) {
+          // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of my 32 with one gather4 per panel;
+          // rows past the tile's length name a row outside the map and arrive as zeros
+          constexpr int NP = D / 64;
+          const int g = lane / NP, pn = lane % NP;
+          const int my_row = row0 + lane < tlen ? pg * p.kv_row_ratio + hkv : p.kv_rows;
+          const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
+          const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
+          if (lane == 0) mbar_arrive_expect_tx(full, 32 * D * 2);
+          else mbar_arrive(full);
+          if (lane < 8 * NP)
+            tma_gather4(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
+                        r0, r1, r2, r3);
+        } else {
+          const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
+          constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
+#pragma unroll 4
+          for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
+            const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside my 32
+            const int ch = lane % CH;
+            const int64_t page = __shfl_sync(0xffffffffu, pg, nl);
+            const bool ok = row0 + nl < tlen;
+            cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
+          }
           cp_async_arrive(full);
         }
-        if (w == 0 && lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
+        if (w == 0 && lane == 0 && ji == 0) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
       }
     }
   } else if (warp == kQWarp) {
     // ============================== Q tile of the job's slot ==============================
     uint32_t q_cnt = 0;  // jobs
-    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+    for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k;
-      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      if (!jobs.get(p, ji, u, hkv, k)) continue;
       // row r = (query r / G, head r % G); rows past q_cnt*G are zero
       const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
       const int q_id0 = k == 0 ? u.q_id0[0] : u.q_id0[1];
@@ -483,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       const int64_t my_q = known_run ? (int64_t)q_id0 + lane : (lane < n_q ? load_index(p.u_q, p.u_q_bytes, q_off + lane) : 0);
       mbar_wait<64>(bar(Q_EMPTY), (q_cnt & 1) ^ 1);
       const uint32_t qs = base + L::kQ;
-      if (lane == 0 && ji == jobs.begin && my_q >= 0) DEFT_TRACE(kTrQIds);
+      if (lane == 0 && ji == 0 && my_q >= 0) DEFT_TRACE(kTrQIds);
       // consecutive query ids: the slot's G heads x 32 queries are ONE box of q's tensor map per panel
       // (rows past q_cnt then hold the next queries or zeros: finite, never stored)
       const int64_t q0 = __shfl_sync(0xffffffffu, my_q, 0);
@@ -510,17 +509,18 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
         cp_async_arrive(bar(Q_FULL));
       }
-      if (lane == 0 && ji == jobs.begin) DEFT_TRACE(kTrQ0Issued);
+      if (lane == 0 && ji == 0) DEFT_TRACE(kTrQ0Issued);
       ++q_cnt;
     }
   } else if (warp == kMaskWarp) {
     // ============================== mask words + dense flag per tile ==============================
     uint32_t m_cnt = 0;  // tiles
-    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+    for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k;
-      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      if (!jobs.get(p, ji, u, hkv, k)) continue;
       const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
       const int64_t mask_off = k == 0 ? u.mask_off[0] : u.mask_off[1];
+      if (mask_off < 0 && u.last_len == kTileN) continue;  // every tile dense: the softmax warps do not ask
       const uint32_t fullw = n_q >= 32 ? 0xffffffffu : ((1u << n_q) - 1u);
       for (int t = 0; t < u.n_tiles; ++t, ++m_cnt) {
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
         if (lane == 0) reinterpret_cast<uint32_t*>(gbase + L::kFlag)[st] = dense ? 1u : 0u;
         mbar_arrive(bar(M_FULL + st));
-        if (lane == 0 && ji == jobs.begin && t == 0) DEFT_TRACE(kTrMask0);
+        if (lane == 0 && ji == 0 && t == 0) DEFT_TRACE(kTrMask0);
       }
     }
   } else if (warp == kMmaWarp) {
@@ -559,11 +559,11 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     const bool leader = lane == 0;
     const uint64_t q_desc = smem_desc_sw128(base + L::kQ, 16, 1024);
     uint32_t k_cnt = 0, g0 = 0, j_cnt = 0;  // K tiles consumed (ring position), tiles of earlier jobs, jobs
-    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+    for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k;
-      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      if (!jobs.get(p, ji, u, hkv, k)) continue;
       const int n = u.n_tiles;
-      const bool tr0 = ji == jobs.begin && leader;
+      const bool tr0 = ji == 0 && leader;
       mbar_wait(bar(Q_FULL), j_cnt & 1);
       if (tr0) DEFT_TRACE(kTrMmaQFull);
       for (int t = 0; t < n; ++t) {
@@ -601,11 +601,11 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     const uint32_t o_tmem = tmem;
     uint32_t v_cnt = 0, g0 = 0, j_cnt = 0;
     volatile uint32_t* pv_cnt = reinterpret_cast<volatile uint32_t*>(gbase + L::kPvCnt);
-    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+    for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k;
-      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      if (!jobs.get(p, ji, u, hkv, k)) continue;
       const int n = u.n_tiles;
-      const bool tr0 = ji == jobs.begin && leader;
+      const bool tr0 = ji == 0 && leader;
       for (int t = 0; t < n; ++t) {
         const uint32_t gt = g0 + t, c = v_cnt + t;
         const int buf = gt % kSBufs, st = c % kVStages;
@@ -653,47 +653,56 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     const uint32_t t_o = t_lane + h * (D / 2);  // my half of the O row
     const float c = p.scale * 1.4426950408889634f;  // scores are handled in the log2 domain
     float* xchg = reinterpret_cast<float*>(gbase + L::kXchg);
-    uint32_t g0 = 0, j_cnt = 0;
+    uint32_t g0 = 0, j_cnt = 0, m_cnt = 0;  // tiles of earlier jobs, jobs, masked tiles
     bool first_job = blockIdx.x == 0;
 
-    for (int ji = jobs.begin; ji < jobs.end; ji += jobs.stride) {
+    for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k;
-      if (!decode(jobs.get(ji), u, hkv, k)) continue;
+      if (!jobs.get(p, ji, u, hkv, k)) continue;
       const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
       const int part_base = k == 0 ? u.part_base[0] : u.part_base[1];
       const bool dbg = p.dbg != nullptr && first_job;
       first_job = false;
       float m_ref = -INFINITY, l_run = 0.f;
 
+      const int64_t mask_off = k == 0 ? u.mask_off[0] : u.mask_off[1];
+      const bool job_dense = mask_off < 0 && u.last_len == kTileN;  // no tile of this job needs a mask
+      float sv[kHalfN];   // my half of the current S row (64 columns): out of TMEM once, kept in registers
+      bool have_next = false;
+
       for (int t = 0; t < u.n_tiles; ++t) {
         const uint32_t gt = g0 + t;
         const int buf = gt % kSBufs;
-        const int mst = gt % kMaskStages;
-        mbar_wait<32>(bar(M_FULL + mst), (gt / kMaskStages) & 1);
-        const uint32_t* ms = reinterpret_cast<const uint32_t*>(gbase + L::kMask) + mst * kTileN;
-        const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[mst] != 0;
-        const bool tr = ji == jobs.begin && (tid & 127) == 0 && t < 5;
+        const bool tr = ji == 0 && (tid & 127) == 0 && t < 5;
         const int tr0 = kTrTile0 + (h == 0 ? 0 : 48) + 8 * t;  // the second half's events sit 48 slots higher
-        mbar_wait<32>(bar(S_FULL + buf), (gt / kSBufs) & 1);
-        tc_fence_after();
-        if (tr) DEFT_TRACE(tr0 + 2);
-
-        // ---- my half of the S row (64 columns) comes out of TMEM once and stays in registers
         const uint32_t t_s = t_lane + 128 + buf * 128 + h * kHalfN;
-        float sv[kHalfN];
+        if (have_next) {  // my half of this tile's S has been on its way since the previous tile's P went out
+          tmem_wait_ld();
+        } else {
+          mbar_wait<32>(bar(S_FULL + buf), (gt / kSBufs) & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv + cb * 32);
-        tmem_wait_ld();
+          for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv + cb * 32);
+          tmem_wait_ld();
+        }
+        if (tr) DEFT_TRACE(tr0 + 2);
         if (dbg && t == 0)
           for (int j = 0; j < kHalfN; ++j) p.dbg[r * kTileN + h * kHalfN + j] = sv[j];
-        if (!dense) {  // masked-out tokens score -inf: my query's token bitmask comes from the mask warp
-          const uint2 rm = qi < 32 ? *reinterpret_cast<const uint2*>(ms + qi * 4 + h * 2) : make_uint2(0u, 0u);
-          const uint32_t rw[2] = {rm.x, rm.y};
+        if (!job_dense) {
+          const int mst = m_cnt % kMaskStages;
+          mbar_wait<32>(bar(M_FULL + mst), (m_cnt / kMaskStages) & 1);
+          ++m_cnt;
+          const uint32_t* ms = reinterpret_cast<const uint32_t*>(gbase + L::kMask) + mst * kTileN;
+          const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[mst] != 0;
+          if (!dense) {  // masked-out tokens score -inf: my query's token bitmask comes from the mask warp
+            const uint2 rm = qi < 32 ? *reinterpret_cast<const uint2*>(ms + qi * 4 + h * 2) : make_uint2(0u, 0u);
+            const uint32_t rw[2] = {rm.x, rm.y};
 #pragma unroll
-          for (int j = 0; j < kHalfN; ++j)
-            if (!((rw[j >> 5] >> (j & 31)) & 1u)) sv[j] = -INFINITY;
+            for (int j = 0; j < kHalfN; ++j)
+              if (!((rw[j >> 5] >> (j & 31)) & 1u)) sv[j] = -INFINITY;
+          }
+          mbar_arrive(bar(M_EMPTY + mst));
         }
-        mbar_arrive(bar(M_EMPTY + mst));
         auto half_max = [&]() {
           float m0 = sv[0], m1 = sv[1], m2 = sv[2], m3 = sv[3];
 #pragma unroll
@@ -772,6 +781,18 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         } while (redo);
         l_run += hsum;
         tmem_st32(t_s, reinterpret_cast<const float*>(pk));  // P_a over columns [0, 32) of S, P_b over [64, 96)
+        // S of the next tile is normally there already (the S issuer runs ahead): my half of it starts its way
+        // out of TMEM now, under the store of P and the hand-off (sv is dead from here to the wait at the loop top)
+        have_next = false;
+        if (t + 1 < u.n_tiles) {
+          const int nb = (gt + 1) % kSBufs;
+          if (mbar_test_wait(bar(S_FULL + nb), ((gt + 1) / kSBufs) & 1)) {
+            tc_fence_after();
+#pragma unroll
+            for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_lane + 128 + nb * 128 + h * kHalfN + cb * 32, sv + cb * 32);
+            have_next = true;
+          }
+        }
         tmem_wait_st();
         tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
         mbar_arrive(bar(P_FULL + 2 * buf + h));
@@ -787,7 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       tc_fence_after();
       pair_sync(warp);
       const float l_row = xq[r] + xq[kRows + r];
-      if (ji == jobs.begin && tid == 0) DEFT_TRACE(kTrEpiBegin);
+      if (ji == 0 && tid == 0) DEFT_TRACE(kTrEpiBegin);
       const bool live = qi < n_q;
       const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
       const int64_t tile = (int64_t)(part_base >> 5) * p.HKV + hkv;
@@ -814,7 +835,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
       }
       if (live && h == 0) p.plse16[tile * R + r] = l_row > 0.f ? (m_ref + log2f(l_row)) * 0.6931471805599453f : -INFINITY;
-      if (ji == jobs.begin && tid == 0) DEFT_TRACE(kTrEpiEnd);
+      if (ji == 0 && tid == 0) DEFT_TRACE(kTrEpiEnd);
     }
   }
   tc_fence_before();

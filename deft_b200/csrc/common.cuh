@@ -30,6 +30,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 static_assert(sizeof(deft_unit_t) == 80, "deft_unit_t is part of the ABI: 80 bytes");
+static_assert(sizeof(deft_job_t) == 96, "deft_job_t is part of the ABI: 96 bytes");
 constexpr int kMaxGroupQ = 32;     // queries per group (reference max_q_len / BLOCK_M, tree_cache.py:623)
 constexpr int kNodeSplit = 256;    // tokens per item when long Node entries are split on the device
 
@@ -80,7 +81,7 @@ struct AttnParams {
   const int32_t* u_csr_off;
   const int32_t* u_csr_rows;
   const int32_t* job_off;  // per-CTA job lists (host-balanced), or null: CTA c runs jobs c, c+grid, ...
-  const int32_t* jobs;
+  const deft_job_t* jobs;  // job records (first job of CTA c at [c], see deft_job_t)
   int32_t n_ctas;          // CTAs the job lists cover (grid size), 0 when job_off is null
   // tile partials: po16 [slot tile][D/8][32*G rows][8] fp16, plse16 [slot tile][32*G] fp32,
   // slot tile = (part_base / 32) * HKV + kv_head

@@ -294,7 +294,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   // and the (unit, kv-head) -> CTA assignment come from a longest-first balance over n_ctas CTAs with
   // the cost model below (tile steps; calibrated on B200).
   std::vector<deft_unit_t> units;
-  std::vector<i32> u_q, u_job_off, u_jobs;
+  std::vector<i32> u_q, u_job_off;
+  std::vector<deft_job_t> u_jobs;
   std::vector<uint32_t> u_mask;
   Csr u_csr;
   u_csr.off.assign((size_t)query_num + 1, 0);
@@ -489,10 +490,25 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
             b.first += ucost[(size_t)ui];
             bins.push(b);
           }
+      // records [0, ctas): every CTA's first job; the others follow, consecutive per CTA
+      auto record = [&](i32 job) {
+        deft_job_t r{};
+        r.job = job;
+        if (job >= 0) r.unit = units[(size_t)((job >> 1) / hkv)];
+        return r;
+      };
+      u_jobs.resize((size_t)ctas);
       u_job_off.push_back(0);
+      i32 total = 0;
       for (i32 c = 0; c < ctas; ++c) {
-        u_jobs.insert(u_jobs.end(), per[(size_t)c].begin(), per[(size_t)c].end());
-        u_job_off.push_back((i32)u_jobs.size());
+        const std::vector<i32>& mine = per[(size_t)c];
+        deft_job_t first = record(mine.empty() ? -1 : mine[0]);
+        first.n_jobs = (i32)mine.size();
+        first.next = (i32)u_jobs.size();
+        u_jobs[(size_t)c] = first;
+        for (size_t i = 1; i < mine.size(); ++i) u_jobs.push_back(record(mine[i]));
+        total += (i32)mine.size();
+        u_job_off.push_back(total);
       }
     }
   }
@@ -517,7 +533,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       {n_csr.off.data(), n_csr.off.size(), 4}, {n_csr.rows.data(), n_csr.rows.size(), 4},
       {units.data(), units.size(), sizeof(deft_unit_t)}, {u_csr.off.data(), u_csr.off.size(), 4},
       {u_csr.rows.data(), u_csr.rows.size(), 4}, {u_kv.data(), u_kv.size(), 4}, {u_mask.data(), u_mask.size(), 4},
-      {u_q.data(), u_q.size(), 4}, {u_job_off.data(), u_job_off.size(), 4}, {u_jobs.data(), u_jobs.size(), 4},
+      {u_q.data(), u_q.size(), 4}, {u_job_off.data(), u_job_off.size(), 4}, {u_jobs.data(), u_jobs.size(), sizeof(deft_job_t)},
   };
   size_t off = 0;
   for (int i = 0; i < DEFT_T_COUNT; ++i) {

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DEFT_B200_ABI_VERSION 2
+#define DEFT_B200_ABI_VERSION 3
 
 enum {
   DEFT_OK = 0,
@@ -120,6 +120,18 @@ typedef struct {
   int32_t pad;
 } deft_unit_t;              /* 80 bytes */
 
+/* One entry of the per-CTA job lists of the unit plan.  A job is ONE slot of a unit on one kv-head:
+ * job = ((unit * HKV + kv_head) << 1) | slot.  The record carries a copy of its unit so that a CTA
+ * starts from one load.  Records [0, n_ctas) are the FIRST job of every CTA (job < 0: none) with, in
+ * n_jobs / next, how many jobs the CTA has and where its further records start (consecutive). */
+typedef struct {
+  int32_t job;
+  int32_t n_jobs;  /* first record of a CTA only: jobs of this CTA (>= 1 when job >= 0) */
+  int32_t next;    /* first record of a CTA only: index of its second record */
+  int32_t pad;
+  deft_unit_t unit;
+} deft_job_t;               /* 96 bytes */
+
 typedef struct {
   /* (1) item/group plan over the reference tables */
   const deft_item_t* items;   /* [dev] */
@@ -137,9 +149,8 @@ typedef struct {
   const int32_t* u_kv;        /* page id per token slot, tiles of 128 */
   const uint32_t* u_mask;     /* 128 words per (tile, slot): bit r = row r of the slot attends */
   const int32_t* u_q;         /* query id per (slot, row) */
-  const int32_t* u_job_off;   /* n_ctas+1: CTA c runs jobs u_jobs[u_job_off[c]:u_job_off[c+1]] */
-  const int32_t* u_jobs;      /* job = ((unit * HKV + kv_head) << 1) | slot of the pair: one CTA works one slot
-                                 of a unit on one kv-head; balanced over CTAs by the builder */
+  const int32_t* u_job_off;   /* n_ctas+1: CTA c has u_job_off[c+1] - u_job_off[c] jobs (u_jobs carries the lists) */
+  const deft_job_t* u_jobs;   /* job records, balanced over CTAs by the builder (see deft_job_t) */
   int32_t n_unit_slots;       /* partial tiles per kv-head */
   int32_t n_ctas;             /* CTAs the job lists were balanced for */
   int32_t hkv;                /* kv-head count the job lists were built for */

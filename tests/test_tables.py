@@ -18,6 +18,7 @@ GROUP = np.dtype([("mask_off", "<i8"), ("q_off", "<i4"), ("q_cnt", "<i4"), ("par
 UNIT = np.dtype([("kv_off", "<i8"), ("mask_off", "<i8", (2,)), ("kv_tile_stride", "<i4"), ("mask_tile_stride", "<i4"),
                  ("n_tiles", "<i4"), ("last_len", "<i4"), ("q_off", "<i4", (2,)), ("q_cnt", "<i4", (2,)),
                  ("part_base", "<i4", (2,)), ("page0", "<i4"), ("q_id0", "<i4", (2,)), ("pad", "<i4")])
+JOB = np.dtype([("job", "<i4"), ("n_jobs", "<i4"), ("next", "<i4"), ("pad", "<i4"), ("unit", UNIT)])
 
 
 def unpack(data, directory):
@@ -25,7 +26,8 @@ def unpack(data, directory):
     for i, name in enumerate(_lib.T_NAMES):
         off, cnt = int(directory[i, 0]), int(directory[i, 1])
         dt = np.dtype("<i8") if i < 12 else (ITEM if name.endswith("items") else GROUP if name.endswith("groups")
-                                             else UNIT if name == "u_units" else np.dtype("<u4") if name == "u_mask"
+                                             else UNIT if name == "u_units" else JOB if name == "u_jobs"
+                                             else np.dtype("<u4") if name == "u_mask"
                                              else np.dtype("<i4"))
         out[name] = np.frombuffer(data, dtype=dt, count=cnt, offset=off)
     return out
@@ -42,7 +44,7 @@ def load(golden_dir, name):
 
 
 def test_struct_sizes():
-    assert ITEM.itemsize == _lib.ITEM_BYTES and GROUP.itemsize == _lib.GROUP_BYTES and UNIT.itemsize == _lib.UNIT_BYTES
+    assert ITEM.itemsize == _lib.ITEM_BYTES and GROUP.itemsize == _lib.GROUP_BYTES and UNIT.itemsize == _lib.UNIT_BYTES and JOB.itemsize == _lib.JOB_BYTES
 
 
 def check_unit_plan(t, scalars, tree, hkv, n_ctas):
@@ -99,10 +101,20 @@ def check_unit_plan(t, scalars, tree, hkv, n_ctas):
         mine = rows[off[q]: off[q + 1]]
         assert len(mine) >= 1 and np.all(np.diff(mine) > 0) and all(row_to_q[int(r)] == q for r in mine)
     job_off, jobs = t["u_job_off"], t["u_jobs"]
-    assert int(scalars[7]) == n_ctas and len(job_off) == n_ctas + 1 and job_off[0] == 0 and job_off[-1] == len(jobs)
-    assert np.all(np.diff(job_off) >= 0)
+    assert int(scalars[7]) == n_ctas and len(job_off) == n_ctas + 1 and job_off[0] == 0 and np.all(np.diff(job_off) >= 0)
+    # records [0, n_ctas): every CTA's first job (with its job count and where its other records start)
+    listed = []
+    for c in range(n_ctas):
+        first = jobs[c]
+        n = int(job_off[c + 1] - job_off[c])
+        assert (first["job"] >= 0) == (n > 0) and int(first["n_jobs"]) == n
+        mine = [first] + [jobs[int(first["next"]) + i] for i in range(n - 1)] if n else []
+        for r in mine:
+            listed.append(int(r["job"]))
+            assert r["unit"] == units[(int(r["job"]) >> 1) // hkv], "the record carries a copy of its unit"
+    assert len(jobs) == n_ctas + sum(max(0, int(d) - 1) for d in np.diff(job_off))
     want_jobs = [((ui * hkv + h) << 1) | k for ui, u in enumerate(units) for h in range(hkv) for k in range(2) if u["q_cnt"][k] > 0]
-    assert sorted(jobs.tolist()) == sorted(want_jobs), "every (unit, kv-head, live slot) job exactly once"
+    assert sorted(listed) == sorted(want_jobs), "every (unit, kv-head, live slot) job exactly once"
 
 
 @pytest.mark.parametrize("name", list(SCENARIOS))

@@ -71,7 +71,7 @@ def main():
                     ev.append((v, f"t{tile}.{TILE[k]}"))
                 v = int(t[c, 64 + 8 * tile + k])
                 if v >= 0:
-                    ev.append((v, f"t{tile}.halfb.{TILE[k]}" if k not in (0, 1) else f"t{tile}.{('k_loop_top', 'k_empty_seen')[k]}"))
+                    ev.append((v, f"t{tile}.halfb.{TILE[k]}" if k not in (0, 1, 5, 6) else f"t{tile}.{({0: 'k_loop_top', 1: 'k_empty_seen', 5: 'k_run_known', 6: 'k_pass0_issued'})[k]}"))
         for v, name in sorted(ev):
             print(f"   {v / ghz / 1e3:8.2f} us  {name}")
 
