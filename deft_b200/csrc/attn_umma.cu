@@ -90,7 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (kSleepNs > 0) __nanosleep(kSleepNs);
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 21)) __trap();
   }
 }
 // arrives on `bar` when all cp.async of this thread issued so far have landed (counts as one arrival)
@@ -345,6 +345,17 @@ __device__ __forceinline__ void pair_sync(int warp) {
   asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
 }
 
+// ... and the same barrier OR-reducing a predicate over the 64 threads
+__device__ __forceinline__ bool pair_sync_or(int warp, bool pred) {
+  uint32_t out;
+  asm volatile(
+      "{ .reg .pred p, q; setp.ne.b32 q, %2, 0; barrier.cta.red.or.pred p, %1, 64, q; selp.u32 %0, 1, 0, p; }"
+      : "=r"(out)
+      : "r"(1 + (warp & 3)), "r"((uint32_t)pred)
+      : "memory");
+  return out != 0;
+}
+
 template <int D, int G>
 __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_constant__ AttnParams p) {
   using L = Layout<D>;
@@ -369,6 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     if (p.tma_q) prefetch_tensormap(&p.tmap_q);
   }
   if (p.plan_fresh) griddep_wait();  // the plan itself comes from the preceding (plan) kernel
+  const Jobs jobs(p);  // (its load is in flight under the barrier set-up and the TMEM allocation below)
   if (tid == 0) {
     for (int s = 0; s < kKStages; ++s) { mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 1); }
     for (int s = 0; s < kVStages; ++s) { mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 1); }
@@ -388,7 +400,6 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gbase + L::kTmemSlot);
 
-  const Jobs jobs(p);
   // Programmatic dependent launch: everything up to here (barrier init, TMEM allocation, job list) overlapped
   // the tail of the preceding kernel; q, the KV pool and the partial workspace may still be in its hands.
   griddep_wait();
@@ -727,6 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         uint32_t pk[kHalfN / 2];
         float hsum;
         bool redo;
+        int n_redo = 0;
         do {
           const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
           float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
@@ -742,12 +754,25 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           // every P >= 0, so a half-row sum below 2^15 proves that no P left fp16's range; a row that had seen
           // nothing yet (m_ref = -inf) asks at its first live token.  (!(x < y) also catches NaN.)
           const bool over = !(hsum < 32768.f) || (m_ref == -INFINITY && hsum > 0.f);
-          float* xr = xq + (round & 1) * (2 * kRows);
-          xr[h * kRows + r] = over ? half_max() : -INFINITY;
-          pair_sync(warp);
-          const float rq = fmaxf(xr[r], xr[kRows + r]);  // the row's request, seen alike by its two threads
-          ++round;
-          redo = __any_sync(0xffffffffu, rq > -INFINITY);  // alike in the two warps: they hold the same rows
+          // the row pairs' two warps learn whether anybody asked (the common answer is no)
+          float rq = -INFINITY;
+          if (!(p.experiment & 1)) {
+            redo = pair_sync_or(warp, over);  // one barrier with an OR reduction; shared memory only on a request
+            if (redo) {
+              float* xr = xq + (round & 1) * (2 * kRows);
+              xr[h * kRows + r] = over ? half_max() : -INFINITY;
+              pair_sync(warp);
+              rq = fmaxf(xr[r], xr[kRows + r]);  // the row's request, seen alike by its two threads
+              ++round;
+            }
+          } else {
+            float* xr = xq + (round & 1) * (2 * kRows);
+            xr[h * kRows + r] = over ? half_max() : -INFINITY;
+            pair_sync(warp);
+            rq = fmaxf(xr[r], xr[kRows + r]);  // the row's request, seen alike by its two threads
+            ++round;
+            redo = __any_sync(0xffffffffu, rq > -INFINITY);  // alike in the two warps: they hold the same rows
+          }
           if (redo) {
             float alpha = 1.f;
             if (rq > -INFINITY) {
@@ -763,7 +788,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
                 uint32_t spins = 0;
                 while (*pv_cnt < gt) {
                   __nanosleep(64);
-                  if (++spins > (1u << 24)) __trap();
+                  if (++spins > (1u << 20)) __trap();
                 }
               }
               tc_fence_after();
@@ -778,6 +803,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
               tmem_wait_st();
             }
           }
+          if (redo && ++n_redo > 4) __trap();  // a raise settles in one more pass: anything else is a bug, not a hang
         } while (redo);
         l_run += hsum;
         tmem_st32(t_s, reinterpret_cast<const float*>(pk));  // P_a over columns [0, 32) of S, P_b over [64, 96)
@@ -839,9 +865,66 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     }
   }
   tc_fence_before();
+  if (p.fuse_merge) __threadfence();  // my partial stores are visible device-wide before this CTA reports in
   __syncthreads();
   if (tid == 0) DEFT_TRACE(kTrEnd);
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
+
+  // ---- fused stage 2.  The grid is one CTA per SM (all co-resident), so it can wait for itself: every CTA
+  // reports in, waits until all have, and then the CTAs share the merge of the partials -- the log-sum-exp
+  // combine of tree_attention.py:297-546 -- without a second launch.  The last CTA out re-arms the counters.
+  // The counter word is self-arming: {epoch of this call : 32, CTAs out : 16, CTAs in : 16}.  A CTA that finds
+  // another epoch in it (a workspace never used, or overwritten since) starts the count itself, so nothing has to
+  // be zeroed; the last CTA out puts the count back to 0 for a replay of the same launch (CUDA graphs).
+  if (p.fuse_merge) {
+    // my first merge item: its plan data (CSR bounds, partial-row ids) is on its way while the grid gathers
+    const int64_t n_items = (int64_t)p.nq * p.HKV * CombineShape<D, G>::NCG;
+    const int64_t it0 = (int64_t)blockIdx.x * 8 + warp;
+    TileMerge<D, G> tm;
+    if (warp < 8 && it0 < n_items) tm.prefetch(p, it0, lane);
+    if (tid == 0) {
+      unsigned long long* word = p.sync;
+      const unsigned long long mine = (unsigned long long)p.epoch << 32;
+      // (atomicAdd when the word already carries my epoch -- a retried compare-and-swap by every CTA would
+      // serialise the whole grid on one L2 line; the swap only installs a new epoch, once per launch)
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(word);
+      bool counted = false;
+      while (!counted) {
+        if ((cur >> 32) == p.epoch) {
+          atomicAdd(word, 1ull);
+          counted = true;
+        } else {
+          const unsigned long long old = atomicCAS(word, cur, mine | 1ull);
+          counted = old == cur;
+          cur = old;
+        }
+      }
+      unsigned long long seen;
+      uint32_t spins = 0;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(word) : "memory");
+        if ((seen >> 32) == p.epoch && (uint32_t)(seen & 0xffffull) >= gridDim.x) break;
+        __nanosleep(100);
+        if (++spins > (1u << 20)) __trap();
+      }
+    }
+    __syncthreads();
+    if (tid == 0) DEFT_TRACE(10);
+    if (warp < 8 && it0 < n_items) {  // the softmax warps: one (query, kv-head, chunk group) item per warp and turn
+      tm.run(p, lane);
+      for (int64_t it = it0 + (int64_t)gridDim.x * 8; it < n_items; it += (int64_t)gridDim.x * 8)
+        combine_tiles_item<D, G, false>(p, it, lane);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      DEFT_TRACE(11);
+      const unsigned long long before = atomicAdd(p.sync, 1ull << 16);
+      if (((before >> 16) & 0xffffull) == gridDim.x - 1) {  // everybody has left the wait above: re-arm
+        __threadfence();
+        *reinterpret_cast<volatile unsigned long long*>(p.sync) = (unsigned long long)p.epoch << 32;
+      }
+    }
+  }
 }
 
 template <int D, int G>
@@ -864,6 +947,10 @@ int launch_t(const AttnParams& p, cudaStream_t stream) {
     grid = (int)(n_jobs < num_sms ? n_jobs : num_sms);
   }
   if (grid <= 0) return DEFT_OK;
+  if (p.fuse_merge && grid > num_sms) {
+    set_error("fused stage 1+2 needs one CTA per SM at most (grid %d, %d SMs)", grid, num_sms);
+    return DEFT_E_ARG;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);

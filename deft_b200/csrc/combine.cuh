@@ -27,26 +27,48 @@ struct CombineShape {
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// The merge of one item in two steps, so that a caller can put a wait between them: prefetch() touches plan
+// data only (what no kernel of the call writes: index arithmetic, the CSR bounds, the first 32 partial-row ids),
+// run() reads the partials.
+template <int D, int G>
+struct TileMerge {
+  using S = CombineShape<D, G>;
+  int q, kvh, g, c, beg, end, first_row;
+  bool active;
+  __device__ __forceinline__ void prefetch(const AttnParams& p, int64_t item, int lane) {
+    const int cg = (int)(item % S::NCG);
+    kvh = (int)((item / S::NCG) % p.HKV);
+    q = (int)(item / ((int64_t)S::NCG * p.HKV));
+    g = lane % G;
+    c = lane / G + cg * S::CPW;
+    active = c < S::CH;
+    beg = p.u_csr_off[q];
+    end = p.u_csr_off[q + 1];
+    first_row = beg + lane < end ? p.u_csr_rows[beg + lane] : -1;
+  }
+  __device__ __forceinline__ void run(const AttnParams& p, int lane) const;
+};
+
 template <int D, int G, bool kWaitDep = false>
 __device__ __forceinline__ void combine_tiles_item(const AttnParams& p, int64_t item, int lane) {
-  using S = CombineShape<D, G>;
-  const int cg = (int)(item % S::NCG), kvh = (int)((item / S::NCG) % p.HKV), q = (int)(item / ((int64_t)S::NCG * p.HKV));
-  const int g = lane % G, c = lane / G + cg * S::CPW;
-  const bool active = c < S::CH;
-  const int beg = p.u_csr_off[q], end = p.u_csr_off[q + 1];
-  const uint4* po = reinterpret_cast<const uint4*>(p.po16);
+  TileMerge<D, G> tm;
+  tm.prefetch(p, item, lane);
+  if constexpr (kWaitDep) {
+    tm.first_row = __shfl_sync(0xffffffffu, tm.first_row, lane);  // the row ids have landed before the wait returns
+    griddep_wait();                                                // stage 1 has completed: its partials are visible
+  }
+  tm.run(p, lane);
+}
 
+template <int D, int G>
+__device__ __forceinline__ void TileMerge<D, G>::run(const AttnParams& p, int lane) const {
+  const uint4* po = reinterpret_cast<const uint4*>(p.po16);
   float m = -INFINITY, L = 0.f, acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   // Batches of 8 partials: the row ids come in with one coalesced load per 32, then the 8 log-sum-exps
   // and the 8 data chunks are all in flight before the first one is consumed.
   constexpr int kBatch = 8;
-  int first_row = beg + lane < end ? p.u_csr_rows[beg + lane] : -1;
-  if constexpr (kWaitDep) {
-    first_row = __shfl_sync(0xffffffffu, first_row, lane);  // the row ids have landed before the wait returns
-    griddep_wait();                                          // stage 1 has completed: its partials are visible
-  }
   for (int i0 = beg; i0 < end; i0 += 32) {
     const int my_row = i0 == beg ? first_row : (i0 + lane < end ? p.u_csr_rows[i0 + lane] : -1);
     const int n_here = min(32, end - i0);

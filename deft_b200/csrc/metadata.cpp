@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <queue>
@@ -332,13 +333,17 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     // tile steps (calibrated on B200): a tile whose 128 pages are consecutive arrives as TMA boxes, a tile of
     // scattered pages is gathered row by row and is bound by that (~1.5x); the constant is a job's start-up
     // + epilogue.
+    const char* env_g = std::getenv("DEFT_PLAN_GATHER_COST");
+    const double gather_cost = env_g ? std::atof(env_g) : 1.5;
     std::vector<double> tile_cost(tiles.size());
     for (size_t t = 0; t < tiles.size(); ++t) {
       bool runp = tiles[t].n_live == 128;
       for (size_t kk = t * 128 + 1; kk < (t + 1) * 128 && runp; ++kk) runp = u_kv[kk] == u_kv[t * 128] + (i32)(kk - t * 128);
-      tile_cost[t] = runp ? 1.0 : 1.5;
+      tile_cost[t] = runp ? 1.0 : gather_cost;
     }
-    const double kJobConst = 2.0;
+    // (DEFT_PLAN_JOB_CONST / DEFT_PLAN_GATHER_COST: calibration overrides for A/B runs on one box)
+    const char* env_c = std::getenv("DEFT_PLAN_JOB_CONST");
+    const double kJobConst = env_c ? std::atof(env_c) : 2.0;
     // pieces of a chain for a given maximum piece cost: (first tile, count), near-equal costs
     std::vector<std::pair<size_t, size_t>> pcs;
     std::vector<double> pcs_cost;
@@ -370,16 +375,30 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       longest = std::max(longest, total);
     }
     std::vector<double> cand;
-    for (double l : {1.5, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 10.0, 12.0, 16.0, 20.0, 24.0, 32.0, 48.0, 64.0, 96.0, 128.0, 192.0, 256.0})
+    for (double l : {1.5, 2.0, 2.5, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.5, 7.0, 7.5, 8.0, 9.0, 10.0, 12.0, 14.0, 16.0, 20.0, 24.0, 32.0, 48.0,
+                     64.0, 96.0, 128.0, 192.0, 256.0})
       if (l < longest) cand.push_back(l);
     cand.push_back(longest);
+    // slots of a pair with at least one attending row in tiles [ta, tb): each is one job per kv-head
+    auto live_slots_in = [&](i32 pr, size_t ta, size_t tb) {
+      int n_live = 0;
+      for (int sl = 0; sl < 2; ++sl) {
+        bool live = false;
+        for (size_t t = ta; t < tb && !live; ++t)
+          if (const uint32_t* w = tile_slot(tiles[t], 2 * pr + sl))
+            for (i32 n = 0; n < tiles[t].n_live && !live; ++n) live = w[n] != 0;
+        n_live += live ? 1 : 0;
+      }
+      return n_live;
+    };
     auto makespan = [&](double max_cost) {
       std::vector<double> costs;
       for (const Chain& c : chains) {
         pieces_of(c, max_cost);
-        const bool pair = slot_cnt(2 * c.pair + 1) > 0;
-        for (double pc : pcs_cost)
-          for (i32 h = 0; h < heads * (pair ? 2 : 1); ++h) costs.push_back(kJobConst + pc);
+        for (size_t pi = 0; pi < pcs.size(); ++pi) {
+          const int n_live = live_slots_in(c.pair, c.t0 + pcs[pi].first, c.t0 + pcs[pi].first + pcs[pi].second);
+          for (i32 h = 0; h < heads * n_live; ++h) costs.push_back(kJobConst + pcs_cost[pi]);
+        }
       }
       std::sort(costs.begin(), costs.end(), [](double a, double b) { return a > b; });
       std::priority_queue<double, std::vector<double>, std::greater<double>> bins;

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Same-box A/B of kernel variants: bash tools/gpu_ab.sh <tag> "<flags a>" "<flags b>" ...  (DEFT_EXPERIMENT values)
+set -u
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+for rep in 1 2; do
+  for F in "$@"; do
+    DEFT_EXPERIMENT=$F timeout 300 python bench.py --steps 30 --no-cpu-baseline > $OUT/bench_${F}_$rep.json 2>> $OUT/bench.err
+    python - <<PY
+import json
+d = json.load(open("$OUT/bench_${F}_$rep.json"))
+print("experiment $F rep $rep: layer-call %.2f us, stage1 %.2f, stage2 %.2f" % (d["us_per_layer_call"], d["us_stage1"], d["us_stage2"]))
+PY
+  done
+done

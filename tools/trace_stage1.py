@@ -19,7 +19,7 @@ from deft_b200 import TreeMetadata, _lib
 from deft_b200.workloads import build_tree
 
 NAMES = {0: "start", 1: "q_ids", 2: "q_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
-         8: "epi_end", 9: "end"}
+         8: "epi_end", 9: "end", 10: "grid_gathered", 11: "merged"}
 TILE = ["k_issued", "mma_k_full(S issued)", "sm_s_full", "sm_ready", "sm_p_arrive", "mma_pa_full", "v_issued", "k_landed"]
 
 
@@ -27,6 +27,7 @@ def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
     show = int(sys.argv[2]) if len(sys.argv) > 2 else 4
     dev = torch.device("cuda:0")
+    _lib.lib.deft_b200_set_experiment(int(os.environ.get("DEFT_EXPERIMENT", "0")))
     if os.environ.get("DEFT_NO_GATHER4"):
         _lib.lib.deft_b200_set_gather4(0)
     tree = build_tree(wl, layers=2, device=dev)
