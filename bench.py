@@ -184,6 +184,8 @@ def main():
     import deft_b200
     if os.environ.get("DEFT_EXPERIMENT"):            # kernel-variant switch for same-box A/B runs (profiling aid)
         deft_b200._lib.lib.deft_b200_set_experiment(int(os.environ["DEFT_EXPERIMENT"]))
+    if os.environ.get("DEFT_PDL"):
+        deft_b200._lib.lib.deft_b200_set_pdl(int(os.environ["DEFT_PDL"]))
     if os.environ.get("DEFT_FUSED"):
         deft_b200._lib.lib.deft_b200_set_fused(int(os.environ["DEFT_FUSED"]))
     from deft_b200 import BLOCK_CONFIG, TreeMetadata, _lib

@@ -279,7 +279,11 @@ int run_stages(const AttnParams& p, bool umma, unsigned long long* sync, cudaStr
     if (rc) return rc;
   }
   if (fuse) return DEFT_OK;
-  if (g_stages & DEFT_STAGE_2) return umma ? launch_stage2_tiles(p, stream) : launch_stage2(p, stream);
+  if (g_stages & DEFT_STAGE_2) {
+    AttnParams p2 = p;
+    p2.experiment = g_experiment;
+    return umma ? launch_stage2_tiles(p2, stream) : launch_stage2(p2, stream);
+  }
   return DEFT_OK;
 }
 

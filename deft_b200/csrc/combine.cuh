@@ -46,7 +46,12 @@ struct TileMerge {
     end = p.u_csr_off[q + 1];
     first_row = beg + lane < end ? p.u_csr_rows[beg + lane] : -1;
   }
-  __device__ __forceinline__ void run(const AttnParams& p, int lane) const;
+  template <int kBatch>
+  __device__ __forceinline__ void run_batched(const AttnParams& p, int lane) const;
+  __device__ __forceinline__ void run(const AttnParams& p, int lane) const {
+    if (p.experiment & 4) run_batched<8>(p, lane);
+    else run_batched<16>(p, lane);
+  }
 };
 
 template <int D, int G, bool kWaitDep = false>
@@ -61,14 +66,14 @@ __device__ __forceinline__ void combine_tiles_item(const AttnParams& p, int64_t 
 }
 
 template <int D, int G>
-__device__ __forceinline__ void TileMerge<D, G>::run(const AttnParams& p, int lane) const {
+template <int kBatch>
+__device__ __forceinline__ void TileMerge<D, G>::run_batched(const AttnParams& p, int lane) const {
   const uint4* po = reinterpret_cast<const uint4*>(p.po16);
   float m = -INFINITY, L = 0.f, acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  // Batches of 8 partials: the row ids come in with one coalesced load per 32, then the 8 log-sum-exps
-  // and the 8 data chunks are all in flight before the first one is consumed.
-  constexpr int kBatch = 8;
+  // Batches of 16 partials (a query of the BASELINE trees has 6-12): the row ids come in with one coalesced load
+  // per 32, then the 16 log-sum-exps and the 16 data chunks are all in flight before the first one is consumed.
   for (int i0 = beg; i0 < end; i0 += 32) {
     const int my_row = i0 == beg ? first_row : (i0 + lane < end ? p.u_csr_rows[i0 + lane] : -1);
     const int n_here = min(32, end - i0);
