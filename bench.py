@@ -289,6 +289,17 @@ def main():
     ev_in = [torch.cuda.Event() for _ in range(LAYERS // CH)]
     ev_out = [torch.cuda.Event() for _ in range(LAYERS // CH)]
 
+    loc_dev = torch.zeros(nq, dtype=torch.int32, device=dev)
+    graphed = args.mode != "seq"
+    if graphed:      # the step's launches (per layer: kv_append + attention) as CUDA graphs, one per chunk of layers
+        step = deft_b200.DecodeStepGraph(kvp, dev_qkv, out, loc_dev, H, HKV, D, mode=args.mode, chunk=CH)
+
+    def after_chunk(c):
+        ev_out[c].record(main)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_out[c])
+            host_out[c * CH: (c + 1) * CH].copy_(out[c * CH: (c + 1) * CH], non_blocking=True)
+
     def step_e2e():
         """Chunk c+1 of the activations comes up while chunk c attends and chunk c-1's outputs go down."""
         s_in.wait_stream(main)                           # the previous step no longer reads dev_qkv
@@ -296,22 +307,22 @@ def main():
             for c in range(LAYERS // CH):
                 dev_qkv[c * CH: (c + 1) * CH].copy_(host_qkv[c * CH: (c + 1) * CH], non_blocking=True)
                 ev_in[c].record(s_in)
-        m = build_meta()                                 # C++ builder + one H2D copy of tables and plan
+        # C++ builder + one H2D copy of tables and plan (into the persistent table buffer of the graphed step)
+        m = step.metadata(trees[0] if T == 1 else trees) if graphed else build_meta()
         table_bytes[0] = m.packed.numel()
-        loc = host_loc.to(dev, non_blocking=True)        # this step's pages (one per leaf)
-        for l in range(LAYERS):
-            if l % CH == 0:
-                main.wait_event(ev_in[l // CH])
-            k_new = dev_qkv[l, :, H * D: (H + HKV) * D].view(nq, HKV, D)
-            v_new = dev_qkv[l, :, (H + HKV) * D:].view(nq, HKV, D)
-            deft_b200.kv_append(kvp.kv_data[l], k_new, v_new, loc)
-            attention(l, dev_qkv, m)
-            if l % CH == CH - 1:
-                c = l // CH
-                ev_out[c].record(main)
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(ev_out[c])
-                    host_out[c * CH: (c + 1) * CH].copy_(out[c * CH: (c + 1) * CH], non_blocking=True)
+        loc_dev.copy_(host_loc, non_blocking=True)       # this step's pages (one per leaf)
+        if graphed:
+            step.run(m, before_chunk=lambda c: main.wait_event(ev_in[c]), after_chunk=after_chunk)
+        else:
+            for l in range(LAYERS):
+                if l % CH == 0:
+                    main.wait_event(ev_in[l // CH])
+                k_new = dev_qkv[l, :, H * D: (H + HKV) * D].view(nq, HKV, D)
+                v_new = dev_qkv[l, :, (H + HKV) * D:].view(nq, HKV, D)
+                deft_b200.kv_append(kvp.kv_data[l], k_new, v_new, loc_dev)
+                attention(l, dev_qkv, m)
+                if l % CH == CH - 1:
+                    after_chunk(l // CH)
         main.wait_stream(s_out)                          # the step ends when the last output is on the host
         main.synchronize()                               # the caller reads the result on the host
 
@@ -343,9 +354,11 @@ def main():
         "clocks": clocks,
         "e2e": {"value": world * nq / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "path": "TreeMetadata.from_tree_cache (C++ builder, 1 upload) + pinned H2D of the fused qkv in 8-layer chunks on a "
-                        "copy stream + kv_append + 32 x tree_attention_subtree_fwd + D2H of the outputs per chunk on a "
-                        "second copy stream; timed until the last output is on the host"},
+                "path": "DecodeStepGraph.metadata (TreeMetadata.from_tree_cache: C++ builder, 1 upload into the persistent table "
+                        "buffer) + pinned H2D of the fused qkv in 8-layer chunks on a copy stream + 32 x (kv_append + "
+                        "tree attention) replayed as 4 CUDA graphs + D2H of the outputs per chunk on a second copy stream; "
+                        "timed until the last output is on the host" if graphed else
+                        "per-layer eager calls (kv_append + token_attention_fwd) between chunked pinned H2D / D2H copies"},
         "gpu_launches": args.steps * LAYERS * 2,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "stage1 (partial softmax over KV items)",

@@ -7,7 +7,9 @@
 // CSR plan of include/deft_b200.h -- into ONE packed buffer that the caller uploads with one copy.
 // No CUDA here: pure host code, re-entrant.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -96,12 +98,22 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       return nullptr;
     }
 
+  const char* prof_env = std::getenv("DEFT_BUILD_PROFILE");
+  const bool prof = prof_env && prof_env[0] == '1';
+  auto t_prof = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "build_tables %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_prof).count());
+    t_prof = now;
+  };
   std::vector<i64> node_q, node_kv, node_q_len, node_kv_len, node_kv_offset_ti;
   std::vector<i64> block_q, block_q_cnts, block_kv, block_masks, block_lens;
   std::vector<deft_item_t> f_items;
   std::vector<deft_group_t> f_groups;
   i64 total_kv_len = 0;
 
+  lap("reference tables");
   // ---- native plan, part 1: fixed query slots.  Queries are ranked in DFS LEAF order (the order the
   // pre-order walk meets the childless nodes), so that every node's query set is a contiguous rank range;
   // slot k holds ranks [32k, 32k+32).  A tile touches few slots and consecutive tiles touch the same ones.
@@ -156,12 +168,18 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     tile.masks.assign(tile.slots.size() * 128, 0u);
     {
       size_t tok = 0;
+      std::vector<uint32_t> words(tile.slots.size());
       for (size_t sg = 0; sg < n_seg; ++sg) {
+        // every token of a segment is attended by the same queries: one word per touched slot, then filled in
+        std::fill(words.begin(), words.end(), 0u);
         for (i64 qv : seg_qs[sg]) {
           const i32 rk = rank_of[(size_t)qv];
           const size_t si = (size_t)(std::lower_bound(tile.slots.begin(), tile.slots.end(), rk / 32) - tile.slots.begin());
-          for (i64 n = 0; n < seg_lens[sg]; ++n) tile.masks[si * 128 + tok + (size_t)n] |= 1u << (rk % 32);
+          words[si] |= 1u << (rk % 32);
         }
+        for (size_t si = 0; si < words.size(); ++si)
+          if (words[si])
+            std::fill_n(tile.masks.begin() + (long)(si * 128 + tok), (size_t)seg_lens[sg], words[si]);
         tok += (size_t)seg_lens[sg];
       }
     }
@@ -261,6 +279,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<i64> node_kv_offset = tix_row ? node_kv_offset_ti : offsets_of(node_kv_len);
   std::vector<i64> block_q_offset = offsets_of(block_q_cnts);
 
+  lap("slots + tiles + flat plan");
   // ---- Node plan: long entries are cut into node_split-token items
   std::vector<deft_item_t> n_items;
   std::vector<deft_group_t> n_groups;
@@ -289,6 +308,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   Csr f_csr = make_csr(f_groups, block_q, query_num);
   Csr n_csr = make_csr(n_groups, node_q, query_num);
 
+  lap("node plan");
   // ---- native plan, part 2: units.  For every PAIR of slots, the tiles touching it form chains of
   // consecutive tiles (the prompt plus the pair's own subtree are contiguous in DFS order); every chain
   // is cut into pieces, one unit per piece.  All units of a pair share their Q tiles.  The piece length
@@ -374,19 +394,33 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       for (size_t t = 0; t < c.n_tiles; ++t) total += tile_cost[c.t0 + t];
       longest = std::max(longest, total);
     }
+    // candidate piece costs: from the cost one CTA would carry if the work split evenly (shorter pieces only
+    // add jobs and partials) up to the longest chain, ~15 % apart
+    double all_cost = 0.0;
+    for (const Chain& c : chains) {
+      double total = 0.0;
+      for (size_t t = 0; t < c.n_tiles; ++t) total += tile_cost[c.t0 + t];
+      all_cost += total * heads * (slot_cnt(2 * c.pair + 1) > 0 ? 2 : 1);
+    }
     std::vector<double> cand;
-    for (double l : {1.5, 2.0, 2.5, 3.0, 3.5, 4.0, 4.5, 5.0, 5.5, 6.0, 6.5, 7.0, 7.5, 8.0, 9.0, 10.0, 12.0, 14.0, 16.0, 20.0, 24.0, 32.0, 48.0,
-                     64.0, 96.0, 128.0, 192.0, 256.0})
-      if (l < longest) cand.push_back(l);
+    for (double l = std::max(1.0, 0.5 * all_cost / ctas); l < longest; l = std::max(l + 0.5, l * 1.15)) cand.push_back(l);
     cand.push_back(longest);
     // slots of a pair with at least one attending row in tiles [ta, tb): each is one job per kv-head
+    // (per-(tile, slot) liveness once, so that every candidate of the search below is O(tiles))
+    std::vector<uint8_t> tile_live(tiles.size() * (size_t)n_slots, 0);
+    for (size_t t = 0; t < tiles.size(); ++t)
+      for (size_t si = 0; si < tiles[t].slots.size(); ++si) {
+        const uint32_t* w = tiles[t].masks.data() + si * 128;
+        bool live = false;
+        for (i32 n = 0; n < tiles[t].n_live && !live; ++n) live = w[n] != 0;
+        tile_live[t * (size_t)n_slots + (size_t)tiles[t].slots[si]] = live ? 1 : 0;
+      }
     auto live_slots_in = [&](i32 pr, size_t ta, size_t tb) {
       int n_live = 0;
       for (int sl = 0; sl < 2; ++sl) {
+        if (2 * pr + sl >= n_slots) continue;
         bool live = false;
-        for (size_t t = ta; t < tb && !live; ++t)
-          if (const uint32_t* w = tile_slot(tiles[t], 2 * pr + sl))
-            for (i32 n = 0; n < tiles[t].n_live && !live; ++n) live = w[n] != 0;
+        for (size_t t = ta; t < tb && !live; ++t) live = tile_live[t * (size_t)n_slots + (size_t)(2 * pr + sl)] != 0;
         n_live += live ? 1 : 0;
       }
       return n_live;
@@ -532,6 +566,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     }
   }
 
+  lap("units + jobs");
   // ---- pack
   deft_tables_t* t = new (std::nothrow) deft_tables_t();
   if (!t) {

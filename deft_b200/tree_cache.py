@@ -323,7 +323,9 @@ class _Staging:
         self.events: List[Optional[torch.cuda.Event]] = [None] * depth
         self.i = 0
 
-    def upload(self, src: np.ndarray, device: torch.device) -> torch.Tensor:
+    def upload(self, src: np.ndarray, device: torch.device, into: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One async H2D copy of ``src``; into the first bytes of ``into`` when given (a persistent device buffer:
+        the tables then keep their addresses from one decode step to the next), else into a fresh tensor."""
         n = src.nbytes
         slot = self.i
         self.i = (self.i + 1) % len(self.bufs)
@@ -334,7 +336,7 @@ class _Staging:
             buf = torch.empty(max(n, 1 << 20), dtype=torch.uint8, pin_memory=True)
             self.bufs[slot] = buf
         buf[:n].numpy()[:] = src
-        out = torch.empty(n, dtype=torch.uint8, device=device)
+        out = into[:n] if into is not None else torch.empty(n, dtype=torch.uint8, device=device)
         out.copy_(buf[:n], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -410,9 +412,11 @@ class TreeMetadata:
     flat_plan: Optional[_lib.Plan] = field(default=None, repr=False)
     node_plan: Optional[_lib.Plan] = field(default=None, repr=False)
     host_tables: Optional[Dict[str, np.ndarray]] = field(default=None, repr=False)
+    layout: bytes = field(default=b"", repr=False)     # directory + scalars: equal layouts = equal pointers and counts
 
     @classmethod
-    def _assemble(cls, tree, flat, max_q_len: int, max_block_len: int, tree_index: bool) -> "TreeMetadata":
+    def _assemble(cls, tree, flat, max_q_len: int, max_block_len: int, tree_index: bool,
+                  device_buffer: Optional[torch.Tensor] = None) -> "TreeMetadata":
         block_len = BLOCK_CONFIG["BLOCK_LEN"]
         if max_block_len == -1:
             max_block_len = BLOCK_CONFIG["MAX_BLOCK_LEN"]
@@ -423,7 +427,9 @@ class TreeMetadata:
         data, directory, scalars = build_tables_host(flat, max_q_len, max_block_len, block_len, max_ctx,
                                                      hkv=hkv, n_ctas=sm_count(device))
         on_gpu = device.type == "cuda"
-        packed = _STAGING.upload(data, device) if on_gpu else torch.from_numpy(data)
+        if device_buffer is not None and (not on_gpu or device_buffer.numel() < data.nbytes):
+            device_buffer = None               # too small (or a CPU pool): a fresh tensor, like without it
+        packed = _STAGING.upload(data, device, device_buffer) if on_gpu else torch.from_numpy(data)
 
         def view(i: int, dtype: torch.dtype, elem: int) -> torch.Tensor:
             off, cnt = int(directory[i, 0]), int(directory[i, 1])
@@ -455,23 +461,30 @@ class TreeMetadata:
                 t[k] = null
         meta = cls(query_num=int(scalars[0]), node_num=int(scalars[1]), total_kv_len=int(scalars[2]),
                    leaf_to_q=flat["leaf_to_q"], block_len=int(scalars[3]), packed=packed,
-                   flat_plan=None if tree_index else plan(12, int(scalars[4])), node_plan=plan(16, int(scalars[5])), **t)
+                   flat_plan=None if tree_index else plan(12, int(scalars[4])), node_plan=plan(16, int(scalars[5])),
+                   layout=directory.tobytes() + scalars.tobytes() + int(base).to_bytes(8, "little"), **t)
         if on_gpu:
             register_plan(meta)
         return meta
 
     @classmethod
-    def from_tree_cache(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":
-        return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=False)
+    def from_tree_cache(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1,
+                        device_buffer: Optional[torch.Tensor] = None) -> "TreeMetadata":
+        """Reference signature (tree_cache.py:618-625) + ``device_buffer``: an optional persistent uint8 CUDA tensor
+        the packed tables are uploaded into, so that consecutive decode steps find them at the same addresses
+        (what a captured CUDA graph of the step needs, see ``decode_step.DecodeStepGraph``)."""
+        return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=False, device_buffer=device_buffer)
 
     @classmethod
-    def from_forest(cls, trees, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":
+    def from_forest(cls, trees, max_q_len: int = 32, max_block_len: int = -1,
+                    device_buffer: Optional[torch.Tensor] = None) -> "TreeMetadata":
         """One metadata object (tables + native plan) for several trees sharing one KV pool: the operators
         then attend the whole batch in one launch.  ``leaf_to_q`` is keyed by ``(tree index, leaf id)``."""
         trees = list(trees)
         assert trees and all(t.token_to_kv_pool is trees[0].token_to_kv_pool for t in trees), \
             "the trees of a forest share one TokenToKVPool"
-        return cls._assemble(trees[0], flatten_forest(trees), max_q_len, max_block_len, tree_index=False)
+        return cls._assemble(trees[0], flatten_forest(trees), max_q_len, max_block_len, tree_index=False,
+                             device_buffer=device_buffer)
 
     @classmethod
     def from_tree_cache_node(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":

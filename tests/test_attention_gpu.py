@@ -284,3 +284,42 @@ def test_argument_errors(dev):
         deft_b200.tree_attention_subtree_fwd(q, kv[:, 0], kv[:, 1], torch.zeros_like(q), 128, i, i, i, i, i, i)
     with pytest.raises(deft_b200._lib.DeftError):
         deft_b200.tree_attention_subtree_fwd(q.cpu(), kv[:, 0].cpu(), kv[:, 1].cpu(), torch.zeros_like(q).cpu(), 128, i, i, i, i, i, i)
+
+
+def test_decode_step_graph_replays_with_new_table_contents(dev):
+    """DecodeStepGraph: the step (kv_append + attention per layer) captured once, replayed while the table layout
+    is unchanged -- with DIFFERENT page ids in the tables (another tree of the same shape over other pages) and new
+    activations -- and equal to the eager per-layer calls."""
+    import deft_b200
+    from deft_b200 import TreeMetadata
+    from deft_b200.workloads import build_forest
+    torch.manual_seed(5)
+    L, H, HKV, D = 3, 32, 8, 128
+    trees = build_forest("cfg3", 2, layers=L, device=dev)      # two trees of one shape over one pool
+    kvp = trees[0].token_to_kv_pool
+    for l in range(L):
+        kvp.kv_data[l].normal_()
+    nq = len(trees[0].leaves)
+    qkv = torch.empty(L, nq, (H + 2 * HKV) * D, dtype=torch.float16, device=dev)
+    out = torch.empty(L, nq, H, D, dtype=torch.float16, device=dev)
+    loc = torch.zeros(nq, dtype=torch.int32, device=dev)
+    step = deft_b200.DecodeStepGraph(kvp, qkv, out, loc, H, HKV, D, mode="flatten", chunk=2)
+    layouts = set()
+    for it, tree in enumerate([trees[0], trees[1], trees[0]]):
+        qkv.normal_()
+        leaves = sorted(tree.leaves.values(), key=lambda x: x.id)
+        loc.copy_(torch.tensor([leaf.kv_indices[-1] for leaf in leaves], dtype=torch.int32))
+        m = step.metadata(tree)
+        layouts.add(m.layout)
+        step.run(m)
+        got = out.clone()
+        # eager reference on a copy of the pool state: the appended rows are already in place, attention only
+        m2 = TreeMetadata.from_tree_cache(tree)
+        want = torch.empty_like(out)
+        for l in range(L):
+            deft_b200.tree_attention_subtree_fwd(qkv[l, :, : H * D].view(nq, H, D), kvp.get_key_buffer(l), kvp.get_value_buffer(l),
+                                                 want[l], 128, m2.block_q, m2.block_q_cnts, m2.block_q_offset, m2.block_bitmasks,
+                                                 m2.block_kv, m2.block_lens)
+            assert torch.equal(kvp.get_key_buffer(l)[loc.long()], qkv[l, :, H * D: (H + HKV) * D].view(nq, HKV, D))
+        assert torch.isfinite(got.float()).all() and torch.equal(got, want), it
+    assert len(layouts) == 1 and step.captures == 1, "same shape, other pages: one capture, replayed"
