@@ -66,6 +66,29 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload: str, mode: str, trees: int):
+    """DRAM bytes per launch of the stage-1 kernel from the newest committed `ncu --set full` capture
+    (profiles/*_ncu_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum, mean over the captured launches).  The
+    captures are taken on the default workload (cfg2, flatten, one tree); anything else reports null."""
+    if workload != "cfg2" or mode != "flatten" or trees != 1:
+        return None, None
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_raw.csv")))
+    if not files:
+        return None, None
+    unit_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        vals = [float(r[ir]) * unit_bytes[units[ir]] + float(r[iw]) * unit_bytes[units[iw]]
+                for r in rows[2:] if len(r) > max(ir, iw) and "stage1" in r[0]]
+        return (sum(vals) / len(vals), os.path.basename(files[-1])) if vals else (None, None)
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -337,6 +360,7 @@ def main():
         return
 
     alg = algorithmic_bytes(args.workload) * T
+    traffic, traffic_src = ncu_traffic(args.workload, args.mode, T)
     peak, peak_src = peaks()
     s1_s = ms_s1 / LAYERS * 1e-3
     achieved = alg / s1_s / 1e9
@@ -361,7 +385,7 @@ def main():
                         "per-layer eager calls (kv_append + token_attention_fwd) between chunked pinned H2D / D2H copies"},
         "gpu_launches": args.steps * LAYERS * 2,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "stage1 (partial softmax over KV items)",
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "stage1 (partial softmax over KV items)",
                      "algorithmic_bytes_per_launch": alg, "us_per_launch": s1_s * 1e6, "peak_source": peak_src},
     }
     if not args.no_cpu_baseline:

@@ -533,6 +533,47 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> bins;
       for (i32 c = 0; c < ctas; ++c) bins.push({0.0, c});
       std::vector<std::vector<i32>> per((size_t)ctas);
+      size_t n_jobs_total = 0;
+      for (const deft_unit_t& u : units) n_jobs_total += (size_t)hkv * (size_t)((u.q_cnt[0] > 0) + (u.q_cnt[1] > 0));
+      // Throughput regime (many jobs per CTA, e.g. a forest of trees): the two slot-jobs of a unit read the same
+      // K/V tiles, so they go to the two CTAs of a PAIR at the same position of their lists -- they then run
+      // side by side and the second read hits L2 instead of HBM.  Latency regime (about one job per CTA): every
+      // job on its own, longest first onto the least loaded CTA (the CTAs all start together anyway).
+      const char* env_p = std::getenv("DEFT_PLAN_PAIR");
+      const bool pair_mode = env_p ? env_p[0] == '1' : (ctas >= 2 && n_jobs_total >= (size_t)4 * (size_t)ctas);
+      if (pair_mode) {
+        const i32 n_pairs_b = ctas / 2;
+        std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> pbins;
+        for (i32 b = 0; b < n_pairs_b; ++b) pbins.push({0.0, b});
+        std::vector<double> load((size_t)ctas, 0.0);
+        for (i32 ui : order) {
+          if (units[(size_t)ui].q_cnt[0] <= 0 || units[(size_t)ui].q_cnt[1] <= 0) continue;
+          for (i32 h = 0; h < hkv; ++h) {
+            Bin b = pbins.top();
+            pbins.pop();
+            for (i32 k = 0; k < 2; ++k) {
+              per[(size_t)(2 * b.second + k)].push_back(((ui * hkv + h) << 1) | k);
+              load[(size_t)(2 * b.second + k)] += ucost[(size_t)ui];
+            }
+            b.first += ucost[(size_t)ui];
+            pbins.push(b);
+          }
+        }
+        while (!bins.empty()) bins.pop();
+        for (i32 c = 0; c < ctas; ++c) bins.push({load[(size_t)c], c});
+        for (i32 ui : order) {
+          const bool a = units[(size_t)ui].q_cnt[0] > 0, b2 = units[(size_t)ui].q_cnt[1] > 0;
+          if (a && b2) continue;
+          const i32 k = a ? 0 : 1;
+          for (i32 h = 0; h < hkv; ++h) {
+            Bin b = bins.top();
+            bins.pop();
+            per[(size_t)b.second].push_back(((ui * hkv + h) << 1) | k);
+            b.first += ucost[(size_t)ui];
+            bins.push(b);
+          }
+        }
+      } else {
       for (i32 ui : order)
         for (i32 h = 0; h < hkv; ++h)
           for (i32 k = 0; k < 2; ++k) {
@@ -543,6 +584,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
             b.first += ucost[(size_t)ui];
             bins.push(b);
           }
+      }
       // records [0, ctas): every CTA's first job; the others follow, consecutive per CTA
       auto record = [&](i32 job) {
         deft_job_t r{};
