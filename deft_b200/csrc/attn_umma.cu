@@ -125,6 +125,35 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
       : "memory");
 }
+// ... and their multicast forms: the box / the four rows land at the same shared-memory offset of every CTA of
+// the cluster named in `mask`, and complete their bytes on the mbarrier at the same offset in each
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::
+      "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tma_gather4_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int r0, int r1, int r2, int r3,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::
+      "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // NB: no fence.proxy.async on the consumer side.  Data staged by cp.async or TMA is handed over through
 // an mbarrier the MMA thread waits on; a proxy fence there also waits for every async-proxy copy still
 // in flight to this CTA (the NEXT tiles' loads), which serialised the tensor pipe behind the loads.
@@ -156,6 +185,11 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 // arrives on `bar` when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ... on the mbarrier at this offset in every CTA of the cluster named in `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -323,12 +357,16 @@ struct Jobs {
       next = 0;
     }
   }
-  // i-th job of this CTA -> (unit, kv-head, slot); a pair's second slot may be empty (then the job is nobody's)
-  __device__ __forceinline__ bool get(const AttnParams& p, int i, deft_unit_t& u, int& hkv, int& k) const {
+  // i-th job of this CTA -> (unit, kv-head, slot); a pair's second slot may be empty (then the job is nobody's).
+  // `shared`: the other CTA of my cluster pair works the other slot of the same (unit, kv-head) at the same
+  // position of its list, so every K/V tile is loaded once for both (each CTA issues half of it, multicast).
+  __device__ __forceinline__ bool get(const AttnParams& p, int i, deft_unit_t& u, int& hkv, int& k, bool& shared) const {
     int job;
+    shared = false;
     if (recs != nullptr) {
       const deft_job_t* r = i == 0 ? recs + blockIdx.x : recs + next + (i - 1);
       job = r->job;
+      shared = r->shared != 0 && p.tma_kv != 0 && p.tma_gather != 0 && p.clustered != 0;
       u = r->unit;
     } else {
       job = (int)blockIdx.x + i * (int)gridDim.x;
@@ -382,8 +420,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   if (p.plan_fresh) griddep_wait();  // the plan itself comes from the preceding (plan) kernel
   const Jobs jobs(p);  // (its load is in flight under the barrier set-up and the TMEM allocation below)
   if (tid == 0) {
-    for (int s = 0; s < kKStages; ++s) { mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 1); }
-    for (int s = 0; s < kVStages; ++s) { mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 1); }
+    for (int s = 0; s < kKStages; ++s) { mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 2); }  // EMPTY: my issuer + the pair's (or mine twice)
+    for (int s = 0; s < kVStages; ++s) { mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 2); }
     mbar_init(bar(Q_FULL), 32); mbar_init(bar(Q_EMPTY), 1);
     for (int m = 0; m < kMaskStages; ++m) { mbar_init(bar(M_FULL + m), 32); mbar_init(bar(M_EMPTY + m), 256); }
     for (int b = 0; b < kSBufs; ++b) {
@@ -397,8 +435,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   if (warp == kMmaWarp) tmem_alloc(base + L::kTmemSlot, kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (p.clustered) cluster_sync();  // the pair's barriers exist before anything of mine is multicast to them
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gbase + L::kTmemSlot);
+  const uint32_t crank = p.clustered ? cluster_ctarank() : 0u;
 
   // Programmatic dependent launch: everything up to here (barrier init, TMEM allocation, job list) overlapped
   // the tail of the preceding kernel; q, the KV pool and the partial workspace may still be in its hands.
@@ -416,8 +456,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     const int row0 = w * 32;  // my 32 rows
     uint32_t cnt = 0;  // tiles produced
     for (int ji = 0; ji < jobs.n; ++ji) {
-      deft_unit_t u; int hkv, k;
-      if (!jobs.get(p, ji, u, hkv, k)) continue;
+      deft_unit_t u; int hkv, k; bool shared;
+      if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       if (warp == kKvWarp0 && lane == 0 && ji == 0) DEFT_TRACE(kTrKUnit);
       const bool known_run = u.page0 >= 0 && p.tma_kv != 0;  // the builder's shortcut: no index-table read at all
       auto page_of = [&](int t) -> int {  // page of my row of tile t (0 past the end)
@@ -441,12 +481,20 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         // 32 consecutive pages of a full tile are ONE box of the pool's tensor map per 64-wide panel
         const int page0 = __shfl_sync(0xffffffffu, pg, 0);
         const bool run = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg == page0 + lane);
+        // shared job: the pair loads every tile ONCE -- the CTA of rank r issues rows [64r, 64r + 64) for both
+        const bool mine = !shared || (uint32_t)(w >> 1) == crank;
         if (run) {
           if (lane == 0) {
             mbar_arrive_expect_tx(full, 32 * D * 2);
+            if (mine) {
 #pragma unroll
-            for (int pn = 0; pn < D / 64; ++pn)
-              tma_load_3d(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0);
+              for (int pn = 0; pn < D / 64; ++pn) {
+                if (shared)
+                  tma_load_3d_mc(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0, 0x3);
+                else
+                  tma_load_3d(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0);
+              }
+            }
           } else {
             mbar_arrive(full);
           }
@@ -460,9 +508,14 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
           if (lane == 0) mbar_arrive_expect_tx(full, 32 * D * 2);
           else mbar_arrive(full);
-          if (lane < 8 * NP)
-            tma_gather4(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
-                        r0, r1, r2, r3);
+          if (mine && lane < 8 * NP) {
+            if (shared)
+              tma_gather4_mc(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
+                             r0, r1, r2, r3, 0x3);
+            else
+              tma_gather4(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
+                          r0, r1, r2, r3);
+          }
         } else {
           const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
           constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
@@ -483,8 +536,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     // ============================== Q tile of the job's slot ==============================
     uint32_t q_cnt = 0;  // jobs
     for (int ji = 0; ji < jobs.n; ++ji) {
-      deft_unit_t u; int hkv, k;
-      if (!jobs.get(p, ji, u, hkv, k)) continue;
+      deft_unit_t u; int hkv, k; bool shared;
+      if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       // row r = (query r / G, head r % G); rows past q_cnt*G are zero
       const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
       const int q_id0 = k == 0 ? u.q_id0[0] : u.q_id0[1];
@@ -527,8 +580,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     // ============================== mask words + dense flag per tile ==============================
     uint32_t m_cnt = 0;  // tiles
     for (int ji = 0; ji < jobs.n; ++ji) {
-      deft_unit_t u; int hkv, k;
-      if (!jobs.get(p, ji, u, hkv, k)) continue;
+      deft_unit_t u; int hkv, k; bool shared;
+      if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
       const int64_t mask_off = k == 0 ? u.mask_off[0] : u.mask_off[1];
       if (mask_off < 0 && u.last_len == kTileN) continue;  // every tile dense: the softmax warps do not ask
@@ -571,8 +624,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     const uint64_t q_desc = smem_desc_sw128(base + L::kQ, 16, 1024);
     uint32_t k_cnt = 0, g0 = 0, j_cnt = 0;  // K tiles consumed (ring position), tiles of earlier jobs, jobs
     for (int ji = 0; ji < jobs.n; ++ji) {
-      deft_unit_t u; int hkv, k;
-      if (!jobs.get(p, ji, u, hkv, k)) continue;
+      deft_unit_t u; int hkv, k; bool shared;
+      if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       const int n = u.n_tiles;
       const bool tr0 = ji == 0 && leader;
       mbar_wait(bar(Q_FULL), j_cnt & 1);
@@ -593,7 +646,12 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
             umma_ss(s_tmem, q_desc + koff, k_desc + koff, kIdescQK, ks > 0);
           }
           umma_commit(bar(S_FULL + sb));
-          umma_commit(bar(K_EMPTY + st));  // K(t) and, after the last tile, Q are free
+          if (shared) {
+            umma_commit_mc(bar(K_EMPTY + st), 0x3);  // K(t) is free here; the pair's producers hear it too
+          } else {
+            umma_commit(bar(K_EMPTY + st));
+            umma_commit(bar(K_EMPTY + st));
+          }
           if (t == n - 1) umma_commit(bar(Q_EMPTY));
         }
         __syncwarp();
@@ -613,8 +671,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     uint32_t v_cnt = 0, g0 = 0, j_cnt = 0;
     volatile uint32_t* pv_cnt = reinterpret_cast<volatile uint32_t*>(gbase + L::kPvCnt);
     for (int ji = 0; ji < jobs.n; ++ji) {
-      deft_unit_t u; int hkv, k;
-      if (!jobs.get(p, ji, u, hkv, k)) continue;
+      deft_unit_t u; int hkv, k; bool shared;
+      if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       const int n = u.n_tiles;
       const bool tr0 = ji == 0 && leader;
       for (int t = 0; t < n; ++t) {
@@ -638,7 +696,12 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
         if (leader) {
           umma_commit(bar(PV_DONE));
-          umma_commit(bar(V_EMPTY + st));
+          if (shared) {
+            umma_commit_mc(bar(V_EMPTY + st), 0x3);
+          } else {
+            umma_commit(bar(V_EMPTY + st));
+            umma_commit(bar(V_EMPTY + st));
+          }
           umma_commit(bar(S_FREE + buf));
           if (t == n - 1) umma_commit(bar(O_DONE));
         }
@@ -668,8 +731,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     bool first_job = blockIdx.x == 0;
 
     for (int ji = 0; ji < jobs.n; ++ji) {
-      deft_unit_t u; int hkv, k;
-      if (!jobs.get(p, ji, u, hkv, k)) continue;
+      deft_unit_t u; int hkv, k; bool shared;
+      if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
       const int part_base = k == 0 ? u.part_base[0] : u.part_base[1];
       const bool dbg = p.dbg != nullptr && first_job;
@@ -867,6 +930,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   tc_fence_before();
   if (p.fuse_merge) __threadfence();  // my partial stores are visible device-wide before this CTA reports in
   __syncthreads();
+  if (p.clustered) cluster_sync();  // the pair no longer multicasts into my shared memory or arrives on my barriers
   if (tid == 0) DEFT_TRACE(kTrEnd);
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 
@@ -956,12 +1020,25 @@ int launch_t(const AttnParams& p, cudaStream_t stream) {
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = L::kAlloc;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // launch early, wait inside (griddep_wait)
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (p.pdl) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // launch early, wait inside (griddep_wait)
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  AttnParams pl = p;
+  pl.clustered = p.job_off != nullptr && grid % 2 == 0 && p.clustered;  // CTA pairs (2c, 2c + 1): see deft_job_t.shared
+  if (pl.clustered) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = p.pdl ? 1 : 0;
-  DEFT_CUDA(cudaLaunchKernelEx(&cfg, stage1_umma_kernel<D, G>, p));
+  cfg.numAttrs = n_attr;
+  DEFT_CUDA(cudaLaunchKernelEx(&cfg, stage1_umma_kernel<D, G>, pl));
   return DEFT_OK;
 }
 

@@ -48,10 +48,7 @@ struct TileMerge {
   }
   template <int kBatch>
   __device__ __forceinline__ void run_batched(const AttnParams& p, int lane) const;
-  __device__ __forceinline__ void run(const AttnParams& p, int lane) const {
-    if (p.experiment & 4) run_batched<8>(p, lane);
-    else run_batched<16>(p, lane);
-  }
+  __device__ __forceinline__ void run(const AttnParams& p, int lane) const { run_batched<16>(p, lane); }
 };
 
 template <int D, int G, bool kWaitDep = false>

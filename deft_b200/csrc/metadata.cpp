@@ -333,16 +333,23 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
 
     struct Chain { i32 pair; size_t t0, n_tiles; };
     std::vector<Chain> chains;
+    // A chain also ends where the set of live slots changes (both -> one, one -> the other): a slot then never
+    // walks tiles none of its rows attends.  (DEFT_PLAN_SPLIT_LIVE=0: chains by contiguity only.)
+    const char* env_s = std::getenv("DEFT_PLAN_SPLIT_LIVE");
+    const bool split_live = !(env_s && env_s[0] == '0');
     for (i32 pr = 0; pr < n_pairs; ++pr) {
       size_t run0 = 0, run_n = 0;
+      int run_sig = 0;
       for (size_t t = 0; t <= tiles.size(); ++t) {
-        const bool hit = t < tiles.size() && (tile_slot(tiles[t], 2 * pr) || tile_slot(tiles[t], 2 * pr + 1));
-        if (hit) {
-          if (run_n == 0) run0 = t;
-          ++run_n;
-        } else if (run_n) {
+        int sig = 0;
+        if (t < tiles.size()) sig = (tile_slot(tiles[t], 2 * pr) ? 1 : 0) | (tile_slot(tiles[t], 2 * pr + 1) ? 2 : 0);
+        if (run_n && (sig == 0 || (split_live && sig != run_sig))) {
           chains.push_back({pr, run0, run_n});
           run_n = 0;
+        }
+        if (sig) {
+          if (run_n == 0) { run0 = t; run_sig = sig; }
+          ++run_n;
         }
       }
     }
@@ -403,7 +410,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       all_cost += total * heads * (slot_cnt(2 * c.pair + 1) > 0 ? 2 : 1);
     }
     std::vector<double> cand;
-    for (double l = std::max(1.0, 0.5 * all_cost / ctas); l < longest; l = std::max(l + 0.5, l * 1.15)) cand.push_back(l);
+    for (double l = std::max(1.0, std::min(0.5 * all_cost / ctas, longest / 8.0)); l < longest; l = std::max(l + 0.5, l * 1.15))
+      cand.push_back(l);
     cand.push_back(longest);
     // slots of a pair with at least one attending row in tiles [ta, tb): each is one job per kv-head
     // (per-(tile, slot) liveness once, so that every candidate of the search below is O(tiles))
@@ -533,6 +541,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> bins;
       for (i32 c = 0; c < ctas; ++c) bins.push({0.0, c});
       std::vector<std::vector<i32>> per((size_t)ctas);
+      std::vector<size_t> n_shared((size_t)ctas, 0);  // leading jobs of a CTA's list shared with its pair
       size_t n_jobs_total = 0;
       for (const deft_unit_t& u : units) n_jobs_total += (size_t)hkv * (size_t)((u.q_cnt[0] > 0) + (u.q_cnt[1] > 0));
       // Throughput regime (many jobs per CTA, e.g. a forest of trees): the two slot-jobs of a unit read the same
@@ -540,7 +549,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       // side by side and the second read hits L2 instead of HBM.  Latency regime (about one job per CTA): every
       // job on its own, longest first onto the least loaded CTA (the CTAs all start together anyway).
       const char* env_p = std::getenv("DEFT_PLAN_PAIR");
-      const bool pair_mode = env_p ? env_p[0] == '1' : (ctas >= 2 && n_jobs_total >= (size_t)4 * (size_t)ctas);
+      const bool pair_mode = ctas >= 2 && ctas % 2 == 0 && (env_p ? env_p[0] == '1' : n_jobs_total >= (size_t)4 * (size_t)ctas);
       if (pair_mode) {
         const i32 n_pairs_b = ctas / 2;
         std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> pbins;
@@ -554,6 +563,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
             for (i32 k = 0; k < 2; ++k) {
               per[(size_t)(2 * b.second + k)].push_back(((ui * hkv + h) << 1) | k);
               load[(size_t)(2 * b.second + k)] += ucost[(size_t)ui];
+              ++n_shared[(size_t)(2 * b.second + k)];
             }
             b.first += ucost[(size_t)ui];
             pbins.push(b);
@@ -600,8 +610,13 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         deft_job_t first = record(mine.empty() ? -1 : mine[0]);
         first.n_jobs = (i32)mine.size();
         first.next = (i32)u_jobs.size();
+        first.shared = n_shared[(size_t)c] > 0 ? 1 : 0;
         u_jobs[(size_t)c] = first;
-        for (size_t i = 1; i < mine.size(); ++i) u_jobs.push_back(record(mine[i]));
+        for (size_t i = 1; i < mine.size(); ++i) {
+          deft_job_t r = record(mine[i]);
+          r.shared = i < n_shared[(size_t)c] ? 1 : 0;
+          u_jobs.push_back(r);
+        }
         total += (i32)mine.size();
         u_job_off.push_back(total);
       }

@@ -134,7 +134,8 @@ typedef struct {
   int32_t job;
   int32_t n_jobs;  /* first record of a CTA only: jobs of this CTA (>= 1 when job >= 0) */
   int32_t next;    /* first record of a CTA only: index of its second record */
-  int32_t pad;
+  int32_t shared;  /* 1: CTA (c ^ 1) holds, at the same position of its list, the other slot of the same (unit,
+                      kv_head): the pair loads every K/V tile once (each CTA half of it, TMA multicast) */
   deft_unit_t unit;
 } deft_job_t;               /* 96 bytes */
 

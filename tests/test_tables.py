@@ -18,7 +18,7 @@ GROUP = np.dtype([("mask_off", "<i8"), ("q_off", "<i4"), ("q_cnt", "<i4"), ("par
 UNIT = np.dtype([("kv_off", "<i8"), ("mask_off", "<i8", (2,)), ("kv_tile_stride", "<i4"), ("mask_tile_stride", "<i4"),
                  ("n_tiles", "<i4"), ("last_len", "<i4"), ("q_off", "<i4", (2,)), ("q_cnt", "<i4", (2,)),
                  ("part_base", "<i4", (2,)), ("page0", "<i4"), ("q_id0", "<i4", (2,)), ("pad", "<i4")])
-JOB = np.dtype([("job", "<i4"), ("n_jobs", "<i4"), ("next", "<i4"), ("pad", "<i4"), ("unit", UNIT)])
+JOB = np.dtype([("job", "<i4"), ("n_jobs", "<i4"), ("next", "<i4"), ("shared", "<i4"), ("unit", UNIT)])
 
 
 def unpack(data, directory):
@@ -109,20 +109,27 @@ def check_unit_plan(t, scalars, tree, hkv, n_ctas):
         n = int(job_off[c + 1] - job_off[c])
         assert (first["job"] >= 0) == (n > 0) and int(first["n_jobs"]) == n
         mine = [first] + [jobs[int(first["next"]) + i] for i in range(n - 1)] if n else []
-        for r in mine:
+        for i, r in enumerate(mine):
             listed.append(int(r["job"]))
             assert r["unit"] == units[(int(r["job"]) >> 1) // hkv], "the record carries a copy of its unit"
+            if r["shared"]:      # the pair CTA holds the other slot of the same (unit, kv-head) at the same position
+                peer = jobs[c ^ 1] if i == 0 else jobs[int(jobs[c ^ 1]["next"]) + i - 1]
+                assert peer["shared"] and int(peer["job"]) == int(r["job"]) ^ 1 and n_ctas % 2 == 0
     assert len(jobs) == n_ctas + sum(max(0, int(d) - 1) for d in np.diff(job_off))
     want_jobs = [((ui * hkv + h) << 1) | k for ui, u in enumerate(units) for h in range(hkv) for k in range(2) if u["q_cnt"][k] > 0]
     assert sorted(listed) == sorted(want_jobs), "every (unit, kv-head, live slot) job exactly once"
 
 
 @pytest.mark.parametrize("name", list(SCENARIOS))
-def test_unit_plan_covers_the_tree(golden_dir, name):
+def test_unit_plan_covers_the_tree(golden_dir, name, monkeypatch):
     z, tree = load(golden_dir, name)
-    for mbl, hkv, n_ctas in ((-1, 2, 148), (128, 8, 16)):
-        t, scalars = build(tree, mbl, hkv=hkv, n_ctas=n_ctas)
-        check_unit_plan(t, scalars, tree, hkv, n_ctas)
+    for pair in ("0", "1"):                 # independent job lists / pair-aligned lists (cluster multicast)
+        monkeypatch.setenv("DEFT_PLAN_PAIR", pair)
+        for mbl, hkv, n_ctas in ((-1, 2, 148), (128, 8, 16)):
+            t, scalars = build(tree, mbl, hkv=hkv, n_ctas=n_ctas)
+            check_unit_plan(t, scalars, tree, hkv, n_ctas)
+            if pair == "1" and (t["u_units"]["q_cnt"][:, 1] > 0).any():
+                assert t["u_jobs"]["shared"].any(), "two-slot units exist: their jobs are paired"
 
 
 def test_forest_plan_covers_every_tree(golden_dir):

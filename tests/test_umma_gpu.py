@@ -266,3 +266,33 @@ def test_fused_merge_equals_separate_stage2(dev, name):
         _lib.lib.deft_b200_set_fused(0)
     assert torch.isfinite(a.float()).all()
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3"])
+def test_cluster_pairs_share_kv_tiles_by_multicast(dev, name, monkeypatch):
+    """Pair-aligned job lists (DEFT_PLAN_PAIR=1: the two slot-jobs of a unit on the two CTAs of a cluster, every
+    K/V tile loaded once for both by TMA multicast -- boxes for the prompt, gather4 for the subtree) give the
+    bit-identical result of the independent job lists."""
+    from deft_b200 import TreeMetadata
+    import deft_b200
+    from deft_b200.workloads import build_tree
+    torch.manual_seed(13)
+    tree = build_tree(name, layers=2, device=dev)
+    kvp = tree.token_to_kv_pool
+    for l in range(2):
+        kvp.kv_data[l].normal_()
+    nq = len(tree.leaves)
+    q = torch.randn(nq, 48 * 128, dtype=torch.float16, device=dev)[:, : 32 * 128].view(nq, 32, 128)
+    outs = []
+    for pair in ("1", "0"):
+        monkeypatch.setenv("DEFT_PLAN_PAIR", pair)
+        m = TreeMetadata.from_tree_cache(tree)
+        o = torch.full((6, nq, 32, 128), float("nan"), dtype=torch.float16, device=dev)
+        for i in range(6):                  # back to back on one workspace, two layer pools
+            deft_b200.tree_attention_subtree_fwd(q, kvp.get_key_buffer(i % 2), kvp.get_value_buffer(i % 2), o[i], 128, m.block_q,
+                                                 m.block_q_cnts, m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens)
+        torch.cuda.synchronize()
+        outs.append(o)
+    assert torch.isfinite(outs[0].float()).all()
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0][0], outs[0][2]) and torch.equal(outs[0][1], outs[0][3])
