@@ -209,8 +209,6 @@ def main():
         deft_b200._lib.lib.deft_b200_set_experiment(int(os.environ["DEFT_EXPERIMENT"]))
     if os.environ.get("DEFT_PDL"):
         deft_b200._lib.lib.deft_b200_set_pdl(int(os.environ["DEFT_PDL"]))
-    if os.environ.get("DEFT_FUSED"):
-        deft_b200._lib.lib.deft_b200_set_fused(int(os.environ["DEFT_FUSED"]))
     from deft_b200 import BLOCK_CONFIG, TreeMetadata, _lib
     from deft_b200.sharding import max_over_ranks
     from deft_b200.workloads import WORKLOADS, algorithmic_bytes, build_forest

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdeft_b200.so")
+LIB_PATH = os.environ.get("DEFT_B200_LIB") or os.path.join(_HERE, "lib", "libdeft_b200.so")   # (override: A/B of two builds)
 
 ABI_VERSION = 3
 T_NAMES = ["node_q", "node_kv", "node_q_len", "node_kv_len", "node_q_offset", "node_kv_offset",
@@ -56,7 +56,6 @@ def _load() -> C.CDLL:
         "deft_b200_set_pdl": (None, [i32]),
         "deft_b200_set_gather4": (None, [i32]),
         "deft_b200_set_experiment": (None, [i32]),
-        "deft_b200_set_fused": (None, [i32]),
         "deft_b200_flatten_workspace_bytes": (sz, [i32, i32, i32, i32, i64, i64, C.POINTER(Plan)]),
         "deft_b200_flatten_fwd": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, i32,
                                             i32, vp, i64, vp, vp, vp, i64, vp, vp, C.POINTER(Plan), vp, sz, vp]),
@@ -82,7 +81,7 @@ def _load() -> C.CDLL:
 
 lib = _load()
 EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_set_stages", "deft_b200_set_stage1_impl",
-           "deft_b200_set_debug_buffer", "deft_b200_set_trace_buffer", "deft_b200_set_tma", "deft_b200_set_pdl", "deft_b200_set_gather4", "deft_b200_set_experiment", "deft_b200_set_fused",
+           "deft_b200_set_debug_buffer", "deft_b200_set_trace_buffer", "deft_b200_set_tma", "deft_b200_set_pdl", "deft_b200_set_gather4", "deft_b200_set_experiment",
            "deft_b200_flatten_workspace_bytes",
            "deft_b200_flatten_fwd", "deft_b200_node_workspace_bytes", "deft_b200_node_fwd", "deft_b200_kv_append",
            "deft_b200_build_tables", "deft_b200_tables_data", "deft_b200_tables_bytes",

@@ -16,8 +16,6 @@ static thread_local bool g_no_tma = false;
 static thread_local bool g_no_pdl = false;
 static thread_local bool g_no_gather4 = false;
 static thread_local int g_experiment = 0;
-static thread_local bool g_no_fuse = true;  // measured on B200 (cfg2): the in-kernel grid wait + merge costs 4.8 us, a second launch 6.0 -- but stage 2
-                                            // as its own kernel overlaps its prologue with stage 1's tail and leaves the SMs to the next call sooner
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -117,7 +115,6 @@ bool use_umma(int32_t H, int32_t HKV, int32_t D) {
 //   warp-FMA path: po [rows][H][D] f32 | plse [rows][H] f32
 //   device-derived plan: items | groups | units | csr_off | csr_rows | cursor | counters
 struct Workspace {
-  unsigned long long* sync;  // grid-wide counter word of the fused kernel (self-arming, see attn_umma.cu)
   float* po;
   float* plse;
   __half* po16;
@@ -141,7 +138,6 @@ Workspace carve(void* base, const Sizes& z, bool umma, bool with_plan, int32_t n
     off += align_up(n);
     return p;
   };
-  w.sync = static_cast<unsigned long long*>(take(256));  // (same place whichever stage-1 kernel runs)
   if (umma) {
     const size_t tile_rows = (size_t)kMaxGroupQ * (H / HKV);
     w.po16 = static_cast<__half*>(take((size_t)z.slots * HKV * tile_rows * D * sizeof(__half)));
@@ -247,16 +243,7 @@ void use_plan(AttnParams& p, const PlanBuffers& pb, int64_t bound) {
   p.plan_fresh = 1;
 }
 
-int run_stages(const AttnParams& p, bool umma, unsigned long long* sync, cudaStream_t stream) {
-  const bool both = (g_stages & DEFT_STAGE_1) && (g_stages & DEFT_STAGE_2);
-  static thread_local int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    DEFT_CUDA(cudaGetDevice(&dev));
-    DEFT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  // the fused kernel waits for its own grid: every CTA must be resident (one per SM)
-  const bool fuse = umma && both && !g_no_fuse && sync != nullptr && (p.job_off == nullptr || p.n_ctas <= num_sms);
+int run_stages(const AttnParams& p, bool umma, cudaStream_t stream) {
   if (g_stages & DEFT_STAGE_1) {
     int rc;
     if (umma) {
@@ -264,27 +251,13 @@ int run_stages(const AttnParams& p, bool umma, unsigned long long* sync, cudaStr
       pd.dbg = g_debug;
       pd.trace = g_trace;
       pd.experiment = g_experiment;
-      if (fuse) {
-        // a tag no earlier call of this process put into a workspace (thread id in the top bits, never 0)
-        static thread_local uint32_t epoch = (uint32_t)(((uintptr_t)&g_error >> 4) << 20);
-        epoch = (epoch & 0xfff00000u) | (((epoch & 0xfffffu) + 1u) & 0xfffffu);
-        if (epoch == 0u) epoch = 1u;
-        pd.fuse_merge = 1;
-        pd.sync = sync;
-        pd.epoch = epoch;
-      }
       rc = launch_stage1_umma(pd, stream);
     } else {
       rc = launch_stage1_fma(p, stream);
     }
     if (rc) return rc;
   }
-  if (fuse) return DEFT_OK;
-  if (g_stages & DEFT_STAGE_2) {
-    AttnParams p2 = p;
-    p2.experiment = g_experiment;
-    return umma ? launch_stage2_tiles(p2, stream) : launch_stage2(p2, stream);
-  }
+  if (g_stages & DEFT_STAGE_2) return umma ? launch_stage2_tiles(p, stream) : launch_stage2(p, stream);
   return DEFT_OK;
 }
 
@@ -318,7 +291,6 @@ void deft_b200_set_tma(int32_t enabled) { g_no_tma = enabled == 0; }
 void deft_b200_set_pdl(int32_t enabled) { g_no_pdl = enabled == 0; }
 void deft_b200_set_gather4(int32_t enabled) { g_no_gather4 = enabled == 0; }
 void deft_b200_set_experiment(int32_t flags) { g_experiment = flags; }
-void deft_b200_set_fused(int32_t enabled) { g_no_fuse = enabled == 0; }
 
 size_t deft_b200_flatten_workspace_bytes(int32_t nq, int32_t H, int32_t HKV, int32_t D,
                                          int64_t n_partials, int64_t n_blocks, const deft_plan_t* plan) {
@@ -376,7 +348,7 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
     }
     use_plan(p, w.pb, n_blocks);
   }
-  return run_stages(p, umma, w.sync, stream);
+  return run_stages(p, umma, stream);
 }
 
 int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
@@ -422,7 +394,7 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
     }
     use_plan(p, w.pb, items);
   }
-  return run_stages(p, umma, w.sync, stream);
+  return run_stages(p, umma, stream);
 }
 
 int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head_stride,

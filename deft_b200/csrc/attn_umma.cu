@@ -819,22 +819,13 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           const bool over = !(hsum < 32768.f) || (m_ref == -INFINITY && hsum > 0.f);
           // the row pairs' two warps learn whether anybody asked (the common answer is no)
           float rq = -INFINITY;
-          if (!(p.experiment & 1)) {
-            redo = pair_sync_or(warp, over);  // one barrier with an OR reduction; shared memory only on a request
-            if (redo) {
-              float* xr = xq + (round & 1) * (2 * kRows);
-              xr[h * kRows + r] = over ? half_max() : -INFINITY;
-              pair_sync(warp);
-              rq = fmaxf(xr[r], xr[kRows + r]);  // the row's request, seen alike by its two threads
-              ++round;
-            }
-          } else {
+          redo = pair_sync_or(warp, over);  // one barrier with an OR reduction; shared memory only on a request
+          if (redo) {
             float* xr = xq + (round & 1) * (2 * kRows);
             xr[h * kRows + r] = over ? half_max() : -INFINITY;
             pair_sync(warp);
             rq = fmaxf(xr[r], xr[kRows + r]);  // the row's request, seen alike by its two threads
             ++round;
-            redo = __any_sync(0xffffffffu, rq > -INFINITY);  // alike in the two warps: they hold the same rows
           }
           if (redo) {
             float alpha = 1.f;
@@ -928,67 +919,11 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     }
   }
   tc_fence_before();
-  if (p.fuse_merge) __threadfence();  // my partial stores are visible device-wide before this CTA reports in
   __syncthreads();
   if (p.clustered) cluster_sync();  // the pair no longer multicasts into my shared memory or arrives on my barriers
   if (tid == 0) DEFT_TRACE(kTrEnd);
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
 
-  // ---- fused stage 2.  The grid is one CTA per SM (all co-resident), so it can wait for itself: every CTA
-  // reports in, waits until all have, and then the CTAs share the merge of the partials -- the log-sum-exp
-  // combine of tree_attention.py:297-546 -- without a second launch.  The last CTA out re-arms the counters.
-  // The counter word is self-arming: {epoch of this call : 32, CTAs out : 16, CTAs in : 16}.  A CTA that finds
-  // another epoch in it (a workspace never used, or overwritten since) starts the count itself, so nothing has to
-  // be zeroed; the last CTA out puts the count back to 0 for a replay of the same launch (CUDA graphs).
-  if (p.fuse_merge) {
-    // my first merge item: its plan data (CSR bounds, partial-row ids) is on its way while the grid gathers
-    const int64_t n_items = (int64_t)p.nq * p.HKV * CombineShape<D, G>::NCG;
-    const int64_t it0 = (int64_t)blockIdx.x * 8 + warp;
-    TileMerge<D, G> tm;
-    if (warp < 8 && it0 < n_items) tm.prefetch(p, it0, lane);
-    if (tid == 0) {
-      unsigned long long* word = p.sync;
-      const unsigned long long mine = (unsigned long long)p.epoch << 32;
-      // (atomicAdd when the word already carries my epoch -- a retried compare-and-swap by every CTA would
-      // serialise the whole grid on one L2 line; the swap only installs a new epoch, once per launch)
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(word);
-      bool counted = false;
-      while (!counted) {
-        if ((cur >> 32) == p.epoch) {
-          atomicAdd(word, 1ull);
-          counted = true;
-        } else {
-          const unsigned long long old = atomicCAS(word, cur, mine | 1ull);
-          counted = old == cur;
-          cur = old;
-        }
-      }
-      unsigned long long seen;
-      uint32_t spins = 0;
-      for (;;) {
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(word) : "memory");
-        if ((seen >> 32) == p.epoch && (uint32_t)(seen & 0xffffull) >= gridDim.x) break;
-        __nanosleep(100);
-        if (++spins > (1u << 20)) __trap();
-      }
-    }
-    __syncthreads();
-    if (tid == 0) DEFT_TRACE(10);
-    if (warp < 8 && it0 < n_items) {  // the softmax warps: one (query, kv-head, chunk group) item per warp and turn
-      tm.run(p, lane);
-      for (int64_t it = it0 + (int64_t)gridDim.x * 8; it < n_items; it += (int64_t)gridDim.x * 8)
-        combine_tiles_item<D, G, false>(p, it, lane);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      DEFT_TRACE(11);
-      const unsigned long long before = atomicAdd(p.sync, 1ull << 16);
-      if (((before >> 16) & 0xffffull) == gridDim.x - 1) {  // everybody has left the wait above: re-arm
-        __threadfence();
-        *reinterpret_cast<volatile unsigned long long*>(p.sync) = (unsigned long long)p.epoch << 32;
-      }
-    }
-  }
 }
 
 template <int D, int G>
@@ -1011,10 +946,6 @@ int launch_t(const AttnParams& p, cudaStream_t stream) {
     grid = (int)(n_jobs < num_sms ? n_jobs : num_sms);
   }
   if (grid <= 0) return DEFT_OK;
-  if (p.fuse_merge && grid > num_sms) {
-    set_error("fused stage 1+2 needs one CTA per SM at most (grid %d, %d SMs)", grid, num_sms);
-    return DEFT_E_ARG;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);

@@ -89,9 +89,6 @@ struct AttnParams {
   float* plse16;
   int32_t pdl;         // launch the tcgen05-path kernels with programmatic stream serialization
   int32_t plan_fresh;  // the unit plan was derived on the device by the preceding kernel of this call
-  int32_t fuse_merge;  // stage 2 runs as the tail of the stage-1 kernel (grid-wide wait on `sync`)
-  unsigned long long* sync;  // self-arming grid counter in the workspace: {epoch : 32, CTAs out : 16, CTAs in : 16}
-  uint32_t epoch;      // this call's tag in that word (never 0)
   int32_t clustered;   // launched as clusters of two CTAs (the plan's job lists pair slot-jobs that share K/V tiles)
   int32_t experiment;  // bit flags switching kernel variants for A/B measurements (deft_b200_set_experiment)
 };

@@ -69,10 +69,6 @@ void deft_b200_set_pdl(int32_t enabled);
  * with TMA tile::gather4 (four K or V rows per instruction) when the pool's token stride is a whole
  * number of head strides. */
 void deft_b200_set_gather4(int32_t enabled);
-/* Option: 0 (default) = stage 2 is its own kernel, 1 = on the tcgen05 path the log-sum-exp merge runs as the
- * tail of the stage-1 kernel (its CTAs, one per SM, wait for each other through a self-arming counter word at the head
- * of the workspace: nothing has to be zeroed). */
-void deft_b200_set_fused(int32_t enabled);
 /* Profiling hook: bit flags selecting kernel variants for A/B measurements on one box (0 = the default path). */
 void deft_b200_set_experiment(int32_t flags);
 

@@ -234,40 +234,6 @@ def test_reference_maximum_is_raised_mid_chain(dev):
     assert torch.allclose(o.double(), want, atol=4e-3, rtol=2e-2), (o.double() - want).abs().max().item()
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3"])
-def test_fused_merge_equals_separate_stage2(dev, name):
-    """The log-sum-exp merge as the tail of the stage-1 kernel (grid-wide wait, one launch) and as its own kernel
-    read the same partials in the same order: bit-identical outputs, also back to back on one workspace."""
-    from deft_b200 import TreeMetadata, _lib
-    import deft_b200
-    from deft_b200.workloads import build_tree
-    torch.manual_seed(11)
-    tree = build_tree(name, layers=2, device=dev)
-    kvp = tree.token_to_kv_pool
-    for l in range(2):
-        kvp.kv_data[l].normal_()
-    nq = len(tree.leaves)
-    q = torch.randn(nq, 48 * 128, dtype=torch.float16, device=dev)[:, : 32 * 128].view(nq, 32, 128)
-    m = TreeMetadata.from_tree_cache(tree)
-
-    def run(fused):
-        _lib.lib.deft_b200_set_fused(fused)
-        o = torch.full((8, nq, 32, 128), float("nan"), dtype=torch.float16, device=dev)
-        for i in range(8):
-            deft_b200.tree_attention_subtree_fwd(q, kvp.get_key_buffer(i % 2), kvp.get_value_buffer(i % 2), o[i], 128,
-                                                 m.block_q, m.block_q_cnts, m.block_q_offset, m.block_bitmasks,
-                                                 m.block_kv, m.block_lens)
-        torch.cuda.synchronize()
-        return o
-
-    try:
-        a, b = run(1), run(0)
-    finally:
-        _lib.lib.deft_b200_set_fused(0)
-    assert torch.isfinite(a.float()).all()
-    assert torch.equal(a, b)
-
-
 @pytest.mark.parametrize("name", ["cfg2", "cfg3"])
 def test_cluster_pairs_share_kv_tiles_by_multicast(dev, name, monkeypatch):
     """Pair-aligned job lists (DEFT_PLAN_PAIR=1: the two slot-jobs of a unit on the two CTAs of a cluster, every

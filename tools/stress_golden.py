@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Repeats the plan-less (device-derived plan) Flatten call on every golden scenario and counts results outside
-the reference tolerance: python tools/stress_golden.py [reps]   (env DEFT_FUSED=0/1, DEFT_EXPERIMENT)"""
+the reference tolerance: python tools/stress_golden.py [reps]   """
 import os
 import sys
 
@@ -18,8 +18,6 @@ KEYS = ["block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    if os.environ.get("DEFT_FUSED"):
-        _lib.lib.deft_b200_set_fused(int(os.environ["DEFT_FUSED"]))
     _lib.lib.deft_b200_set_stage1_impl(_lib.STAGE1_UMMA)
     dev = torch.device("cuda:0")
     for name in SCENARIOS:
