@@ -23,7 +23,7 @@ ITEM_BYTES = 24
 GROUP_BYTES = 24
 UNIT_BYTES = 80
 JOB_BYTES = 96
-N_SCALARS = 8
+N_SCALARS = 9
 
 
 class Plan(C.Structure):
@@ -32,7 +32,7 @@ class Plan(C.Structure):
                 ("n_items", C.c_int32), ("n_groups", C.c_int32), ("n_part_rows", C.c_int32), ("n_units", C.c_int32),
                 ("units", C.c_void_p), ("u_csr_off", C.c_void_p), ("u_csr_rows", C.c_void_p), ("u_kv", C.c_void_p),
                 ("u_mask", C.c_void_p), ("u_q", C.c_void_p), ("u_job_off", C.c_void_p), ("u_jobs", C.c_void_p),
-                ("n_unit_slots", C.c_int32), ("n_ctas", C.c_int32), ("hkv", C.c_int32), ("pad", C.c_int32)]
+                ("n_unit_slots", C.c_int32), ("n_ctas", C.c_int32), ("hkv", C.c_int32), ("paired", C.c_int32)]
 
 
 class DeftError(RuntimeError):

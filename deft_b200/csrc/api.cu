@@ -221,7 +221,7 @@ int use_plan(AttnParams& p, const deft_plan_t* plan, bool umma) {
     p.u_csr_off = plan->u_csr_off; p.u_csr_rows = plan->u_csr_rows;
     if (plan->u_job_off && plan->u_jobs && plan->hkv == p.HKV && plan->n_ctas > 0) {
       p.job_off = plan->u_job_off; p.jobs = plan->u_jobs; p.n_ctas = plan->n_ctas;
-      p.clustered = 1;  // (the launch drops it when the grid is odd)
+      p.clustered = plan->paired;  // pair-aligned lists: clusters of two CTAs (the launch drops it when the grid is odd)
     }
   } else {
     p.items = plan->items; p.groups = plan->groups;

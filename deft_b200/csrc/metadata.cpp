@@ -66,7 +66,7 @@ std::vector<i64> offsets_of(const std::vector<i64>& lens) {  // cat([0], cumsum(
 struct deft_tables {
   std::vector<unsigned char> packed;
   i64 dir[2 * DEFT_T_COUNT];
-  i64 scalars[8];
+  i64 scalars[9];
 };
 
 extern "C" {
@@ -317,6 +317,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<deft_unit_t> units;
   std::vector<i32> u_q, u_job_off;
   std::vector<deft_job_t> u_jobs;
+  bool plan_paired = false;  // the job lists pair slot-jobs on CTAs (2c, 2c + 1): launch as clusters of two
   std::vector<uint32_t> u_mask;
   Csr u_csr;
   u_csr.off.assign((size_t)query_num + 1, 0);
@@ -550,6 +551,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       // job on its own, longest first onto the least loaded CTA (the CTAs all start together anyway).
       const char* env_p = std::getenv("DEFT_PLAN_PAIR");
       const bool pair_mode = ctas >= 2 && ctas % 2 == 0 && (env_p ? env_p[0] == '1' : n_jobs_total >= (size_t)4 * (size_t)ctas);
+      plan_paired = pair_mode;
       if (pair_mode) {
         const i32 n_pairs_b = ctas / 2;
         std::priority_queue<Bin, std::vector<Bin>, std::greater<Bin>> pbins;
@@ -663,6 +665,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   t->scalars[5] = n_rows;
   t->scalars[6] = n_unit_slots;
   t->scalars[7] = u_job_off.empty() ? 0 : (i64)u_job_off.size() - 1;
+  t->scalars[8] = plan_paired ? 1 : 0;
   return t;
 }
 

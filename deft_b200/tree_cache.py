@@ -451,7 +451,7 @@ class TreeMetadata:
                              n_part_rows=rows, n_units=int(directory[U, 1]),
                              units=addr(U), u_csr_off=addr(U + 1), u_csr_rows=addr(U + 2), u_kv=addr(U + 3),
                              u_mask=addr(U + 4), u_q=addr(U + 5), u_job_off=addr(U + 6), u_jobs=addr(U + 7),
-                             n_unit_slots=int(scalars[6]), n_ctas=int(scalars[7]), hkv=hkv, pad=0)
+                             n_unit_slots=int(scalars[6]), n_ctas=int(scalars[7]), hkv=hkv, paired=int(scalars[8]))
 
         if tree_index:
             null = torch.empty(0, dtype=torch.int64, device=device)

@@ -157,7 +157,7 @@ typedef struct {
   int32_t n_unit_slots;       /* partial tiles per kv-head */
   int32_t n_ctas;             /* CTAs the job lists were balanced for */
   int32_t hkv;                /* kv-head count the job lists were built for */
-  int32_t pad;
+  int32_t paired;             /* 1: pair-aligned job lists (deft_job_t.shared): the kernel is launched as clusters of 2 */
 } deft_plan_t;
 
 /* ------------------------------------------------------------------------------------------
@@ -264,8 +264,8 @@ size_t deft_b200_tables_bytes(const deft_tables_t* t);
 /* dir[2*i] = byte offset of array i in the packed buffer, dir[2*i+1] = element count */
 int deft_b200_tables_directory(const deft_tables_t* t, int64_t* dir /* [2*DEFT_T_COUNT] */);
 /* scalars: {query_num, node_num, total_kv_len, block_len, flat_part_rows, node_part_rows,
- *           n_unit_slots, n_ctas} */
-int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [8] */);
+ *           n_unit_slots, n_ctas, paired (1: the job lists are pair-aligned, see deft_job_t.shared)} */
+int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [9] */);
 void deft_b200_tables_free(deft_tables_t* t);
 
 #ifdef __cplusplus
