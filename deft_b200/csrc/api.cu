@@ -388,8 +388,14 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
     if (rc) return rc;
   } else {
     if (g_stages & DEFT_STAGE_PLAN) {
-      rc = launch_plan_node(kv_offset, kv_len, q_offset, q_len, node_q, n_entries,
-                            total_kv_bound > 0 ? kNodeSplit : 0, nq, w.pb, stream);
+      // long entries are cut into items of `split` tokens: kNodeSplit (what the workspace was sized for) when
+      // the call is small, longer -- fewer jobs and partials -- when there is work for several waves of CTAs
+      int32_t split = 0;
+      if (total_kv_bound > 0) {
+        const int64_t want = total_kv_bound * HKV / (2 * 148) / 128 * 128;
+        split = (int32_t)(want < kNodeSplit ? kNodeSplit : want > 2048 ? 2048 : want);
+      }
+      rc = launch_plan_node(kv_offset, kv_len, q_offset, q_len, node_q, n_entries, split, nq, w.pb, stream);
       if (rc) return rc;
     }
     use_plan(p, w.pb, items);

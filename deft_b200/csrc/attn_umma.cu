@@ -114,6 +114,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {  // (a 96-byte record may straddle two lines: both)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(ptr) + 80));
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -368,9 +372,11 @@ struct Jobs {
       job = r->job;
       shared = r->shared != 0 && p.tma_kv != 0 && p.tma_gather != 0 && p.clustered != 0;
       u = r->unit;
+      if (i + 1 < n) prefetch_l1(recs + next + i);  // the next job's record: no load latency between two jobs
     } else {
       job = (int)blockIdx.x + i * (int)gridDim.x;
       u = p.units[(job >> 1) / p.HKV];
+      if (i + 1 < n) prefetch_l1(p.units + ((job + (int)gridDim.x) >> 1) / p.HKV);
     }
     k = job & 1;
     hkv = (job >> 1) % p.HKV;
