@@ -349,6 +349,7 @@ struct Jobs {
       recs = p.jobs;
       n = next = 0;
       if ((int)blockIdx.x < p.n_ctas) {
+        prefetch_l1(recs + blockIdx.x);  // (the record may straddle two lines: both are on their way)
         const int4 hdr = *reinterpret_cast<const int4*>(recs + blockIdx.x);
         n = hdr.x >= 0 ? hdr.y : 0;
         next = hdr.z;
@@ -461,10 +462,11 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     const int FULL = kv == 0 ? K_FULL : V_FULL, EMPTY = kv == 0 ? K_EMPTY : V_EMPTY;
     const int row0 = w * 32;  // my 32 rows
     uint32_t cnt = 0;  // tiles produced
+    if (warp == kKvWarp0 && lane == 0) DEFT_TRACE(12);
     for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k; bool shared;
       if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
-      if (warp == kKvWarp0 && lane == 0 && ji == 0) DEFT_TRACE(kTrKUnit);
+      if (warp == kKvWarp0 && lane == 0 && ji == 0 && u.n_tiles > 0) DEFT_TRACE(kTrKUnit);
       const bool known_run = u.page0 >= 0 && p.tma_kv != 0;  // the builder's shortcut: no index-table read at all
       auto page_of = [&](int t) -> int {  // page of my row of tile t (0 past the end)
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;

@@ -19,7 +19,7 @@ from deft_b200 import TreeMetadata, _lib
 from deft_b200.workloads import build_tree
 
 NAMES = {0: "start", 1: "q_ids", 2: "q_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
-         8: "epi_end", 9: "end", 10: "grid_gathered", 11: "merged"}
+         8: "epi_end", 9: "end", 12: "k_role_entry"}
 TILE = ["k_issued", "mma_k_full(S issued)", "sm_s_full", "sm_ready", "sm_p_arrive", "mma_pa_full", "v_issued", "k_landed"]
 
 
@@ -48,7 +48,8 @@ def main():
         call(0)
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    flush.zero_()                               # push the KV pool out of L2
+    if not os.environ.get("TRACE_NOFLUSH"):
+        flush.zero_()                           # push the KV pool out of L2
     call(1)                                     # plan tables warm in L2 (as inside a decode step: 32 layers share
     torch.cuda.synchronize()                    # them), layer 0's KV stays cold
     _lib.lib.deft_b200_set_trace_buffer(trace.data_ptr())
