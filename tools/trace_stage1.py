@@ -30,14 +30,20 @@ def main():
     _lib.lib.deft_b200_set_experiment(int(os.environ.get("DEFT_EXPERIMENT", "0")))
     if os.environ.get("DEFT_NO_GATHER4"):
         _lib.lib.deft_b200_set_gather4(0)
-    tree = build_tree(wl, layers=2, device=dev)
+    n_trees = int(os.environ.get("TRACE_TREES", "1"))
+    if n_trees > 1:
+        from deft_b200.workloads import build_forest
+        trees = build_forest(wl, n_trees, layers=2, device=dev)
+        tree = trees[0]
+    else:
+        tree = build_tree(wl, layers=2, device=dev)
     kvp = tree.token_to_kv_pool
     for l in range(2):
         kvp.kv_data[l].normal_()
-    nq = len(tree.leaves)
+    nq = len(tree.leaves) * n_trees
     q = torch.randn(nq, 48 * 128, dtype=torch.float16, device=dev)[:, : 32 * 128].view(nq, 32, 128)
     o = torch.empty(nq, 32, 128, dtype=torch.float16, device=dev)
-    m = TreeMetadata.from_tree_cache(tree)
+    m = TreeMetadata.from_tree_cache(tree) if n_trees == 1 else TreeMetadata.from_forest(trees)
     trace = torch.full((256, 128), -1, dtype=torch.int32, device=dev)
 
     def call(layer):
