@@ -69,6 +69,25 @@ struct deft_tables {
   i64 scalars[9];
 };
 
+namespace {
+// Storage kept from one call to the next (per thread): the tables of a decode step are a few hundred KB, and fresh
+// allocations of that size are handed back to the kernel at every free and page-faulted in again at the next build
+// (measured: a third of the build time).  Everything is cleared, nothing is read, at the start of a build.
+struct Scratch {
+  std::vector<i64> node_q, node_kv, node_q_len, node_kv_len, node_kv_offset_ti;
+  std::vector<i64> block_q, block_q_cnts, block_kv, block_masks, block_lens;
+  std::vector<i32> u_kv;
+  std::vector<uint32_t> u_mask;
+  std::vector<i64> kvs;
+  deft_tables* spare = nullptr;   // a freed handle whose packed buffer is reused by the next build
+  // the last plan search: the piece length depends only on the chains' shape, which most decode steps keep
+  std::vector<uint64_t> plan_key;
+  double plan_len = 0.0;
+  ~Scratch() { delete spare; }
+};
+thread_local Scratch g_scratch;
+}  // namespace
+
 extern "C" {
 
 deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, const int64_t* kv_off,
@@ -107,8 +126,13 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     std::fprintf(stderr, "build_tables %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_prof).count());
     t_prof = now;
   };
-  std::vector<i64> node_q, node_kv, node_q_len, node_kv_len, node_kv_offset_ti;
-  std::vector<i64> block_q, block_q_cnts, block_kv, block_masks, block_lens;
+  Scratch& S = g_scratch;
+  auto& node_q = S.node_q; auto& node_kv = S.node_kv; auto& node_q_len = S.node_q_len; auto& node_kv_len = S.node_kv_len;
+  auto& node_kv_offset_ti = S.node_kv_offset_ti;
+  auto& block_q = S.block_q; auto& block_q_cnts = S.block_q_cnts; auto& block_kv = S.block_kv;
+  auto& block_masks = S.block_masks; auto& block_lens = S.block_lens;
+  node_q.clear(); node_kv.clear(); node_q_len.clear(); node_kv_len.clear(); node_kv_offset_ti.clear();
+  block_q.clear(); block_q_cnts.clear(); block_kv.clear(); block_masks.clear(); block_lens.clear();
   std::vector<deft_item_t> f_items;
   std::vector<deft_group_t> f_groups;
   i64 total_kv_len = 0;
@@ -139,7 +163,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     std::vector<uint32_t> masks;   // [touched slot][128]: bit r = rank 32*slot + r attends the token
   };
   std::vector<Tile> tiles;
-  std::vector<i32> u_kv;
+  auto& u_kv = S.u_kv;
+  u_kv.clear();
 
   // open block (tree_cache.py:654-658)
   std::vector<i64> seg_tokens;
@@ -147,28 +172,29 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<std::vector<i64>> seg_qs;  // sorted query ids per segment
   std::vector<i64> uni;                  // union, kept sorted + unique at close time
 
+  std::vector<uint32_t> words;
   auto close_block = [&]() {  // pack_new_block, tree_cache.py:661-723
     const i64 n_live = (i64)seg_tokens.size();
-    std::vector<i64> toks(seg_tokens);
-    std::vector<i64> lens(seg_lens);
-    size_t n_seg = seg_qs.size();
-    if (n_live < block_len) {
-      toks.resize((size_t)block_len, -1);
-      lens.push_back(block_len - n_live);
-      // the pad segment has an empty query set: handled by n_seg below
-    }
-    std::sort(uni.begin(), uni.end());
+    const size_t n_seg = seg_qs.size();
+    const i64 n_pad = n_live < block_len ? block_len - n_live : 0;  // the pad segment has an empty query set
+    if (n_seg > 1) std::sort(uni.begin(), uni.end());  // one segment: its sorted query list is the union already
     uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
     Tile tile;
     tile.n_live = (i32)n_live;
-    for (i64 tk : toks) u_kv.push_back(tk < 0 ? 0 : (i32)tk);
-    for (i64 qv : uni) tile.slots.push_back(rank_of[(size_t)qv] / 32);
+    {
+      const size_t k0 = u_kv.size();
+      u_kv.resize(k0 + (size_t)block_len, 0);
+      for (i64 i = 0; i < n_live; ++i) u_kv[k0 + (size_t)i] = (i32)seg_tokens[(size_t)i];
+    }
+    for (i64 qv : uni) {
+      const i32 sl = rank_of[(size_t)qv] / 32;
+      if (std::find(tile.slots.begin(), tile.slots.end(), sl) == tile.slots.end()) tile.slots.push_back(sl);
+    }
     std::sort(tile.slots.begin(), tile.slots.end());
-    tile.slots.erase(std::unique(tile.slots.begin(), tile.slots.end()), tile.slots.end());
     tile.masks.assign(tile.slots.size() * 128, 0u);
     {
       size_t tok = 0;
-      std::vector<uint32_t> words(tile.slots.size());
+      words.resize(tile.slots.size());
       for (size_t sg = 0; sg < n_seg; ++sg) {
         // every token of a segment is attended by the same queries: one word per touched slot, then filled in
         std::fill(words.begin(), words.end(), 0u);
@@ -197,18 +223,23 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       f_groups.push_back(g);
       block_q.insert(block_q.end(), uni.begin() + (long)s0, uni.begin() + (long)s1);
       block_q_cnts.push_back((i64)(s1 - s0));
-      block_kv.insert(block_kv.end(), toks.begin(), toks.end());
+      block_kv.insert(block_kv.end(), seg_tokens.begin(), seg_tokens.end());
+      block_kv.insert(block_kv.end(), (size_t)n_pad, (i64)-1);
       block_lens.push_back(n_live);
-      for (size_t s = 0; s < lens.size(); ++s) {
+      for (size_t s = 0; s < n_seg; ++s) {
         i64 bits = 0;
-        if (s < n_seg)
+        if (n_seg == 1) {
+          bits = (i64)(((uint64_t)1 << (s1 - s0)) - 1);   // the sub-list [s0, s1) IS the segment's query set (<= 32 of them)
+        } else {
           for (i64 qv : seg_qs[s]) {
             // position of qv inside the sub-list [s0, s1)
             auto it = std::lower_bound(uni.begin() + (long)s0, uni.begin() + (long)s1, qv);
             if (it != uni.begin() + (long)s1 && *it == qv) bits |= (i64)1 << (it - (uni.begin() + (long)s0));
           }
-        block_masks.insert(block_masks.end(), (size_t)lens[s], bits);
+        }
+        block_masks.insert(block_masks.end(), (size_t)seg_lens[s], bits);
       }
+      block_masks.insert(block_masks.end(), (size_t)n_pad, (i64)0);
     }
     tiles.push_back(std::move(tile));
     item.n_grp = (i32)f_groups.size() - item.grp_off;
@@ -217,7 +248,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     seg_tokens.clear(); seg_lens.clear(); seg_qs.clear(); uni.clear();
   };
 
-  std::vector<i64> kvs, q;
+  auto& kvs = S.kvs;
+  std::vector<i64> q;
   for (i32 n = 0; n < n_nodes; ++n) {  // pre-order visit == the reference's recursive dfs (:725-791)
     const i64 k0 = kv_off[n], k1 = kv_off[n + 1], q0 = q_off[n], q1 = q_off[n + 1];
     if (k1 < k0 || q1 <= q0) {
@@ -240,7 +272,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       return nullptr;
     }
     const i64 step = max_block_len == -1 ? n_kv : max_block_len;
-    if (!tix_row) std::sort(kvs.begin(), kvs.end());  // :736 (the tree-index table keeps page order)
+    const bool kv_sorted = std::is_sorted(kvs.begin(), kvs.end());  // pages of a node are handed out ascending
+    if (!tix_row && !kv_sorted) std::sort(kvs.begin(), kvs.end());  // :736 (the tree-index table keeps page order)
     for (size_t s0 = 0; s0 < q.size(); s0 += (size_t)max_q_len) {
       const size_t s1 = std::min(q.size(), s0 + (size_t)max_q_len);
       for (i64 c0 = 0; c0 < n_kv; c0 += step) {
@@ -252,7 +285,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         else node_kv.insert(node_kv.end(), kvs.begin() + c0, kvs.begin() + c1);
       }
     }
-    if (tix_row) std::sort(kvs.begin(), kvs.end());
+    if (tix_row && !kv_sorted) std::sort(kvs.begin(), kvs.end());
     // flatten packing (:763-788)
     i64 room = block_len - (i64)seg_tokens.size();
     i64 done = 0;
@@ -318,7 +351,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<i32> u_q, u_job_off;
   std::vector<deft_job_t> u_jobs;
   bool plan_paired = false;  // the job lists pair slot-jobs on CTAs (2c, 2c + 1): launch as clusters of two
-  std::vector<uint32_t> u_mask;
+  auto& u_mask = S.u_mask;
+  u_mask.clear();
   Csr u_csr;
   u_csr.off.assign((size_t)query_num + 1, 0);
   i32 n_unit_slots = 0;
@@ -455,11 +489,35 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
       return worst;
     };
+    // The search depends only on the shape of the work (chains, tile costs, liveness, grid): consecutive decode steps
+    // mostly keep it, so the last answer is kept per thread under a hash of exactly those inputs.  (A colliding
+    // hash could only cost balance, never correctness: any piece length gives a valid plan.)
+    std::vector<uint64_t> key;
+    {
+      uint64_t hsh = 1469598103934665603ull;
+      auto mix = [&](uint64_t v) { hsh = (hsh ^ v) * 1099511628211ull; };
+      for (const Chain& c : chains) { mix((uint64_t)c.pair); mix(c.t0); mix(c.n_tiles); }
+      for (double tc : tile_cost) { uint64_t b; std::memcpy(&b, &tc, 8); mix(b); }
+      for (size_t i = 0; i + 8 <= tile_live.size(); i += 8) { uint64_t b; std::memcpy(&b, tile_live.data() + i, 8); mix(b); }
+      for (size_t i = tile_live.size() & ~(size_t)7; i < tile_live.size(); ++i) mix(tile_live[i]);
+      uint64_t bj, bg;
+      std::memcpy(&bj, &kJobConst, 8);
+      std::memcpy(&bg, &gather_cost, 8);
+      key = {hsh, (uint64_t)chains.size(), (uint64_t)tiles.size(), (uint64_t)n_slots, (uint64_t)query_num,
+             (uint64_t)heads, (uint64_t)ctas, bj, bg};
+    }
     double best_len = cand.back();
-    double best = -1.0;
-    for (double l : cand) {  // ascending: ties go to the longer piece (fewer partials)
-      const double m = makespan(l);
-      if (best < 0.0 || m <= best + 1e-9) { best = m; best_len = l; }
+    const char* env_k = std::getenv("DEFT_PLAN_CACHE");
+    if (!(env_k && env_k[0] == '0') && key == S.plan_key) {
+      best_len = S.plan_len;
+    } else {
+      double best = -1.0;
+      for (double l : cand) {  // ascending: ties go to the longer piece (fewer partials)
+        const double m = makespan(l);
+        if (best < 0.0 || m <= best + 1e-9) { best = m; best_len = l; }
+      }
+      S.plan_key = key;
+      S.plan_len = best_len;
     }
 
     std::vector<double> ucost;
@@ -627,7 +685,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
 
   lap("units + jobs");
   // ---- pack
-  deft_tables_t* t = new (std::nothrow) deft_tables_t();
+  deft_tables_t* t = S.spare ? S.spare : new (std::nothrow) deft_tables_t();
+  S.spare = nullptr;
   if (!t) {
     deft::set_error("build_tables: out of memory");
     return nullptr;
@@ -654,9 +713,14 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     t->dir[2 * i + 1] = (i64)src[i].n;
     off += (src[i].n * src[i].elem + 255) / 256 * 256;
   }
-  t->packed.assign(std::max<size_t>(off, 256), 0);
-  for (int i = 0; i < DEFT_T_COUNT; ++i)
-    if (src[i].n) std::memcpy(t->packed.data() + t->dir[2 * i], src[i].p, src[i].n * src[i].elem);
+  t->packed.resize(std::max<size_t>(off, 256));
+  for (int i = 0; i < DEFT_T_COUNT; ++i) {  // every byte is written: the tables, and zeros up to the next 256-byte boundary
+    unsigned char* dst = t->packed.data() + t->dir[2 * i];
+    const size_t nb = src[i].n * src[i].elem;
+    const size_t end = (i + 1 < DEFT_T_COUNT ? (size_t)t->dir[2 * i + 2] : t->packed.size()) - (size_t)t->dir[2 * i];
+    if (nb) std::memcpy(dst, src[i].p, nb);
+    std::memset(dst + nb, 0, end - nb);
+  }
   t->scalars[0] = query_num;
   t->scalars[1] = (i64)node_q_len.size();
   t->scalars[2] = total_kv_len;
@@ -684,6 +748,9 @@ int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out) {
   return DEFT_OK;
 }
 
-void deft_b200_tables_free(deft_tables_t* t) { delete t; }
+void deft_b200_tables_free(deft_tables_t* t) {
+  if (t && !g_scratch.spare) g_scratch.spare = t;   // its buffer serves the next build of this thread
+  else delete t;
+}
 
 }  // extern "C"
