@@ -56,7 +56,19 @@ class KVCacheUpdater:
         kv_append(kv, cache_k, cache_v, self.device_loc())
 
 
+_PAUSE_EPOCH = [0]     # moved whenever a node's ``paused`` flag changes (part of flatten_tree's cache key)
+
+
 class TreeNode:
+    @property
+    def paused(self) -> bool:
+        return self._paused
+
+    @paused.setter
+    def paused(self, value: bool) -> None:
+        self._paused = bool(value)
+        _PAUSE_EPOCH[0] += 1
+
     def __init__(self, id: int, node_indices_id: Optional[int] = None,
                  node_indices: Optional[torch.Tensor] = None) -> None:
         self.id = id
@@ -67,7 +79,7 @@ class TreeNode:
         self.kv_indices: List[int] = []
         self.parent: Optional["TreeNode"] = None
         self.refs: Set["TreeNode"] = set()
-        self.paused = False
+        self._paused = False
         self.node_indices_id = node_indices_id
         self.node_indices = node_indices
         self.cumulative_logprob = 0.0
@@ -114,6 +126,7 @@ class TreeCache:
         self.use_tree_index = use_tree_index
         self.layer_num = layer_num
         self.deleted_token_num = 0
+        self._topo_version = 0      # bumped by every change of nodes / leaves / refs: flatten_tree keeps the walk
 
     # ---- construction -------------------------------------------------------------------
     def _take_index_row(self):
@@ -128,6 +141,7 @@ class TreeCache:
         ids = prompt_ids.tolist() if hasattr(prompt_ids, "tolist") else list(prompt_ids)
         n = len(ids)
         rid, row = self._take_index_row()
+        self._topo_version += 1
         root = TreeNode(0, rid, row)
         root.token_ids = ids
         root.positions = list(range(n))
@@ -148,6 +162,7 @@ class TreeCache:
         return KVCacheUpdater(self.token_to_kv_pool, cache_loc, is_prompt=True)
 
     def new_node(self, parent: TreeNode) -> TreeNode:
+        self._topo_version += 1
         rid, row = self._take_index_row()
         node = TreeNode(self.node_cnt, rid, row)
         self.node_cnt += 1
@@ -189,6 +204,7 @@ class TreeCache:
 
     def branch(self, node: TreeNode, branch_cnt: int) -> List[TreeNode]:
         assert node.id in self.leaves
+        self._topo_version += 1
         self.leaves.pop(node.id)
         path_len = node.positions[-1] + 1
         req = self.leaf_to_req.pop(node.id)
@@ -213,6 +229,7 @@ class TreeCache:
     def cut(self, node: TreeNode, record_deleted: bool = False) -> List[TreeNode]:
         assert len(node.children) == 0
         assert node.id in self.leaves
+        self._topo_version += 1
         self.leaves.pop(node.id)
         self.remove_ref(node)
         self.req_to_token_pool.free(self.leaf_to_req.pop(node.id))
@@ -234,6 +251,7 @@ class TreeCache:
         return deleted
 
     def add_ref(self, node: TreeNode) -> None:
+        self._topo_version += 1
         ref = node
         cur: Optional[TreeNode] = node
         while cur is not None:
@@ -241,6 +259,7 @@ class TreeCache:
             cur = cur.parent
 
     def remove_ref(self, node: TreeNode) -> None:
+        self._topo_version += 1
         ref = node
         cur: Optional[TreeNode] = node
         while cur is not None:
@@ -248,6 +267,7 @@ class TreeCache:
             cur = cur.parent
 
     def free(self) -> None:
+        self._topo_version += 1
         self.root = None
         self.nodes.clear()
         self.leaves.clear()
@@ -260,16 +280,47 @@ class TreeCache:
 # ------------------------------------------------------------------------------------------------
 # metadata
 # ------------------------------------------------------------------------------------------------
-def flatten_tree(tree) -> Dict[str, Any]:
-    """Any ``TreeCache``-shaped object -> the flat arrays ``deft_b200_build_tables`` takes.
+def _node_pages(node) -> np.ndarray:
+    """``node.kv_indices`` as int64, converted once and extended as the list grows.
 
-    Nodes in DFS pre-order, children in dict (creation) order -- the visiting order of
-    tree_cache.py:725-791; queries = rank of each ref'd leaf by ascending leaf id (:650-652).
+    The page list of a node only ever grows by appends (``append_index``, tree_cache.py:126) or is replaced by a
+    new list object (:210, :332); the cache is keyed on the list object and its first/last cached entries, and a
+    list that shrank or was swapped is converted afresh.  (4096 prompt pages cost 0.25 ms to convert: more than
+    the C++ builder takes for the whole tree.)
     """
-    leaf_to_q = {leaf.id: i for i, leaf in enumerate(sorted(tree.leaves.values(), key=lambda x: x.id))}
+    lst = node.kv_indices
+    n = len(lst)
+    c = getattr(node, "_kv_np", None)
+    if c is not None:
+        src, arr, m, first, last, view = c
+        if src is lst and m <= n and (m == 0 or (first == lst[0] and last == lst[m - 1])):
+            if m == n:
+                return view
+            if n > arr.shape[0]:
+                grown = np.empty(max(n + 64, 2 * arr.shape[0]), dtype=np.int64)
+                grown[:m] = arr[:m]
+                arr = grown
+            arr[m:n] = lst[m:n]
+            view = arr[:n]
+            node._kv_np = (lst, arr, n, lst[0], lst[n - 1], view)
+            return view
+    arr = np.empty(n + 64, dtype=np.int64)
+    arr[:n] = lst
+    view = arr[:n]
+    try:
+        node._kv_np = (lst, arr, n, lst[0] if n else 0, lst[n - 1] if n else 0, view)
+    except AttributeError:        # a node type with __slots__: no cache
+        pass
+    return view
+
+
+def _walk(tree):
+    """DFS pre-order walk: (nodes, parent, q_off, qs, tix, leaf_to_q)."""
+    leaf_to_q = {lid: i for i, lid in enumerate(sorted(tree.leaves))}      # leaves is keyed by leaf id
+    nodes: List[Any] = []
     parent: List[int] = []
-    kv_lists: List[List[int]] = []
-    q_lists: List[List[int]] = []
+    qs: List[int] = []
+    q_len: List[int] = []
     tix: List[int] = []
     stack = [(tree.root, -1)]
     while stack:
@@ -277,21 +328,46 @@ def flatten_tree(tree) -> Dict[str, Any]:
         if node.paused:
             continue
         me = len(parent)
+        nodes.append(node)
         parent.append(par)
-        kv_lists.append(node.kv_indices)
-        q_lists.append([leaf_to_q[r.id] for r in node.refs if not r.paused])
+        n0 = len(qs)
+        qs.extend([leaf_to_q[r.id] for r in node.refs if not r.paused])
+        q_len.append(len(qs) - n0)
         tix.append(-1 if node.node_indices_id is None else node.node_indices_id)
-        for child in reversed(list(node.children.values())):
-            stack.append((child, me))
-    n = len(parent)
-    kv_off = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum([len(x) for x in kv_lists], out=kv_off[1:])
-    q_off = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum([len(x) for x in q_lists], out=q_off[1:])
-    kv = np.fromiter(chain.from_iterable(kv_lists), dtype=np.int64, count=int(kv_off[-1]))
-    qs = np.fromiter(chain.from_iterable(q_lists), dtype=np.int64, count=int(q_off[-1]))
-    return dict(parent=np.asarray(parent, dtype=np.int32), kv_off=kv_off, kv=kv, q_off=q_off, qs=qs,
-                tix=np.asarray(tix, dtype=np.int64), leaf_to_q=leaf_to_q)
+        if node.children:
+            for child in reversed(list(node.children.values())):
+                stack.append((child, me))
+    q_off = np.zeros(len(parent) + 1, dtype=np.int64)
+    np.cumsum(q_len, out=q_off[1:])
+    return (nodes, np.asarray(parent, dtype=np.int32), q_off, np.asarray(qs, dtype=np.int64),
+            np.asarray(tix, dtype=np.int64), leaf_to_q)
+
+
+def flatten_tree(tree) -> Dict[str, Any]:
+    """Any ``TreeCache``-shaped object -> the flat arrays ``deft_b200_build_tables`` takes.
+
+    Nodes in DFS pre-order, children in dict (creation) order -- the visiting order of
+    tree_cache.py:725-791; queries = rank of each ref'd leaf by ascending leaf id (:650-652).
+    A decode step that only appended pages (``alloc``) keeps the topology: for our ``TreeCache`` (which counts
+    its structural changes) the walk is kept and only the page lists are gathered again.
+    """
+    ver = getattr(tree, "_topo_version", None)
+    topo = None
+    if ver is not None:
+        key = (ver, _PAUSE_EPOCH[0], id(tree.root))
+        c = getattr(tree, "_flat_topo", None)
+        if c is not None and c[0] == key:
+            topo = c[1]
+    if topo is None:
+        topo = _walk(tree)
+        if ver is not None:
+            tree._flat_topo = (key, topo)
+    nodes, parent, q_off, qs, tix, leaf_to_q = topo
+    kv_arrs = [_node_pages(n) for n in nodes]
+    kv_off = np.zeros(len(nodes) + 1, dtype=np.int64)
+    np.cumsum([a.shape[0] for a in kv_arrs], out=kv_off[1:])
+    kv = np.concatenate(kv_arrs) if kv_arrs else np.zeros(0, dtype=np.int64)
+    return dict(parent=parent, kv_off=kv_off, kv=kv, q_off=q_off, qs=qs, tix=tix, leaf_to_q=leaf_to_q)
 
 
 def flatten_forest(trees) -> Dict[str, Any]:
@@ -323,25 +399,36 @@ class _Staging:
         self.events: List[Optional[torch.cuda.Event]] = [None] * depth
         self.i = 0
 
-    def upload(self, src: np.ndarray, device: torch.device, into: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """One async H2D copy of ``src``; into the first bytes of ``into`` when given (a persistent device buffer:
-        the tables then keep their addresses from one decode step to the next), else into a fresh tensor."""
-        n = src.nbytes
+    def reserve(self, n: int) -> torch.Tensor:
+        """The next pinned buffer of the ring, at least ``n`` bytes, no longer read by an earlier copy."""
         slot = self.i
         self.i = (self.i + 1) % len(self.bufs)
         if self.events[slot] is not None:
             self.events[slot].synchronize()
+            self.events[slot] = None
         buf = self.bufs[slot]
         if buf is None or buf.numel() < n:
             buf = torch.empty(max(n, 1 << 20), dtype=torch.uint8, pin_memory=True)
             self.bufs[slot] = buf
-        buf[:n].numpy()[:] = src
+        self._slot = slot
+        return buf
+
+    def send(self, buf: torch.Tensor, n: int, device: torch.device, into: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One async H2D copy of the first ``n`` bytes of the reserved buffer; into the first bytes of ``into`` when
+        given (a persistent device buffer: the tables then keep their addresses from one decode step to the next),
+        else into a fresh tensor."""
         out = into[:n] if into is not None else torch.empty(n, dtype=torch.uint8, device=device)
         out.copy_(buf[:n], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self.events[slot] = ev
+        self.events[self._slot] = ev
         return out
+
+    def upload(self, src: np.ndarray, device: torch.device, into: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n = src.nbytes
+        buf = self.reserve(n)
+        buf[:n].numpy()[:] = src
+        return self.send(buf, n, device, into)
 
 
 _STAGING = _Staging()
@@ -363,28 +450,36 @@ def sm_count(device: Optional[torch.device]) -> int:
 
 def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: int = -1,
                       block_len: int = 128, tree_index_max_ctx: int = 0, node_split: int = NODE_SPLIT,
-                      hkv: int = 0, n_ctas: int = 148):
-    """Runs the C++ builder; returns (packed bytes as numpy uint8, directory, scalars)."""
-    def ptr(a: np.ndarray):
-        return a.ctypes.data_as(C.c_void_p)
+                      hkv: int = 0, n_ctas: int = 148, reserve=None):
+    """Runs the C++ builder; returns (packed bytes as numpy uint8, directory, scalars).
+
+    ``reserve(nbytes) -> uint8 tensor`` (optional) supplies the destination -- the pinned staging buffer of the
+    upload -- so that the tables are copied once, straight out of the builder; the first return value is then
+    ``(tensor, nbytes)`` instead of an array."""
     query_num = len(flat["leaf_to_q"])
     use_tix = tree_index_max_ctx > 0
-    h = _lib.lib.deft_b200_build_tables(len(flat["parent"]), ptr(flat["parent"]), ptr(flat["kv_off"]), ptr(flat["kv"]),
-                                        ptr(flat["q_off"]), ptr(flat["qs"]), ptr(flat["tix"]) if use_tix else None,
+    h = _lib.lib.deft_b200_build_tables(len(flat["parent"]), flat["parent"].ctypes.data, flat["kv_off"].ctypes.data,
+                                        flat["kv"].ctypes.data, flat["q_off"].ctypes.data, flat["qs"].ctypes.data,
+                                        flat["tix"].ctypes.data if use_tix else None,
                                         tree_index_max_ctx, query_num, block_len, max_q_len, max_block_len, node_split,
                                         hkv, n_ctas)
     if not h:
         raise _lib.DeftError(f"deft_b200_build_tables failed: {_lib.last_error()}")
     try:
         nbytes = _lib.lib.deft_b200_tables_bytes(h)
-        data = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(_lib.lib.deft_b200_tables_data(h))).copy()
-        directory = np.zeros(2 * _lib.T_COUNT, dtype=np.int64)
-        _lib.check(_lib.lib.deft_b200_tables_directory(h, ptr(directory)))
-        scalars = np.zeros(_lib.N_SCALARS, dtype=np.int64)
-        _lib.check(_lib.lib.deft_b200_tables_scalars(h, ptr(scalars)))
+        src = _lib.lib.deft_b200_tables_data(h)
+        if reserve is not None:
+            buf = reserve(nbytes)
+            C.memmove(buf.data_ptr(), src, nbytes)
+            data = (buf, nbytes)
+        else:
+            data = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(src)).copy()
+        meta = np.empty(2 * _lib.T_COUNT + _lib.N_SCALARS, dtype=np.int64)
+        _lib.check(_lib.lib.deft_b200_tables_directory(h, meta.ctypes.data))
+        _lib.check(_lib.lib.deft_b200_tables_scalars(h, meta.ctypes.data + 16 * _lib.T_COUNT))
     finally:
         _lib.lib.deft_b200_tables_free(h)
-    return data, directory.reshape(-1, 2), scalars
+    return data, meta[: 2 * _lib.T_COUNT].reshape(-1, 2), meta[2 * _lib.T_COUNT:]
 
 
 @dataclass
@@ -424,31 +519,35 @@ class TreeMetadata:
         pool = tree.token_to_kv_pool           # ours, or the reference's (which has no .device)
         device = getattr(pool, "device", None) or pool.kv_data[0].device
         hkv = int(pool.kv_data[0].shape[2]) if len(pool.kv_data) else 0     # kv_data[l] is [size, 2, HKV, D]
-        data, directory, scalars = build_tables_host(flat, max_q_len, max_block_len, block_len, max_ctx,
-                                                     hkv=hkv, n_ctas=sm_count(device))
         on_gpu = device.type == "cuda"
-        if device_buffer is not None and (not on_gpu or device_buffer.numel() < data.nbytes):
-            device_buffer = None               # too small (or a CPU pool): a fresh tensor, like without it
-        packed = _STAGING.upload(data, device, device_buffer) if on_gpu else torch.from_numpy(data)
-
-        def view(i: int, dtype: torch.dtype, elem: int) -> torch.Tensor:
-            off, cnt = int(directory[i, 0]), int(directory[i, 1])
-            return packed[off: off + cnt * elem].view(dtype)
-
-        t = {name: view(i, torch.int64, 8) for i, name in enumerate(_lib.T_NAMES[:12])}
+        data, directory, scalars = build_tables_host(flat, max_q_len, max_block_len, block_len, max_ctx,
+                                                     hkv=hkv, n_ctas=sm_count(device),
+                                                     reserve=_STAGING.reserve if on_gpu else None)
+        if on_gpu:
+            buf, nbytes = data
+            if device_buffer is not None and device_buffer.numel() < nbytes:
+                device_buffer = None           # too small: a fresh tensor, like without it
+            packed = _STAGING.send(buf, nbytes, device, device_buffer)
+        else:
+            packed = torch.from_numpy(data)
+        directory = directory.tolist()
+        p64 = packed.view(torch.int64)         # every table starts on a 256-byte boundary of the packed buffer
+        t = {name: p64[directory[i][0] >> 3: (directory[i][0] >> 3) + directory[i][1]]
+             for i, name in enumerate(_lib.T_NAMES[:12])}
         base = packed.data_ptr()
+        dir_bytes = np.asarray(directory, dtype=np.int64).tobytes()
 
         U = _lib.T_NAMES.index("u_units")
 
         def addr(i: int) -> Optional[int]:
-            return base + int(directory[i, 0]) if int(directory[i, 1]) > 0 else None
+            return base + directory[i][0] if directory[i][1] > 0 else None
 
         def plan(first: int, rows: int) -> _lib.Plan:
             """Item/group layer of one operator + the native unit layer (shared by both operators)."""
-            return _lib.Plan(items=base + int(directory[first, 0]), groups=base + int(directory[first + 1, 0]),
-                             csr_off=base + int(directory[first + 2, 0]), csr_rows=base + int(directory[first + 3, 0]),
-                             n_items=int(directory[first, 1]), n_groups=int(directory[first + 1, 1]),
-                             n_part_rows=rows, n_units=int(directory[U, 1]),
+            return _lib.Plan(items=base + directory[first][0], groups=base + directory[first + 1][0],
+                             csr_off=base + directory[first + 2][0], csr_rows=base + directory[first + 3][0],
+                             n_items=directory[first][1], n_groups=directory[first + 1][1],
+                             n_part_rows=rows, n_units=directory[U][1],
                              units=addr(U), u_csr_off=addr(U + 1), u_csr_rows=addr(U + 2), u_kv=addr(U + 3),
                              u_mask=addr(U + 4), u_q=addr(U + 5), u_job_off=addr(U + 6), u_jobs=addr(U + 7),
                              n_unit_slots=int(scalars[6]), n_ctas=int(scalars[7]), hkv=hkv, paired=int(scalars[8]))
@@ -462,7 +561,7 @@ class TreeMetadata:
         meta = cls(query_num=int(scalars[0]), node_num=int(scalars[1]), total_kv_len=int(scalars[2]),
                    leaf_to_q=flat["leaf_to_q"], block_len=int(scalars[3]), packed=packed,
                    flat_plan=None if tree_index else plan(12, int(scalars[4])), node_plan=plan(16, int(scalars[5])),
-                   layout=directory.tobytes() + scalars.tobytes() + int(base).to_bytes(8, "little"), **t)
+                   layout=dir_bytes + scalars.tobytes() + int(base).to_bytes(8, "little"), **t)
         if on_gpu:
             register_plan(meta)
         return meta

@@ -103,3 +103,68 @@ def test_pool_allocator_contract():
 def test_unpaged_mode_is_refused():
     with pytest.raises(NotImplementedError):
         TreeCache(torch.float16, 1, 16, 1, None, None, None, use_paged_memory=False)
+
+
+def _fresh_flat(tree):
+    """flatten_tree with every cache dropped (the walk and the per-node page arrays)."""
+    from deft_b200.tree_cache import flatten_tree
+    if hasattr(tree, "_flat_topo"):
+        del tree._flat_topo
+    for n in tree.nodes.values():
+        if hasattr(n, "_kv_np"):
+            del n._kv_np
+    return flatten_tree(tree)
+
+
+def test_flatten_tree_caches_follow_every_mutation():
+    """The kept walk / page arrays of flatten_tree give what a fresh walk gives after alloc, branch, cut and merge."""
+    import random
+    from deft_b200.tree_cache import flatten_tree
+    rng = random.Random(7)
+    r2t = ReqToTokenPool(size=256, max_context_len=512, device="cpu")
+    kvp = TokenToKVPool(size=8192, dtype=torch.float16, head_num=1, head_dim=16, layer_num=1, device="cpu")
+    tree = TreeCache(torch.float16, 1, 16, 1, r2t, kvp, None, True, False)
+    tree.init_prompt(torch.arange(1, 201, dtype=torch.int32))
+
+    def check():
+        got = flatten_tree(tree)              # cached path
+        again = flatten_tree(tree)            # nothing changed in between
+        want = _fresh_flat(tree)
+        for k in ("parent", "kv_off", "kv", "q_off", "qs", "tix"):
+            assert np.array_equal(got[k], want[k]), k
+            assert np.array_equal(again[k], want[k]), k
+        assert got["leaf_to_q"] == want["leaf_to_q"]
+
+    check()
+    for step in range(60):
+        op = rng.random()
+        leaves = sorted(tree.leaves.values(), key=lambda x: x.id)
+        if op < 0.25 and len(leaves) < 24:
+            leaf = rng.choice(leaves)
+            if leaf.get_len() > 0:
+                tree.branch(leaf, rng.choice((2, 3)))
+        elif op < 0.35 and len(leaves) > 2:
+            tree.cut(rng.choice(leaves))
+        elif op < 0.40:
+            leaf = rng.choice(leaves)
+            leaf.paused = False                # the setter moves the epoch: the walk is redone, same result
+        for leaf in tree.leaves.values():      # a decode step: one token and one page per leaf
+            leaf.append_token(step)
+        tree.alloc()
+        check()
+
+
+def test_plan_search_cache_gives_the_cold_answer(monkeypatch):
+    """Two builds in a row (the second takes the remembered piece length) equal a build with the memory off."""
+    from deft_b200.tree_cache import build_tables_host, flatten_tree
+    from deft_b200.workloads import build_tree
+    for name in ("cfg3", "cfg2"):
+        tree = build_tree(name, layers=1, device=torch.device("cpu"), H=4, HKV=2, D=16)
+        flat = flatten_tree(tree)
+        a, da, sa = build_tables_host(flat, hkv=2, n_ctas=148)
+        b, db, sb = build_tables_host(flat, hkv=2, n_ctas=148)
+        monkeypatch.setenv("DEFT_PLAN_CACHE", "0")
+        c, dc, sc = build_tables_host(flat, hkv=2, n_ctas=148)
+        monkeypatch.delenv("DEFT_PLAN_CACHE")
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+        assert np.array_equal(da, db) and np.array_equal(da, dc) and np.array_equal(sa, sc)
