@@ -199,7 +199,8 @@ def test_programmatic_dependent_launch_is_race_free(dev, name):
         assert torch.equal(a[i], a[i - 4])
 
 
-def test_reference_maximum_is_raised_mid_chain(dev):
+@pytest.mark.parametrize("subtree_ramp", [False, True])
+def test_reference_maximum_is_raised_mid_chain(dev, subtree_ramp):
     """Scores that grow along the KV chain: the tile exponentials overflow the fp16 range of P against the first
     tile's maximum, so the kernel must raise its reference maximum, rescale the accumulator in TMEM and redo the
     tile (attn_umma.cu, the rare path of the softmax warps).  Compared with fp64 per-leaf attention."""
@@ -214,6 +215,9 @@ def test_reference_maximum_is_raised_mid_chain(dev):
     # K magnitude grows with the page id: x1 at the start of the prompt, x24 at its end and in the subtree
     pool = kv.shape[0]
     ramp = (1.0 + 23.0 * torch.clamp(torch.arange(pool, device=dev, dtype=torch.float32) / 4096.0, max=1.0)).half()
+    if subtree_ramp:   # ... and keeps growing through the subtree pages: the raise then also hits MASKED tiles
+        idx = torch.arange(pool, device=dev, dtype=torch.float32)
+        ramp = (ramp.float() + 40.0 * torch.clamp(idx - 4096.0, min=0.0) / max(pool - 4096, 1)).half()
     kv[:, 0].mul_(ramp[:, None, None])
     K, V = kvp.get_key_buffer(0), kvp.get_value_buffer(0)
     nq = len(tree.leaves)

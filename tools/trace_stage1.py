@@ -19,7 +19,11 @@ from deft_b200 import TreeMetadata, _lib
 from deft_b200.workloads import build_tree
 
 NAMES = {0: "start", 1: "q_ids", 2: "q_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
-         8: "epi_end", 9: "end", 12: "k_role_entry"}
+         8: "epi_end", 9: "end", 12: "k_role_entry",
+         112: "t2.exp_done", 113: "t2.sync_or_done", 114: "t2.p_st_issued", 115: "t2.next_s_ld_issued", 116: "t2.p_st_landed",
+         117: "t3.s_was_prefetched", 118: "t2.mask_full_seen", 119: "t2.mask_applied",
+         120: "t1.maskwarp_words_loaded", 121: "t1.maskwarp_full_arrive", 122: "t2.maskwarp_words_loaded", 123: "t2.maskwarp_full_arrive",
+         124: "t3.maskwarp_words_loaded", 125: "t3.maskwarp_full_arrive"}
 TILE = ["k_issued", "mma_k_full(S issued)", "sm_s_full", "sm_ready", "sm_p_arrive", "mma_pa_full", "v_issued", "k_landed"]
 
 
