@@ -201,7 +201,13 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    json_out = sys.stdout
     if world > 1:
+        # NCCL writes its banner ("NCCL version ...") to fd 1 when NCCL_DEBUG is set: the JSON line keeps the real
+        # stdout, everything else that writes to fd 1 goes to stderr
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     import deft_b200
@@ -388,7 +394,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.workload, args.cpu_reps)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -72,6 +72,13 @@ def main():
     active = [c for c in range(t.shape[0]) if ends[c] >= 0]
     print(f"{wl}: {len(active)} CTAs traced; end (us): min {ends[active].min() / ghz / 1e3:.2f} "
           f"max {ends[active].max() / ghz / 1e3:.2f} mean {ends[active].mean() / ghz / 1e3:.2f}")
+    if os.environ.get("TRACE_TABLE"):      # one line per CTA: first S issued, tiles seen (of the first job, <= 6), epilogue, end
+        for c in sorted(active, key=lambda c: -ends[c]):
+            s0 = t[c, 16 + 1]
+            nt = sum(1 for tile in range(6) if t[c, 16 + 8 * tile + 4] >= 0)
+            last_p = max([t[c, 16 + 8 * tile + 4] for tile in range(6)] + [-1])
+            print(f"cta {c:3d}  S0 {s0 / ghz / 1e3:6.2f}  tiles>={nt}  last_p {last_p / ghz / 1e3:6.2f}  epi {t[c, 7] / ghz / 1e3:6.2f}..{t[c, 8] / ghz / 1e3:6.2f}  end {ends[c] / ghz / 1e3:6.2f}")
+        return
     order = sorted(active, key=lambda c: -ends[c])
     for c in order[:show] + [order[len(order) // 2]] + order[-1:]:
         print(f"--- CTA {c}")
