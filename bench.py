@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--mode", default="flatten", choices=["flatten", "node", "node_chunk", "seq"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--e2e-chunk", type=int, default=8, choices=[1, 2, 4, 8, 16, 32],
+                    help="layers per H2D / graph / D2H chunk of the end-to-end leg")
     ap.add_argument("--trees-per-gpu", type=int, default=1,
                     help="independent trees of the workload batched into ONE launch per layer (BASELINE cfg 5)")
     return ap.parse_args()
@@ -312,7 +314,7 @@ def main():
     table_bytes = [0]
     main = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()      # H2D and D2H ride their own copy engines
-    CH = 8                                                       # layers per copy chunk
+    CH = args.e2e_chunk                                          # layers per copy chunk (and per CUDA graph)
     ev_in = [torch.cuda.Event() for _ in range(LAYERS // CH)]
     ev_out = [torch.cuda.Event() for _ in range(LAYERS // CH)]
 
@@ -382,10 +384,10 @@ def main():
         "clocks": clocks,
         "e2e": {"value": world * nq / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "path": "DecodeStepGraph.metadata (TreeMetadata.from_tree_cache: C++ builder, 1 upload into the persistent table "
-                        "buffer) + pinned H2D of the fused qkv in 8-layer chunks on a copy stream + 32 x (kv_append + "
-                        "tree attention) replayed as 4 CUDA graphs + D2H of the outputs per chunk on a second copy stream; "
-                        "timed until the last output is on the host" if graphed else
+                "path": ("DecodeStepGraph.metadata (TreeMetadata.from_tree_cache: C++ builder, 1 upload into the persistent table "
+                         "buffer) + pinned H2D of the fused qkv in %d-layer chunks on a copy stream + 32 x (kv_append + "
+                         "tree attention) replayed as %d CUDA graphs + D2H of the outputs per chunk on a second copy stream; "
+                         "timed until the last output is on the host" % (CH, LAYERS // CH)) if graphed else
                         "per-layer eager calls (kv_append + token_attention_fwd) between chunked pinned H2D / D2H copies"},
         "gpu_launches": args.steps * LAYERS * 2,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -315,6 +315,11 @@ def test_decode_step_graph_replays_with_new_table_contents(dev):
         got = out.clone()
         # eager reference on a copy of the pool state: the appended rows are already in place, attention only
         m2 = TreeMetadata.from_tree_cache(tree)
+        # (from the second build on, m shares its views and plans with the previous step's metadata: same layout,
+        # same persistent buffer -- they must show THIS step's tables)
+        assert m.leaf_to_q == m2.leaf_to_q
+        for k in ("block_q", "block_kv", "block_bitmasks", "node_kv", "node_q"):
+            assert torch.equal(getattr(m, k), getattr(m2, k)), (it, k)
         want = torch.empty_like(out)
         for l in range(L):
             deft_b200.tree_attention_subtree_fwd(qkv[l, :, : H * D].view(nq, H, D), kvp.get_key_buffer(l), kvp.get_value_buffer(l),
