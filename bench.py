@@ -332,17 +332,24 @@ def main():
     def step_e2e():
         """Chunk c+1 of the activations comes up while chunk c attends and chunk c-1's outputs go down."""
         s_in.wait_stream(main)                           # the previous step no longer reads dev_qkv
-        with torch.cuda.stream(s_in):
-            for c in range(LAYERS // CH):
-                dev_qkv[c * CH: (c + 1) * CH].copy_(host_qkv[c * CH: (c + 1) * CH], non_blocking=True)
-                ev_in[c].record(s_in)
+
+        def upload(chunks):
+            with torch.cuda.stream(s_in):
+                for c in chunks:
+                    dev_qkv[c * CH: (c + 1) * CH].copy_(host_qkv[c * CH: (c + 1) * CH], non_blocking=True)
+                    ev_in[c].record(s_in)
+
+        upload(range(1))                                 # the first chunk of activations goes up under the table build
         # C++ builder + one H2D copy of tables and plan (into the persistent table buffer of the graphed step)
         m = step.metadata(trees[0] if T == 1 else trees) if graphed else build_meta()
         table_bytes[0] = m.packed.numel()
         loc_dev.copy_(host_loc, non_blocking=True)       # this step's pages (one per leaf)
         if graphed:
-            step.run(m, before_chunk=lambda c: main.wait_event(ev_in[c]), after_chunk=after_chunk)
+            # the other chunks queue BEHIND the tables on the H2D engine, and are enqueued once chunk 0 is launched
+            step.run(m, before_chunk=lambda c: main.wait_event(ev_in[c]),
+                     after_chunk=lambda c: (upload(range(1, LAYERS // CH)) if c == 0 else None, after_chunk(c)))
         else:
+            upload(range(1, LAYERS // CH))
             for l in range(LAYERS):
                 if l % CH == 0:
                     main.wait_event(ev_in[l // CH])
@@ -385,7 +392,8 @@ def main():
         "e2e": {"value": world * nq / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "path": ("DecodeStepGraph.metadata (TreeMetadata.from_tree_cache: C++ builder, 1 upload into the persistent table "
-                         "buffer) + pinned H2D of the fused qkv in %d-layer chunks on a copy stream + 32 x (kv_append + "
+                         "buffer; the first chunk of activations goes up under the build, the others queue behind the tables) + pinned H2D "
+                         "of the fused qkv in %d-layer chunks on a copy stream + 32 x (kv_append + "
                          "tree attention) replayed as %d CUDA graphs + D2H of the outputs per chunk on a second copy stream; "
                          "timed until the last output is on the host" % (CH, LAYERS // CH)) if graphed else
                         "per-layer eager calls (kv_append + token_attention_fwd) between chunked pinned H2D / D2H copies"},

@@ -266,6 +266,9 @@ __global__ void kv_append_kernel(__half* k, __half* v, int64_t kv_tok_stride, in
                                  int64_t new_head_stride, const int32_t* loc, int n, int HKV, int CH) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
   const int64_t total = (int64_t)n * HKV * CH;
+  // launched programmatically (the launch and the block scheduling overlap the previous kernel's tail): nothing is
+  // read or written before the previous kernel's memory is visible.  A no-op for a plain launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (i >= total) return;
   const int ch = (int)(i % CH), h = (int)((i / CH) % HKV), r = (int)(i / ((int64_t)CH * HKV));
   const int64_t src = (int64_t)r * new_row_stride + (int64_t)h * new_head_stride + ch * 8;
@@ -418,11 +421,18 @@ int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head
   const int CH = D / 8;
   const int64_t total = (int64_t)n * HKV * CH;
   const int threads = 256;
-  kv_append_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(
-      static_cast<__half*>(k), static_cast<__half*>(v), kv_tok_stride, kv_head_stride,
-      static_cast<const __half*>(new_k), static_cast<const __half*>(new_v), new_row_stride,
-      new_head_stride, cache_loc, n, HKV, CH);
-  DEFT_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((total + threads - 1) / threads));
+  cfg.blockDim = dim3(threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_no_pdl ? 0 : 1;
+  DEFT_CUDA(cudaLaunchKernelEx(&cfg, kv_append_kernel, static_cast<__half*>(k), static_cast<__half*>(v), kv_tok_stride,
+                               kv_head_stride, static_cast<const __half*>(new_k), static_cast<const __half*>(new_v),
+                               new_row_stride, new_head_stride, cache_loc, n, HKV, CH));
   return DEFT_OK;
 }
 
