@@ -268,6 +268,9 @@ __global__ void kv_append_kernel(__half* k, __half* v, int64_t kv_tok_stride, in
   const int64_t total = (int64_t)n * HKV * CH;
   // launched programmatically (the launch and the block scheduling overlap the previous kernel's tail): nothing is
   // read or written before the previous kernel's memory is visible.  A no-op for a plain launch.
+  // ... and the kernel after this one (stage 1) may start ITS prologue right away (barrier init, TMEM allocation, job
+  // record, tensor-map prefetch: ~1.5 us): it waits for this grid's completion before it touches the pool
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (i >= total) return;
   const int ch = (int)(i % CH), h = (int)((i / CH) % HKV), r = (int)(i / ((int64_t)CH * HKV));
