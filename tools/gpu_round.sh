@@ -20,6 +20,9 @@ done
 for M in node node_chunk; do
   timeout 300 python bench.py --mode $M --steps 20 --no-cpu-baseline > $OUT/bench_$M.json 2>> $OUT/bench.err; cat $OUT/bench_$M.json
 done
+timeout 300 python bench.py --trees-per-gpu 64 --steps 10 --no-cpu-baseline > $OUT/bench_forest64.json 2>> $OUT/bench.err; cat $OUT/bench_forest64.json
+timeout 300 python bench.py --mode seq --steps 10 --no-cpu-baseline > $OUT/bench_seq.json 2>> $OUT/bench.err; cat $OUT/bench_seq.json
+timeout 120 python tools/e2e_breakdown.py > $OUT/e2e_breakdown.txt 2>&1; tail -2 $OUT/e2e_breakdown.txt
 echo "== bench --impl reference"
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_reference.json 2>> $OUT/bench.err; cat $OUT/bench_reference.json
 echo "== ncu launch list"
