@@ -161,6 +161,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     i32 n_live;
     std::vector<i32> slots;        // query slots with at least one attending row, ascending
     std::vector<uint32_t> masks;   // [touched slot][128]: bit r = rank 32*slot + r attends the token
+    std::vector<uint32_t> rows_or; // [touched slot]: OR of the slot's words over the live tokens
+    std::vector<uint8_t> dense;    // [touched slot]: 128 live tokens, every row of the slot attends every one
   };
   std::vector<Tile> tiles;
   auto& u_kv = S.u_kv;
@@ -192,6 +194,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     }
     std::sort(tile.slots.begin(), tile.slots.end());
     tile.masks.assign(tile.slots.size() * 128, 0u);
+    tile.rows_or.assign(tile.slots.size(), 0u);
+    tile.dense.assign(tile.slots.size(), n_live == 128 ? 1 : 0);
     {
       size_t tok = 0;
       words.resize(tile.slots.size());
@@ -203,9 +207,14 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
           const size_t si = (size_t)(std::lower_bound(tile.slots.begin(), tile.slots.end(), rk / 32) - tile.slots.begin());
           words[si] |= 1u << (rk % 32);
         }
-        for (size_t si = 0; si < words.size(); ++si)
-          if (words[si])
-            std::fill_n(tile.masks.begin() + (long)(si * 128 + tok), (size_t)seg_lens[sg], words[si]);
+        for (size_t si = 0; si < words.size(); ++si) {
+          if (seg_lens[sg] <= 0) continue;
+          if (words[si]) std::fill_n(tile.masks.begin() + (long)(si * 128 + tok), (size_t)seg_lens[sg], words[si]);
+          tile.rows_or[si] |= words[si];
+          const i32 cnt = std::min(32, query_num - 32 * tile.slots[si]);
+          const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+          if ((words[si] & full) != full) tile.dense[si] = 0;
+        }
         tok += (size_t)seg_lens[sg];
       }
     }
@@ -452,12 +461,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     // (per-(tile, slot) liveness once, so that every candidate of the search below is O(tiles))
     std::vector<uint8_t> tile_live(tiles.size() * (size_t)n_slots, 0);
     for (size_t t = 0; t < tiles.size(); ++t)
-      for (size_t si = 0; si < tiles[t].slots.size(); ++si) {
-        const uint32_t* w = tiles[t].masks.data() + si * 128;
-        bool live = false;
-        for (i32 n = 0; n < tiles[t].n_live && !live; ++n) live = w[n] != 0;
-        tile_live[t * (size_t)n_slots + (size_t)tiles[t].slots[si]] = live ? 1 : 0;
-      }
+      for (size_t si = 0; si < tiles[t].slots.size(); ++si)
+        tile_live[t * (size_t)n_slots + (size_t)tiles[t].slots[si]] = tiles[t].rows_or[si] != 0 ? 1 : 0;
     auto live_slots_in = [&](i32 pr, size_t ta, size_t tb) {
       int n_live = 0;
       for (int sl = 0; sl < 2; ++sl) {
@@ -533,13 +538,23 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         i32 live_slots[2];
         uint32_t live_rows[2] = {0u, 0u};
         int n_live_slots = 0;
+        bool dense[2] = {true, true};
         for (int sl = 0; sl < 2; ++sl) {
           const i32 slot = 2 * c.pair + sl;
           uint32_t rows = 0;
-          for (size_t t = ta; t < tb; ++t)
-            if (const uint32_t* w = tile_slot(tiles[t], slot))
-              for (i32 n = 0; n < tiles[t].n_live; ++n) rows |= w[n];
-          if (rows) { live_slots[n_live_slots] = slot; live_rows[n_live_slots] = rows; ++n_live_slots; }
+          bool all_dense = true;
+          for (size_t t = ta; t < tb; ++t) {
+            const Tile& tl = tiles[t];
+            auto it = std::lower_bound(tl.slots.begin(), tl.slots.end(), slot);
+            if (it != tl.slots.end() && *it == slot) {
+              const size_t si = (size_t)(it - tl.slots.begin());
+              rows |= tl.rows_or[si];
+              all_dense = all_dense && tl.dense[si] != 0;
+            } else {
+              all_dense = false;
+            }
+          }
+          if (rows) { live_slots[n_live_slots] = slot; live_rows[n_live_slots] = rows; dense[n_live_slots] = all_dense; ++n_live_slots; }
         }
         if (n_live_slots == 0) continue;
         deft_unit_t u{};
@@ -549,19 +564,15 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         u.n_tiles = (i32)pc.second;
         u.last_len = tiles[tb - 1].n_live;
         const i64 mask_base = (i64)u_mask.size();
-        bool dense[2] = {true, true};
-        for (size_t t = ta; t < tb; ++t)
-          for (int k = 0; k < n_live_slots; ++k) {
-            const uint32_t* w = tile_slot(tiles[t], live_slots[k]);
-            const i32 cnt = slot_cnt(live_slots[k]);
-            const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-            if (tiles[t].n_live != 128) dense[k] = false;
-            for (i32 n = 0; n < 128; ++n) {
-              const uint32_t word = w && n < tiles[t].n_live ? w[n] : 0u;
-              u_mask.push_back(word);
-              if (n < tiles[t].n_live && (word & full) != full) dense[k] = false;
+        const bool unit_dense = dense[0] && (n_live_slots < 2 || dense[1]);  // nothing would read its masks
+        if (!unit_dense)
+          for (size_t t = ta; t < tb; ++t)
+            for (int k = 0; k < n_live_slots; ++k) {
+              const uint32_t* w = tile_slot(tiles[t], live_slots[k]);
+              const size_t at = u_mask.size();
+              u_mask.resize(at + 128, 0u);   // tokens past the tile's live ones stay zero (the masks' own tail is zero too)
+              if (w) std::copy(w, w + tiles[t].n_live, u_mask.begin() + (long)at);
             }
-          }
         u.mask_off[1] = -1;
         u.q_id0[0] = u.q_id0[1] = -1;
         {  // shortcut: all tiles full and on consecutive pages
@@ -581,7 +592,6 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
           for (i32 rr = 0; rr < u.q_cnt[k]; ++rr)
             if ((live_rows[k] >> rr) & 1u) rows_of[(size_t)u_q[(size_t)u.q_off[k] + (size_t)rr]].push_back(u.part_base[k] + rr);
         }
-        if (dense[0] && (n_live_slots < 2 || dense[1])) u_mask.resize((size_t)mask_base);  // nothing reads them
         units.push_back(u);
         ucost.push_back(kJobConst + chain_cost[pi]);
       }
