@@ -76,5 +76,27 @@ def one(record):
               + ", ".join(f"chunk{c} done {b.elapsed_time(gc[c]):.3f}" for c in range(NC))
               + ", last D2H done %.3f" % b.elapsed_time(g["end"]))
 
-for i in range(8):
-    one(i >= 5)
+if os.environ.get("META_PARTS"):     # where step.metadata() spends its time inside a step
+    from deft_b200 import tree_cache as tc
+    acc = {}
+
+    def timed(name, fn):
+        def w(*a, **k):
+            t0 = time.perf_counter()
+            r = fn(*a, **k)
+            acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0
+            return r
+        return w
+    tc.flatten_tree = timed("flatten_tree", tc.flatten_tree)
+    tc.build_tables_host = timed("build_tables_host (incl. reserve + copy into pinned)", tc.build_tables_host)
+    tc._STAGING.reserve = timed("staging.reserve", tc._STAGING.reserve)
+    tc._STAGING.send = timed("staging.send (cudaMemcpyAsync + event)", tc._STAGING.send)
+    tc.register_plan = timed("register_plan", tc.register_plan)
+    step.metadata = timed("step.metadata total", step.metadata)
+
+for i in range(10):
+    if i == 5 and os.environ.get("META_PARTS"):
+        acc.clear()                   # the first steps allocate the pinned staging ring and capture the graphs
+    one(i >= 7)
+if os.environ.get("META_PARTS"):
+    print("per step (us): " + ", ".join(f"{k} {v / 5 * 1e6:.0f}" for k, v in acc.items()))
