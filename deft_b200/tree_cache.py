@@ -378,16 +378,31 @@ def flatten_forest(trees) -> Dict[str, Any]:
     batched mode (one tree per ``TreeMetadata``); this is the multi-tree extension SURVEY.md 8(d) cfg 5 asks for.
     """
     parts = [flatten_tree(t) for t in trees]
-    node_off = np.cumsum([0] + [len(p["parent"]) for p in parts])
-    q_base = np.cumsum([0] + [len(p["leaf_to_q"]) for p in parts])
-    parent = np.concatenate([np.where(p["parent"] >= 0, p["parent"] + node_off[i], -1) for i, p in enumerate(parts)])
+    n_nodes = np.fromiter((len(p["parent"]) for p in parts), dtype=np.int64, count=len(parts))
+    n_kv = np.fromiter((len(p["kv"]) for p in parts), dtype=np.int64, count=len(parts))
+    n_qs = np.fromiter((len(p["qs"]) for p in parts), dtype=np.int64, count=len(parts))
+    n_q = np.fromiter((len(p["leaf_to_q"]) for p in parts), dtype=np.int64, count=len(parts))
+
+    def starts(counts: np.ndarray) -> np.ndarray:          # exclusive prefix sums
+        out = np.zeros(len(counts), dtype=np.int64)
+        np.cumsum(counts[:-1], out=out[1:])
+        return out
+
+    node_off, kv_base, qs_base, q_base = starts(n_nodes), starts(n_kv), starts(n_qs), starts(n_q)
+    parent = np.concatenate([p["parent"] for p in parts]).astype(np.int64)
+    parent = np.where(parent >= 0, parent + np.repeat(node_off, n_nodes), -1).astype(np.int32)
     kv = np.concatenate([p["kv"] for p in parts])
-    qs = np.concatenate([p["qs"] + q_base[i] for i, p in enumerate(parts)])
-    kv_off = np.concatenate([[0]] + [p["kv_off"][1:] + sum(len(x["kv"]) for x in parts[:i]) for i, p in enumerate(parts)])
-    q_off = np.concatenate([[0]] + [p["q_off"][1:] + sum(len(x["qs"]) for x in parts[:i]) for i, p in enumerate(parts)])
-    leaf_to_q = {(i, leaf): q + int(q_base[i]) for i, p in enumerate(parts) for leaf, q in p["leaf_to_q"].items()}
-    return dict(parent=parent.astype(np.int32), kv_off=kv_off.astype(np.int64), kv=kv.astype(np.int64),
-                q_off=q_off.astype(np.int64), qs=qs.astype(np.int64), tix=np.concatenate([p["tix"] for p in parts]),
+    qs = np.concatenate([p["qs"] for p in parts]) + np.repeat(q_base, n_qs)
+    kv_off = np.zeros(int(n_nodes.sum()) + 1, dtype=np.int64)
+    kv_off[1:] = np.concatenate([p["kv_off"][1:] for p in parts]) + np.repeat(kv_base, n_nodes)
+    q_off = np.zeros(int(n_nodes.sum()) + 1, dtype=np.int64)
+    q_off[1:] = np.concatenate([p["q_off"][1:] for p in parts]) + np.repeat(qs_base, n_nodes)
+    leaf_to_q: Dict[Any, int] = {}
+    for i, p in enumerate(parts):
+        b = int(q_base[i])
+        for leaf, q in p["leaf_to_q"].items():
+            leaf_to_q[(i, leaf)] = q + b
+    return dict(parent=parent, kv_off=kv_off, kv=kv, q_off=q_off, qs=qs, tix=np.concatenate([p["tix"] for p in parts]),
                 leaf_to_q=leaf_to_q)
 
 
