@@ -381,21 +381,32 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     // walks tiles none of its rows attends.  (DEFT_PLAN_SPLIT_LIVE=0: chains by contiguity only.)
     const char* env_s = std::getenv("DEFT_PLAN_SPLIT_LIVE");
     const bool split_live = !(env_s && env_s[0] == '0');
-    for (i32 pr = 0; pr < n_pairs; ++pr) {
-      size_t run0 = 0, run_n = 0;
-      int run_sig = 0;
-      for (size_t t = 0; t <= tiles.size(); ++t) {
-        int sig = 0;
-        if (t < tiles.size()) sig = (tile_slot(tiles[t], 2 * pr) ? 1 : 0) | (tile_slot(tiles[t], 2 * pr + 1) ? 2 : 0);
-        if (run_n && (sig == 0 || (split_live && sig != run_sig))) {
-          chains.push_back({pr, run0, run_n});
-          run_n = 0;
-        }
-        if (sig) {
-          if (run_n == 0) { run0 = t; run_sig = sig; }
-          ++run_n;
+    {
+      // one pass over the tiles, every tile visiting only the pairs it touches (a forest has as many pairs as trees
+      // and every tile belongs to one of them): a pair's run ends at a gap or, with split_live, where its set of
+      // live slots changes
+      struct Run { size_t run0 = 0, run_n = 0, last = 0; int sig = 0; };
+      std::vector<Run> runs((size_t)n_pairs);
+      auto close_run = [&](i32 pr) {
+        Run& r = runs[(size_t)pr];
+        if (r.run_n) chains.push_back({pr, r.run0, r.run_n});
+        r.run_n = 0;
+      };
+      for (size_t t = 0; t < tiles.size(); ++t) {
+        const std::vector<i32>& sl = tiles[t].slots;  // ascending
+        for (size_t i = 0; i < sl.size();) {
+          const i32 pr = sl[i] / 2;
+          int sig = 0;
+          for (; i < sl.size() && sl[i] / 2 == pr; ++i) sig |= (sl[i] & 1) ? 2 : 1;
+          Run& r = runs[(size_t)pr];
+          if (r.run_n && (r.last + 1 != t || (split_live && sig != r.sig))) close_run(pr);
+          if (r.run_n == 0) { r.run0 = t; r.sig = sig; }
+          ++r.run_n;
+          r.last = t;
         }
       }
+      for (i32 pr = 0; pr < n_pairs; ++pr) close_run(pr);
+      std::sort(chains.begin(), chains.end(), [](const Chain& a, const Chain& b) { return a.pair != b.pair ? a.pair < b.pair : a.t0 < b.t0; });
     }
 
     const i32 heads = hkv > 0 ? hkv : 1;
