@@ -493,6 +493,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
           for (i32 h = 0; h < heads * n_live; ++h) costs.push_back(kJobConst + pcs_cost[pi]);
         }
       }
+      if (costs.size() <= (size_t)ctas)  // a CTA each: the longest job is the makespan
+        return costs.empty() ? 0.0 : *std::max_element(costs.begin(), costs.end());
       std::sort(costs.begin(), costs.end(), [](double a, double b) { return a > b; });
       std::priority_queue<double, std::vector<double>, std::greater<double>> bins;
       for (i32 c = 0; c < ctas; ++c) bins.push(0.0);
@@ -528,8 +530,19 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       best_len = S.plan_len;
     } else {
       double best = -1.0;
+      // the pieces of a chain depend on the candidate only through their NUMBER: neighbouring candidates that cut
+      // every chain into the same number of pieces have the same makespan
+      std::vector<double> chain_total(chains.size(), 0.0);
+      for (size_t ci = 0; ci < chains.size(); ++ci)
+        for (size_t t = 0; t < chains[ci].n_tiles; ++t) chain_total[ci] += tile_cost[chains[ci].t0 + t];
+      std::vector<size_t> nps(chains.size()), prev_nps;
+      double prev_m = 0.0;
       for (double l : cand) {  // ascending: ties go to the longer piece (fewer partials)
-        const double m = makespan(l);
+        for (size_t ci = 0; ci < chains.size(); ++ci)
+          nps[ci] = std::max<size_t>(1, (size_t)std::ceil(chain_total[ci] / l - 1e-9));
+        const double m = nps == prev_nps ? prev_m : makespan(l);
+        prev_nps = nps;
+        prev_m = m;
         if (best < 0.0 || m <= best + 1e-9) { best = m; best_len = l; }
       }
       S.plan_key = key;

@@ -300,9 +300,12 @@ def _node_pages(node) -> np.ndarray:
                 grown = np.empty(max(n + 64, 2 * arr.shape[0]), dtype=np.int64)
                 grown[:m] = arr[:m]
                 arr = grown
-            arr[m:n] = lst[m:n]
+            if n == m + 1:
+                arr[m] = lst[m]              # a decode step: one page more
+            else:
+                arr[m:n] = lst[m:n]
             view = arr[:n]
-            node._kv_np = (lst, arr, n, lst[0], lst[n - 1], view)
+            node._kv_np = (lst, arr, n, first if m else lst[0], lst[n - 1], view)
             return view
     arr = np.empty(n + 64, dtype=np.int64)
     arr[:n] = lst
