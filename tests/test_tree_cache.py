@@ -168,3 +168,49 @@ def test_plan_search_cache_gives_the_cold_answer(monkeypatch):
         monkeypatch.delenv("DEFT_PLAN_CACHE")
         assert np.array_equal(a, b) and np.array_equal(a, c)
         assert np.array_equal(da, db) and np.array_equal(da, dc) and np.array_equal(sa, sc)
+
+
+def test_flatten_tree_on_a_foreign_tree_object():
+    """A TreeCache-shaped object that does not count its structural changes (the reference's own class): the walk is
+    redone at every call, the per-node page arrays follow appends and list replacements."""
+    from types import SimpleNamespace as NS
+    from deft_b200.tree_cache import flatten_tree
+
+    class Node:                                    # hashable by identity, like the reference's TreeNode
+        def __init__(self, i, pages):
+            self.id, self.children, self.kv_indices, self.parent = i, {}, list(pages), None
+            self.refs, self.paused, self.node_indices_id = set(), False, None
+
+    node = Node
+
+    root, a, b = node(0, range(10, 30)), node(1, [40, 42]), node(2, [41, 43])
+    for ch in (a, b):
+        ch.parent = root
+        root.children[ch.id] = ch
+        ch.refs.add(ch)
+        root.refs.add(ch)
+    tree = NS(root=root, leaves={1: a, 2: b}, nodes={0: root, 1: a, 2: b})
+
+    def expect():
+        order = [root] + list(root.children.values())
+        return np.concatenate([np.asarray(n.kv_indices, dtype=np.int64) for n in order])
+
+    assert np.array_equal(flatten_tree(tree)["kv"], expect())
+    a.kv_indices.append(44)                       # append_index
+    b.kv_indices.append(45)
+    assert np.array_equal(flatten_tree(tree)["kv"], expect())
+    a.kv_indices = [7, 8, 9]                      # replaced by a new list (reset_node_KV + re-alloc)
+    assert np.array_equal(flatten_tree(tree)["kv"], expect())
+    a.kv_indices = a.kv_indices[:2]               # a shorter NEW list
+    assert np.array_equal(flatten_tree(tree)["kv"], expect())
+    c = node(3, [50])                             # structural change without any counter: seen at the next call
+    c.parent = a
+    a.children[3] = c
+    tree.leaves = {2: b, 3: c}
+    tree.nodes[3] = c
+    a.refs.discard(a); root.refs.discard(a)
+    for n in (c, a, root):
+        n.refs.add(c)
+    f = flatten_tree(tree)
+    assert f["parent"].tolist() == [-1, 0, 1, 0] and f["leaf_to_q"] == {2: 0, 3: 1}
+    assert np.array_equal(f["kv"], np.asarray(list(range(10, 30)) + [7, 8, 50, 41, 43, 45], dtype=np.int64))
