@@ -57,3 +57,28 @@ def test_reductions_world_size_2_gloo():
 
 def test_single_process_is_identity():
     assert max_over_ranks(3.5, torch.device("cpu")) == 3.5 and sum_over_ranks(2.0, torch.device("cpu")) == 2.0
+
+
+def test_reference_arm_prints_one_contract_line_and_other_ranks_stay_silent():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours): one JSON line with the contract's keys
+    on rank 0, nothing and exit 0 on any other rank.  Runs the small cfg1 workload on the host cores."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "1",
+           "--warmup", "0", "--gpus", "2"]
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 2
+    for k in ("metric", "unit", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    env["RANK"] = env["LOCAL_RANK"] = "1"
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300, cwd=root)
+    assert r.returncode == 0 and r.stdout.strip() == "", (r.returncode, r.stdout, r.stderr[-500:])
