@@ -28,6 +28,26 @@ except AttributeError:                    # pragma: no cover - older / newer tor
 
 def _current_stream(t: torch.Tensor) -> int:
     return _raw_stream(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on_device(t: torch.Tensor):
+    """The C ABI launches on the current device: switch to the tensors' device around a call made from another one
+    (a process driving several GPUs); nothing in the common single-device case."""
+    idx = t.device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(idx)
 _WORKSPACES: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
@@ -99,10 +119,11 @@ def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Ten
         need = ws_need[geom] = _lib.lib.deft_b200_flatten_workspace_bytes(nq, H, HKV, D, n_partials, n_blocks, plan_ref)
     ws = _workspace(query_states.device, stream, need)
     qs, ks, os_ = query_states.stride(), key_buffer.stride(), output.stride()
-    rc = _lib.lib.deft_b200_flatten_fwd(
-        query_states.data_ptr(), qs[0], qs[1], key_buffer.data_ptr(), value_buffer.data_ptr(), ks[0], ks[1],
-        key_buffer.shape[0], output.data_ptr(), os_[0], os_[1], nq, H, HKV, D, int(block_len),
-        p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, ws.data_ptr(), ws.numel(), stream)
+    with _on_device(query_states):
+        rc = _lib.lib.deft_b200_flatten_fwd(
+            query_states.data_ptr(), qs[0], qs[1], key_buffer.data_ptr(), value_buffer.data_ptr(), ks[0], ks[1],
+            key_buffer.shape[0], output.data_ptr(), os_[0], os_[1], nq, H, HKV, D, int(block_len),
+            p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, ws.data_ptr(), ws.numel(), stream)
     if rc:
         _lib.check(rc)
 
@@ -130,13 +151,15 @@ def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, val
     need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, HKV, D, n_partials, n_entries, total_kv_bound,
                                                    C.byref(plan) if plan is not None else None)
     ws = _workspace(query_states.device, stream, need)
-    _lib.check(_lib.lib.deft_b200_node_fwd(
-        query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
-        key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1), key_buffer.shape[0],
-        output.data_ptr(), output.stride(0), output.stride(1), nq, H, HKV, D,
-        KV_indices.data_ptr(), KV_indices.element_size(), kv_off.data_ptr(), kv_len.data_ptr(), node_q.data_ptr(),
-        n_partials, q_off.data_ptr(), q_len.data_ptr(), n_entries, total_kv_bound,
-        C.byref(plan) if plan is not None else None, ws.data_ptr(), ws.numel(), stream))
+    with _on_device(query_states):
+        rc = _lib.lib.deft_b200_node_fwd(
+            query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
+            key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1), key_buffer.shape[0],
+            output.data_ptr(), output.stride(0), output.stride(1), nq, H, HKV, D,
+            KV_indices.data_ptr(), KV_indices.element_size(), kv_off.data_ptr(), kv_len.data_ptr(), node_q.data_ptr(),
+            n_partials, q_off.data_ptr(), q_len.data_ptr(), n_entries, total_kv_bound,
+            C.byref(plan) if plan is not None else None, ws.data_ptr(), ws.numel(), stream)
+    _lib.check(rc)
 
 
 _SEQ_CONST: Dict[Tuple[int, int], Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -170,11 +193,13 @@ def token_attention_fwd(q: torch.Tensor, k_buffer: torch.Tensor, v_buffer: torch
     stream = _current_stream(q)
     need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, HKV, D, nq, nq, total_kv_bound, None)
     ws = _workspace(q.device, stream, need)
-    _lib.check(_lib.lib.deft_b200_node_fwd(
-        q.data_ptr(), q.stride(0), q.stride(1), k_buffer.data_ptr(), v_buffer.data_ptr(), k_buffer.stride(0),
-        k_buffer.stride(1), k_buffer.shape[0], o.data_ptr(), o.stride(0), o.stride(1), nq, H, HKV, D,
-        req_to_token.data_ptr(), 4, kv_off.data_ptr(), kv_len.data_ptr(), ids.data_ptr(), nq, ids.data_ptr(),
-        ones.data_ptr(), nq, total_kv_bound, None, ws.data_ptr(), ws.numel(), stream))
+    with _on_device(q):
+        rc = _lib.lib.deft_b200_node_fwd(
+            q.data_ptr(), q.stride(0), q.stride(1), k_buffer.data_ptr(), v_buffer.data_ptr(), k_buffer.stride(0),
+            k_buffer.stride(1), k_buffer.shape[0], o.data_ptr(), o.stride(0), o.stride(1), nq, H, HKV, D,
+            req_to_token.data_ptr(), 4, kv_off.data_ptr(), kv_len.data_ptr(), ids.data_ptr(), nq, ids.data_ptr(),
+            ones.data_ptr(), nq, total_kv_bound, None, ws.data_ptr(), ws.numel(), stream)
+    _lib.check(rc)
 
 
 def kv_append(kv_layer: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tensor, cache_loc: torch.Tensor) -> None:
@@ -192,7 +217,8 @@ def kv_append(kv_layer: torch.Tensor, cache_k: torch.Tensor, cache_v: torch.Tens
     assert cache_loc.numel() == n and kv_layer.shape[1] == 2 and kv_layer.shape[2] == HKV and kv_layer.shape[3] == D
     stream = _current_stream(kv_layer)
     k_ptr = kv_layer.data_ptr()
-    rc = _lib.lib.deft_b200_kv_append(k_ptr, k_ptr + ls[1] * 2, ls[0], ls[2], cache_k.data_ptr(), cache_v.data_ptr(),
-                                      ks[0], ks[1], cache_loc.data_ptr(), n, HKV, D, stream)
+    with _on_device(kv_layer):
+        rc = _lib.lib.deft_b200_kv_append(k_ptr, k_ptr + ls[1] * 2, ls[0], ls[2], cache_k.data_ptr(), cache_v.data_ptr(),
+                                          ks[0], ks[1], cache_loc.data_ptr(), n, HKV, D, stream)
     if rc:
         _lib.check(rc)

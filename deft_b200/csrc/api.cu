@@ -2,6 +2,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -44,24 +46,31 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// fp16 tensor [d2][d1][d0] with element strides s1, s2; box {64, b1, b2}; 128-byte swizzle.  Small
-// per-thread cache: a decode step calls with the same 32 layer pools over and over.
+// fp16 tensor [d2][d1][d0] with element strides s1, s2; box {64, b1, b2}; 128-byte swizzle.
 struct MapKey {
   const void* ptr; int64_t d0, d1, d2, s1, s2; int32_t b1, b2;
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 && b1 == o.b1 && b2 == o.b2;
   }
 };
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {(uint64_t)k.d0, (uint64_t)k.d1, (uint64_t)k.d2, (uint64_t)k.s1, (uint64_t)k.s2, (uint64_t)k.b1, (uint64_t)k.b2})
+      h = (h ^ v) * 0x100000001B3ull + (h >> 29);
+    return (size_t)h;
+  }
+};
+// Per-thread cache: a decode step calls with the same layer pools over and over (5 maps per call: 160 keys for 32
+// layers, 400 for 80), in cyclic order -- a hash map, emptied if a caller ever walks through thousands of buffers.
 bool make_map(CUtensorMap* out, const MapKey& key) {
-  constexpr int kCache = 128;
-  struct Entry { MapKey key; CUtensorMap map; };
-  static thread_local Entry cache[kCache];
-  static thread_local int used = 0, next = 0;
-  for (int i = 0; i < used; ++i)
-    if (cache[i].key == key) {
-      *out = cache[i].map;
-      return true;
-    }
+  constexpr size_t kMaxEntries = 4096;
+  static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
   EncodeTiledFn fn = encode_tiled_fn();
   const bool two_d = key.d2 == 0 && key.b2 == 0;  // [d1][d0], box {64, b1}
   if (!fn || key.d0 < 64 || key.d1 <= 0 || (!two_d && key.d2 <= 0)) return false;
@@ -74,9 +83,8 @@ bool make_map(CUtensorMap* out, const MapKey& key) {
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return false;
-  const int slot = used < kCache ? used++ : (next = (next + 1) % kCache);
-  cache[slot].key = key;
-  cache[slot].map = map;
+  if (cache.size() >= kMaxEntries) cache.clear();
+  cache.emplace(key, map);
   *out = map;
   return true;
 }

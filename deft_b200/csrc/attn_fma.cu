@@ -218,12 +218,13 @@ __global__ void __launch_bounds__(kThreads) stage1_fma_kernel(const AttnParams p
 
 template <int D, int G>
 int launch_t(const AttnParams& p, cudaStream_t stream) {
-  static bool configured = false;  // benign race: the attribute call is idempotent
+  static PerDeviceOnce once;  // per device; benign race: the attribute call is idempotent
   const size_t smem = sizeof(Smem<D, G>);
-  if (!configured) {
+  const int dev = current_device_index();
+  if (once.slot[dev] == 0) {
     DEFT_CUDA(cudaFuncSetAttribute(stage1_fma_kernel<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
-    configured = true;
+    once.slot[dev] = 1;
   }
   dim3 grid(p.n_items, p.HKV);
   stage1_fma_kernel<D, G><<<grid, kThreads, smem, stream>>>(p);

@@ -990,16 +990,15 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
 
 template <int D, int G>
 int launch_t(const AttnParams& p, cudaStream_t stream) {
-  static bool configured = false;
-  static int num_sms = 0;
+  static PerDeviceOnce once;  // per device: the attribute belongs to the current device's copy of the function
   using L = Layout<D>;
-  if (!configured) {
+  const int dev = current_device_index();
+  int num_sms = once.slot[dev];
+  if (num_sms == 0) {
     DEFT_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<D, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
     DEFT_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<D, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kAlloc));
-    int dev = 0;
-    DEFT_CUDA(cudaGetDevice(&dev));
     DEFT_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
+    once.slot[dev] = num_sms;
   }
   int grid;
   if (p.job_off != nullptr) {

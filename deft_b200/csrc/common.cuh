@@ -29,6 +29,18 @@ void set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
+// Once-only launch configuration is PER DEVICE: cudaFuncSetAttribute applies to the device that is current, and a
+// process may drive several GPUs.  slot[d] == 0: device d has not been configured yet (value = its SM count after).
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+  int slot[kMaxDevices];  // zero-initialised (static storage); a racing second configuration is idempotent
+};
+inline int current_device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+
 static_assert(sizeof(deft_unit_t) == 80, "deft_unit_t is part of the ABI: 80 bytes");
 static_assert(sizeof(deft_job_t) == 96, "deft_job_t is part of the ABI: 96 bytes");
 constexpr int kMaxGroupQ = 32;     // queries per group (reference max_q_len / BLOCK_M, tree_cache.py:623)

@@ -19,7 +19,9 @@ _PATCHED: List[tuple] = []
 
 
 def _swap(module, name: str, value) -> None:
-    _PATCHED.append((module, name, getattr(module, name)))
+    # the raw attribute (for a class: the classmethod object itself, not the bound method getattr would build)
+    old = vars(module)[name] if name in vars(module) else getattr(module, name)
+    _PATCHED.append((module, name, old))
     setattr(module, name, value)
 
 

@@ -96,12 +96,14 @@ class TokenToKVPool:
     def add_refs(self, token_index: IndexLike) -> None:
         idx = _as_index(token_index)
         self.alloc_ct += len(idx)
-        np.add.at(self.mem_state, idx, 1)
+        # the reference's `mem_state[token_index] += 1` (memory_pool.py:92-94) is an indexed read-modify-write: a page
+        # named twice in the list is incremented ONCE; plain fancy indexing has the same semantics (np.add.at has not)
+        self.mem_state[idx] += 1
 
     def decrease_refs(self, token_index: IndexLike) -> int:
         idx = _as_index(token_index)
         self.alloc_ct -= len(idx)
-        np.subtract.at(self.mem_state, idx, 1)
+        self.mem_state[idx] -= 1           # once per distinct page, like the reference (memory_pool.py:96-98)
         return int(np.count_nonzero(self.mem_state[idx] == 0))
 
     def clear(self) -> None:

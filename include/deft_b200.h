@@ -11,8 +11,10 @@
  *   - all tensors are caller-owned and must outlive the (asynchronous) call
  *   - launches go to the cudaStream_t passed as `void* stream` (0 = legacy default stream)
  *   - return 0 on success, a negative DEFT_E_* code otherwise; deft_b200_last_error() gives text
- *   - thread-compatible: no global mutable state besides a thread-local error string and
- *     once-only cudaFuncSetAttribute calls
+ *   - launches happen on the CURRENT device, which must be the device `stream` and the tensors belong to (the
+ *     Python shim switches to the tensors' device around a call when it is not the current one)
+ *   - thread-compatible: no global mutable state besides a thread-local error string, per-thread tensor-map
+ *     caches and once-only PER-DEVICE cudaFuncSetAttribute calls (a process may drive several GPUs)
  *   - activations / KV are IEEE fp16 (the reference hard-codes torch.float16, model_runner.py:271,336)
  */
 #ifndef DEFT_B200_H_

@@ -197,7 +197,7 @@ def per_leaf_reference(q, K, V, paths):
     return out
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3b", "cfg4"])
 def test_baseline_configs_full_size(dev, name):
     """BASELINE.json shapes at full size: all three operator modes agree with per-leaf attention."""
     from deft_b200 import BLOCK_CONFIG, TreeMetadata
@@ -273,6 +273,56 @@ def test_forest_batch_in_one_launch(dev):
         one = run_flatten(q[off: off + n], K, V, {k: getattr(mt, k) for k in TABLE_KEYS})
         assert torch.allclose(one.float(), got[off: off + n].float(), atol=5e-4, rtol=5e-3)
         off += n
+
+
+def test_forest_of_64_cfg2_trees_matches_per_leaf_attention(dev):
+    """The regime bench.py's cfg5 block measures (64 cfg2 trees per GPU: pair-aligned plan, ~76 jobs per CTA, cluster
+    multicast), against per-leaf fp32 attention on a sample of 8 of the 64 trees, and against the unpaired plan."""
+    from deft_b200 import TreeMetadata, _lib
+    from deft_b200.workloads import build_forest
+    torch.manual_seed(64)
+    trees = build_forest("cfg2", 64, layers=1, device=dev)
+    kvp = trees[0].token_to_kv_pool
+    kvp.kv_data[0].normal_()
+    K, V = kvp.get_key_buffer(0), kvp.get_value_buffer(0)
+    m = TreeMetadata.from_forest(trees)
+    nq = m.query_num
+    assert nq == 64 * 64 and m.flat_plan.paired == 1, "a forest this size is planned as cluster pairs"
+    q = torch.randn(nq, 48 * 128, dtype=torch.float16, device=dev)[:, : 32 * 128].view(nq, 32, 128)
+    t = {k: getattr(m, k) for k in TABLE_KEYS}
+    got = run_flatten(q, K, V, t)
+    assert torch.isfinite(got.float()).all()
+    for ti in (0, 7, 13, 21, 34, 42, 55, 63):
+        want = per_leaf_reference(q[ti * 64: (ti + 1) * 64], K, V, orc.leaf_paths(trees[ti]))
+        g = got[ti * 64: (ti + 1) * 64].float()
+        assert torch.allclose(g, want, atol=ATOL, rtol=RTOL), (ti, (g - want).abs().max().item())
+    assert torch.equal(got, run_flatten(q, K, V, t)), "deterministic"
+    assert torch.allclose(got.float(), run_node(q, K, V, t).float(), atol=5e-4, rtol=5e-3)
+
+
+def test_two_devices_in_one_process():
+    """Per-device launch configuration (cudaFuncSetAttribute, SM count): the same process attends on cuda:0 and on
+    cuda:1, from either current device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from deft_b200 import TreeMetadata
+    from deft_b200.workloads import build_tree
+    outs = []
+    for d in (0, 1, 0):
+        dv = torch.device("cuda", d)
+        torch.manual_seed(3)
+        tree = build_tree("cfg3", layers=1, device=dv)
+        kvp = tree.token_to_kv_pool
+        kvp.kv_data[0].copy_(torch.randn(kvp.kv_data[0].shape, dtype=torch.float16))
+        nq = len(tree.leaves)
+        q = torch.randn(nq, 32, 128, dtype=torch.float16).to(dv)
+        m = TreeMetadata.from_tree_cache(tree)
+        torch.cuda.set_device(0)                 # the call finds its device from the tensors, not from the current one
+        o = run_flatten(q, kvp.get_key_buffer(0), kvp.get_value_buffer(0), {k: getattr(m, k) for k in TABLE_KEYS})
+        want = per_leaf_reference(q, kvp.get_key_buffer(0), kvp.get_value_buffer(0), orc.leaf_paths(tree))
+        assert torch.allclose(o.float(), want, atol=ATOL, rtol=RTOL), d
+        outs.append(o.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 def test_argument_errors(dev):

@@ -214,3 +214,68 @@ def test_flatten_tree_on_a_foreign_tree_object():
     f = flatten_tree(tree)
     assert f["parent"].tolist() == [-1, 0, 1, 0] and f["leaf_to_q"] == {2: 0, 3: 1}
     assert np.array_equal(f["kv"], np.asarray(list(range(10, 30)) + [7, 8, 50, 41, 43, 45], dtype=np.int64))
+
+
+def test_add_refs_counts_a_page_named_twice_once_like_the_reference():
+    """``mem_state[idx] += 1`` (reference memory_pool.py:92-98) is an indexed read-modify-write: duplicates in the
+    index list move the refcount ONCE.  ``alloc_ct`` counts list entries."""
+    kvp = TokenToKVPool(size=16, dtype=torch.float16, head_num=1, head_dim=16, layer_num=0, device="cpu")
+    want = torch.zeros(16, dtype=torch.int16)
+    idx = torch.tensor([3, 5, 5, 7, 3, 3])
+    kvp.add_refs(idx)
+    want[idx] += 1
+    assert np.array_equal(kvp.mem_state, want.numpy()) and kvp.alloc_ct == 6
+    kvp.add_refs([5, 9])
+    want[torch.tensor([5, 9])] += 1
+    freed = kvp.decrease_refs(torch.tensor([5, 5, 9]))
+    want[torch.tensor([5, 5, 9])] -= 1
+    assert np.array_equal(kvp.mem_state, want.numpy())
+    assert freed == int((want[torch.tensor([5, 5, 9])] == 0).sum()) and kvp.alloc_ct == 5
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg3b", "cfg4"])
+def test_workload_scripts_and_their_pure_python_replay(name):
+    """The scripts of deft_b200/workload_scripts.py: the closed-form counts, the TreeCache replay and the pure-Python
+    replay bench.py's reference arm uses (oracle/sim_tree.py) agree on every page list."""
+    from oracle import deft_oracle as orc
+    from oracle.sim_tree import SimTree
+    from deft_b200.workloads import (WORKLOADS, algorithmic_flops, build_tree, max_path_len, n_leaves, n_nodes,
+                                     unique_kv_tokens)
+    tree = build_tree(name, layers=0, device=torch.device("cpu"), H=4, HKV=2, D=16)
+    sim = SimTree().replay(WORKLOADS[name][0])
+    assert sorted(tree.nodes) == sorted(sim.nodes) and sorted(tree.leaves) == sorted(sim.leaves)
+    for i, n in tree.nodes.items():
+        assert n.kv_indices == sim.nodes[i].kv_indices, (name, i)
+        assert (n.parent.id if n.parent else -1) == (sim.nodes[i].parent.id if sim.nodes[i].parent else -1)
+    paths = orc.leaf_paths(tree)
+    assert all(np.array_equal(a, b) for a, b in zip(paths, orc.leaf_paths(sim)))
+    assert unique_kv_tokens(name) == sum(len(n.kv_indices) for n in tree.nodes.values()) == sim.next_page
+    assert n_leaves(name) == len(tree.leaves) and n_nodes(name) == len(tree.nodes)
+    assert max_path_len(name) == max(len(p) for p in paths)
+    assert algorithmic_flops(name, H=32, D=128) == sum(len(p) for p in paths) * 32 * 4 * 128
+
+
+def test_cfg3b_is_a_medusa_style_sparse_tree():
+    """BASELINE configs[2] / SURVEY.md 8d cfg 3b: width 6, depth 5, 63 one-token nodes chosen best-first by path score."""
+    from deft_b200.workloads import build_tree, medusa_tree
+    paths = medusa_tree()
+    assert len(paths) == 63 and len(set(paths)) == 63
+    assert max(len(p) for p in paths) == 5 and max(max(p) for p in paths) <= 5
+    chosen = set(paths)
+    for p in paths:                                   # a node's parent and its better-ranked siblings are in the tree
+        assert len(p) == 1 or p[:-1] in chosen
+        assert p[-1] == 0 or p[:-1] + (p[-1] - 1,) in chosen
+    p_r = [0.6 * 0.4 ** r for r in range(6)]
+    score = lambda path: float(np.prod([p_r[r] for r in path]))
+    worst = min(score(p) for p in paths)
+    for p in paths:                                   # nothing left out scores better than the worst node taken
+        if len(p) < 5:
+            for r in range(6):
+                if p + (r,) not in chosen:
+                    assert score(p + (r,)) <= worst + 1e-15
+    tree = build_tree("cfg3b", layers=0, device=torch.device("cpu"), H=4, HKV=2, D=16)
+    assert len(tree.nodes) == 64 and len(tree.root.kv_indices) == 2048
+    assert all(len(n.kv_indices) == 1 for n in tree.nodes.values() if n is not tree.root)
+    assert tree.root.kv_indices == list(range(2048))
+    m = TreeMetadata.from_tree_cache(tree)
+    assert m.query_num == len(tree.leaves) == 29 and m.total_kv_len == 2048 + 63
