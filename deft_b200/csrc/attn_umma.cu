@@ -1,310 +1,72 @@
-// Stage 1, tensor-core path (sm_100a): tcgen05.mma with TMEM accumulators, warp-specialised
-// persistent CTAs walking the unit plan.
+// Stage 1, tensor-core path (sm_100a): tcgen05.mma with TMEM accumulators, warp-specialised persistent CTAs
+// walking the unit plan.  Third generation of the kernel ("task-parity softmax groups").
 //
-// One job = (unit, kv-head).  A unit is a chain of KV tiles (128 tokens x D, K and V) attended by one
-// or two *slots* of <= 32 queries; with G = H/HKV query heads per kv-head a slot is one M = 128 UMMA
-// tile (row r = query r/G, head r%G).  Each KV tile is gathered from the token-granular paged pool
-// ONCE into 128B-swizzled shared memory and serves both slots and all G heads:
+// One job = (unit, kv-head, slot): ONE slot of <= 32 queries x G = H/HKV heads = one M = 128 UMMA accumulator,
+// along the unit's chain of KV tiles (128 tokens x D, K and V, gathered from the token-granular paged pool into
+// 128B-swizzled shared memory by TMA boxes / TMA gather4 / cp.async).  Per KV tile t of the chain:
 //
-//   S_s[128 x 128]  = Q_s[128 x D] . K^T        tcgen05.mma kind::f16, SS: A/B K-major SW128 smem -> TMEM
-//   P_s             = exp2(S_s*c - m_ref), masked by the per-token row bitmask; written back over S_s
-//                     in TMEM as packed fp16 (the A operand of the next MMA never touches smem)
-//   O_s[128 x D]   += P_s[128 x 128] . V        tcgen05.mma TS: A = P_s in TMEM, B = V (MN-major SW128 smem)
+//   S(t)[128 x 128] = Q[128 x D] . K(t)^T     tcgen05.mma kind::f16, SS (Q, K in swizzled smem) -> TMEM
+//   P(t)            = exp2(S*c - m_ref)       one softmax THREAD per row: the whole 128-column row comes out of TMEM
+//                                             once, the row maximum is thread-local (no exchange), P goes back to
+//                                             TMEM as packed fp16 -- the A operand of the next MMA
+//   O[128 x D]     += P(t) . V(t)             tcgen05.mma TS (A = P in TMEM, B = V MN-major swizzled smem)
 //
-// The chain is walked with an online softmax whose reference maximum m_ref is only raised when a tile
-// exceeds it by more than 2^8 (P stays <= 256 in fp16, O and l stay consistent), so the accumulator in
-// TMEM is almost never rescaled.  ONE partial (O/l as fp16, log-sum-exp as fp32) leaves the SM per
-// (job, slot); stage 2 (combine.cu) merges the partials of every query.
+// The softmax is what binds a tile step (16 K exponentials per tile on the SM's 16-lane MUFU = 0.53 us, the same as
+// the two MMAs on the tensor pipe), and a single chain of softmax threads leaves the MUFU idle while it waits for
+// TMEM loads, stores and barriers.  So the CTA's work is a sequence of TASKS -- the tiles of job 0, the epilogue of
+// job 0, the tiles of job 1, ... -- dealt alternately to TWO softmax groups (warps 0-3 and 4-7, 128 threads each, both
+// on all four sub-partitions): while one group is in the latency-bound part of its task the other one is in its
+// exponentials.  Each group has its own S buffer and its own P buffer in TMEM:
 //
-// Warp roles (512 threads, 1 CTA per SM, all 512 TMEM columns):
-//   warps 0-3   softmax + epilogue of slot 0 (thread = row = TMEM lane; 200 registers via setmaxnreg:
-//               the whole 128-column S row is read from TMEM once and kept in registers)
-//   warps 4-7   softmax + epilogue of slot 1; the two slots ping-pong on the tensor pipe:
-//               S_0(t) S_1(t) PV_0(t) | S_0(t+1) PV_1(t) S_1(t+1) PV_0(t+1) | ...
-//   warp  8/9   MMA issuer of slot 0 / slot 1 (one elected thread each; warp 8 also owns the TMEM allocation).
-//               One issuer per slot: a single thread's issue stream (~110 cycles per MMA with its waits and
-//               commits) was the serial bottleneck of a two-slot step
-//   warp  10    Q tiles of both slots: one TMA box per 64-wide panel when a slot's query ids are
-//               consecutive, else cp.async 16-byte gathers
-//   warp  11    per-(tile, slot) row masks (token bitmask per query, transposed from the per-token
-//               words of the table) + "dense tile" flag
-//   warps 12-15 K / V producers: each warp owns 32 token rows of every tile -- one TMA box per panel
-//               when its 32 pages are consecutive (prompt), else cp.async 16-byte gathers (the in-flight
-//               depth of cp.async is per warp, hence four warps)
-// All hand-offs are mbarriers (cp.async arrive-on, tcgen05.commit, plain arrive); no __syncthreads in
-// the steady state.
+//   TMEM (512 columns):  O [0, 128)   S_A [128, 256)   S_B [256, 384)   P_A [384, 448)   P_B [448, 512)
 //
-// Reference semantics: DeFT/deft/layers/attention/tree_attention.py:860-976 (Flatten stage 1) and
-// :170-293 (Node stage 1).
-#include "combine.cuh"
+// S_g is free again as soon as the group has the row in registers (the S issuer then computes the group's NEXT tile
+// into it while the exponentials run), P_g when P V of the tile has completed.  Both groups accumulate into the ONE
+// O: they share the row's reference maximum m_ref (shared memory, one float per row).  Order is kept by a chain of
+// "checked" barriers: task k reads / raises m_ref only after task k-1 has done so.  A tile whose row maximum exceeds
+// m_ref by more than 2^15 raises it: the thread waits for P V of the previous tile, rescales its row of O in TMEM
+// and publishes the new m_ref before it lets task k+1 go on (test_reference_maximum_is_raised_mid_chain).  The row
+// sums are kept per thread and merged in the epilogue (log-sum-exp per group, through shared memory).  The epilogue
+// of a job is a task like any other: one group turns O into the job's partial (O / l as fp16 + log-sum-exp) while
+// the other group already works the first tile of the next job.
+//
+// Warp roles (512 threads, 1 CTA per SM, register budgets moved with setmaxnreg: softmax 184, the rest 72):
+//   warps 0-3 / 4-7   softmax group A / B (thread = row = TMEM lane)
+//   warp  8           S issuer (one elected thread), TMEM alloc / dealloc
+//   warp  9           P V issuer
+//   warp  10          Q tile: one TMA box per panel when the slot's query ids are consecutive, else cp.async gathers
+//   warp  11          row masks: per-token words -> per-query token bitmasks (warp-shuffle bit transpose) + "dense
+//                     tile" flag; skipped for jobs whose tiles are all dense (the prompt)
+//   warps 12-13/14-15 K / V producers, 64 rows each, on rings of their own.  32 consecutive pages = ONE TMA box per
+//                     panel, scattered pages = TMA tile::gather4, or cp.async when TMA is switched off
+// Cluster pairs (throughput regime, pair-aligned job lists): the two CTAs of a cluster work the two slots of the same
+// (unit, kv-head); each K/V tile is loaded ONCE, the CTA of rank r issuing rows [64r, 64r + 64) with
+// .multicast::cluster into both CTAs' shared memory.
+//
+// Reference semantics: DeFT/deft/layers/attention/tree_attention.py:860-976 (Flatten stage 1) and :170-293 (Node
+// stage 1).  The previous generation (two threads per row, S triple-buffered) is kept in attn_umma_v2.cu behind
+// deft_b200_set_experiment(16) for same-box A/B measurements.
+#include "umma_ptx.cuh"
 
 namespace deft {
+int launch_stage1_umma_v2(const AttnParams& p, cudaStream_t stream);
 namespace {
+using namespace umma;
 
-constexpr int kTileN = 128;  // tokens per KV tile (= the reference's BLOCK_LEN)
-constexpr int kHalfN = 64;   // ... worked by the tensor pipe and the softmax warps in two halves
-constexpr int kRows = 128;   // UMMA M
-constexpr int kThreads = 640;  // 20 warps: 5 register-budget groups of 4 (setmaxnreg works per warpgroup)
-constexpr int kMmaWarp = 8, kQWarp = 9, kMaskWarp = 10, kPvWarp = 11, kKvWarp0 = 12;  // 12-15: K producers; 16-19: V
-// a gathering warp is bound by its copies in flight (~8 x 512 bytes against the memory latency), so scattered
-// pages want many producer warps: four per operand, 32 rows each
-constexpr int kSoftmaxRegs = 152, kProducerRegs = 56;  // 256 * 152 + 384 * 56 <= 64 K registers (launch: 96 each)
-constexpr int kKStages = 3, kVStages = 2, kMaskStages = 2;
-constexpr int kSBufs = 3;  // S tiles in TMEM: O [0, 128) + 3 x 128 columns = all 512
+constexpr int kThreads = 512;  // 16 warps: 4 register-budget groups of 4 (setmaxnreg works per warpgroup)
+constexpr int kMmaWarp = 8, kPvWarp = 9, kQWarp = 10, kMaskWarp = 11, kKvWarp0 = 12;  // 12-13: K producers; 14-15: V
+constexpr int kSoftmaxRegs = 184, kProducerRegs = 72;  // 256 * 184 + 256 * 72 = 64 K registers (launch: 128 each)
+constexpr int kKStages = 3, kVStages = 2, kMaskStages = 4;
+constexpr float kRaise = 15.f;  // a row maximum this far (log2) above m_ref raises it: P <= 2^15 stays in fp16's range
 
-// ------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// non-blocking poll (try_wait may suspend the warp for a while; a loop polling two barriers must not)
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a launch failure (trap) instead of a hung GPU.
-// kSleepNs > 0: the waiting warp backs off between polls -- the producer / issuer warps share their SM
-// sub-partition's issue slots with a softmax warp and must not spin in them.
-template <int kSleepNs = 0>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (kSleepNs > 0) __nanosleep(kSleepNs);
-    if (++spins > (1u << 21)) __trap();
-  }
-}
-// arrives on `bar` when all cp.async of this thread issued so far have landed (counts as one arrival)
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 16-byte global->shared copy; src_bytes = 0 zero-fills
-__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {  // no arrival
-  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
-}
-// TMA: one box of a 3-D tensor map -> shared memory (swizzled by the map), completes `bytes` on `bar`
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_l1(const void* ptr) {  // (a 96-byte record may straddle two lines: both)
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(ptr) + 80));
-}
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-// TMA tile::gather4: four arbitrary rows of a 2-D tensor map (box {64, 1}) -> four consecutive 128-byte rows of
-// shared memory (swizzled by the map), completes 4 x 128 bytes on `bar`; rows outside the tensor read as zeros
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int r0, int r1, int r2, int r3) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-      : "memory");
-}
-// ... and their multicast forms: the box / the four rows land at the same shared-memory offset of every CTA of
-// the cluster named in `mask`, and complete their bytes on the mbarrier at the same offset in each
-__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::
-      "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tma_gather4_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int r0, int r1, int r2, int r3,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;" ::
-      "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// NB: no fence.proxy.async on the consumer side.  Data staged by cp.async or TMA is handed over through
-// an mbarrier the MMA thread waits on; a proxy fence there also waits for every async-proxy copy still
-// in flight to this CTA (the NEXT tiles' loads), which serialised the tensor pipe behind the loads.
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; }" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p; }" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-// arrives on `bar` when every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// ... on the mbarrier at this offset in every CTA of the cluster named in `mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
-  uint32_t* r = reinterpret_cast<uint32_t*>(v);
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; exp2(-inf) = 0
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// 32 x 32 bit-matrix transpose across a warp: lane l holds row l; on return lane l holds column l
-// (bit b of the result = bit l of lane b's input).  Five butterfly stages of one shuffle each.
-__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
-#pragma unroll
-  for (int st = 0; st < 5; ++st) {
-    const int j = 16 >> st;
-    const uint32_t m = st == 0 ? 0x0000FFFFu : st == 1 ? 0x00FF00FFu : st == 2 ? 0x0F0F0F0Fu : st == 3 ? 0x33333333u : 0x55555555u;
-    const uint32_t other = __shfl_xor_sync(0xffffffffu, x, j);
-    x = (lane & j) ? ((x & (m << j)) | ((other >> j) & m)) : ((x & m) | ((other & m) << j));
-  }
-  return x;
-}
-// exp2(x) where `bit` is set, else 0: the MUFU instruction itself is predicated
-__device__ __forceinline__ float exp2_if(float x, uint32_t bit) {
-  float y;
-  asm("{ .reg .pred p; setp.ne.u32 p, %2, 0; mov.f32 %0, 0f00000000; @p ex2.approx.ftz.f32 %0, %1; }" : "=f"(y) : "f"(x), "r"(bit));
-  return y;
-}
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-// ------------------------------------------------------------------------------------------------
-// UMMA descriptors (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
-// ------------------------------------------------------------------------------------------------
-// shared-memory matrix descriptor, 128-byte swizzle; offsets in bytes
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
-  return d;
-}
-// instruction descriptor: fp16 x fp16 -> fp32, M = 128
-__host__ __device__ constexpr uint32_t instr_desc(int n, bool b_mn_major) {
-  return (1u << 4)                         // c_format = F32
-         | (0u << 7) | (0u << 10)          // a_format = b_format = F16
-         | (0u << 15)                      // A K-major
-         | ((b_mn_major ? 1u : 0u) << 16)  // B major
-         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
-}
-
-// One operand tile in shared memory: [D/64 or 2 panels][128 rows][128 bytes], 16-byte chunks XOR-swizzled
-// by (row & 7) -- the canonical SWIZZLE_128B layout.  For K-major operands (Q, K) a row is an M/N
-// index and a panel is 64 elements of the contraction dim; for the MN-major operand (V) a row is a
-// token (contraction index) and a panel is 64 elements of D.
-constexpr int kPanelBytes = kRows * 128;
-__device__ __forceinline__ uint32_t tile_off(int row, int chunk16) {
-  return (uint32_t)((chunk16 >> 3) * kPanelBytes + row * 128 + (((chunk16 & 7) ^ (row & 7)) << 4));
-}
-
-// Optional per-CTA timeline (test/profiling hook, deft_b200_set_trace_buffer): trace[cta][event] =
-// SM cycles since the CTA started.  Events: see kTrace* below; per-tile events take 8 slots per tile.
+// Optional per-CTA timeline (test/profiling hook, deft_b200_set_trace_buffer): trace[cta][event] = SM cycles since the
+// CTA started.  Per-tile events of the first job's first six tiles take 8 slots each from kTrTile0.
 constexpr int kTraceSlots = 128;
 enum : int {
-  kTrStart = 0, kTrQIds = 1, kTrQ0Issued = 2, kTrQ1Issued = 3, kTrMask0 = 4, kTrKUnit = 5, kTrMmaQFull = 6, kTrEpiBegin = 7,
-  kTrEpiEnd = 8, kTrEnd = 9,
-  kTrTile0 = 16,  // + 8 * tile: K issued, K_FULL seen by MMA, S_FULL seen by softmax 0, pass 1 done, P_FULL arrive,
-                  //             P_FULL seen by MMA, V issued, (spare)
+  kTrStart = 0, kTrQIds = 1, kTrQIssued = 2, kTrMask0 = 4, kTrKUnit = 5, kTrMmaQFull = 6, kTrEpiBegin = 7, kTrEpiEnd = 8,
+  kTrEnd = 9, kTrEpiODone = 10, kTrKRole = 12,
+  kTrTile0 = 16,  // + 8 * tile: K issued, S issued, S in registers, checked, P half 0 handed, P half 1 handed, V issued,
+                  //             P V issued
 };
 #define DEFT_TRACE(ev)                                                                          \
   do {                                                                                          \
@@ -317,11 +79,12 @@ enum : int {
   Q_FULL = V_EMPTY + kVStages, Q_EMPTY = Q_FULL + 1,
   M_FULL = Q_EMPTY + 1,                    // [stage]
   M_EMPTY = M_FULL + kMaskStages,
-  S_FULL = M_EMPTY + kMaskStages,          // [S buffer]: S of one tile is in TMEM
-  P_FULL = S_FULL + kSBufs,                // [S buffer][half]: P of one 64-token half has been written over S
-  S_FREE = P_FULL + 2 * kSBufs,            // [S buffer]: P V of the buffer's tile has completed
-  PV_DONE = S_FREE + kSBufs,               // one phase per tile: P V of the tile has landed in O
-  O_DONE = PV_DONE + 1,                    // one phase per job: the last P V has landed, O is complete
+  S_FULL = M_EMPTY + kMaskStages,          // [group]: S of the group's tile is in TMEM
+  S_FREE = S_FULL + 2,                     // [group]: the group has the row in registers
+  P_FULL = S_FREE + 2,                     // [group][half]: P of one 64-token half is in TMEM
+  P_FREE = P_FULL + 4,                     // [group]: P V of the group's tile has completed
+  CHK = P_FREE + 2,                        // [group]: the group's task has read / raised the shared reference maximum
+  O_DONE = CHK + 2,                        // one phase per job: the last P V has landed, O is complete
   O_EMPTY = O_DONE + 1,                    // one phase per job: the epilogue has read O
   kNumBars = O_EMPTY + 1
 };
@@ -332,21 +95,19 @@ struct Layout {
   static constexpr int kQ = 0;
   static constexpr int kK = kQ + kOperandBytes;                            // [stage]
   static constexpr int kV = kK + kKStages * kOperandBytes;                 // [stage]
-  static constexpr int kMask = kV + kVStages * kOperandBytes;              // [stage][128] u32
+  static constexpr int kMask = kV + kVStages * kOperandBytes;              // [stage][32 queries][4] u32
   static constexpr int kFlag = kMask + kMaskStages * kTileN * 4;           // [stage] u32
-  static constexpr int kPvCnt = kFlag + 16;                                // u32: tiles whose P V the issuer has seen complete
-  static constexpr int kXchg = kPvCnt + 16;                                 // [tile parity][round parity][half][128] f32
-  static constexpr int kBars = kXchg + 2 * 2 * 2 * kRows * 4;
+  static constexpr int kMref = kFlag + kMaskStages * 4;                    // [128] f32: the rows' reference maximum (log2 domain)
+  static constexpr int kLse = kMref + kRows * 4;                           // [job parity][group][128] f32: m + log2(l) per group
+  static constexpr int kBars = kLse + 2 * 2 * kRows * 4;
   static constexpr int kTmemSlot = kBars + kNumBars * 8;
   static constexpr int kBytes = kTmemSlot + 16;
   static constexpr int kAlloc = kBytes + 1024;  // slack for the manual 1024-byte alignment
 };
 
-// The jobs of one CTA.  job = ((unit * HKV + kv-head) << 1) | slot of the unit's pair: one CTA works ONE
-// slot (<= 32 queries x G heads = one M = 128 accumulator) over the unit's chain of KV tiles; the two
-// slots of a pair are separate jobs, on different SMs when the balance allows (their K/V tile reads meet
-// in L2).  Either the host-balanced record lists (deft_job_t: the CTA's first record sits at [blockIdx.x]
-// and carries its unit, so a CTA starts from ONE load), or jobs c, c + grid, ... over the unit table.
+// The jobs of one CTA.  job = ((unit * HKV + kv-head) << 1) | slot of the unit's pair.  Either the host-balanced
+// record lists (deft_job_t: the CTA's first record sits at [blockIdx.x] and carries its unit, so a CTA starts from
+// ONE load), or jobs c, c + grid, ... over the unit table.
 struct Jobs {
   const deft_job_t* recs;  // null: strided over the unit table
   int n, next;
@@ -391,28 +152,16 @@ struct Jobs {
   }
 };
 
-// pair of warps w, w + 4 (the two threads of a row sit in them): named barrier 1 + (w & 3)
-__device__ __forceinline__ void pair_sync(int warp) {
-  asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
-}
-
-// ... and the same barrier OR-reducing a predicate over the 64 threads
-__device__ __forceinline__ bool pair_sync_or(int warp, bool pred) {
-  uint32_t out;
-  asm volatile(
-      "{ .reg .pred p, q; setp.ne.b32 q, %2, 0; barrier.cta.red.or.pred p, %1, 64, q; selp.u32 %0, 1, 0, p; }"
-      : "=r"(out)
-      : "r"(1 + (warp & 3)), "r"((uint32_t)pred)
-      : "memory");
-  return out != 0;
-}
+// the factor that takes a sum kept against the reference `from` to the reference `to` >= from (no NaN for -inf)
+__device__ __forceinline__ float rescale(float from, float to) { return from == to ? 1.f : fast_exp2(from - to); }
 
 template <int D, int G, bool kDbg>
 __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_constant__ AttnParams p) {
   using L = Layout<D>;
   constexpr int CH = D / 8;           // 16-byte chunks per row
   constexpr int R = kMaxGroupQ * G;   // live rows of a full slot
-  constexpr uint32_t kTmemCols = 512; // O [0, D)   S_0 [128, 256)   S_1 [256, 384)   S_2 [384, 512)
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kColS = 128, kColP = 384;  // S_g at kColS + 128 g, P_g at kColP + 64 g
   constexpr uint32_t kIdescQK = instr_desc(kTileN, false);
   constexpr uint32_t kIdescPV = instr_desc(D, true);
 
@@ -433,16 +182,16 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   if (p.plan_fresh) griddep_wait();  // the plan itself comes from the preceding (plan) kernel
   const Jobs jobs(p);  // (its load is in flight under the barrier set-up and the TMEM allocation below)
   if (tid == 0) {
-    for (int s = 0; s < kKStages; ++s) { mbar_init(bar(K_FULL + s), 128); mbar_init(bar(K_EMPTY + s), 2); }  // EMPTY: my issuer + the pair's (or mine twice)
-    for (int s = 0; s < kVStages; ++s) { mbar_init(bar(V_FULL + s), 128); mbar_init(bar(V_EMPTY + s), 2); }
+    for (int s = 0; s < kKStages; ++s) { mbar_init(bar(K_FULL + s), 64); mbar_init(bar(K_EMPTY + s), 2); }  // EMPTY: my issuer + the pair's (or mine twice)
+    for (int s = 0; s < kVStages; ++s) { mbar_init(bar(V_FULL + s), 64); mbar_init(bar(V_EMPTY + s), 2); }
     mbar_init(bar(Q_FULL), 32); mbar_init(bar(Q_EMPTY), 1);
-    for (int m = 0; m < kMaskStages; ++m) { mbar_init(bar(M_FULL + m), 32); mbar_init(bar(M_EMPTY + m), 256); }
-    for (int b = 0; b < kSBufs; ++b) {
-      mbar_init(bar(S_FULL + b), 1); mbar_init(bar(S_FREE + b), 1);
-      for (int h = 0; h < 2; ++h) mbar_init(bar(P_FULL + 2 * b + h), 128);
+    for (int m = 0; m < kMaskStages; ++m) { mbar_init(bar(M_FULL + m), 32); mbar_init(bar(M_EMPTY + m), 128); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(bar(S_FULL + g), 1); mbar_init(bar(S_FREE + g), 128); mbar_init(bar(P_FREE + g), 1);
+      mbar_init(bar(CHK + g), 128);
+      for (int h = 0; h < 2; ++h) mbar_init(bar(P_FULL + 2 * g + h), 128);
     }
-    mbar_init(bar(PV_DONE), 1); mbar_init(bar(O_DONE), 1); mbar_init(bar(O_EMPTY), 256);
-    *reinterpret_cast<volatile uint32_t*>(gbase + L::kPvCnt) = 0u;
+    mbar_init(bar(O_DONE), 1); mbar_init(bar(O_EMPTY), 128);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(base + L::kTmemSlot, kTmemCols);
@@ -458,49 +207,56 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   griddep_wait();
   if (tid == 0) DEFT_TRACE(kTrStart);
   if (warp >= 8) {
-  reg_dealloc<kProducerRegs>();  // warps 8-19: three whole warpgroups give registers away
+  reg_dealloc<kProducerRegs>();  // warps 8-15: two whole warpgroups give registers away
   if (warp >= kKvWarp0) {
     // ============================== K / V producers ==============================
-    // warps 12-15: K rows [32w, 32w + 32) of every tile; warps 16-19: V likewise.  K and V run on rings of their
-    // own (K is released as soon as S is done, a tile earlier than V).
-    const int kv = (warp - kKvWarp0) >> 2, w = (warp - kKvWarp0) & 3;
+    // warps 12-13: K rows [64w, 64w + 64) of every tile, as two blocks of 32; warps 14-15: V likewise.  K and V run on
+    // rings of their own (K is released as soon as S is done, a tile earlier than V).
+    const int kv = (warp - kKvWarp0) >> 1, w = (warp - kKvWarp0) & 1;
     const int stages = kv == 0 ? kKStages : kVStages;
     const int FULL = kv == 0 ? K_FULL : V_FULL, EMPTY = kv == 0 ? K_EMPTY : V_EMPTY;
-    const int row0 = w * 32;  // my 32 rows
     uint32_t cnt = 0;  // tiles produced
-    if (warp == kKvWarp0 && lane == 0) DEFT_TRACE(12);
+    if (warp == kKvWarp0 && lane == 0) DEFT_TRACE(kTrKRole);
     for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k; bool shared;
       if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       if (warp == kKvWarp0 && lane == 0 && ji == 0 && u.n_tiles > 0) DEFT_TRACE(kTrKUnit);
       const bool known_run = u.page0 >= 0 && p.tma_kv != 0;  // the builder's shortcut: no index-table read at all
-      auto page_of = [&](int t) -> int {  // page of my row of tile t (0 past the end)
+      auto page_of = [&](int t, int row) -> int {  // page of `row` of tile t (0 past the end)
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
-        if (known_run) return u.page0 + t * kTileN + row0 + lane;
-        return t < u.n_tiles && row0 + lane < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row0 + lane) : 0;
+        if (known_run) return u.page0 + t * kTileN + row;
+        return t < u.n_tiles && row < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row) : 0;
       };
-      int pg_next = page_of(0);
+      int pg_next0 = page_of(0, w * 64 + lane), pg_next1 = page_of(0, w * 64 + 32 + lane);
+      // shared job: the pair loads every tile ONCE -- the CTA of rank r issues rows [64r, 64r + 64) for both
+      const bool mine = !shared || (uint32_t)w == crank;
       for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
         const int st = cnt % stages;
         const uint32_t ph = ((cnt / stages) & 1) ^ 1;
-        const int pg = pg_next;
-        pg_next = page_of(t + 1);  // the next tile's page ids are in flight while this tile is issued
-        const bool trp = kv == 0 && w == 0 && lane == 0 && ji == 0 && t < 6;
-        if (trp) DEFT_TRACE(64 + 8 * t + 0);
+        const int pg[2] = {pg_next0, pg_next1};
+        pg_next0 = page_of(t + 1, w * 64 + lane);  // the next tile's page ids are in flight while this tile is issued
+        pg_next1 = page_of(t + 1, w * 64 + 32 + lane);
         mbar_wait<64>(bar(EMPTY + st), ph);
-        if (trp) DEFT_TRACE(64 + 8 * t + 1);
         const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
         const uint32_t full = bar(FULL + st);
-        // 32 consecutive pages of a full tile are ONE box of the pool's tensor map per 64-wide panel
-        const int page0 = __shfl_sync(0xffffffffu, pg, 0);
-        const bool run = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg == page0 + lane);
-        // shared job: the pair loads every tile ONCE -- the CTA of rank r issues rows [64r, 64r + 64) for both
-        const bool mine = !shared || (uint32_t)(w >> 1) == crank;
-        if (run) {
-          if (lane == 0) {
-            mbar_arrive_expect_tx(full, 32 * D * 2);
-            if (mine) {
+        bool run[2];
+        uint32_t tx = 0;  // bytes the TMA engine completes on MY barrier for my 64 rows (whichever CTA issues them)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int page0 = __shfl_sync(0xffffffffu, pg[b], 0);
+          // 32 consecutive pages of a full tile are ONE box of the pool's tensor map per 64-wide panel
+          run[b] = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg[b] == page0 + lane);
+          if (run[b] || p.tma_gather != 0) tx += 32 * D * 2;
+        }
+        if (lane == 0 && tx != 0) mbar_expect_tx(full, tx);
+        bool any_cp_async = false;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int row0 = w * 64 + b * 32;  // this block's 32 rows
+          const int page0 = __shfl_sync(0xffffffffu, pg[b], 0);
+          if (run[b]) {
+            if (lane == 0 && mine) {
 #pragma unroll
               for (int pn = 0; pn < D / 64; ++pn) {
                 if (shared)
@@ -509,41 +265,39 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
                   tma_load_3d(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0);
               }
             }
+          } else if (p.tma_gather != 0) {
+            // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of the block with one gather4 per panel;
+            // rows past the tile's length name a row outside the map and arrive as zeros
+            constexpr int NP = D / 64;
+            const int g = lane / NP, pn = lane % NP;
+            const int my_row = row0 + lane < tlen ? pg[b] * p.kv_row_ratio + hkv : p.kv_rows;
+            const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
+            const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
+            if (mine && lane < 8 * NP) {
+              if (shared)
+                tma_gather4_mc(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
+                               r0, r1, r2, r3, 0x3);
+              else
+                tma_gather4(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
+                            r0, r1, r2, r3);
+            }
           } else {
-            mbar_arrive(full);
-          }
-        } else if (p.tma_gather != 0) {
-          // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of my 32 with one gather4 per panel;
-          // rows past the tile's length name a row outside the map and arrive as zeros
-          constexpr int NP = D / 64;
-          const int g = lane / NP, pn = lane % NP;
-          const int my_row = row0 + lane < tlen ? pg * p.kv_row_ratio + hkv : p.kv_rows;
-          const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
-          const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
-          if (lane == 0) mbar_arrive_expect_tx(full, 32 * D * 2);
-          else mbar_arrive(full);
-          if (mine && lane < 8 * NP) {
-            if (shared)
-              tma_gather4_mc(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
-                             r0, r1, r2, r3, 0x3);
-            else
-              tma_gather4(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
-                          r0, r1, r2, r3);
-          }
-        } else {
-          const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
-          constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
+            const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
+            constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
 #pragma unroll 4
-          for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
-            const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside my 32
-            const int ch = lane % CH;
-            const int64_t page = __shfl_sync(0xffffffffu, pg, nl);
-            const bool ok = row0 + nl < tlen;
-            cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
+            for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
+              const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside the block
+              const int ch = lane % CH;
+              const int64_t page = __shfl_sync(0xffffffffu, pg[b], nl);
+              const bool ok = row0 + nl < tlen;
+              cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
+            }
+            any_cp_async = true;
           }
-          cp_async_arrive(full);
         }
-        if (w == 0 && lane == 0 && ji == 0) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
+        if (any_cp_async) cp_async_arrive(full);  // arrives once my copies have landed
+        else mbar_arrive(full);
+        if (w == 0 && lane == 0 && ji == 0 && t < 6) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
       }
     }
   } else if (warp == kQWarp) {
@@ -587,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
         cp_async_arrive(bar(Q_FULL));
       }
-      if (lane == 0 && ji == 0) DEFT_TRACE(kTrQ0Issued);
+      if (lane == 0 && ji == 0) DEFT_TRACE(kTrQIssued);
       ++q_cnt;
     }
   } else if (warp == kMaskWarp) {
@@ -616,13 +370,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           dense = dense && ((m[j] & fullw) == fullw);
         }
         dense = __all_sync(0xffffffffu, dense);
-        if (lane == 0 && ji == 0 && t >= 1 && t <= 3) DEFT_TRACE(120 + 2 * (t - 1));
         mbar_wait<64>(bar(M_EMPTY + st), ((m_cnt / kMaskStages) & 1) ^ 1);
         uint32_t* ms = reinterpret_cast<uint32_t*>(gbase + L::kMask) + st * kTileN;
         if (!dense) {
           // transpose to row masks: lane = query, word j bit n = the query attends token 32j + n
-          // (one copy of the transpose in the binary: this warp's loop shares the SM's 32 KB instruction cache with the
-          // softmax, producer and issuer loops)
 #pragma unroll 1
           for (int j = 0; j < kTileN / 32; ++j) {
             const uint32_t w = j == 0 ? m[0] : j == 1 ? m[1] : j == 2 ? m[2] : m[3];
@@ -632,18 +383,17 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         if (lane == 0) reinterpret_cast<uint32_t*>(gbase + L::kFlag)[st] = dense ? 1u : 0u;
         mbar_arrive(bar(M_FULL + st));
         if (lane == 0 && ji == 0 && t == 0) DEFT_TRACE(kTrMask0);
-        if (lane == 0 && ji == 0 && t >= 1 && t <= 3) DEFT_TRACE(121 + 2 * (t - 1));
       }
     }
   } else if (warp == kMmaWarp) {
     // ============================== S issuer ==============================
     // The whole warp runs the (uniform) control flow and the waits; lane 0 alone executes the tcgen05.mma /
-    // tcgen05.commit instructions.  S is triple-buffered in TMEM: S(t) = Q K(t)^T is issued as soon as K(t) has
-    // landed and P V of tile t - 3 (the buffer's previous tenant) has completed, i.e. up to two tiles ahead of
-    // the softmax warps, which therefore never wait for the tensor pipe in the steady state.
+    // tcgen05.commit instructions.  S(t) = Q K(t)^T goes into the S buffer of the group that will work tile t, as soon
+    // as K(t) has landed and the group has taken its previous tile's row out of the buffer -- i.e. while that group is
+    // still in the exponentials of its previous tile.
     const bool leader = lane == 0;
     const uint64_t q_desc = smem_desc_sw128(base + L::kQ, 16, 1024);
-    uint32_t k_cnt = 0, g0 = 0, j_cnt = 0;  // K tiles consumed (ring position), tiles of earlier jobs, jobs
+    uint32_t k_cnt = 0, task = 0, j_cnt = 0, tc0 = 0, tc1 = 0;  // K tiles consumed, tasks, jobs, tile tasks per group
     for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k; bool shared;
       if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
@@ -651,14 +401,13 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       const bool tr0 = ji == 0 && leader;
       mbar_wait(bar(Q_FULL), j_cnt & 1);
       if (tr0) DEFT_TRACE(kTrMmaQFull);
-      for (int t = 0; t < n; ++t) {
-        const uint32_t gt = g0 + t, c = k_cnt + t;
-        const int sb = gt % kSBufs, st = c % kKStages;
-        if (gt >= (uint32_t)kSBufs) mbar_wait(bar(S_FREE + sb), (gt / kSBufs - 1) & 1);
-        mbar_wait(bar(K_FULL + st), (c / kKStages) & 1);
+      for (int t = 0; t < n; ++t, ++task) {
+        const int g = task & 1, st = (k_cnt + t) % kKStages;
+        const uint32_t c = g == 0 ? tc0++ : tc1++;
+        if (c >= 1) mbar_wait(bar(S_FREE + g), (c - 1) & 1);
+        mbar_wait(bar(K_FULL + st), ((k_cnt + t) / kKStages) & 1);
         tc_fence_after();
-        if (tr0) DEFT_TRACE(kTrTile0 + 8 * t + 1);
-        const uint32_t s_tmem = tmem + 128 + sb * 128;
+        const uint32_t s_tmem = tmem + kColS + g * 128;
         const uint64_t k_desc = smem_desc_sw128(base + L::kK + st * L::kOperandBytes, 16, 1024);
         if (leader) {
 #pragma unroll
@@ -666,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
             const uint64_t koff = (uint64_t)(((ks >> 2) * kPanelBytes + (ks & 3) * 32) >> 4);
             umma_ss(s_tmem, q_desc + koff, k_desc + koff, kIdescQK, ks > 0);
           }
-          umma_commit(bar(S_FULL + sb));
+          umma_commit(bar(S_FULL + g));
           if (shared) {
             umma_commit_mc(bar(K_EMPTY + st), 0x3);  // K(t) is free here; the pair's producers hear it too
           } else {
@@ -676,38 +425,34 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           if (t == n - 1) umma_commit(bar(Q_EMPTY));
         }
         __syncwarp();
+        if (tr0 && t < 6) DEFT_TRACE(kTrTile0 + 8 * t + 1);
       }
+      ++task;  // the job's epilogue task
       k_cnt += n;
-      g0 += n;
       ++j_cnt;
     }
   } else if (warp == kPvWarp) {
     // ============================== P V issuer ==============================
-    // O (+)= P(t) V(t) in two 64-token halves, each as soon as the softmax warps have written that half of P
-    // over S(t).  After a tile's MMAs and commits this warp sees the tile's PV_DONE phase through and publishes
-    // the count of completed tiles (the softmax warps' rare rescale path reads it: a parity wait is sound only
-    // one phase ahead of what is known complete, and only this warp sees every phase).
+    // O (+)= P(t) V(t) in two 64-token halves, each as soon as the tile's group has written that half of P.
     const bool leader = lane == 0;
     const uint32_t o_tmem = tmem;
-    uint32_t v_cnt = 0, g0 = 0, j_cnt = 0;
-    volatile uint32_t* pv_cnt = reinterpret_cast<volatile uint32_t*>(gbase + L::kPvCnt);
+    uint32_t v_cnt = 0, task = 0, j_cnt = 0, tc0 = 0, tc1 = 0;
     for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k; bool shared;
       if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       const int n = u.n_tiles;
       const bool tr0 = ji == 0 && leader;
-      for (int t = 0; t < n; ++t) {
-        const uint32_t gt = g0 + t, c = v_cnt + t;
-        const int buf = gt % kSBufs, st = c % kVStages;
-        mbar_wait(bar(V_FULL + st), (c / kVStages) & 1);
-        if (t == 0) mbar_wait(bar(O_EMPTY), (j_cnt & 1) ^ 1);
+      for (int t = 0; t < n; ++t, ++task) {
+        const int g = task & 1, st = (v_cnt + t) % kVStages;
+        const uint32_t c = g == 0 ? tc0++ : tc1++;
+        mbar_wait(bar(V_FULL + st), ((v_cnt + t) / kVStages) & 1);
+        if (t == 0 && j_cnt > 0) mbar_wait(bar(O_EMPTY), (j_cnt - 1) & 1);  // the previous job's epilogue has read O
         const uint64_t v_desc = smem_desc_sw128(base + L::kV + st * L::kOperandBytes, kPanelBytes, 1024);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          mbar_wait(bar(P_FULL + 2 * buf + half), (gt / kSBufs) & 1);
+          mbar_wait(bar(P_FULL + 2 * g + half), c & 1);
           tc_fence_after();
-          if (tr0 && half == 0) DEFT_TRACE(kTrTile0 + 8 * t + 5);
-          const uint32_t p_tmem = tmem + 128 + buf * 128 + half * kHalfN;  // P_a: columns [0, 32), P_b: [64, 96) of S
+          const uint32_t p_tmem = tmem + kColP + g * 64 + half * 32;  // 64 tokens = 32 columns of packed fp16 pairs
           if (leader) {
 #pragma unroll
             for (int ks = 0; ks < kHalfN / 16; ++ks)
@@ -716,268 +461,221 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           }
         }
         if (leader) {
-          umma_commit(bar(PV_DONE));
           if (shared) {
             umma_commit_mc(bar(V_EMPTY + st), 0x3);
           } else {
             umma_commit(bar(V_EMPTY + st));
             umma_commit(bar(V_EMPTY + st));
           }
-          umma_commit(bar(S_FREE + buf));
+          umma_commit(bar(P_FREE + g));
           if (t == n - 1) umma_commit(bar(O_DONE));
         }
         __syncwarp();
-        mbar_wait(bar(PV_DONE), gt & 1);
-        if (leader) *pv_cnt = gt + 1;
+        if (tr0 && t < 6) DEFT_TRACE(kTrTile0 + 8 * t + 7);
       }
+      ++task;
       v_cnt += n;
-      g0 += n;
       ++j_cnt;
     }
   }
   } else {
     reg_alloc<kSoftmaxRegs>();   // warps 0-7
-    // ============================== softmax + epilogue ==============================
-    // Two threads per row: warp w < 4 takes columns [0, 64) of every S tile, warp w + 4 columns [64, 128) of
-    // the same 32 rows (the same TMEM lanes).  They agree on the row's reference maximum through shared
-    // memory and a named barrier of the two warps, once per tile.
-    const int h = warp >> 2;
-    const int r = tid & 127;  // my row == my TMEM lane
+    // ============================== softmax groups + epilogue ==============================
+    const int g = warp >> 2;     // my group: tasks with (task & 1) == g are mine
+    const int r = tid & 127;     // my row == my TMEM lane
     const int qi = r / G;
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t t_o = t_lane + h * (D / 2);  // my half of the O row
+    const uint32_t t_s = t_lane + kColS + g * 128, t_p = t_lane + kColP + g * 64;
     const float c = p.scale * 1.4426950408889634f;  // scores are handled in the log2 domain
-    float* xchg = reinterpret_cast<float*>(gbase + L::kXchg);
-    uint32_t g0 = 0, j_cnt = 0, m_cnt = 0;  // tiles of earlier jobs, jobs, masked tiles
+    volatile float* m_ref = reinterpret_cast<volatile float*>(gbase + L::kMref);
+    volatile float* lse_s = reinterpret_cast<volatile float*>(gbase + L::kLse);  // [job parity][group][row]
+    // tasks, jobs, MY tile tasks, THEIR tile tasks, masked tiles (of both groups)
+    uint32_t task = 0, j_cnt = 0, tcnt = 0, ocnt = 0, m_cnt = 0;
     bool first_job = blockIdx.x == 0;
+
+    // task k waits until task k - 1 (the other group's) has read / raised the shared reference maximum
+    auto wait_checked = [&](uint32_t k) {
+      if (k > 0) mbar_wait<32>(bar(CHK + (g ^ 1)), ((k - 1) >> 1) & 1);
+    };
 
     for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k; bool shared;
       if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
+      const int n = u.n_tiles;
       const int n_q = k == 0 ? u.q_cnt[0] : u.q_cnt[1];
       const int part_base = k == 0 ? u.part_base[0] : u.part_base[1];
       const bool dbg = kDbg && p.dbg != nullptr && first_job;  // (the dumps live in an instantiation of their own)
       first_job = false;
-      float m_ref = -INFINITY, l_run = 0.f;
-
       const int64_t mask_off = k == 0 ? u.mask_off[0] : u.mask_off[1];
       const bool job_dense = mask_off < 0 && u.last_len == kTileN;  // no tile of this job needs a mask
-      float sv[kHalfN];   // my half of the current S row (64 columns): out of TMEM once, kept in registers
-      bool have_next = false;
+      const uint32_t jp = j_cnt & 1;
+      const uint32_t task0 = task;                                    // task of tile 0
+      const int my_last = ((task0 + n - 1) & 1) == (uint32_t)g ? n - 1 : n - 2;  // my last tile of the job (-1: none)
+      float m_loc = -INFINITY, l_run = 0.f;   // the reference maximum my sum is kept against, my sum over MY tiles
 
-      for (int t = 0; t < u.n_tiles; ++t) {
-        const uint32_t gt = g0 + t;
-        const int buf = gt % kSBufs;
-        const bool tr = ji == 0 && (tid & 127) == 0 && t < 5;
-        const int tr0 = kTrTile0 + (h == 0 ? 0 : 48) + 8 * t;  // the second half's events sit 48 slots higher
-        const uint32_t t_s = t_lane + 128 + buf * 128 + h * kHalfN;
-        if (have_next) {  // my half of this tile's S has been on its way since the previous tile's P went out
-          tmem_wait_ld();
-        } else {
-          mbar_wait<32>(bar(S_FULL + buf), (gt / kSBufs) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv + cb * 32);
-          tmem_wait_ld();
+      for (int t = 0; t < n; ++t, ++task) {
+        if ((task & 1) != (uint32_t)g) {      // the other group's tile
+          if (!job_dense) ++m_cnt;
+          ++ocnt;
+          continue;
         }
-        if (tr) DEFT_TRACE(tr0 + 2);
-        if (tr && t == 3 && h == 0 && have_next) DEFT_TRACE(117);   // tile 3's S came out of TMEM ahead of time
-        if (dbg && t == 0)
-          for (int j = 0; j < kHalfN; ++j) p.dbg[r * kTileN + h * kHalfN + j] = sv[j];
-        uint32_t rw[2] = {0xffffffffu, 0xffffffffu};  // my query's token bitmask over my 64 columns (kept: a redo re-masks)
-        bool masked = false;                           // CTA-uniform: this tile carries a mask
-        auto apply_mask = [&]() {
-          if ((rw[0] & rw[1]) != 0xffffffffu) {
+        const uint32_t cn = tcnt++;
+        const bool tr = ji == 0 && (tid & 127) == 0 && t < 6;
+        float sv[kTileN];   // my S row: out of TMEM once, kept in registers
+        mbar_wait<32>(bar(S_FULL + g), cn & 1);
+        tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < kHalfN; ++j)
-              if (!((rw[j >> 5] >> (j & 31)) & 1u)) sv[j] = -INFINITY;
-          }
-        };
+        for (int cb = 0; cb < kTileN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv + cb * 32);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(bar(S_FREE + g));   // the S issuer may compute my next tile into the buffer
+        if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 2);
+        if (dbg && t == 0)
+          for (int j = 0; j < kTileN; ++j) p.dbg[r * kTileN + j] = sv[j];
+
+        // ---- mask: tokens my query does not attend score -inf
         if (!job_dense) {
           const int mst = m_cnt % kMaskStages;
           mbar_wait<32>(bar(M_FULL + mst), (m_cnt / kMaskStages) & 1);
-          if (tr && t == 2 && h == 0) DEFT_TRACE(118);
           ++m_cnt;
           const uint32_t* ms = reinterpret_cast<const uint32_t*>(gbase + L::kMask) + mst * kTileN;
           const bool dense = reinterpret_cast<const volatile uint32_t*>(gbase + L::kFlag)[mst] != 0;
-          if (!dense) {  // masked-out tokens score -inf: my query's token bitmask comes from the mask warp
-            const uint2 rm = qi < 32 ? *reinterpret_cast<const uint2*>(ms + qi * 4 + h * 2) : make_uint2(0u, 0u);
-            rw[0] = rm.x; rw[1] = rm.y;
-            if (t == 0) apply_mask();   // the first tile's exact maximum needs S masked ...
-            else masked = true;         // ... later tiles mask inside the exp loop (no pass of its own over S)
+          if (!dense) {
+            const uint4 rm = qi < 32 ? *reinterpret_cast<const uint4*>(ms + qi * 4) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int j = 0; j < kTileN; ++j) {
+              const uint32_t w = (j >> 5) == 0 ? rm.x : (j >> 5) == 1 ? rm.y : (j >> 5) == 2 ? rm.z : rm.w;
+              if (!((w >> (j & 31)) & 1u)) sv[j] = -INFINITY;
+            }
           }
-          if (tr && t == 2 && h == 0) DEFT_TRACE(119);
           mbar_arrive(bar(M_EMPTY + mst));
         }
-        auto half_max = [&]() {
+        // ---- my row's maximum (thread-local)
+        float mt;
+        {
           float m0 = sv[0], m1 = sv[1], m2 = sv[2], m3 = sv[3];
 #pragma unroll
-          for (int j = 4; j < kHalfN; j += 4) {
+          for (int j = 4; j < kTileN; j += 4) {
             m0 = fmaxf(m0, sv[j]); m1 = fmaxf(m1, sv[j + 1]); m2 = fmaxf(m2, sv[j + 2]); m3 = fmaxf(m3, sv[j + 3]);
           }
-          return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;  // c > 0; -inf when the row attends nothing here
-        };
-        // ---- reference maximum m_ref (shared by the row's two threads).  The first tile of a job sets it to
-        // the exact row maximum.  Every later tile is exponentiated against the m_ref it finds (no dependent
-        // max -> exp chain); only if a half row's exponentials sum past 2^15 (a P might leave fp16) does its
-        // thread ask for a raise, and then both threads rescale their half of O and redo the tile.
-        int round = 0;
-        float* xq = xchg + (gt & 1) * (4 * kRows);  // [round parity][half][row]
-        if (t == 0) {
-          xq[h * kRows + r] = half_max();
-          pair_sync(warp);
-          m_ref = fmaxf(xq[r], xq[kRows + r]);
-          round = 1;
+          mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;  // c > 0; -inf when the row attends nothing here
         }
-        if (tr) DEFT_TRACE(tr0 + 3);
-        uint32_t pk[kHalfN / 2];
-        float hsum;
-        bool redo;
-        int n_redo = 0;
-        do {
-          const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
-          float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-          if (!masked) {
-#pragma unroll
-            for (int j = 0; j < kHalfN; j += 4) {
-              const float e0 = fast_exp2(fmaf(sv[j], c, -m_use)), e1 = fast_exp2(fmaf(sv[j + 1], c, -m_use));
-              const float e2 = fast_exp2(fmaf(sv[j + 2], c, -m_use)), e3 = fast_exp2(fmaf(sv[j + 3], c, -m_use));
-              ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
-              pk[j / 2] = pack_half2(e0, e1);
-              pk[j / 2 + 1] = pack_half2(e2, e3);
-            }
-          } else {
-            // masked tile: P = 0 where my query does not attend the token; the exponential is predicated on the
-            // mask bit, so a column no row of the warp attends costs no MUFU cycles at all
-#pragma unroll
-            for (int j = 0; j < kHalfN; j += 4) {
-              const uint32_t w = rw[j >> 5];
-              const float e0 = exp2_if(fmaf(sv[j], c, -m_use), w & (1u << (j & 31)));
-              const float e1 = exp2_if(fmaf(sv[j + 1], c, -m_use), w & (1u << ((j + 1) & 31)));
-              const float e2 = exp2_if(fmaf(sv[j + 2], c, -m_use), w & (1u << ((j + 2) & 31)));
-              const float e3 = exp2_if(fmaf(sv[j + 3], c, -m_use), w & (1u << ((j + 3) & 31)));
-              ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
-              pk[j / 2] = pack_half2(e0, e1);
-              pk[j / 2 + 1] = pack_half2(e2, e3);
-            }
-          }
-          hsum = (ps0 + ps1) + (ps2 + ps3);
-          if (tr && t == 2 && h == 0) DEFT_TRACE(112);
-          // sv is dead from here (unless the tile is redone: S(t) is still in TMEM then, P has not been written over
-          // it).  S of the next tile is normally there already (the S issuer runs ahead): my half of it starts its
-          // way out of TMEM now, under the agreement barrier, the store of P and the hand-off.
-          have_next = false;
-          if (t + 1 < u.n_tiles) {
-            const int nb = (gt + 1) % kSBufs;
-            if (mbar_test_wait(bar(S_FULL + nb), ((gt + 1) / kSBufs) & 1)) {
-              tc_fence_after();
-#pragma unroll
-              for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_lane + 128 + nb * 128 + h * kHalfN + cb * 32, sv + cb * 32);
-              have_next = true;
-            }
-          }
-          // every P >= 0, so a half-row sum below 2^15 proves that no P left fp16's range; a row that had seen
-          // nothing yet (m_ref = -inf) asks at its first live token.  (!(x < y) also catches NaN.)
-          const bool over = !(hsum < 32768.f) || (m_ref == -INFINITY && hsum > 0.f);
-          // the row pairs' two warps learn whether anybody asked (the common answer is no)
-          float rq = -INFINITY;
-          redo = pair_sync_or(warp, over);  // one barrier with an OR reduction; shared memory only on a request
-          if (tr && t == 2 && h == 0) DEFT_TRACE(113);
-          if (redo) {
-            // back to this tile's S: whatever was on its way for the next tile lands first, then S(t) again
-            if (have_next) tmem_wait_ld();
-            have_next = false;
-#pragma unroll
-            for (int cb = 0; cb < kHalfN / 32; ++cb) tmem_ld32_nowait(t_s + cb * 32, sv + cb * 32);
-            tmem_wait_ld();
-            apply_mask();
-            masked = false;   // S carries -inf now: the plain loop
-            float* xr = xq + (round & 1) * (2 * kRows);
-            xr[h * kRows + r] = over ? half_max() : -INFINITY;
-            pair_sync(warp);
-            rq = fmaxf(xr[r], xr[kRows + r]);  // the row's request, seen alike by its two threads
-            ++round;
-          }
-          if (redo) {
-            float alpha = 1.f;
-            if (rq > -INFINITY) {
-              alpha = fast_exp2(m_ref - rq);  // 0 when m_ref = -inf
-              m_ref = rq;
-              l_run *= alpha;
-            }
-            if (t > 0) {
-              // P V of the previous tile has landed in O (this tile's waits on my P): the issuer warp follows
-              // the PV_DONE phases and publishes how many tiles are complete
-              {
-                volatile uint32_t* pv_cnt = reinterpret_cast<volatile uint32_t*>(gbase + L::kPvCnt);
-                uint32_t spins = 0;
-                while (*pv_cnt < gt) {
-                  __nanosleep(64);
-                  if (++spins > (1u << 20)) __trap();
-                }
-              }
-              tc_fence_after();
-              float* ov = reinterpret_cast<float*>(pk);  // P is recomputed: its registers carry O meanwhile
+        // ---- the shared reference maximum, in task order
+        wait_checked(task);
+        const float m_cur = t == 0 ? -INFINITY : m_ref[r];
+        if (m_cur != m_loc) {          // another tile of the row raised it since my last tile
+          l_run *= rescale(m_loc, m_cur);
+          m_loc = m_cur;
+        }
+        if (t == 0 || mt > m_cur + kRaise) {
+          if (t > 0) {
+            // P V of every earlier tile of the job has landed in O once the OTHER group's P buffer is free again: tile
+            // t - 1 is theirs (their tile task ocnt - 1), and the tensor pipe completes in order.  Their next tile's
+            // P V cannot complete before mine, so the barrier is at most this one phase ahead: a sound parity wait.
+            mbar_wait<64>(bar(P_FREE + (g ^ 1)), (ocnt - 1) & 1);
+            tc_fence_after();
+            const float alpha = m_cur == -INFINITY ? 0.f : fast_exp2(m_cur - mt);
+            float ov[32];
 #pragma unroll 1
-              for (int cb = 0; cb < D / 64; ++cb) {
-                tmem_ld32(t_o + cb * 32, ov);
+            for (int cb = 0; cb < D / 32; ++cb) {
+              tmem_ld32(t_lane + cb * 32, ov);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) ov[j] *= alpha;
-                tmem_st32(t_o + cb * 32, ov);
-              }
-              tmem_wait_st();
+              for (int j = 0; j < 32; ++j) ov[j] *= alpha;
+              tmem_st32(t_lane + cb * 32, ov);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            l_run *= alpha;
+          }
+          m_ref[r] = mt;
+          m_loc = mt;
+        }
+        mbar_arrive(bar(CHK + g));
+        if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 3);
+
+        // ---- P = exp2(S c - m_ref), 64 tokens at a time; each half goes to the tensor pipe as soon as it is in TMEM
+        const float m_use = m_loc == -INFINITY ? 0.f : m_loc;
+        if (cn >= 1) mbar_wait<32>(bar(P_FREE + g), (cn - 1) & 1);   // P V of my previous tile has read my P buffer
+        float hs = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pk[kHalfN / 2];
+          float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < kHalfN; j += 4) {
+            const int jj = h * kHalfN + j;
+            const float e0 = fast_exp2(fmaf(sv[jj], c, -m_use)), e1 = fast_exp2(fmaf(sv[jj + 1], c, -m_use));
+            const float e2 = fast_exp2(fmaf(sv[jj + 2], c, -m_use)), e3 = fast_exp2(fmaf(sv[jj + 3], c, -m_use));
+            ps0 += e0; ps1 += e1; ps2 += e2; ps3 += e3;
+            pk[j / 2] = pack_half2(e0, e1);
+            pk[j / 2 + 1] = pack_half2(e2, e3);
+          }
+          hs += (ps0 + ps1) + (ps2 + ps3);
+          tmem_st32(t_p + h * 32, reinterpret_cast<const float*>(pk));
+          if (h == 1 && t == my_last) {
+            // my last tile of the job: my share of the row sum goes to the epilogue as a log-sum-exp (log2 domain)
+            const float l_fin = l_run + hs;
+            lse_s[(jp * 2 + g) * kRows + r] = l_fin > 0.f ? m_loc + log2f(l_fin) : -INFINITY;
+          }
+          tmem_wait_st();
+          tc_fence_before();  // my TMEM stores (P, a rescaled O) are ordered before the MMA issued after the barrier
+          mbar_arrive(bar(P_FULL + 2 * g + h));
+          if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 4 + h);
+        }
+        l_run += hs;
+      }
+
+      // ---- the job's epilogue task: partial = O / l as fp16, log-sum-exp in the natural-log domain
+      if ((task & 1) == (uint32_t)g) {
+        wait_checked(task);
+        const float m_fin = m_ref[r];        // every tile of the job has passed its check
+        mbar_arrive(bar(CHK + g));           // the next job's first tile may overwrite it
+        mbar_wait<32>(bar(O_DONE), j_cnt & 1);
+        tc_fence_after();
+        if (ji == 0 && r == 0) DEFT_TRACE(kTrEpiODone);
+        float l_row = 0.f;
+        {
+          const bool both = n >= 2;
+          const int g0 = task0 & 1;          // the group of tile 0
+          const float la = (both || g0 == 0) ? lse_s[(jp * 2 + 0) * kRows + r] : -INFINITY;
+          const float lb = (both || g0 == 1) ? lse_s[(jp * 2 + 1) * kRows + r] : -INFINITY;
+          if (la > -INFINITY) l_row += fast_exp2(la - m_fin);
+          if (lb > -INFINITY) l_row += fast_exp2(lb - m_fin);
+        }
+        if (ji == 0 && r == 0) DEFT_TRACE(kTrEpiBegin);
+        const bool live = qi < n_q;
+        const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
+        const int64_t tile = (int64_t)(part_base >> 5) * p.HKV + hkv;
+        uint4* dst = reinterpret_cast<uint4*>(p.po16) + tile * (CH * R) + r;  // [chunk][row] of 16 bytes
+#pragma unroll
+        for (int hb = 0; hb < D / 64; ++hb) {
+          float ov[64];
+          tmem_ld32_nowait(t_lane + hb * 64, ov);
+          tmem_ld32_nowait(t_lane + hb * 64 + 32, ov + 32);
+          tmem_wait_ld();
+          if (hb == D / 64 - 1) {
+            tc_fence_before();  // my reads of O are ordered before the next job's first P V (accumulate = 0)
+            mbar_arrive(bar(O_EMPTY));
+          }
+          if (dbg)
+            for (int j = 0; j < 64; ++j) p.dbg[kRows * kTileN + r * D + hb * 64 + j] = ov[j];
+          if (live) {
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+              uint4 o4;
+              o4.x = pack_half2(ov[c8 * 8 + 0] * inv, ov[c8 * 8 + 1] * inv);
+              o4.y = pack_half2(ov[c8 * 8 + 2] * inv, ov[c8 * 8 + 3] * inv);
+              o4.z = pack_half2(ov[c8 * 8 + 4] * inv, ov[c8 * 8 + 5] * inv);
+              o4.w = pack_half2(ov[c8 * 8 + 6] * inv, ov[c8 * 8 + 7] * inv);
+              dst[(hb * 8 + c8) * R] = o4;
             }
           }
-          if (redo && ++n_redo > 4) __trap();  // a raise settles in one more pass: anything else is a bug, not a hang
-        } while (redo);
-        l_run += hsum;
-        tmem_st32(t_s, reinterpret_cast<const float*>(pk));  // P_a over columns [0, 32) of S, P_b over [64, 96)
-        if (tr && t == 2 && h == 0) DEFT_TRACE(114);
-        if (tr && t == 2 && h == 0) DEFT_TRACE(115);
-        tmem_wait_st();
-        if (tr && t == 2 && h == 0) DEFT_TRACE(116);
-        tc_fence_before();  // my TMEM stores (P, rescaled O) are ordered before the MMA issued after the barrier
-        mbar_arrive(bar(P_FULL + 2 * buf + h));
-        if (tr) DEFT_TRACE(tr0 + 4);
-      }
-      g0 += u.n_tiles;
-
-      // ---- epilogue: partial = O / l as fp16, log-sum-exp in the natural-log domain
-      float* xq = xchg + (g0 & 1) * (4 * kRows) + 2 * kRows;  // a slot no tile of this parity is using right now
-      xq[h * kRows + r] = l_run;
-      mbar_wait(bar(O_DONE), j_cnt & 1);
-      ++j_cnt;
-      tc_fence_after();
-      pair_sync(warp);
-      const float l_row = xq[r] + xq[kRows + r];
-      if (ji == 0 && tid == 0) DEFT_TRACE(kTrEpiBegin);
-      const bool live = qi < n_q;
-      const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
-      const int64_t tile = (int64_t)(part_base >> 5) * p.HKV + hkv;
-      uint4* dst = reinterpret_cast<uint4*>(p.po16) + tile * (CH * R) + r;  // [chunk][row] of 16 bytes
-      {
-        float ov[D / 2];  // my half of the O row in one round trip to TMEM
-#pragma unroll
-        for (int cb = 0; cb < D / 64; ++cb) tmem_ld32_nowait(t_o + cb * 32, ov + cb * 32);
-        tmem_wait_ld();
-        tc_fence_before();  // my reads of O are ordered before the next job's first P V (accumulate = 0)
-        mbar_arrive(bar(O_EMPTY));
-        if (dbg)
-          for (int j = 0; j < D / 2; ++j) p.dbg[kRows * kTileN + r * D + h * (D / 2) + j] = ov[j];
-        if (live) {
-#pragma unroll
-          for (int c8 = 0; c8 < D / 16; ++c8) {
-            uint4 o4;
-            o4.x = pack_half2(ov[c8 * 8 + 0] * inv, ov[c8 * 8 + 1] * inv);
-            o4.y = pack_half2(ov[c8 * 8 + 2] * inv, ov[c8 * 8 + 3] * inv);
-            o4.z = pack_half2(ov[c8 * 8 + 4] * inv, ov[c8 * 8 + 5] * inv);
-            o4.w = pack_half2(ov[c8 * 8 + 6] * inv, ov[c8 * 8 + 7] * inv);
-            dst[(h * (D / 16) + c8) * R] = o4;
-          }
         }
+        if (live) p.plse16[tile * R + r] = l_row > 0.f ? (m_fin + log2f(l_row)) * 0.6931471805599453f : -INFINITY;
+        if (ji == 0 && r == 0) DEFT_TRACE(kTrEpiEnd);
       }
-      if (live && h == 0) p.plse16[tile * R + r] = l_row > 0.f ? (m_ref + log2f(l_row)) * 0.6931471805599453f : -INFINITY;
-      if (ji == 0 && tid == 0) DEFT_TRACE(kTrEpiEnd);
+      ++task;
+      ++j_cnt;
     }
   }
   tc_fence_before();
@@ -985,7 +683,6 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   if (p.clustered) cluster_sync();  // the pair no longer multicasts into my shared memory or arrives on my barriers
   if (tid == 0) DEFT_TRACE(kTrEnd);
   if (warp == kMmaWarp) tmem_dealloc(tmem, kTmemCols);
-
 }
 
 template <int D, int G>
@@ -1045,6 +742,7 @@ bool stage1_umma_supported(const AttnParams& p) {
 
 int launch_stage1_umma(const AttnParams& p, cudaStream_t stream) {
   if (p.n_units <= 0) return DEFT_OK;
+  if (p.experiment & 16) return launch_stage1_umma_v2(p, stream);  // the previous generation, for same-box A/B runs
   const int G = p.H / p.HKV;
 #define DEFT_CASE(DD, GG) \
   if (p.D == DD && G == GG) return launch_t<DD, GG>(p, stream);

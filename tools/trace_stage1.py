@@ -19,12 +19,8 @@ from deft_b200 import TreeMetadata, _lib
 from deft_b200.workloads import build_tree
 
 NAMES = {0: "start", 1: "q_ids", 2: "q_issued", 4: "mask0", 5: "k_unit", 6: "mma_q_full", 7: "epi_begin",
-         8: "epi_end", 9: "end", 12: "k_role_entry",
-         112: "t2.exp_done", 113: "t2.sync_or_done", 114: "t2.p_st_issued", 115: "t2.next_s_ld_issued", 116: "t2.p_st_landed",
-         117: "t3.s_was_prefetched", 118: "t2.mask_full_seen", 119: "t2.mask_applied",
-         120: "t1.maskwarp_words_loaded", 121: "t1.maskwarp_full_arrive", 122: "t2.maskwarp_words_loaded", 123: "t2.maskwarp_full_arrive",
-         124: "t3.maskwarp_words_loaded", 125: "t3.maskwarp_full_arrive"}
-TILE = ["k_issued", "mma_k_full(S issued)", "sm_s_full", "sm_ready", "sm_p_arrive", "mma_pa_full", "v_issued", "k_landed"]
+         8: "epi_end", 9: "end", 10: "epi_o_done", 12: "k_role_entry"}
+TILE = ["k_issued", "s_issued", "sm_s_in_regs", "sm_checked", "sm_p0_handed", "sm_p1_handed", "v_issued", "pv_issued"]
 
 
 def main():
@@ -75,8 +71,8 @@ def main():
     if os.environ.get("TRACE_TABLE"):      # one line per CTA: first S issued, tiles seen (of the first job, <= 6), epilogue, end
         for c in sorted(active, key=lambda c: -ends[c]):
             s0 = t[c, 16 + 1]
-            nt = sum(1 for tile in range(6) if t[c, 16 + 8 * tile + 4] >= 0)
-            last_p = max([t[c, 16 + 8 * tile + 4] for tile in range(6)] + [-1])
+            nt = sum(1 for tile in range(6) if t[c, 16 + 8 * tile + 5] >= 0)
+            last_p = max([t[c, 16 + 8 * tile + 5] for tile in range(6)] + [-1])
             print(f"cta {c:3d}  S0 {s0 / ghz / 1e3:6.2f}  tiles>={nt}  last_p {last_p / ghz / 1e3:6.2f}  epi {t[c, 7] / ghz / 1e3:6.2f}..{t[c, 8] / ghz / 1e3:6.2f}  end {ends[c] / ghz / 1e3:6.2f}")
         return
     order = sorted(active, key=lambda c: -ends[c])
@@ -88,9 +84,6 @@ def main():
                 v = int(t[c, 16 + 8 * tile + k])
                 if v >= 0:
                     ev.append((v, f"t{tile}.{TILE[k]}"))
-                v = int(t[c, 64 + 8 * tile + k])
-                if v >= 0:
-                    ev.append((v, f"t{tile}.halfb.{TILE[k]}" if k not in (0, 1, 5, 6) else f"t{tile}.{({0: 'k_loop_top', 1: 'k_empty_seen', 5: 'k_run_known', 6: 'k_pass0_issued'})[k]}"))
         for v, name in sorted(ev):
             print(f"   {v / ghz / 1e3:8.2f} us  {name}")
 
