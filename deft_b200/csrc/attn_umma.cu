@@ -64,7 +64,7 @@ constexpr float kRaise = 15.f;  // a row maximum this far (log2) above m_ref rai
 constexpr int kTraceSlots = 128;
 enum : int {
   kTrStart = 0, kTrQIds = 1, kTrQIssued = 2, kTrMask0 = 4, kTrKUnit = 5, kTrMmaQFull = 6, kTrEpiBegin = 7, kTrEpiEnd = 8,
-  kTrEnd = 9, kTrEpiODone = 10, kTrKRole = 12,
+  kTrEnd = 9, kTrEpiODone = 10, kTrKRole = 12, kTrJob0 = 64,  // + 2 * job: epilogue end | tiles and kind of the job
   kTrTile0 = 16,  // + 8 * tile: K issued, S issued, S in registers, checked, P half 0 handed, P half 1 handed, V issued,
                   //             P V issued
 };
@@ -227,7 +227,9 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         if (known_run) return u.page0 + t * kTileN + row;
         return t < u.n_tiles && row < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row) : 0;
       };
+      // the page ids of a tile are asked for two tiles ahead of their use (a table read costs about a tile step)
       int pg_next0 = page_of(0, w * 64 + lane), pg_next1 = page_of(0, w * 64 + 32 + lane);
+      int pg_after0 = page_of(1, w * 64 + lane), pg_after1 = page_of(1, w * 64 + 32 + lane);
       // shared job: the pair loads every tile ONCE -- the CTA of rank r issues rows [64r, 64r + 64) for both
       const bool mine = !shared || (uint32_t)w == crank;
       for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
@@ -235,8 +237,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         const int st = cnt % stages;
         const uint32_t ph = ((cnt / stages) & 1) ^ 1;
         const int pg[2] = {pg_next0, pg_next1};
-        pg_next0 = page_of(t + 1, w * 64 + lane);  // the next tile's page ids are in flight while this tile is issued
-        pg_next1 = page_of(t + 1, w * 64 + 32 + lane);
+        pg_next0 = pg_after0;
+        pg_next1 = pg_after1;
+        pg_after0 = page_of(t + 2, w * 64 + lane);
+        pg_after1 = page_of(t + 2, w * 64 + 32 + lane);
         mbar_wait<64>(bar(EMPTY + st), ph);
         const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
         const uint32_t full = bar(FULL + st);
@@ -251,20 +255,25 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
         if (lane == 0 && tx != 0) mbar_expect_tx(full, tx);
         bool any_cp_async = false;
+        {
+          // runs: lane (block, panel) issues ONE box -- a thread's TMA instructions go out one after the other, four of
+          // them from one lane cost more than a tile step
+          constexpr int NP = D / 64;
+          const int page0_0 = __shfl_sync(0xffffffffu, pg[0], 0), page0_1 = __shfl_sync(0xffffffffu, pg[1], 0);
+          const int b = lane / NP, pn = lane % NP;
+          if (mine && lane < 2 * NP && (b == 0 ? run[0] : run[1])) {
+            const uint32_t dst = dst_base + pn * kPanelBytes + (w * 64 + b * 32) * 128;
+            if (shared)
+              tma_load_3d_mc(dst, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, b == 0 ? page0_0 : page0_1, 0x3);
+            else
+              tma_load_3d(dst, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, b == 0 ? page0_0 : page0_1);
+          }
+        }
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const int row0 = w * 64 + b * 32;  // this block's 32 rows
-          const int page0 = __shfl_sync(0xffffffffu, pg[b], 0);
           if (run[b]) {
-            if (lane == 0 && mine) {
-#pragma unroll
-              for (int pn = 0; pn < D / 64; ++pn) {
-                if (shared)
-                  tma_load_3d_mc(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0, 0x3);
-                else
-                  tma_load_3d(dst_base + pn * kPanelBytes + row0 * 128, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, page0);
-              }
-            }
+            // (issued above)
           } else if (p.tma_gather != 0) {
             // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of the block with one gather4 per panel;
             // rows past the tile's length name a row outside the map and arrive as zeros
@@ -567,14 +576,20 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           l_run *= rescale(m_loc, m_cur);
           m_loc = m_cur;
         }
-        if (t == 0 || mt > m_cur + kRaise) {
-          if (t > 0) {
+        if (t == 0) {
+          m_ref[r] = mt;
+          m_loc = mt;
+        } else {
+          const bool raise = mt > m_cur + kRaise;
+          // tcgen05.ld / st are warp-wide: if any row of my warp raises, the whole warp rewrites its 32 rows of O
+          // (the rows that do not raise with a factor of one)
+          if (__any_sync(0xffffffffu, raise)) {
             // P V of every earlier tile of the job has landed in O once the OTHER group's P buffer is free again: tile
             // t - 1 is theirs (their tile task ocnt - 1), and the tensor pipe completes in order.  Their next tile's
             // P V cannot complete before mine, so the barrier is at most this one phase ahead: a sound parity wait.
             mbar_wait<64>(bar(P_FREE + (g ^ 1)), (ocnt - 1) & 1);
             tc_fence_after();
-            const float alpha = m_cur == -INFINITY ? 0.f : fast_exp2(m_cur - mt);
+            const float alpha = !raise ? 1.f : m_cur == -INFINITY ? 0.f : fast_exp2(m_cur - mt);
             float ov[32];
 #pragma unroll 1
             for (int cb = 0; cb < D / 32; ++cb) {
@@ -585,10 +600,12 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
             }
             tmem_wait_st();
             tc_fence_before();
-            l_run *= alpha;
+            if (raise) {
+              l_run *= alpha;
+              m_ref[r] = mt;
+              m_loc = mt;
+            }
           }
-          m_ref[r] = mt;
-          m_loc = mt;
         }
         mbar_arrive(bar(CHK + g));
         if (tr) DEFT_TRACE(kTrTile0 + 8 * t + 3);
@@ -673,6 +690,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         }
         if (live) p.plse16[tile * R + r] = l_row > 0.f ? (m_fin + log2f(l_row)) * 0.6931471805599453f : -INFINITY;
         if (ji == 0 && r == 0) DEFT_TRACE(kTrEpiEnd);
+        if (r == 0 && j_cnt < 32 && p.trace != nullptr) {   // per-job record: epilogue end, tiles and kind of the job
+          DEFT_TRACE(kTrJob0 + 2 * (int)j_cnt);
+          p.trace[(int64_t)blockIdx.x * kTraceSlots + kTrJob0 + 2 * (int)j_cnt + 1] = n | ((u.page0 >= 0) << 16) | ((int)shared << 17) | ((int)job_dense << 18);
+        }
       }
       ++task;
       ++j_cnt;

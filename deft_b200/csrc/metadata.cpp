@@ -76,7 +76,7 @@ namespace {
 struct Scratch {
   std::vector<i64> node_q, node_kv, node_q_len, node_kv_len, node_kv_offset_ti;
   std::vector<i64> block_q, block_q_cnts, block_kv, block_masks, block_lens;
-  std::vector<i32> u_kv;
+  std::vector<i32> u_kv, u_node;   // page id / node per token slot of the native tiles
   std::vector<uint32_t> u_mask;
   std::vector<i64> kvs;
   deft_tables* spare = nullptr;   // a freed handle whose packed buffer is reused by the next build
@@ -166,11 +166,14 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   };
   std::vector<Tile> tiles;
   auto& u_kv = S.u_kv;
+  auto& u_node = S.u_node;
   u_kv.clear();
+  u_node.clear();
 
   // open block (tree_cache.py:654-658)
   std::vector<i64> seg_tokens;
   std::vector<i64> seg_lens;
+  std::vector<i32> seg_node;             // the node every segment comes from
   std::vector<std::vector<i64>> seg_qs;  // sorted query ids per segment
   std::vector<i64> uni;                  // union, kept sorted + unique at close time
 
@@ -186,7 +189,11 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     {
       const size_t k0 = u_kv.size();
       u_kv.resize(k0 + (size_t)block_len, 0);
+      u_node.resize(k0 + (size_t)block_len, -1);
       for (i64 i = 0; i < n_live; ++i) u_kv[k0 + (size_t)i] = (i32)seg_tokens[(size_t)i];
+      size_t tk = k0;
+      for (size_t sg = 0; sg < n_seg; ++sg)
+        for (i64 i = 0; i < seg_lens[sg]; ++i) u_node[tk++] = seg_node[sg];
     }
     for (i64 qv : uni) {
       const i32 sl = rank_of[(size_t)qv] / 32;
@@ -254,7 +261,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     item.n_grp = (i32)f_groups.size() - item.grp_off;
     item.cost = item.kv_len * item.n_grp;
     if (item.n_grp > 0) f_items.push_back(item);
-    seg_tokens.clear(); seg_lens.clear(); seg_qs.clear(); uni.clear();
+    seg_tokens.clear(); seg_lens.clear(); seg_qs.clear(); seg_node.clear(); uni.clear();
   };
 
   auto& kvs = S.kvs;
@@ -302,12 +309,14 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       if (n_kv - done < room) {
         seg_tokens.insert(seg_tokens.end(), kvs.begin() + done, kvs.end());
         seg_lens.push_back(n_kv - done);
+        seg_node.push_back(n);
         seg_qs.push_back(q);
         uni.insert(uni.end(), q.begin(), q.end());
         break;
       }
       seg_tokens.insert(seg_tokens.end(), kvs.begin() + done, kvs.begin() + done + room);
       seg_lens.push_back(room);
+      seg_node.push_back(n);
       seg_qs.push_back(q);
       uni.insert(uni.end(), q.begin(), q.end());
       close_block();
@@ -320,6 +329,116 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<i64> node_q_offset = offsets_of(node_q_len);
   std::vector<i64> node_kv_offset = tix_row ? node_kv_offset_ti : offsets_of(node_kv_len);
   std::vector<i64> block_q_offset = offsets_of(block_q_cnts);
+
+  // ---- native plan, part 1b: regroup the scattered tokens into page-consecutive blocks.
+  // The kernel loads a tile as four blocks of 32 rows: 32 CONSECUTIVE pages are one TMA box per panel, anything else
+  // is gathered row by row (TMA gather4), which costs the SM's copy engine ~3.5x the time (2.2 us against 0.6 us per
+  // K + V tile: a scattered tile is bound by that, not by the softmax or the tensor pipe).  The reference's DFS order
+  // (kept bit for bit in block_kv) strings a subtree's tokens node by node, but the allocator hands one decode step's
+  // pages to the leaves in ascending order (tree_cache.py:261-283), so the tokens of ONE step over 32 neighbouring
+  // leaves sit on 32 consecutive pages.  The order of tokens inside the native tiles is free (a softmax does not care,
+  // the per-token masks travel with the tokens): within every stretch of tiles that are not page runs already, the
+  // tokens whose pages form runs of >= 32 with the same set of attending slots are moved to the front as aligned
+  // blocks, ordered by (slots, page); the rest keeps its DFS order.  DEFT_PLAN_REGROUP=0 switches this off.
+  {
+    const char* env_r = std::getenv("DEFT_PLAN_REGROUP");
+    const bool regroup = block_len == 128 && !(env_r && env_r[0] == '0');
+    auto tile_is_run = [&](size_t t) {
+      if (tiles[t].n_live != 128) return false;
+      for (size_t kk = t * 128 + 1; kk < (t + 1) * 128; ++kk)
+        if (u_kv[kk] != u_kv[t * 128] + (i32)(kk - t * 128)) return false;
+      return true;
+    };
+    // per node (lazily): the words of its attending ranks, slot by slot, and its slot range
+    std::vector<std::vector<std::pair<i32, uint32_t>>> node_words((size_t)n_nodes);
+    std::vector<char> node_done((size_t)n_nodes, 0);
+    auto words_of = [&](i32 n) -> const std::vector<std::pair<i32, uint32_t>>& {
+      if (!node_done[(size_t)n]) {
+        auto& w = node_words[(size_t)n];
+        for (i64 i = q_off[n]; i < q_off[n + 1]; ++i) {
+          const i32 rk = rank_of[(size_t)qs[i]];
+          auto it = std::find_if(w.begin(), w.end(), [&](const std::pair<i32, uint32_t>& e) { return e.first == rk / 32; });
+          if (it == w.end()) w.emplace_back(rk / 32, 1u << (rk % 32));
+          else it->second |= 1u << (rk % 32);
+        }
+        std::sort(w.begin(), w.end());
+        node_done[(size_t)n] = 1;
+      }
+      return node_words[(size_t)n];
+    };
+    struct Tok { i32 page, node, pos; i64 sig; };
+    std::vector<Tok> toks, sorted;
+    std::vector<char> in_block;
+    std::vector<i32> new_kv, new_node;
+    for (size_t t0 = 0; regroup && t0 < tiles.size();) {
+      if (tile_is_run(t0)) { ++t0; continue; }
+      size_t t1 = t0 + 1;
+      while (t1 < tiles.size() && !tile_is_run(t1)) ++t1;
+      // the stretch [t0, t1): its live tokens in DFS order
+      toks.clear();
+      for (size_t t = t0; t < t1; ++t)
+        for (i32 i = 0; i < tiles[t].n_live; ++i) {
+          const i32 nd = u_node[t * 128 + (size_t)i];
+          const auto& w = words_of(nd);
+          const i64 sig = w.empty() ? -1 : ((i64)w.front().first << 32) | (i64)w.back().first;
+          toks.push_back({u_kv[t * 128 + (size_t)i], nd, (i32)toks.size(), sig});
+        }
+      sorted = toks;
+      std::sort(sorted.begin(), sorted.end(), [](const Tok& a, const Tok& b) { return a.sig != b.sig ? a.sig < b.sig : a.page < b.page; });
+      in_block.assign(toks.size(), 0);
+      new_kv.clear();
+      new_node.clear();
+      for (size_t i = 0; i < sorted.size();) {   // runs of consecutive pages with one set of slots -> whole blocks of 32
+        size_t j = i + 1;
+        while (j < sorted.size() && sorted[j].sig == sorted[i].sig && sorted[j].page == sorted[j - 1].page + 1) ++j;
+        const size_t n_blk = (j - i) / 32;
+        for (size_t k = i; k < i + n_blk * 32; ++k) {
+          in_block[(size_t)sorted[k].pos] = 1;
+          new_kv.push_back(sorted[k].page);
+          new_node.push_back(sorted[k].node);
+        }
+        i = j;
+      }
+      if (!new_kv.empty()) {
+        for (const Tok& tk : toks)               // the rest, in DFS order
+          if (!in_block[(size_t)tk.pos]) {
+            new_kv.push_back(tk.page);
+            new_node.push_back(tk.node);
+          }
+        // rewrite the stretch: same tiles, same live counts (only the last tile of all can be short)
+        size_t at = 0;
+        for (size_t t = t0; t < t1; ++t) {
+          Tile& tl = tiles[t];
+          const i32 n_live = tl.n_live;
+          tl.slots.clear();
+          for (i32 i = 0; i < n_live; ++i) {
+            u_kv[t * 128 + (size_t)i] = new_kv[at + (size_t)i];
+            u_node[t * 128 + (size_t)i] = new_node[at + (size_t)i];
+            for (const auto& e : words_of(new_node[at + (size_t)i]))
+              if (std::find(tl.slots.begin(), tl.slots.end(), e.first) == tl.slots.end()) tl.slots.push_back(e.first);
+          }
+          std::sort(tl.slots.begin(), tl.slots.end());
+          tl.masks.assign(tl.slots.size() * 128, 0u);
+          tl.rows_or.assign(tl.slots.size(), 0u);
+          tl.dense.assign(tl.slots.size(), n_live == 128 ? 1 : 0);
+          for (size_t si = 0; si < tl.slots.size(); ++si) {
+            const i32 cnt = std::min(32, query_num - 32 * tl.slots[si]);
+            const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+            for (i32 i = 0; i < n_live; ++i) {
+              uint32_t word = 0;
+              for (const auto& e : words_of(new_node[at + (size_t)i]))
+                if (e.first == tl.slots[si]) word = e.second;
+              tl.masks[si * 128 + (size_t)i] = word;
+              tl.rows_or[si] |= word;
+              if ((word & full) != full) tl.dense[si] = 0;
+            }
+          }
+          at += (size_t)n_live;
+        }
+      }
+      t0 = t1;
+    }
+  }
 
   lap("slots + tiles + flat plan");
   // ---- Node plan: long entries are cut into node_split-token items
@@ -416,12 +535,20 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     // scattered pages is gathered row by row and is bound by that (~1.5x); the constant is a job's start-up
     // + epilogue.
     const char* env_g = std::getenv("DEFT_PLAN_GATHER_COST");
-    const double gather_cost = env_g ? std::atof(env_g) : 1.5;
+    const double gather_cost = env_g ? std::atof(env_g) : 2.2;
     std::vector<double> tile_cost(tiles.size());
     for (size_t t = 0; t < tiles.size(); ++t) {
-      bool runp = tiles[t].n_live == 128;
-      for (size_t kk = t * 128 + 1; kk < (t + 1) * 128 && runp; ++kk) runp = u_kv[kk] == u_kv[t * 128] + (i32)(kk - t * 128);
-      tile_cost[t] = runp ? 1.0 : gather_cost;
+      // the kernel loads a tile as four blocks of 32 rows: a block of consecutive pages of a full tile is a TMA box
+      int scattered = 4;
+      if (tiles[t].n_live == 128) {
+        scattered = 0;
+        for (size_t b = 0; b < 4; ++b) {
+          bool runp = true;
+          for (size_t kk = t * 128 + b * 32 + 1; kk < t * 128 + (b + 1) * 32 && runp; ++kk) runp = u_kv[kk] == u_kv[kk - 1] + 1;
+          scattered += runp ? 0 : 1;
+        }
+      }
+      tile_cost[t] = 1.0 + (gather_cost - 1.0) * scattered / 4.0;
     }
     // (DEFT_PLAN_JOB_CONST / DEFT_PLAN_GATHER_COST: calibration overrides for A/B runs on one box)
     const char* env_c = std::getenv("DEFT_PLAN_JOB_CONST");

@@ -68,6 +68,27 @@ def main():
     active = [c for c in range(t.shape[0]) if ends[c] >= 0]
     print(f"{wl}: {len(active)} CTAs traced; end (us): min {ends[active].min() / ghz / 1e3:.2f} "
           f"max {ends[active].max() / ghz / 1e3:.2f} mean {ends[active].mean() / ghz / 1e3:.2f}")
+    if os.environ.get("TRACE_JOBS"):       # per job of a few CTAs: duration, tiles, kind -> us per tile by kind
+        import collections
+        agg = collections.defaultdict(lambda: [0.0, 0, 0])
+        for c in active:
+            prev = t[c, 16 + 2] if t[c, 16 + 2] >= 0 else t[c, 0]      # first S in registers
+            for j in range(32):
+                e, info = int(t[c, 64 + 2 * j]), int(t[c, 65 + 2 * j])
+                if e < 0:
+                    break
+                n, box, shared, dense = info & 0xffff, (info >> 16) & 1, (info >> 17) & 1, (info >> 18) & 1
+                if j > 0:
+                    key = ("box" if box else "gathered/mixed", "shared" if shared else "own", "dense" if dense else "masked")
+                    agg[key][0] += (e - prev) / ghz / 1e3
+                    agg[key][1] += n
+                    agg[key][2] += 1
+                if c in active[:3]:
+                    print(f"cta {c} job {j}: {n:3d} tiles box={box} shared={shared} dense={dense}  {(e - prev) / ghz / 1e3:7.2f} us  = {(e - prev) / ghz / 1e3 / n:5.2f} us/tile")
+                prev = e
+        for key, (us, tiles, jobs) in sorted(agg.items()):
+            print(f"{key}: {jobs} jobs, {tiles} tiles, {us / tiles:.3f} us per tile (job boundary included), {tiles / jobs:.1f} tiles per job")
+        return
     if os.environ.get("TRACE_TABLE"):      # one line per CTA: first S issued, tiles seen (of the first job, <= 6), epilogue, end
         for c in sorted(active, key=lambda c: -ends[c]):
             s0 = t[c, 16 + 1]
