@@ -95,7 +95,11 @@ void setup_tma(AttnParams& p, int64_t kv_pool_tokens) {
   const int G = p.H / p.HKV;
   if (kv_pool_tokens > 0 && p.kv_head_stride >= p.D && p.kv_tok_stride >= p.D) {
     p.tma_kv = make_map(&p.tmap_k, MapKey{p.k, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 32}) &&
-               make_map(&p.tmap_v, MapKey{p.v, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 32});
+               make_map(&p.tmap_v, MapKey{p.v, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 32}) &&
+               make_map(&p.tmap_k16, MapKey{p.k, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 16}) &&
+               make_map(&p.tmap_v16, MapKey{p.v, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 16}) &&
+               make_map(&p.tmap_k8, MapKey{p.k, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 8}) &&
+               make_map(&p.tmap_v8, MapKey{p.v, p.D, p.HKV, kv_pool_tokens, p.kv_head_stride, p.kv_tok_stride, 1, 8});
     // gather4 view: head rows at a constant pitch (the token stride must be a whole number of head strides)
     const int64_t ratio = p.kv_tok_stride / p.kv_head_stride;
     const int64_t rows = (kv_pool_tokens - 1) * ratio + p.HKV;

@@ -244,51 +244,78 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         mbar_wait<64>(bar(EMPTY + st), ph);
         const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
         const uint32_t full = bar(FULL + st);
-        bool run[2];
+        // My 64 rows go as two blocks of 32.  Inside a block, aligned runs of consecutive pages are TMA boxes -- 32 rows,
+        // else 16, else 8 -- and what is left is gathered four rows at a time (gather4), or copied with cp.async when
+        // TMA is switched off.  The copy engine is bound by the NUMBER of these instructions, so the builder lays the
+        // scattered tokens out as such runs wherever the pages allow (metadata.cpp, part 1b).  Rows past the tile's
+        // length and dummy tokens (page < 0) arrive as zeros: they name a row outside the gather map.
+        constexpr int NP = D / 64;
+        const bool sub_boxes = p.tma_kv != 0 && p.tma_gather != 0;
         uint32_t tx = 0;  // bytes the TMA engine completes on MY barrier for my 64 rows (whichever CTA issues them)
+        bool run32[2];
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const int page0 = __shfl_sync(0xffffffffu, pg[b], 0);
-          // 32 consecutive pages of a full tile are ONE box of the pool's tensor map per 64-wide panel
-          run[b] = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg[b] == page0 + lane);
-          if (run[b] || p.tma_gather != 0) tx += 32 * D * 2;
+          run32[b] = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg[b] >= 0 && pg[b] == page0 + lane);
+          if (run32[b] || p.tma_gather != 0) tx += 32 * D * 2;
         }
         if (lane == 0 && tx != 0) mbar_expect_tx(full, tx);
         bool any_cp_async = false;
-        {
-          // runs: lane (block, panel) issues ONE box -- a thread's TMA instructions go out one after the other, four of
-          // them from one lane cost more than a tile step
-          constexpr int NP = D / 64;
-          const int page0_0 = __shfl_sync(0xffffffffu, pg[0], 0), page0_1 = __shfl_sync(0xffffffffu, pg[1], 0);
-          const int b = lane / NP, pn = lane % NP;
-          if (mine && lane < 2 * NP && (b == 0 ? run[0] : run[1])) {
-            const uint32_t dst = dst_base + pn * kPanelBytes + (w * 64 + b * 32) * 128;
-            if (shared)
-              tma_load_3d_mc(dst, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, b == 0 ? page0_0 : page0_1, 0x3);
-            else
-              tma_load_3d(dst, kv == 0 ? &p.tmap_k : &p.tmap_v, full, pn * 64, hkv, b == 0 ? page0_0 : page0_1);
-          }
-        }
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const int row0 = w * 64 + b * 32;  // this block's 32 rows
-          if (run[b]) {
-            // (issued above)
+          const bool ok = row0 + lane < tlen && pg[b] >= 0;
+          const uint32_t dst_blk = dst_base + row0 * 128;
+          if (run32[b] || sub_boxes) {
+            // d = page - lane is constant over a run of consecutive pages
+            const unsigned same = run32[b] ? 0xffffffffu : __match_any_sync(0xffffffffu, ok ? pg[b] - lane : (int)0x80000000 + lane);
+            const unsigned m16 = 0xffffu << (lane & 16), m8 = 0xffu << (lane & 24);
+            const bool r16 = !run32[b] && (same & m16) == m16, r8 = !run32[b] && !r16 && (same & m8) == m8;
+            const int page32 = __shfl_sync(0xffffffffu, pg[b], 0), page16 = __shfl_sync(0xffffffffu, pg[b], lane & 16);
+            const int page8 = __shfl_sync(0xffffffffu, pg[b], lane & 24);
+            const int li = lane & 7, g4 = li / NP, pn = li % NP;  // gather role inside my chunk of 8 rows
+            const int my_row = ok ? pg[b] * p.kv_row_ratio + hkv : p.kv_rows;
+            const int src = (lane & 24) + ((4 * g4) & 7);
+            const int r0 = __shfl_sync(0xffffffffu, my_row, src), r1 = __shfl_sync(0xffffffffu, my_row, src + 1);
+            const int r2 = __shfl_sync(0xffffffffu, my_row, src + 2), r3 = __shfl_sync(0xffffffffu, my_row, src + 3);
+            if (mine) {
+              const CUtensorMap* m32 = kv == 0 ? &p.tmap_k : &p.tmap_v;
+              const CUtensorMap* m16p = kv == 0 ? &p.tmap_k16 : &p.tmap_v16;
+              const CUtensorMap* m8p = kv == 0 ? &p.tmap_k8 : &p.tmap_v8;
+              const CUtensorMap* mg = kv == 0 ? &p.tmap_kg : &p.tmap_vg;
+              if (run32[b]) {
+                if (lane < NP) {
+                  if (shared) tma_load_3d_mc(dst_blk + lane * kPanelBytes, m32, full, lane * 64, hkv, page32, 0x3);
+                  else tma_load_3d(dst_blk + lane * kPanelBytes, m32, full, lane * 64, hkv, page32);
+                }
+              } else if (r16) {
+                if ((lane & 15) < NP) {
+                  const uint32_t dst = dst_blk + (lane & 15) * kPanelBytes + (lane & 16) * 128;
+                  if (shared) tma_load_3d_mc(dst, m16p, full, (lane & 15) * 64, hkv, page16, 0x3);
+                  else tma_load_3d(dst, m16p, full, (lane & 15) * 64, hkv, page16);
+                }
+              } else if (r8) {
+                if (li < NP) {
+                  const uint32_t dst = dst_blk + li * kPanelBytes + (lane & 24) * 128;
+                  if (shared) tma_load_3d_mc(dst, m8p, full, li * 64, hkv, page8, 0x3);
+                  else tma_load_3d(dst, m8p, full, li * 64, hkv, page8);
+                }
+              } else if (li < 2 * NP) {
+                const uint32_t dst = dst_blk + pn * kPanelBytes + ((lane & 24) + 4 * g4) * 128;
+                if (shared) tma_gather4_mc(dst, mg, full, pn * 64, r0, r1, r2, r3, 0x3);
+                else tma_gather4(dst, mg, full, pn * 64, r0, r1, r2, r3);
+              }
+            }
           } else if (p.tma_gather != 0) {
-            // scattered pages: lane (g, panel) moves the four rows 4g .. 4g+3 of the block with one gather4 per panel;
-            // rows past the tile's length name a row outside the map and arrive as zeros
-            constexpr int NP = D / 64;
+            // (boxes switched off, gather4 on: every row is gathered)
             const int g = lane / NP, pn = lane % NP;
-            const int my_row = row0 + lane < tlen ? pg[b] * p.kv_row_ratio + hkv : p.kv_rows;
+            const int my_row = ok ? pg[b] * p.kv_row_ratio + hkv : p.kv_rows;
             const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
             const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
             if (mine && lane < 8 * NP) {
-              if (shared)
-                tma_gather4_mc(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
-                               r0, r1, r2, r3, 0x3);
-              else
-                tma_gather4(dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64,
-                            r0, r1, r2, r3);
+              const uint32_t dst = dst_blk + pn * kPanelBytes + 4 * g * 128;
+              if (shared) tma_gather4_mc(dst, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64, r0, r1, r2, r3, 0x3);
+              else tma_gather4(dst, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64, r0, r1, r2, r3);
             }
           } else {
             const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
@@ -298,8 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
               const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside the block
               const int ch = lane % CH;
               const int64_t page = __shfl_sync(0xffffffffu, pg[b], nl);
-              const bool ok = row0 + nl < tlen;
-              cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + page * p.kv_tok_stride + ch * 8, ok ? 16u : 0u);
+              const bool okr = row0 + nl < tlen && page >= 0;
+              cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + (okr ? page : 0) * p.kv_tok_stride + ch * 8, okr ? 16u : 0u);
             }
             any_cp_async = true;
           }

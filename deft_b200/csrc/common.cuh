@@ -55,6 +55,7 @@ struct AttnParams {
   //                    tile::gather4 form (four arbitrary rows per instruction) for pages that are not consecutive;
   //                    row of (page, kv-head) = page * kv_row_ratio + kv-head, rows >= kv_rows read as zeros
   CUtensorMap tmap_k, tmap_v, tmap_q, tmap_kg, tmap_vg;
+  CUtensorMap tmap_k16, tmap_v16, tmap_k8, tmap_v8;  // tmap_k / tmap_v with boxes of 16 and 8 pages (aligned runs inside a block)
   int32_t tma_kv, tma_q, tma_gather;
   int32_t kv_row_ratio, kv_rows;
   const __half* q;

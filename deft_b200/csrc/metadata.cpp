@@ -330,16 +330,19 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<i64> node_kv_offset = tix_row ? node_kv_offset_ti : offsets_of(node_kv_len);
   std::vector<i64> block_q_offset = offsets_of(block_q_cnts);
 
-  // ---- native plan, part 1b: regroup the scattered tokens into page-consecutive blocks.
-  // The kernel loads a tile as four blocks of 32 rows: 32 CONSECUTIVE pages are one TMA box per panel, anything else
-  // is gathered row by row (TMA gather4), which costs the SM's copy engine ~3.5x the time (2.2 us against 0.6 us per
-  // K + V tile: a scattered tile is bound by that, not by the softmax or the tensor pipe).  The reference's DFS order
-  // (kept bit for bit in block_kv) strings a subtree's tokens node by node, but the allocator hands one decode step's
-  // pages to the leaves in ascending order (tree_cache.py:261-283), so the tokens of ONE step over 32 neighbouring
-  // leaves sit on 32 consecutive pages.  The order of tokens inside the native tiles is free (a softmax does not care,
-  // the per-token masks travel with the tokens): within every stretch of tiles that are not page runs already, the
-  // tokens whose pages form runs of >= 32 with the same set of attending slots are moved to the front as aligned
-  // blocks, ordered by (slots, page); the rest keeps its DFS order.  DEFT_PLAN_REGROUP=0 switches this off.
+  // ---- native plan, part 1b: regroup the scattered tokens into page-consecutive chunks.
+  // The kernel loads a tile as four blocks of 32 rows.  32 CONSECUTIVE pages are one TMA box per panel, 16 or 8
+  // consecutive pages (aligned inside the block) smaller boxes, anything else is gathered four rows at a time (TMA
+  // gather4) -- and the SM's copy engine is bound by the NUMBER of such instructions: 2.2 us per K + V tile of gathered
+  // rows against 0.6 us for boxes, more than the softmax and the tensor pipe need for the tile.  The reference's DFS
+  // order (kept bit for bit in block_kv) strings a subtree's tokens node by node, but the allocator hands one decode
+  // step's pages to the leaves in ascending order (tree_cache.py:261-283), so the tokens of ONE step over neighbouring
+  // leaves sit on consecutive pages.  The order of tokens inside the native tiles is free (a softmax does not care,
+  // the per-token masks travel with the tokens).  Within every stretch of tiles that are not page runs already, the
+  // tokens are grouped by the set of slots that attend them (so that a slot walks whole tiles of its own), and inside
+  // a group laid out as aligned chunks of 32 / 16 / 8 / 4 / 2 / 1 consecutive pages, longest first.  A group is padded
+  // to whole blocks with dummy tokens (page -1: a zero row nobody attends), a stretch to whole tiles unless it ends
+  // the table.  DEFT_PLAN_REGROUP=0 switches this off.
   {
     const char* env_r = std::getenv("DEFT_PLAN_REGROUP");
     const bool regroup = block_len == 128 && !(env_r && env_r[0] == '0');
@@ -349,10 +352,12 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         if (u_kv[kk] != u_kv[t * 128] + (i32)(kk - t * 128)) return false;
       return true;
     };
-    // per node (lazily): the words of its attending ranks, slot by slot, and its slot range
+    // per node (lazily): the words of its attending ranks, slot by slot
     std::vector<std::vector<std::pair<i32, uint32_t>>> node_words((size_t)n_nodes);
     std::vector<char> node_done((size_t)n_nodes, 0);
+    const std::vector<std::pair<i32, uint32_t>> no_words;
     auto words_of = [&](i32 n) -> const std::vector<std::pair<i32, uint32_t>>& {
+      if (n < 0) return no_words;
       if (!node_done[(size_t)n]) {
         auto& w = node_words[(size_t)n];
         for (i64 i = q_off[n]; i < q_off[n + 1]; ++i) {
@@ -366,57 +371,71 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
       return node_words[(size_t)n];
     };
-    struct Tok { i32 page, node, pos; i64 sig; };
-    std::vector<Tok> toks, sorted;
-    std::vector<char> in_block;
+    struct Tok { i32 page, node; i64 sig; };
+    struct Chunk { i32 first, len; };       // a run of `len` (power of two) consecutive pages: tokens [first, first + len) of `sorted`
+    std::vector<Tok> sorted;
+    std::vector<Chunk> chunks;
     std::vector<i32> new_kv, new_node;
+    std::vector<Tile> new_tiles;
     for (size_t t0 = 0; regroup && t0 < tiles.size();) {
       if (tile_is_run(t0)) { ++t0; continue; }
       size_t t1 = t0 + 1;
       while (t1 < tiles.size() && !tile_is_run(t1)) ++t1;
-      // the stretch [t0, t1): its live tokens in DFS order
-      toks.clear();
+      const bool at_end = t1 == tiles.size();
+      // the stretch [t0, t1): its live tokens, by (slots that attend, page)
+      sorted.clear();
       for (size_t t = t0; t < t1; ++t)
         for (i32 i = 0; i < tiles[t].n_live; ++i) {
           const i32 nd = u_node[t * 128 + (size_t)i];
+          if (nd < 0) continue;
           const auto& w = words_of(nd);
           const i64 sig = w.empty() ? -1 : ((i64)w.front().first << 32) | (i64)w.back().first;
-          toks.push_back({u_kv[t * 128 + (size_t)i], nd, (i32)toks.size(), sig});
+          sorted.push_back({u_kv[t * 128 + (size_t)i], nd, sig});
         }
-      sorted = toks;
       std::sort(sorted.begin(), sorted.end(), [](const Tok& a, const Tok& b) { return a.sig != b.sig ? a.sig < b.sig : a.page < b.page; });
-      in_block.assign(toks.size(), 0);
       new_kv.clear();
       new_node.clear();
-      for (size_t i = 0; i < sorted.size();) {   // runs of consecutive pages with one set of slots -> whole blocks of 32
-        size_t j = i + 1;
-        while (j < sorted.size() && sorted[j].sig == sorted[i].sig && sorted[j].page == sorted[j - 1].page + 1) ++j;
-        const size_t n_blk = (j - i) / 32;
-        for (size_t k = i; k < i + n_blk * 32; ++k) {
-          in_block[(size_t)sorted[k].pos] = 1;
-          new_kv.push_back(sorted[k].page);
-          new_node.push_back(sorted[k].node);
+      bool any_chunk = false;
+      for (size_t g0 = 0; g0 < sorted.size();) {            // one group of slots at a time
+        size_t g1 = g0;
+        while (g1 < sorted.size() && sorted[g1].sig == sorted[g0].sig) ++g1;
+        chunks.clear();
+        for (size_t i = g0; i < g1;) {                       // runs of consecutive pages -> power-of-two chunks
+          size_t j = i + 1;
+          while (j < g1 && sorted[j].page == sorted[j - 1].page + 1) ++j;
+          size_t at = i;
+          for (i32 len = 32; len >= 1; len >>= 1)
+            while (j - at >= (size_t)len) {
+              chunks.push_back({(i32)at, len});
+              at += (size_t)len;
+            }
+          i = j;
         }
-        i = j;
-      }
-      if (!new_kv.empty()) {
-        for (const Tok& tk : toks)               // the rest, in DFS order
-          if (!in_block[(size_t)tk.pos]) {
-            new_kv.push_back(tk.page);
-            new_node.push_back(tk.node);
+        std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.len > b.len; });
+        for (const Chunk& c : chunks) {
+          any_chunk = any_chunk || c.len >= 8;
+          for (i32 k = 0; k < c.len; ++k) {
+            new_kv.push_back(sorted[(size_t)(c.first + k)].page);
+            new_node.push_back(sorted[(size_t)(c.first + k)].node);
           }
-        // rewrite the stretch: same tiles, same live counts (only the last tile of all can be short)
-        size_t at = 0;
-        for (size_t t = t0; t < t1; ++t) {
-          Tile& tl = tiles[t];
-          const i32 n_live = tl.n_live;
-          tl.slots.clear();
-          for (i32 i = 0; i < n_live; ++i) {
-            u_kv[t * 128 + (size_t)i] = new_kv[at + (size_t)i];
-            u_node[t * 128 + (size_t)i] = new_node[at + (size_t)i];
+        }
+        const bool last_group = g1 == sorted.size();
+        if (!(last_group && at_end))
+          while (new_kv.size() % (last_group ? 128 : 32)) {  // dummy tokens: whole blocks per group, whole tiles per stretch
+            new_kv.push_back(-1);
+            new_node.push_back(-1);
+          }
+        g0 = g1;
+      }
+      if (any_chunk) {
+        new_tiles.clear();
+        for (size_t at = 0; at < new_kv.size(); at += 128) {
+          Tile tl;
+          const i32 n_live = (i32)std::min<size_t>(128, new_kv.size() - at);
+          tl.n_live = n_live;
+          for (i32 i = 0; i < n_live; ++i)
             for (const auto& e : words_of(new_node[at + (size_t)i]))
               if (std::find(tl.slots.begin(), tl.slots.end(), e.first) == tl.slots.end()) tl.slots.push_back(e.first);
-          }
           std::sort(tl.slots.begin(), tl.slots.end());
           tl.masks.assign(tl.slots.size() * 128, 0u);
           tl.rows_or.assign(tl.slots.size(), 0u);
@@ -433,8 +452,19 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
               if ((word & full) != full) tl.dense[si] = 0;
             }
           }
-          at += (size_t)n_live;
+          new_tiles.push_back(std::move(tl));
         }
+        // splice: tiles, page ids and nodes of the stretch
+        const size_t n_new = new_tiles.size();
+        tiles.erase(tiles.begin() + (long)t0, tiles.begin() + (long)t1);
+        tiles.insert(tiles.begin() + (long)t0, std::make_move_iterator(new_tiles.begin()), std::make_move_iterator(new_tiles.end()));
+        new_kv.resize(n_new * 128, 0);
+        new_node.resize(n_new * 128, -1);
+        u_kv.erase(u_kv.begin() + (long)(t0 * 128), u_kv.begin() + (long)(t1 * 128));
+        u_kv.insert(u_kv.begin() + (long)(t0 * 128), new_kv.begin(), new_kv.end());
+        u_node.erase(u_node.begin() + (long)(t0 * 128), u_node.begin() + (long)(t1 * 128));
+        u_node.insert(u_node.begin() + (long)(t0 * 128), new_node.begin(), new_node.end());
+        t1 = t0 + n_new;
       }
       t0 = t1;
     }
@@ -538,14 +568,23 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     const double gather_cost = env_g ? std::atof(env_g) : 2.2;
     std::vector<double> tile_cost(tiles.size());
     for (size_t t = 0; t < tiles.size(); ++t) {
-      // the kernel loads a tile as four blocks of 32 rows: a block of consecutive pages of a full tile is a TMA box
-      int scattered = 4;
+      // the kernel loads a tile as four blocks of 32 rows; what a block costs the copy engine goes with its TMA
+      // instructions per panel: one box for 32 consecutive pages, a box per aligned run of 16 or 8, a gather4 per
+      // four rows of anything else (8 per block: the gather cost above)
+      double scattered = 4.0;
       if (tiles[t].n_live == 128) {
-        scattered = 0;
-        for (size_t b = 0; b < 4; ++b) {
-          bool runp = true;
-          for (size_t kk = t * 128 + b * 32 + 1; kk < t * 128 + (b + 1) * 32 && runp; ++kk) runp = u_kv[kk] == u_kv[kk - 1] + 1;
-          scattered += runp ? 0 : 1;
+        scattered = 0.0;
+        for (size_t c8 = 0; c8 < 16; ++c8) {   // aligned chunks of 8 rows
+          const size_t k0 = t * 128 + c8 * 8;
+          auto runs = [&](size_t from, size_t len) {
+            if (u_kv[from] < 0) return false;
+            for (size_t kk = from + 1; kk < from + len; ++kk)
+              if (u_kv[kk] != u_kv[kk - 1] + 1) return false;
+            return true;
+          };
+          const size_t b32 = t * 128 + (c8 / 4) * 32, b16 = t * 128 + (c8 / 2) * 16;
+          const double instr = runs(b32, 32) ? 0.25 : runs(b16, 16) ? 0.5 : runs(k0, 8) ? 1.0 : 2.0;  // of this chunk, per panel
+          scattered += (instr - 0.25) / (2.0 - 0.25) / 4.0;
         }
       }
       tile_cost[t] = 1.0 + (gather_cost - 1.0) * scattered / 4.0;

@@ -166,12 +166,15 @@ def test_unit_plan_cfg2_shape(golden_dir):
     assert np.all(root["page0"] == root["kv_off"]) and np.all(units["q_id0"][:, 0] >= 0), "prompt pages and leaf ids are runs"
     loads = np.diff(t["u_job_off"])
     n_jobs = 8 * int((units["q_cnt"] > 0).sum())           # one job per (unit, kv-head, live slot)
-    assert loads.max() <= 2 and loads.min() >= 1 and loads.sum() == n_jobs, "cfg2: about one job per CTA, every CTA has work"
+    assert loads.max() <= 2 and int((loads > 0).sum()) >= 140 and loads.sum() == n_jobs, "cfg2: about one job per CTA"
     # the subtree's tokens are regrouped: the deepest level (32 neighbouring leaves x 16 decode steps per slot) sits on
-    # runs of 32 consecutive pages -> whole tiles of TMA boxes; every token still appears exactly once
-    blocks = t["u_kv"][4096: 4096 + 2016 // 32 * 32].reshape(-1, 32)
-    assert int(sum((np.diff(b) == 1).all() for b in blocks)) >= 32
-    assert sorted(t["u_kv"][4096: 4096 + 2016].tolist()) == list(range(4096, 4096 + 2016))
+    # runs of 32 consecutive pages -> whole tiles of TMA boxes, the level above on runs of 16, ...; every token still
+    # appears exactly once, dummy tokens (page -1) pad a slot's group to whole blocks
+    sub = t["u_kv"][4096:]
+    assert int(sum((np.diff(b) == 1).all() for b in sub[: len(sub) // 32 * 32].reshape(-1, 32))) >= 32
+    assert int(sum((np.diff(b) == 1).all() for b in sub[: len(sub) // 8 * 8].reshape(-1, 8))) >= 32 * 4 + 16 * 2 + 16
+    live = sub[: (int(units["n_tiles"].sum()) - 33) * 128 + int(units["last_len"][np.argmax(units["kv_off"])])]
+    assert sorted(live[live >= 0].tolist()) == list(range(4096, 4096 + 2016)) and int((live < 0).sum()) <= 31
     # far fewer partial rows than the reference's 2246 (one per (sub-block, query))
     assert len(t["u_csr_rows"]) < 1400
 
