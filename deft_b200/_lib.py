@@ -11,12 +11,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEFT_B200_LIB") or os.path.join(_HERE, "lib", "libdeft_b200.so")   # (override: A/B of two builds)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 T_NAMES = ["node_q", "node_kv", "node_q_len", "node_kv_len", "node_q_offset", "node_kv_offset",
            "block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv", "block_lens",
            "flat_items", "flat_groups", "flat_csr_off", "flat_csr_rows",
            "node_items", "node_groups", "node_csr_off", "node_csr_rows",
-           "u_units", "u_csr_off", "u_csr_rows", "u_kv", "u_mask", "u_q", "u_job_off", "u_jobs"]
+           "u_units", "u_csr_off", "u_csr_rows", "u_kv", "u_mask", "u_q", "u_job_off", "u_jobs", "u_blk"]
 T_COUNT = len(T_NAMES)
 STAGE1_AUTO, STAGE1_FMA, STAGE1_UMMA = 0, 1, 2
 ITEM_BYTES = 24
@@ -31,7 +31,7 @@ class Plan(C.Structure):
     _fields_ = [("items", C.c_void_p), ("groups", C.c_void_p), ("csr_off", C.c_void_p), ("csr_rows", C.c_void_p),
                 ("n_items", C.c_int32), ("n_groups", C.c_int32), ("n_part_rows", C.c_int32), ("n_units", C.c_int32),
                 ("units", C.c_void_p), ("u_csr_off", C.c_void_p), ("u_csr_rows", C.c_void_p), ("u_kv", C.c_void_p),
-                ("u_mask", C.c_void_p), ("u_q", C.c_void_p), ("u_job_off", C.c_void_p), ("u_jobs", C.c_void_p),
+                ("u_blk", C.c_void_p), ("u_mask", C.c_void_p), ("u_q", C.c_void_p), ("u_job_off", C.c_void_p), ("u_jobs", C.c_void_p),
                 ("n_unit_slots", C.c_int32), ("n_ctas", C.c_int32), ("hkv", C.c_int32), ("paired", C.c_int32)]
 
 

@@ -228,6 +228,7 @@ int use_plan(AttnParams& p, const deft_plan_t* plan, bool umma) {
                    "plan has no unit layer (rebuild the tables with this library version)");
     p.units = plan->units; p.n_units = plan->n_units; p.n_units_dev = nullptr;
     p.u_kv = plan->u_kv; p.u_kv_bytes = 4;
+    p.u_blk = plan->u_blk;
     p.u_mask = plan->u_mask; p.u_mask_bytes = 4;
     p.u_q = plan->u_q; p.u_q_bytes = 4;
     p.u_csr_off = plan->u_csr_off; p.u_csr_rows = plan->u_csr_rows;
@@ -249,6 +250,7 @@ void use_plan(AttnParams& p, const PlanBuffers& pb, int64_t bound) {
   p.n_items = (int32_t)bound; p.n_items_dev = pb.counters;
   p.units = pb.units; p.n_units = (int32_t)bound; p.n_units_dev = pb.counters + 2;
   p.u_kv = p.kv_idx; p.u_kv_bytes = p.kv_idx_bytes;
+  p.u_blk = nullptr;
   p.u_mask = p.masks; p.u_mask_bytes = 8;
   p.u_q = p.q_list; p.u_q_bytes = 8;
   p.u_csr_off = pb.csr_off; p.u_csr_rows = pb.csr_rows;

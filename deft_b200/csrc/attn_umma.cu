@@ -210,130 +210,172 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   reg_dealloc<kProducerRegs>();  // warps 8-15: two whole warpgroups give registers away
   if (warp >= kKvWarp0) {
     // ============================== K / V producers ==============================
-    // warps 12-13: K rows [64w, 64w + 64) of every tile, as two blocks of 32; warps 14-15: V likewise.  K and V run on
-    // rings of their own (K is released as soon as S is done, a tile earlier than V).
+    // warps 12-13: K rows [64w, 64w + 64) of every tile; warps 14-15: V likewise.  K and V run on rings of their own (K
+    // is released as soon as S is done, a tile earlier than V).  Three ways to load a tile:
+    //  (a) the unit's tokens sit on consecutive pages (page0 >= 0: a prompt): lane (block of 32 rows, panel) issues
+    //      one TMA box, nothing is looked up;
+    //  (b) native tables (p.u_blk): the builder has laid the scattered tokens out as aligned runs of 32 / 16 / 8
+    //      consecutive pages wherever the pages allow (metadata.cpp, part 1b) and says so per chunk of 8 rows: lane
+    //      (chunk, role) issues a box for a run, or gather4s for four arbitrary rows.  The copy engine is bound by the
+    //      NUMBER of these instructions: a tile of gather4s costs it 2.2 us, a tile of boxes 0.6 us.  The descriptors
+    //      and page ids are asked for two tiles ahead of their use (a table read costs about a tile step);
+    //  (c) anything else (the reference's int64 tables, TMA or gather4 switched off): per block of 32 rows a box when
+    //      its pages are consecutive, else gather4, else cp.async.
+    // Rows past the tile's length and dummy tokens (page < 0) arrive as zeros: they name a row outside the gather map.
+    constexpr int NP = D / 64;
     const int kv = (warp - kKvWarp0) >> 1, w = (warp - kKvWarp0) & 1;
     const int stages = kv == 0 ? kKStages : kVStages;
     const int FULL = kv == 0 ? K_FULL : V_FULL, EMPTY = kv == 0 ? K_EMPTY : V_EMPTY;
+    const CUtensorMap* m32 = kv == 0 ? &p.tmap_k : &p.tmap_v;
+    const CUtensorMap* mg = kv == 0 ? &p.tmap_kg : &p.tmap_vg;
+    const bool native = p.u_blk != nullptr && p.u_kv_bytes == 4 && p.tma_kv != 0 && p.tma_gather != 0;
     uint32_t cnt = 0;  // tiles produced
     if (warp == kKvWarp0 && lane == 0) DEFT_TRACE(kTrKRole);
     for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k; bool shared;
       if (!jobs.get(p, ji, u, hkv, k, shared)) continue;
       if (warp == kKvWarp0 && lane == 0 && ji == 0 && u.n_tiles > 0) DEFT_TRACE(kTrKUnit);
-      const bool known_run = u.page0 >= 0 && p.tma_kv != 0;  // the builder's shortcut: no index-table read at all
-      auto page_of = [&](int t, int row) -> int {  // page of `row` of tile t (0 past the end)
-        const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
-        if (known_run) return u.page0 + t * kTileN + row;
-        return t < u.n_tiles && row < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row) : 0;
-      };
-      // the page ids of a tile are asked for two tiles ahead of their use (a table read costs about a tile step)
-      int pg_next0 = page_of(0, w * 64 + lane), pg_next1 = page_of(0, w * 64 + 32 + lane);
-      int pg_after0 = page_of(1, w * 64 + lane), pg_after1 = page_of(1, w * 64 + 32 + lane);
+      const bool known_run = u.page0 >= 0 && p.tma_kv != 0;
       // shared job: the pair loads every tile ONCE -- the CTA of rank r issues rows [64r, 64r + 64) for both
       const bool mine = !shared || (uint32_t)w == crank;
-      for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
-        const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
-        const int st = cnt % stages;
-        const uint32_t ph = ((cnt / stages) & 1) ^ 1;
-        const int pg[2] = {pg_next0, pg_next1};
-        pg_next0 = pg_after0;
-        pg_next1 = pg_after1;
-        pg_after0 = page_of(t + 2, w * 64 + lane);
-        pg_after1 = page_of(t + 2, w * 64 + 32 + lane);
-        mbar_wait<64>(bar(EMPTY + st), ph);
-        const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
-        const uint32_t full = bar(FULL + st);
-        // My 64 rows go as two blocks of 32.  Inside a block, aligned runs of consecutive pages are TMA boxes -- 32 rows,
-        // else 16, else 8 -- and what is left is gathered four rows at a time (gather4), or copied with cp.async when
-        // TMA is switched off.  The copy engine is bound by the NUMBER of these instructions, so the builder lays the
-        // scattered tokens out as such runs wherever the pages allow (metadata.cpp, part 1b).  Rows past the tile's
-        // length and dummy tokens (page < 0) arrive as zeros: they name a row outside the gather map.
-        constexpr int NP = D / 64;
-        const bool sub_boxes = p.tma_kv != 0 && p.tma_gather != 0;
-        uint32_t tx = 0;  // bytes the TMA engine completes on MY barrier for my 64 rows (whichever CTA issues them)
-        bool run32[2];
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int page0 = __shfl_sync(0xffffffffu, pg[b], 0);
-          run32[b] = known_run || __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg[b] >= 0 && pg[b] == page0 + lane);
-          if (run32[b] || p.tma_gather != 0) tx += 32 * D * 2;
+      if (known_run) {
+        // ---- (a)
+        for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
+          const int st = cnt % stages;
+          mbar_wait<64>(bar(EMPTY + st), ((cnt / stages) & 1) ^ 1);
+          const uint32_t full = bar(FULL + st);
+          if (lane == 0) mbar_expect_tx(full, 64 * D * 2);
+          if (mine && lane < 2 * NP) {
+            const int b = lane / NP, pn = lane % NP;
+            const uint32_t dst = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes + pn * kPanelBytes + (w * 64 + b * 32) * 128;
+            const int page = u.page0 + t * kTileN + w * 64 + b * 32;
+            if (shared) tma_load_3d_mc(dst, m32, full, pn * 64, hkv, page, 0x3);
+            else tma_load_3d(dst, m32, full, pn * 64, hkv, page);
+          }
+          mbar_arrive(full);
+          if (w == 0 && lane == 0 && ji == 0 && t < 6) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
         }
-        if (lane == 0 && tx != 0) mbar_expect_tx(full, tx);
-        bool any_cp_async = false;
+      } else if (native) {
+        // ---- (b) lane = (chunk c of my 8, role li): boxes are issued by li < NP (panel li); gather4s by li < 2 NP
+        // (rows 4 g4 .. 4 g4 + 3 of the chunk, panel pn)
+        const int c = lane >> 2, li = lane & 3;
+        const int g4 = li / NP, pn = li % NP;
+        const int32_t* blk = p.u_blk + (u.kv_off >> 7) * 16 + w * 8 + c;
+        const int32_t* pgs = reinterpret_cast<const int32_t*>(p.u_kv) + u.kv_off + w * 64 + c * 8 + (g4 & 1) * 4;
+        auto desc_of = [&](int t) { return t < u.n_tiles ? blk[t * 16] : 0; };
+        auto pages_of = [&](int t) { return t < u.n_tiles ? *reinterpret_cast<const int4*>(pgs + t * kTileN) : make_int4(-1, -1, -1, -1); };
+        int d_next = desc_of(0), d_after = desc_of(1);
+        int4 g_next = pages_of(0), g_after = pages_of(1);
+        for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
+          const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
+          const int st = cnt % stages;
+          const int desc = d_next;
+          const int4 pg = g_next;
+          d_next = d_after;
+          g_next = g_after;
+          d_after = desc_of(t + 2);
+          g_after = pages_of(t + 2);
+          mbar_wait<64>(bar(EMPTY + st), ((cnt / stages) & 1) ^ 1);
+          const uint32_t full = bar(FULL + st);
+          if (lane == 0) mbar_expect_tx(full, 64 * D * 2);
+          if (mine) {
+            const uint32_t dst = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes + (w * 64 + c * 8) * 128;
+            const int kind = desc >> 28, page = desc & 0x0fffffff;
+            if (kind == 3) {
+              if ((c & 3) == 0 && li < NP) {
+                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m32, full, li * 64, hkv, page, 0x3);
+                else tma_load_3d(dst + li * kPanelBytes, m32, full, li * 64, hkv, page);
+              }
+            } else if (kind == 2) {
+              if ((c & 1) == 0 && li < NP) {
+                const CUtensorMap* m16 = kv == 0 ? &p.tmap_k16 : &p.tmap_v16;
+                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m16, full, li * 64, hkv, page, 0x3);
+                else tma_load_3d(dst + li * kPanelBytes, m16, full, li * 64, hkv, page);
+              }
+            } else if (kind == 1) {
+              if (li < NP) {
+                const CUtensorMap* m8 = kv == 0 ? &p.tmap_k8 : &p.tmap_v8;
+                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m8, full, li * 64, hkv, page, 0x3);
+                else tma_load_3d(dst + li * kPanelBytes, m8, full, li * 64, hkv, page);
+              }
+            } else if (li < 2 * NP) {
+              const int row = w * 64 + c * 8 + g4 * 4;   // my four rows of the tile
+              const int r0 = row + 0 < tlen && pg.x >= 0 ? pg.x * p.kv_row_ratio + hkv : p.kv_rows;
+              const int r1 = row + 1 < tlen && pg.y >= 0 ? pg.y * p.kv_row_ratio + hkv : p.kv_rows;
+              const int r2 = row + 2 < tlen && pg.z >= 0 ? pg.z * p.kv_row_ratio + hkv : p.kv_rows;
+              const int r3 = row + 3 < tlen && pg.w >= 0 ? pg.w * p.kv_row_ratio + hkv : p.kv_rows;
+              if (shared) tma_gather4_mc(dst + pn * kPanelBytes + g4 * 4 * 128, mg, full, pn * 64, r0, r1, r2, r3, 0x3);
+              else tma_gather4(dst + pn * kPanelBytes + g4 * 4 * 128, mg, full, pn * 64, r0, r1, r2, r3);
+            }
+          }
+          mbar_arrive(full);
+          if (w == 0 && lane == 0 && ji == 0 && t < 6) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
+        }
+      } else {
+        // ---- (c)
+        auto page_of = [&](int t, int row) -> int {  // page of `row` of tile t (-1 past the end)
+          const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
+          return t < u.n_tiles && row < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row) : -1;
+        };
+        int pg_next0 = page_of(0, w * 64 + lane), pg_next1 = page_of(0, w * 64 + 32 + lane);
+        for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
+          const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
+          const int st = cnt % stages;
+          const int pg[2] = {pg_next0, pg_next1};
+          pg_next0 = page_of(t + 1, w * 64 + lane);  // the next tile's page ids are in flight while this tile is issued
+          pg_next1 = page_of(t + 1, w * 64 + 32 + lane);
+          mbar_wait<64>(bar(EMPTY + st), ((cnt / stages) & 1) ^ 1);
+          const uint32_t dst_base = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes;
+          const uint32_t full = bar(FULL + st);
+          bool run[2];
+          uint32_t tx = 0;  // bytes the TMA engine completes on MY barrier for my 64 rows (whichever CTA issues them)
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const int row0 = w * 64 + b * 32;  // this block's 32 rows
-          const bool ok = row0 + lane < tlen && pg[b] >= 0;
-          const uint32_t dst_blk = dst_base + row0 * 128;
-          if (run32[b] || sub_boxes) {
-            // d = page - lane is constant over a run of consecutive pages
-            const unsigned same = run32[b] ? 0xffffffffu : __match_any_sync(0xffffffffu, ok ? pg[b] - lane : (int)0x80000000 + lane);
-            const unsigned m16 = 0xffffu << (lane & 16), m8 = 0xffu << (lane & 24);
-            const bool r16 = !run32[b] && (same & m16) == m16, r8 = !run32[b] && !r16 && (same & m8) == m8;
-            const int page32 = __shfl_sync(0xffffffffu, pg[b], 0), page16 = __shfl_sync(0xffffffffu, pg[b], lane & 16);
-            const int page8 = __shfl_sync(0xffffffffu, pg[b], lane & 24);
-            const int li = lane & 7, g4 = li / NP, pn = li % NP;  // gather role inside my chunk of 8 rows
-            const int my_row = ok ? pg[b] * p.kv_row_ratio + hkv : p.kv_rows;
-            const int src = (lane & 24) + ((4 * g4) & 7);
-            const int r0 = __shfl_sync(0xffffffffu, my_row, src), r1 = __shfl_sync(0xffffffffu, my_row, src + 1);
-            const int r2 = __shfl_sync(0xffffffffu, my_row, src + 2), r3 = __shfl_sync(0xffffffffu, my_row, src + 3);
-            if (mine) {
-              const CUtensorMap* m32 = kv == 0 ? &p.tmap_k : &p.tmap_v;
-              const CUtensorMap* m16p = kv == 0 ? &p.tmap_k16 : &p.tmap_v16;
-              const CUtensorMap* m8p = kv == 0 ? &p.tmap_k8 : &p.tmap_v8;
-              const CUtensorMap* mg = kv == 0 ? &p.tmap_kg : &p.tmap_vg;
-              if (run32[b]) {
-                if (lane < NP) {
-                  if (shared) tma_load_3d_mc(dst_blk + lane * kPanelBytes, m32, full, lane * 64, hkv, page32, 0x3);
-                  else tma_load_3d(dst_blk + lane * kPanelBytes, m32, full, lane * 64, hkv, page32);
-                }
-              } else if (r16) {
-                if ((lane & 15) < NP) {
-                  const uint32_t dst = dst_blk + (lane & 15) * kPanelBytes + (lane & 16) * 128;
-                  if (shared) tma_load_3d_mc(dst, m16p, full, (lane & 15) * 64, hkv, page16, 0x3);
-                  else tma_load_3d(dst, m16p, full, (lane & 15) * 64, hkv, page16);
-                }
-              } else if (r8) {
-                if (li < NP) {
-                  const uint32_t dst = dst_blk + li * kPanelBytes + (lane & 24) * 128;
-                  if (shared) tma_load_3d_mc(dst, m8p, full, li * 64, hkv, page8, 0x3);
-                  else tma_load_3d(dst, m8p, full, li * 64, hkv, page8);
-                }
-              } else if (li < 2 * NP) {
-                const uint32_t dst = dst_blk + pn * kPanelBytes + ((lane & 24) + 4 * g4) * 128;
+          for (int b = 0; b < 2; ++b) {
+            const int page0 = __shfl_sync(0xffffffffu, pg[b], 0);
+            run[b] = __all_sync(0xffffffffu, p.tma_kv != 0 && tlen == kTileN && pg[b] >= 0 && pg[b] == page0 + lane);
+            if (run[b] || p.tma_gather != 0) tx += 32 * D * 2;
+          }
+          if (lane == 0 && tx != 0) mbar_expect_tx(full, tx);
+          bool any_cp_async = false;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int row0 = w * 64 + b * 32;  // this block's 32 rows
+            const bool ok = row0 + lane < tlen && pg[b] >= 0;
+            const int page0 = __shfl_sync(0xffffffffu, pg[b], 0);
+            if (run[b]) {
+              if (mine && lane < NP) {
+                if (shared) tma_load_3d_mc(dst_base + lane * kPanelBytes + row0 * 128, m32, full, lane * 64, hkv, page0, 0x3);
+                else tma_load_3d(dst_base + lane * kPanelBytes + row0 * 128, m32, full, lane * 64, hkv, page0);
+              }
+            } else if (p.tma_gather != 0) {
+              // lane (g, panel) moves the four rows 4g .. 4g+3 of the block with one gather4 per panel
+              const int g = lane / NP, pn = lane % NP;
+              const int my_row = ok ? pg[b] * p.kv_row_ratio + hkv : p.kv_rows;
+              const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
+              const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
+              if (mine && lane < 8 * NP) {
+                const uint32_t dst = dst_base + pn * kPanelBytes + (row0 + 4 * g) * 128;
                 if (shared) tma_gather4_mc(dst, mg, full, pn * 64, r0, r1, r2, r3, 0x3);
                 else tma_gather4(dst, mg, full, pn * 64, r0, r1, r2, r3);
               }
-            }
-          } else if (p.tma_gather != 0) {
-            // (boxes switched off, gather4 on: every row is gathered)
-            const int g = lane / NP, pn = lane % NP;
-            const int my_row = ok ? pg[b] * p.kv_row_ratio + hkv : p.kv_rows;
-            const int r0 = __shfl_sync(0xffffffffu, my_row, (4 * g) & 31), r1 = __shfl_sync(0xffffffffu, my_row, (4 * g + 1) & 31);
-            const int r2 = __shfl_sync(0xffffffffu, my_row, (4 * g + 2) & 31), r3 = __shfl_sync(0xffffffffu, my_row, (4 * g + 3) & 31);
-            if (mine && lane < 8 * NP) {
-              const uint32_t dst = dst_blk + pn * kPanelBytes + 4 * g * 128;
-              if (shared) tma_gather4_mc(dst, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64, r0, r1, r2, r3, 0x3);
-              else tma_gather4(dst, kv == 0 ? &p.tmap_kg : &p.tmap_vg, full, pn * 64, r0, r1, r2, r3);
-            }
-          } else {
-            const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
-            constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
+            } else {
+              const __half* src_base = (kv == 0 ? p.k : p.v) + (int64_t)hkv * p.kv_head_stride;
+              constexpr int TOK_PER_INSTR = 32 / CH;  // tokens covered by one warp-wide copy
 #pragma unroll 4
-            for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
-              const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside the block
-              const int ch = lane % CH;
-              const int64_t page = __shfl_sync(0xffffffffu, pg[b], nl);
-              const bool okr = row0 + nl < tlen && page >= 0;
-              cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + (okr ? page : 0) * p.kv_tok_stride + ch * 8, okr ? 16u : 0u);
+              for (int i = 0; i < 32 / TOK_PER_INSTR; ++i) {
+                const int nl = i * TOK_PER_INSTR + lane / CH;  // row inside the block
+                const int ch = lane % CH;
+                const int64_t page = __shfl_sync(0xffffffffu, pg[b], nl);
+                const bool okr = row0 + nl < tlen && page >= 0;
+                cp_async_16(dst_base + tile_off(row0 + nl, ch), src_base + (okr ? page : 0) * p.kv_tok_stride + ch * 8, okr ? 16u : 0u);
+              }
+              any_cp_async = true;
             }
-            any_cp_async = true;
           }
+          if (any_cp_async) cp_async_arrive(full);  // arrives once my copies have landed
+          else mbar_arrive(full);
+          if (w == 0 && lane == 0 && ji == 0 && t < 6) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
         }
-        if (any_cp_async) cp_async_arrive(full);  // arrives once my copies have landed
-        else mbar_arrive(full);
-        if (w == 0 && lane == 0 && ji == 0 && t < 6) DEFT_TRACE(kTrTile0 + 8 * t + (kv == 0 ? 0 : 6));
       }
     }
   } else if (warp == kQWarp) {
@@ -390,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       const int64_t mask_off = k == 0 ? u.mask_off[0] : u.mask_off[1];
       if (mask_off < 0 && u.last_len == kTileN) continue;  // every tile dense: the softmax warps do not ask
       const uint32_t fullw = n_q >= 32 ? 0xffffffffu : ((1u << n_q) - 1u);
-      for (int t = 0; t < u.n_tiles; ++t, ++m_cnt) {
+      for (int t = u.dense_tiles; t < u.n_tiles; ++t, ++m_cnt) {   // (the unit's leading dense tiles: nobody asks)
         const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
         const int st = m_cnt % kMaskStages;
         // per-token words: bit r = row r of the slot attends token lane + 32j (loaded ahead of the wait)
@@ -551,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
 
       for (int t = 0; t < n; ++t, ++task) {
         if ((task & 1) != (uint32_t)g) {      // the other group's tile
-          if (!job_dense) ++m_cnt;
+          if (!job_dense && t >= u.dense_tiles) ++m_cnt;
           ++ocnt;
           continue;
         }
@@ -569,8 +611,9 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         if (dbg && t == 0)
           for (int j = 0; j < kTileN; ++j) p.dbg[r * kTileN + j] = sv[j];
 
-        // ---- mask: tokens my query does not attend score -inf
-        if (!job_dense) {
+        // ---- mask: tokens my query does not attend score -inf (the unit's leading dense tiles -- a prompt ahead of the
+        // subtree -- carry none)
+        if (!job_dense && t >= u.dense_tiles) {
           const int mst = m_cnt % kMaskStages;
           mbar_wait<32>(bar(M_FULL + mst), (m_cnt / kMaskStages) & 1);
           ++m_cnt;

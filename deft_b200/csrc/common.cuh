@@ -89,6 +89,7 @@ struct AttnParams {
   const int32_t* n_units_dev;  // device-resident unit count (device-built plans), or null
   int32_t n_units;             // launch bound on the unit count
   const void* u_kv;    int32_t u_kv_bytes;    // page id per token slot
+  const int32_t* u_blk;                       // load descriptor per chunk of 8 token slots (native tables), or null
   const void* u_mask;  int32_t u_mask_bytes;  // per-token row bitmask, may be null
   const void* u_q;     int32_t u_q_bytes;     // query id per (slot, row)
   const int32_t* u_csr_off;

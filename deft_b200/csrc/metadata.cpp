@@ -76,7 +76,8 @@ namespace {
 struct Scratch {
   std::vector<i64> node_q, node_kv, node_q_len, node_kv_len, node_kv_offset_ti;
   std::vector<i64> block_q, block_q_cnts, block_kv, block_masks, block_lens;
-  std::vector<i32> u_kv, u_node;   // page id / node per token slot of the native tiles
+  std::vector<i32> u_kv, u_blk;             // native tiles: page id per token slot, load descriptor per chunk of 8 slots
+  std::vector<i32> tok_page, tok_node;      // the trees' tokens in DFS order (page id, node)
   std::vector<uint32_t> u_mask;
   std::vector<i64> kvs;
   deft_tables* spare = nullptr;   // a freed handle whose packed buffer is reused by the next build
@@ -166,65 +167,24 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   };
   std::vector<Tile> tiles;
   auto& u_kv = S.u_kv;
-  auto& u_node = S.u_node;
+  auto& tok_page = S.tok_page;
+  auto& tok_node = S.tok_node;
   u_kv.clear();
-  u_node.clear();
+  tok_page.clear();
+  tok_node.clear();
 
   // open block (tree_cache.py:654-658)
   std::vector<i64> seg_tokens;
   std::vector<i64> seg_lens;
-  std::vector<i32> seg_node;             // the node every segment comes from
   std::vector<std::vector<i64>> seg_qs;  // sorted query ids per segment
   std::vector<i64> uni;                  // union, kept sorted + unique at close time
 
-  std::vector<uint32_t> words;
   auto close_block = [&]() {  // pack_new_block, tree_cache.py:661-723
     const i64 n_live = (i64)seg_tokens.size();
     const size_t n_seg = seg_qs.size();
     const i64 n_pad = n_live < block_len ? block_len - n_live : 0;  // the pad segment has an empty query set
     if (n_seg > 1) std::sort(uni.begin(), uni.end());  // one segment: its sorted query list is the union already
     uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
-    Tile tile;
-    tile.n_live = (i32)n_live;
-    {
-      const size_t k0 = u_kv.size();
-      u_kv.resize(k0 + (size_t)block_len, 0);
-      u_node.resize(k0 + (size_t)block_len, -1);
-      for (i64 i = 0; i < n_live; ++i) u_kv[k0 + (size_t)i] = (i32)seg_tokens[(size_t)i];
-      size_t tk = k0;
-      for (size_t sg = 0; sg < n_seg; ++sg)
-        for (i64 i = 0; i < seg_lens[sg]; ++i) u_node[tk++] = seg_node[sg];
-    }
-    for (i64 qv : uni) {
-      const i32 sl = rank_of[(size_t)qv] / 32;
-      if (std::find(tile.slots.begin(), tile.slots.end(), sl) == tile.slots.end()) tile.slots.push_back(sl);
-    }
-    std::sort(tile.slots.begin(), tile.slots.end());
-    tile.masks.assign(tile.slots.size() * 128, 0u);
-    tile.rows_or.assign(tile.slots.size(), 0u);
-    tile.dense.assign(tile.slots.size(), n_live == 128 ? 1 : 0);
-    {
-      size_t tok = 0;
-      words.resize(tile.slots.size());
-      for (size_t sg = 0; sg < n_seg; ++sg) {
-        // every token of a segment is attended by the same queries: one word per touched slot, then filled in
-        std::fill(words.begin(), words.end(), 0u);
-        for (i64 qv : seg_qs[sg]) {
-          const i32 rk = rank_of[(size_t)qv];
-          const size_t si = (size_t)(std::lower_bound(tile.slots.begin(), tile.slots.end(), rk / 32) - tile.slots.begin());
-          words[si] |= 1u << (rk % 32);
-        }
-        for (size_t si = 0; si < words.size(); ++si) {
-          if (seg_lens[sg] <= 0) continue;
-          if (words[si]) std::fill_n(tile.masks.begin() + (long)(si * 128 + tok), (size_t)seg_lens[sg], words[si]);
-          tile.rows_or[si] |= words[si];
-          const i32 cnt = std::min(32, query_num - 32 * tile.slots[si]);
-          const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-          if ((words[si] & full) != full) tile.dense[si] = 0;
-        }
-        tok += (size_t)seg_lens[sg];
-      }
-    }
     deft_item_t item{};
     item.kv_off = (i64)block_lens.size() * block_len;
     item.kv_len = (i32)n_live;
@@ -257,11 +217,10 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
       block_masks.insert(block_masks.end(), (size_t)n_pad, (i64)0);
     }
-    tiles.push_back(std::move(tile));
     item.n_grp = (i32)f_groups.size() - item.grp_off;
     item.cost = item.kv_len * item.n_grp;
     if (item.n_grp > 0) f_items.push_back(item);
-    seg_tokens.clear(); seg_lens.clear(); seg_qs.clear(); seg_node.clear(); uni.clear();
+    seg_tokens.clear(); seg_lens.clear(); seg_qs.clear(); uni.clear();
   };
 
   auto& kvs = S.kvs;
@@ -302,6 +261,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
     }
     if (tix_row && !kv_sorted) std::sort(kvs.begin(), kvs.end());
+    for (i64 kvp : kvs) { tok_page.push_back((i32)kvp); tok_node.push_back(n); }   // the native tiler's token stream (DFS order)
     // flatten packing (:763-788)
     i64 room = block_len - (i64)seg_tokens.size();
     i64 done = 0;
@@ -309,14 +269,12 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       if (n_kv - done < room) {
         seg_tokens.insert(seg_tokens.end(), kvs.begin() + done, kvs.end());
         seg_lens.push_back(n_kv - done);
-        seg_node.push_back(n);
         seg_qs.push_back(q);
         uni.insert(uni.end(), q.begin(), q.end());
         break;
       }
       seg_tokens.insert(seg_tokens.end(), kvs.begin() + done, kvs.begin() + done + room);
       seg_lens.push_back(room);
-      seg_node.push_back(n);
       seg_qs.push_back(q);
       uni.insert(uni.end(), q.begin(), q.end());
       close_block();
@@ -330,28 +288,25 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<i64> node_kv_offset = tix_row ? node_kv_offset_ti : offsets_of(node_kv_len);
   std::vector<i64> block_q_offset = offsets_of(block_q_cnts);
 
-  // ---- native plan, part 1b: regroup the scattered tokens into page-consecutive chunks.
-  // The kernel loads a tile as four blocks of 32 rows.  32 CONSECUTIVE pages are one TMA box per panel, 16 or 8
-  // consecutive pages (aligned inside the block) smaller boxes, anything else is gathered four rows at a time (TMA
-  // gather4) -- and the SM's copy engine is bound by the NUMBER of such instructions: 2.2 us per K + V tile of gathered
-  // rows against 0.6 us for boxes, more than the softmax and the tensor pipe need for the tile.  The reference's DFS
-  // order (kept bit for bit in block_kv) strings a subtree's tokens node by node, but the allocator hands one decode
-  // step's pages to the leaves in ascending order (tree_cache.py:261-283), so the tokens of ONE step over neighbouring
-  // leaves sit on consecutive pages.  The order of tokens inside the native tiles is free (a softmax does not care,
-  // the per-token masks travel with the tokens).  Within every stretch of tiles that are not page runs already, the
-  // tokens are grouped by the set of slots that attend them (so that a slot walks whole tiles of its own), and inside
-  // a group laid out as aligned chunks of 32 / 16 / 8 / 4 / 2 / 1 consecutive pages, longest first.  A group is padded
-  // to whole blocks with dummy tokens (page -1: a zero row nobody attends), a stretch to whole tiles unless it ends
-  // the table.  DEFT_PLAN_REGROUP=0 switches this off.
+  // ---- native plan, part 1b: the native tiles.
+  // The reference cuts the DFS-ordered token stream of the whole table into blocks of 128 (block_kv above, bit for bit).
+  // The native tiles are cut from the same tokens, tree by tree, with two freedoms the kernel's arithmetic allows (a
+  // softmax does not care about the order of its tokens, and the per-token masks travel with them):
+  //  * every tree starts a new tile, and a stretch of >= 128 consecutive pages attended by one set of slots (a prompt)
+  //    becomes whole RUN tiles from its first token on -- four TMA boxes per operand, no mask, and chains that do not
+  //    straddle trees (a forest's trees are independent jobs);
+  //  * what is left (the subtree) is grouped by the set of slots that attend it, so that a slot walks whole tiles of
+  //    its own, and inside a group laid out as aligned chunks of 32 / 16 / 8 / 4 / 2 / 1 consecutive pages, longest
+  //    first.  The kernel loads a tile as blocks of 32 rows: 32 consecutive pages are one TMA box per panel, aligned
+  //    runs of 16 or 8 smaller boxes, the rest goes four rows at a time (TMA gather4) -- and the SM's copy engine is
+  //    bound by the NUMBER of such instructions: 2.2 us per K + V tile of gathered rows against 0.6 us for boxes, more
+  //    than the softmax and the tensor pipe need for the tile.  The allocator hands one decode step's pages to the
+  //    leaves in ascending order (tree_cache.py:261-283), so the tokens of one step over neighbouring leaves DO sit on
+  //    consecutive pages; the DFS order just strings them node by node.  A group is padded to whole blocks with dummy
+  //    tokens (page -1: a zero row nobody attends).  DEFT_PLAN_REGROUP=0: the rest keeps its DFS order.
   {
     const char* env_r = std::getenv("DEFT_PLAN_REGROUP");
-    const bool regroup = block_len == 128 && !(env_r && env_r[0] == '0');
-    auto tile_is_run = [&](size_t t) {
-      if (tiles[t].n_live != 128) return false;
-      for (size_t kk = t * 128 + 1; kk < (t + 1) * 128; ++kk)
-        if (u_kv[kk] != u_kv[t * 128] + (i32)(kk - t * 128)) return false;
-      return true;
-    };
+    const bool regroup = !(env_r && env_r[0] == '0');
     // per node (lazily): the words of its attending ranks, slot by slot
     std::vector<std::vector<std::pair<i32, uint32_t>>> node_words((size_t)n_nodes);
     std::vector<char> node_done((size_t)n_nodes, 0);
@@ -371,102 +326,127 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
       return node_words[(size_t)n];
     };
+    auto sig_of = [&](i32 n) -> i64 {
+      const auto& w = words_of(n);
+      return w.empty() ? -1 : ((i64)w.front().first << 32) | (i64)w.back().first;
+    };
+    // one native tile from up to 128 (page, node) tokens; node < 0: a dummy token
+    auto emit_tile = [&](const i32* pages, const i32* nodes, i32 n_live) {
+      Tile tl;
+      tl.n_live = n_live;
+      const size_t k0 = u_kv.size();
+      u_kv.resize(k0 + 128, 0);
+      i32 last_node = -2;
+      for (i32 i = 0; i < n_live; ++i) {
+        u_kv[k0 + (size_t)i] = pages[i];
+        if (nodes[i] == last_node) continue;     // (tokens come node by node)
+        last_node = nodes[i];
+        for (const auto& e : words_of(nodes[i]))
+          if (std::find(tl.slots.begin(), tl.slots.end(), e.first) == tl.slots.end()) tl.slots.push_back(e.first);
+      }
+      std::sort(tl.slots.begin(), tl.slots.end());
+      tl.masks.assign(tl.slots.size() * 128, 0u);
+      tl.rows_or.assign(tl.slots.size(), 0u);
+      tl.dense.assign(tl.slots.size(), n_live == 128 ? 1 : 0);
+      for (size_t si = 0; si < tl.slots.size(); ++si) {
+        const i32 cnt = std::min(32, query_num - 32 * tl.slots[si]);
+        const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        i32 cached_node = -2;
+        uint32_t word = 0;
+        for (i32 i = 0; i < n_live; ++i) {
+          if (nodes[i] != cached_node) {
+            cached_node = nodes[i];
+            word = 0;
+            for (const auto& e : words_of(nodes[i]))
+              if (e.first == tl.slots[si]) word = e.second;
+          }
+          tl.masks[si * 128 + (size_t)i] = word;
+          tl.rows_or[si] |= word;
+          if ((word & full) != full) tl.dense[si] = 0;
+        }
+      }
+      tiles.push_back(std::move(tl));
+    };
     struct Tok { i32 page, node; i64 sig; };
-    struct Chunk { i32 first, len; };       // a run of `len` (power of two) consecutive pages: tokens [first, first + len) of `sorted`
-    std::vector<Tok> sorted;
+    struct Chunk { i32 first, len; };       // `len` (a power of two) consecutive pages: tokens [first, first + len) of `rest`
+    std::vector<Tok> rest;
     std::vector<Chunk> chunks;
-    std::vector<i32> new_kv, new_node;
-    std::vector<Tile> new_tiles;
-    for (size_t t0 = 0; regroup && t0 < tiles.size();) {
-      if (tile_is_run(t0)) { ++t0; continue; }
-      size_t t1 = t0 + 1;
-      while (t1 < tiles.size() && !tile_is_run(t1)) ++t1;
-      const bool at_end = t1 == tiles.size();
-      // the stretch [t0, t1): its live tokens, by (slots that attend, page)
-      sorted.clear();
-      for (size_t t = t0; t < t1; ++t)
-        for (i32 i = 0; i < tiles[t].n_live; ++i) {
-          const i32 nd = u_node[t * 128 + (size_t)i];
-          if (nd < 0) continue;
-          const auto& w = words_of(nd);
-          const i64 sig = w.empty() ? -1 : ((i64)w.front().first << 32) | (i64)w.back().first;
-          sorted.push_back({u_kv[t * 128 + (size_t)i], nd, sig});
-        }
-      std::sort(sorted.begin(), sorted.end(), [](const Tok& a, const Tok& b) { return a.sig != b.sig ? a.sig < b.sig : a.page < b.page; });
-      new_kv.clear();
-      new_node.clear();
-      bool any_chunk = false;
-      for (size_t g0 = 0; g0 < sorted.size();) {            // one group of slots at a time
-        size_t g1 = g0;
-        while (g1 < sorted.size() && sorted[g1].sig == sorted[g0].sig) ++g1;
-        chunks.clear();
-        for (size_t i = g0; i < g1;) {                       // runs of consecutive pages -> power-of-two chunks
-          size_t j = i + 1;
-          while (j < g1 && sorted[j].page == sorted[j - 1].page + 1) ++j;
-          size_t at = i;
-          for (i32 len = 32; len >= 1; len >>= 1)
-            while (j - at >= (size_t)len) {
-              chunks.push_back({(i32)at, len});
-              at += (size_t)len;
-            }
-          i = j;
-        }
-        std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& a, const Chunk& b) { return a.len > b.len; });
-        for (const Chunk& c : chunks) {
-          any_chunk = any_chunk || c.len >= 8;
-          for (i32 k = 0; k < c.len; ++k) {
-            new_kv.push_back(sorted[(size_t)(c.first + k)].page);
-            new_node.push_back(sorted[(size_t)(c.first + k)].node);
-          }
-        }
-        const bool last_group = g1 == sorted.size();
-        if (!(last_group && at_end))
-          while (new_kv.size() % (last_group ? 128 : 32)) {  // dummy tokens: whole blocks per group, whole tiles per stretch
-            new_kv.push_back(-1);
-            new_node.push_back(-1);
-          }
-        g0 = g1;
+    std::vector<i32> out_page, out_node;
+    const size_t n_tok = tok_page.size();
+    for (size_t a = 0; a < n_tok;) {
+      // the tokens [a, b) of one tree (its nodes are consecutive in the pre-order; parent -1 starts the next tree)
+      size_t b = a + 1;
+      while (b < n_tok && !(tok_node[b] != tok_node[b - 1] && parent[tok_node[b]] == -1)) ++b;
+      rest.clear();
+      out_page.clear();
+      out_node.clear();
+      for (size_t i = a; i < b;) {
+        // a stretch of consecutive pages attended by one set of slots
+        const i64 sig = sig_of(tok_node[i]);
+        size_t j = i + 1;
+        while (j < b && tok_page[j] == tok_page[j - 1] + 1 && (tok_node[j] == tok_node[j - 1] || sig_of(tok_node[j]) == sig)) ++j;
+        const size_t whole = (j - i) / 128 * 128;
+        for (size_t k = i; k < i + whole; k += 128) emit_tile(&tok_page[k], &tok_node[k], 128);   // RUN tiles
+        for (size_t k = i + whole; k < j; ++k) rest.push_back({tok_page[k], tok_node[k], sig});
+        i = j;
       }
-      if (any_chunk) {
-        new_tiles.clear();
-        for (size_t at = 0; at < new_kv.size(); at += 128) {
-          Tile tl;
-          const i32 n_live = (i32)std::min<size_t>(128, new_kv.size() - at);
-          tl.n_live = n_live;
-          for (i32 i = 0; i < n_live; ++i)
-            for (const auto& e : words_of(new_node[at + (size_t)i]))
-              if (std::find(tl.slots.begin(), tl.slots.end(), e.first) == tl.slots.end()) tl.slots.push_back(e.first);
-          std::sort(tl.slots.begin(), tl.slots.end());
-          tl.masks.assign(tl.slots.size() * 128, 0u);
-          tl.rows_or.assign(tl.slots.size(), 0u);
-          tl.dense.assign(tl.slots.size(), n_live == 128 ? 1 : 0);
-          for (size_t si = 0; si < tl.slots.size(); ++si) {
-            const i32 cnt = std::min(32, query_num - 32 * tl.slots[si]);
-            const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-            for (i32 i = 0; i < n_live; ++i) {
-              uint32_t word = 0;
-              for (const auto& e : words_of(new_node[at + (size_t)i]))
-                if (e.first == tl.slots[si]) word = e.second;
-              tl.masks[si * 128 + (size_t)i] = word;
-              tl.rows_or[si] |= word;
-              if ((word & full) != full) tl.dense[si] = 0;
-            }
+      if (regroup) {
+        std::stable_sort(rest.begin(), rest.end(), [](const Tok& x, const Tok& y) { return x.sig != y.sig ? x.sig < y.sig : x.page < y.page; });
+        for (size_t g0 = 0; g0 < rest.size();) {                // one group of slots at a time
+          size_t g1 = g0;
+          while (g1 < rest.size() && rest[g1].sig == rest[g0].sig) ++g1;
+          chunks.clear();
+          for (size_t i = g0; i < g1;) {                         // runs of consecutive pages -> power-of-two chunks
+            size_t j = i + 1;
+            while (j < g1 && rest[j].page == rest[j - 1].page + 1) ++j;
+            size_t at = i;
+            for (i32 len = 32; len >= 1; len >>= 1)
+              while (j - at >= (size_t)len) {
+                chunks.push_back({(i32)at, len});
+                at += (size_t)len;
+              }
+            i = j;
           }
-          new_tiles.push_back(std::move(tl));
+          std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& x, const Chunk& y) { return x.len > y.len; });
+          for (const Chunk& c : chunks)
+            for (i32 k = 0; k < c.len; ++k) {
+              out_page.push_back(rest[(size_t)(c.first + k)].page);
+              out_node.push_back(rest[(size_t)(c.first + k)].node);
+            }
+          if (g1 < rest.size())
+            while (out_page.size() % 32) {                       // whole blocks per group: the next group's runs stay aligned
+              out_page.push_back(-1);
+              out_node.push_back(-1);
+            }
+          g0 = g1;
         }
-        // splice: tiles, page ids and nodes of the stretch
-        const size_t n_new = new_tiles.size();
-        tiles.erase(tiles.begin() + (long)t0, tiles.begin() + (long)t1);
-        tiles.insert(tiles.begin() + (long)t0, std::make_move_iterator(new_tiles.begin()), std::make_move_iterator(new_tiles.end()));
-        new_kv.resize(n_new * 128, 0);
-        new_node.resize(n_new * 128, -1);
-        u_kv.erase(u_kv.begin() + (long)(t0 * 128), u_kv.begin() + (long)(t1 * 128));
-        u_kv.insert(u_kv.begin() + (long)(t0 * 128), new_kv.begin(), new_kv.end());
-        u_node.erase(u_node.begin() + (long)(t0 * 128), u_node.begin() + (long)(t1 * 128));
-        u_node.insert(u_node.begin() + (long)(t0 * 128), new_node.begin(), new_node.end());
-        t1 = t0 + n_new;
+      } else {
+        for (const Tok& tk : rest) { out_page.push_back(tk.page); out_node.push_back(tk.node); }
       }
-      t0 = t1;
+      for (size_t k = 0; k < out_page.size(); k += 128)
+        emit_tile(&out_page[k], &out_node[k], (i32)std::min<size_t>(128, out_page.size() - k));
+      a = b;
+    }
+  }
+
+  // per chunk of 8 token slots: how the kernel's producers load it (deft_plan_t.u_blk)
+  auto& u_blk = S.u_blk;
+  u_blk.assign(tiles.size() * 16, 0);
+  for (size_t t = 0; t < tiles.size(); ++t) {
+    auto runs = [&](size_t from, size_t len) {   // `len` live tokens on consecutive pages
+      if (from + len > (size_t)tiles[t].n_live || u_kv[t * 128 + from] < 0) return false;
+      for (size_t kk = t * 128 + from + 1; kk < t * 128 + from + len; ++kk)
+        if (u_kv[kk] != u_kv[kk - 1] + 1) return false;
+      return true;
+    };
+    for (size_t c = 0; c < 16; ++c) {
+      const i32 kind = runs(c / 4 * 32, 32) ? 3 : runs(c / 2 * 16, 16) ? 2 : runs(c * 8, 8) ? 1 : 0;
+      const i32 page = u_kv[t * 128 + c * 8];
+      if (page >= (1 << 28)) {
+        deft::set_error("build_tables: page id %d does not fit the 28 bits of a load descriptor", page);
+        return nullptr;
+      }
+      u_blk[t * 16 + c] = (kind << 28) | (kind ? page : 0);
     }
   }
 
@@ -568,24 +548,13 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     const double gather_cost = env_g ? std::atof(env_g) : 2.2;
     std::vector<double> tile_cost(tiles.size());
     for (size_t t = 0; t < tiles.size(); ++t) {
-      // the kernel loads a tile as four blocks of 32 rows; what a block costs the copy engine goes with its TMA
-      // instructions per panel: one box for 32 consecutive pages, a box per aligned run of 16 or 8, a gather4 per
-      // four rows of anything else (8 per block: the gather cost above)
-      double scattered = 4.0;
-      if (tiles[t].n_live == 128) {
-        scattered = 0.0;
-        for (size_t c8 = 0; c8 < 16; ++c8) {   // aligned chunks of 8 rows
-          const size_t k0 = t * 128 + c8 * 8;
-          auto runs = [&](size_t from, size_t len) {
-            if (u_kv[from] < 0) return false;
-            for (size_t kk = from + 1; kk < from + len; ++kk)
-              if (u_kv[kk] != u_kv[kk - 1] + 1) return false;
-            return true;
-          };
-          const size_t b32 = t * 128 + (c8 / 4) * 32, b16 = t * 128 + (c8 / 2) * 16;
-          const double instr = runs(b32, 32) ? 0.25 : runs(b16, 16) ? 0.5 : runs(k0, 8) ? 1.0 : 2.0;  // of this chunk, per panel
-          scattered += (instr - 0.25) / (2.0 - 0.25) / 4.0;
-        }
+      // what a tile costs the copy engine goes with its TMA instructions per panel: one box per aligned run of 32 / 16 / 8
+      // consecutive pages, a gather4 per four rows of anything else (the gather cost above: a tile of nothing else)
+      double scattered = 0.0;
+      for (size_t c = 0; c < 16; ++c) {
+        const i32 kind = u_blk[t * 16 + c] >> 28;
+        const double instr = kind == 3 ? 0.25 : kind == 2 ? 0.5 : kind == 1 ? 1.0 : 2.0;   // of this chunk
+        scattered += (instr - 0.25) / (2.0 - 0.25) / 4.0;
       }
       tile_cost[t] = 1.0 + (gather_cost - 1.0) * scattered / 4.0;
     }
@@ -765,6 +734,16 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
             }
         u.mask_off[1] = -1;
         u.q_id0[0] = u.q_id0[1] = -1;
+        u.dense_tiles = 0;     // leading tiles every live slot attends densely (a prompt ahead of the subtree)
+        for (size_t t = ta; t < tb; ++t) {
+          bool all = true;
+          for (int k = 0; k < n_live_slots && all; ++k) {
+            auto it = std::lower_bound(tiles[t].slots.begin(), tiles[t].slots.end(), live_slots[k]);
+            all = it != tiles[t].slots.end() && *it == live_slots[k] && tiles[t].dense[(size_t)(it - tiles[t].slots.begin())] != 0;
+          }
+          if (!all) break;
+          ++u.dense_tiles;
+        }
         {  // shortcut: all tiles full and on consecutive pages
           const size_t k0 = ta * 128, k1 = tb * 128;
           bool runp = tiles[tb - 1].n_live == 128;
@@ -906,6 +885,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       {units.data(), units.size(), sizeof(deft_unit_t)}, {u_csr.off.data(), u_csr.off.size(), 4},
       {u_csr.rows.data(), u_csr.rows.size(), 4}, {u_kv.data(), u_kv.size(), 4}, {u_mask.data(), u_mask.size(), 4},
       {u_q.data(), u_q.size(), 4}, {u_job_off.data(), u_job_off.size(), 4}, {u_jobs.data(), u_jobs.size(), sizeof(deft_job_t)},
+      {u_blk.data(), u_blk.size(), 4},
   };
   size_t off = 0;
   for (int i = 0; i < DEFT_T_COUNT; ++i) {

@@ -566,7 +566,7 @@ class TreeMetadata:
                              csr_off=base + directory[first + 2][0], csr_rows=base + directory[first + 3][0],
                              n_items=directory[first][1], n_groups=directory[first + 1][1],
                              n_part_rows=rows, n_units=directory[U][1],
-                             units=addr(U), u_csr_off=addr(U + 1), u_csr_rows=addr(U + 2), u_kv=addr(U + 3),
+                             units=addr(U), u_csr_off=addr(U + 1), u_csr_rows=addr(U + 2), u_kv=addr(U + 3), u_blk=addr(U + 8),
                              u_mask=addr(U + 4), u_q=addr(U + 5), u_job_off=addr(U + 6), u_jobs=addr(U + 7),
                              n_unit_slots=int(scalars[6]), n_ctas=int(scalars[7]), hkv=hkv, paired=int(scalars[8]))
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEFT_B200_ABI_VERSION 3
+#define DEFT_B200_ABI_VERSION 4
 
 enum {
   DEFT_OK = 0,
@@ -121,7 +121,8 @@ typedef struct {
   int32_t page0;            /* >= 0: every tile is full and the unit's tokens sit on consecutive pages
                                page0, page0 + 1, ... (the prompt) */
   int32_t q_id0[2];         /* >= 0: the slot's queries have consecutive ids q_id0[s], q_id0[s] + 1, ... */
-  int32_t pad;
+  int32_t dense_tiles;      /* the unit's first dense_tiles tiles are full and attended by every row of its live
+                               slots (a prompt ahead of the first subtree tile): no mask is read for them */
 } deft_unit_t;              /* 80 bytes */
 
 /* One entry of the per-CTA job lists of the unit plan.  A job is ONE slot of a unit on one kv-head:
@@ -151,7 +152,10 @@ typedef struct {
   const deft_unit_t* units;
   const int32_t* u_csr_off;   /* nq+1 */
   const int32_t* u_csr_rows;
-  const int32_t* u_kv;        /* page id per token slot, tiles of 128 */
+  const int32_t* u_kv;        /* page id per token slot, tiles of 128; -1 = dummy token (a zero row nobody attends) */
+  const int32_t* u_blk;       /* per chunk of 8 token slots (16 per tile): how the chunk is loaded, (kind << 28) | first page.
+                                 kind 3 / 2 / 1: the chunk lies in an aligned run of 32 / 16 / 8 consecutive pages (one TMA
+                                 box per panel for the whole run), 0: gathered four rows at a time.  May be NULL. */
   const uint32_t* u_mask;     /* 128 words per (tile, slot): bit r = row r of the slot attends */
   const int32_t* u_q;         /* query id per (slot, row) */
   const int32_t* u_job_off;   /* n_ctas+1: CTA c has u_job_off[c+1] - u_job_off[c] jobs (u_jobs carries the lists) */
@@ -249,7 +253,7 @@ enum {
   DEFT_T_FLAT_ITEMS, DEFT_T_FLAT_GROUPS, DEFT_T_FLAT_CSR_OFF, DEFT_T_FLAT_CSR_ROWS, /* Flatten plan */
   DEFT_T_NODE_ITEMS, DEFT_T_NODE_GROUPS, DEFT_T_NODE_CSR_OFF, DEFT_T_NODE_CSR_ROWS, /* Node plan */
   DEFT_T_U_UNITS, DEFT_T_U_CSR_OFF, DEFT_T_U_CSR_ROWS, DEFT_T_U_KV, DEFT_T_U_MASK, DEFT_T_U_Q,
-  DEFT_T_U_JOB_OFF, DEFT_T_U_JOBS,                                    /* native unit plan */
+  DEFT_T_U_JOB_OFF, DEFT_T_U_JOBS, DEFT_T_U_BLK,                      /* native unit plan */
   DEFT_T_COUNT
 };
 

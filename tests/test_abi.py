@@ -27,7 +27,7 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_version_and_struct_layout():
     assert _lib.lib.deft_b200_abi_version() == _lib.ABI_VERSION
-    assert C.sizeof(_lib.Plan) == 128      # deft_plan_t: item/group layer (48 bytes) + unit layer
+    assert C.sizeof(_lib.Plan) == 136      # deft_plan_t: item/group layer (48 bytes) + unit layer (9 pointers + 4 ints)
 
 
 def test_argument_errors_are_reported_not_crashed():

@@ -17,7 +17,7 @@ ITEM = np.dtype([("kv_off", "<i8"), ("kv_len", "<i4"), ("grp_off", "<i4"), ("n_g
 GROUP = np.dtype([("mask_off", "<i8"), ("q_off", "<i4"), ("q_cnt", "<i4"), ("part_base", "<i4"), ("pad", "<i4")])
 UNIT = np.dtype([("kv_off", "<i8"), ("mask_off", "<i8", (2,)), ("kv_tile_stride", "<i4"), ("mask_tile_stride", "<i4"),
                  ("n_tiles", "<i4"), ("last_len", "<i4"), ("q_off", "<i4", (2,)), ("q_cnt", "<i4", (2,)),
-                 ("part_base", "<i4", (2,)), ("page0", "<i4"), ("q_id0", "<i4", (2,)), ("pad", "<i4")])
+                 ("part_base", "<i4", (2,)), ("page0", "<i4"), ("q_id0", "<i4", (2,)), ("dense_tiles", "<i4")])
 JOB = np.dtype([("job", "<i4"), ("n_jobs", "<i4"), ("next", "<i4"), ("shared", "<i4"), ("unit", UNIT)])
 
 
