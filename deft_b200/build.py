@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "lib", "obj")
 LIB = os.path.join(PKG, "lib", "libdeft_b200.so")
 
-SOURCES = ["api.cu", "attn_fma.cu", "attn_umma.cu", "attn_umma_v2.cu", "combine.cu", "plan.cu", "metadata.cpp"]
+SOURCES = ["api.cu", "attn_fma.cu", "attn_umma.cu", "combine.cu", "plan.cu", "metadata.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
          "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -44,12 +44,11 @@
 // .multicast::cluster into both CTAs' shared memory.
 //
 // Reference semantics: DeFT/deft/layers/attention/tree_attention.py:860-976 (Flatten stage 1) and :170-293 (Node
-// stage 1).  The previous generation (two threads per row, S triple-buffered) is kept in attn_umma_v2.cu behind
-// deft_b200_set_experiment(16) for same-box A/B measurements.
+// stage 1).  Same-box A/B against the previous generation (two threads per row agreeing on the maximum through a named
+// barrier, S triple-buffered with P written in place): DESIGN.md section 6.
 #include "umma_ptx.cuh"
 
 namespace deft {
-int launch_stage1_umma_v2(const AttnParams& p, cudaStream_t stream);
 namespace {
 using namespace umma;
 
@@ -833,7 +832,6 @@ bool stage1_umma_supported(const AttnParams& p) {
 
 int launch_stage1_umma(const AttnParams& p, cudaStream_t stream) {
   if (p.n_units <= 0) return DEFT_OK;
-  if (p.experiment & 16) return launch_stage1_umma_v2(p, stream);  // the previous generation, for same-box A/B runs
   const int G = p.H / p.HKV;
 #define DEFT_CASE(DD, GG) \
   if (p.D == DD && G == GG) return launch_t<DD, GG>(p, stream);

@@ -66,12 +66,15 @@ __global__ void __launch_bounds__(kThreads) stage2_kernel(const AttnParams p) {
 
 // Standalone merge of the tile partials of the tcgen05 stage 1 (one warp per item, combine.cuh).  Used
 // when the fused tail of the stage-1 kernel is disabled or cannot run (see attn_umma.cu).
-template <int D, int G>
+// kBatch partials of a query are in flight at a time.  16 suits a single tree (a query of the BASELINE trees has 6-12
+// partials, the kernel is one wave of latency-bound warps); a forest has thousands of queries with two or three
+// partials each, and what binds it is how many warps fit an SM: 4 in flight need a third of the registers.
+template <int D, int G, int kBatch>
 __global__ void __launch_bounds__(kThreads) stage2_tiles_kernel(const AttnParams p) {
   griddep_launch_dependents();  // the next kernel of the stream may start its own prologue
   const int64_t w = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (w >= (int64_t)p.nq * p.HKV * CombineShape<D, G>::NCG) return;
-  combine_tiles_item<D, G, true>(p, w, threadIdx.x & 31);
+  combine_tiles_item<D, G, true, kBatch>(p, w, threadIdx.x & 31);
 }
 
 template <int D, int G>
@@ -87,7 +90,8 @@ int launch_tiles_t(const AttnParams& p, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 1 : 0;
-  DEFT_CUDA(cudaLaunchKernelEx(&cfg, stage2_tiles_kernel<D, G>, p));
+  if (warps >= 148 * 64 * 2) DEFT_CUDA(cudaLaunchKernelEx(&cfg, stage2_tiles_kernel<D, G, 4>, p));   // several waves of warps
+  else DEFT_CUDA(cudaLaunchKernelEx(&cfg, stage2_tiles_kernel<D, G, 16>, p));
   return DEFT_OK;
 }
 

@@ -51,7 +51,7 @@ struct TileMerge {
   __device__ __forceinline__ void run(const AttnParams& p, int lane) const { run_batched<16>(p, lane); }
 };
 
-template <int D, int G, bool kWaitDep = false>
+template <int D, int G, bool kWaitDep = false, int kBatch = 16>
 __device__ __forceinline__ void combine_tiles_item(const AttnParams& p, int64_t item, int lane) {
   TileMerge<D, G> tm;
   tm.prefetch(p, item, lane);
@@ -59,7 +59,7 @@ __device__ __forceinline__ void combine_tiles_item(const AttnParams& p, int64_t 
     tm.first_row = __shfl_sync(0xffffffffu, tm.first_row, lane);  // the row ids have landed before the wait returns
     griddep_wait();                                                // stage 1 has completed: its partials are visible
   }
-  tm.run(p, lane);
+  tm.template run_batched<kBatch>(p, lane);
 }
 
 template <int D, int G>
