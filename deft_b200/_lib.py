@@ -23,7 +23,7 @@ ITEM_BYTES = 24
 GROUP_BYTES = 24
 UNIT_BYTES = 80
 JOB_BYTES = 96
-N_SCALARS = 9
+N_SCALARS = 10
 
 
 class Plan(C.Structure):
@@ -63,7 +63,10 @@ def _load() -> C.CDLL:
         "deft_b200_node_fwd": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, i32,
                                          vp, i32, vp, vp, vp, i64, vp, vp, i64, i64, C.POINTER(Plan), vp, sz, vp]),
         "deft_b200_kv_append": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, i64, vp, i32, i32, i32, vp]),
-        "deft_b200_build_tables": (vp, [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32]),
+        "deft_b200_build_tables": (vp, [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
+        "deft_b200_layout_new": (vp, []),
+        "deft_b200_layout_free": (None, [vp]),
+        "deft_b200_layout_version": (i64, [vp]),
         "deft_b200_tables_data": (vp, [vp]),
         "deft_b200_tables_bytes": (sz, [vp]),
         "deft_b200_tables_directory": (C.c_int, [vp, vp]),
@@ -84,7 +87,8 @@ EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_set_stage
            "deft_b200_set_debug_buffer", "deft_b200_set_trace_buffer", "deft_b200_set_tma", "deft_b200_set_pdl", "deft_b200_set_gather4", "deft_b200_set_experiment",
            "deft_b200_flatten_workspace_bytes",
            "deft_b200_flatten_fwd", "deft_b200_node_workspace_bytes", "deft_b200_node_fwd", "deft_b200_kv_append",
-           "deft_b200_build_tables", "deft_b200_tables_data", "deft_b200_tables_bytes",
+           "deft_b200_build_tables", "deft_b200_layout_new", "deft_b200_layout_free", "deft_b200_layout_version",
+           "deft_b200_tables_data", "deft_b200_tables_bytes",
            "deft_b200_tables_directory", "deft_b200_tables_scalars", "deft_b200_tables_free"]
 
 

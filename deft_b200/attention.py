@@ -107,8 +107,10 @@ def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Ten
                                output: torch.Tensor, block_len: int, block_q: torch.Tensor,
                                block_q_cnts: torch.Tensor, block_q_offset: torch.Tensor,
                                block_bitmasks: torch.Tensor, block_kv: torch.Tensor, block_lens: torch.Tensor,
-                               plan: Optional[Plan] = None) -> None:
-    """DeFT-Flatten attention; writes ``output`` in place (tree_attention.py:552-667)."""
+                               plan: Optional[Plan] = None, workspace: Optional[torch.Tensor] = None) -> None:
+    """DeFT-Flatten attention; writes ``output`` in place (tree_attention.py:552-667).  ``workspace``: an optional
+    caller-owned uint8 CUDA tensor for the partial-softmax buffers (a captured CUDA graph keeps its address); by
+    default a per-(device, stream) buffer that grows on demand."""
     nq, H, HKV, D = _check_qkvo(query_states, key_buffer, value_buffer, output)
     (p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, ws_need, _keep) = _flat_tables(
         block_q, block_q_cnts, block_q_offset, block_bitmasks, block_kv, block_lens, plan)
@@ -117,7 +119,7 @@ def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Ten
     need = ws_need.get(geom)
     if need is None:
         need = ws_need[geom] = _lib.lib.deft_b200_flatten_workspace_bytes(nq, H, HKV, D, n_partials, n_blocks, plan_ref)
-    ws = _workspace(query_states.device, stream, need)
+    ws = workspace if workspace is not None else _workspace(query_states.device, stream, need)
     qs, ks, os_ = query_states.stride(), key_buffer.stride(), output.stride()
     with _on_device(query_states):
         rc = _lib.lib.deft_b200_flatten_fwd(
@@ -131,7 +133,8 @@ def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Ten
 def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, value_buffer: torch.Tensor,
                        output: torch.Tensor, KV_indices: torch.Tensor, KV_indices_offset: torch.Tensor,
                        KV_len: torch.Tensor, KVMapQ_List: torch.Tensor, KVMapQ_List_Offset: torch.Tensor,
-                       KVMapQ_List_Len: torch.Tensor, plan: Optional[Plan] = None) -> None:
+                       KVMapQ_List_Len: torch.Tensor, plan: Optional[Plan] = None,
+                       workspace: Optional[torch.Tensor] = None) -> None:
     """DeFT-Node / Node-Chunk / Tree-Index attention; writes ``output`` in place (tree_attention.py:14-68)."""
     from .tree_cache import lookup_plan
     nq, H, HKV, D = _check_qkvo(query_states, key_buffer, value_buffer, output)
@@ -150,7 +153,7 @@ def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, val
     stream = _current_stream(query_states)
     need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, HKV, D, n_partials, n_entries, total_kv_bound,
                                                    C.byref(plan) if plan is not None else None)
-    ws = _workspace(query_states.device, stream, need)
+    ws = workspace if workspace is not None else _workspace(query_states.device, stream, need)
     with _on_device(query_states):
         rc = _lib.lib.deft_b200_node_fwd(
             query_states.data_ptr(), query_states.stride(0), query_states.stride(1),

@@ -66,7 +66,16 @@ std::vector<i64> offsets_of(const std::vector<i64>& lens) {  // cat([0], cumsum(
 struct deft_tables {
   std::vector<unsigned char> packed;
   i64 dir[2 * DEFT_T_COUNT];
-  i64 scalars[9];
+  i64 scalars[10];
+};
+
+// Capacities of the packed buffer's regions, kept from one build to the next (deft_b200_layout_new): a table that
+// fits its region keeps its offset, so the device addresses a captured CUDA graph was given stay valid while the
+// tree grows.  A table that outgrows its region takes ~25 % more than it needs and moves the version on.
+struct deft_layout {
+  i64 cap_bytes[DEFT_T_COUNT] = {0};
+  i64 slot_cap = 0;      // unit slots (partial tiles per kv-head) the workspace is carved for
+  i64 version = 0;
 };
 
 namespace {
@@ -96,7 +105,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
                                       const int64_t* tix_row, int64_t tix_max_ctx,
                                       int32_t query_num, int32_t block_len, int32_t max_q_len,
                                       int32_t max_block_len, int32_t node_split, int32_t hkv,
-                                      int32_t n_ctas) {
+                                      int32_t n_ctas, deft_layout_t* layout) {
   if (n_nodes <= 0 || !parent || !kv_off || !kv || !q_off || !qs) {
     deft::set_error("build_tables: null or empty tree");
     return nullptr;
@@ -887,11 +896,23 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       {u_q.data(), u_q.size(), 4}, {u_job_off.data(), u_job_off.size(), 4}, {u_jobs.data(), u_jobs.size(), sizeof(deft_job_t)},
       {u_blk.data(), u_blk.size(), 4},
   };
+  if (layout) {   // capacity-padded regions: offsets only move when a table outgrows its region
+    bool grow = n_unit_slots > layout->slot_cap;
+    for (int i = 0; i < DEFT_T_COUNT; ++i) grow = grow || (i64)((src[i].n * src[i].elem + 255) / 256 * 256) > layout->cap_bytes[i];
+    if (grow) {     // ... and then every region takes its headroom afresh: the tables grow together, so do the layouts
+      for (int i = 0; i < DEFT_T_COUNT; ++i) {
+        const size_t region = (src[i].n * src[i].elem + 255) / 256 * 256;
+        layout->cap_bytes[i] = std::max<i64>(layout->cap_bytes[i], (i64)((region + region / 4 + 1024 + 255) / 256 * 256));
+      }
+      layout->slot_cap = std::max<i64>(layout->slot_cap, n_unit_slots + n_unit_slots / 4 + 8);
+      ++layout->version;
+    }
+  }
   size_t off = 0;
   for (int i = 0; i < DEFT_T_COUNT; ++i) {
     t->dir[2 * i] = (i64)off;
     t->dir[2 * i + 1] = (i64)src[i].n;
-    off += (src[i].n * src[i].elem + 255) / 256 * 256;
+    off += layout ? (size_t)layout->cap_bytes[i] : (src[i].n * src[i].elem + 255) / 256 * 256;
   }
   t->packed.resize(std::max<size_t>(off, 256));
   for (int i = 0; i < DEFT_T_COUNT; ++i) {  // every byte is written: the tables, and zeros up to the next 256-byte boundary
@@ -910,6 +931,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   t->scalars[6] = n_unit_slots;
   t->scalars[7] = u_job_off.empty() ? 0 : (i64)u_job_off.size() - 1;
   t->scalars[8] = plan_paired ? 1 : 0;
+  t->scalars[9] = layout ? layout->slot_cap : n_unit_slots;
   return t;
 }
 
@@ -927,6 +949,10 @@ int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out) {
   std::memcpy(out, t->scalars, sizeof(t->scalars));
   return DEFT_OK;
 }
+
+deft_layout_t* deft_b200_layout_new(void) { return new (std::nothrow) deft_layout_t(); }
+void deft_b200_layout_free(deft_layout_t* l) { delete l; }
+int64_t deft_b200_layout_version(const deft_layout_t* l) { return l ? l->version : -1; }
 
 void deft_b200_tables_free(deft_tables_t* t) {
   if (t && !g_scratch.spare) g_scratch.spare = t;   // its buffer serves the next build of this thread

@@ -1,24 +1,33 @@
-"""A decode step's attention work as CUDA graphs.
+"""A decode step's attention work as CUDA graphs that survive the tree growing.
 
 Per layer a decode step does ``KVCacheUpdater.update`` (append this step's K/V rows, tree_cache.py:67-76) and one
 tree-attention call (deft_attention.py:110-151 / 72-108).  From Python that is three launches and ~45 us of host
 time per layer -- more than the kernels take -- so the step is captured ONCE into CUDA graphs (one per chunk of
-layers, so that host<->device copies of the neighbouring chunks can overlap) and replayed for as long as the table
-LAYOUT (sizes, offsets, counts, addresses: ``TreeMetadata.layout``) is the same; the table CONTENTS (page ids, masks,
-job lists) are free to change from step to step because they live in one persistent device buffer the graphs point
-into.  A different layout re-captures.  This is SURVEY.md 8(f) item 4.
+layers, so that host<->device copies of the neighbouring chunks can overlap) and replayed.
+
+What a captured launch holds is device ADDRESSES (tables, workspace, activations) and a few scalars (grid, cluster
+pairing); every count the kernels need they read from the tables themselves (job records, CSR bounds).  A real
+decode loop appends a page per leaf every step (``TreeCache.alloc``, tree_generate.py:109), so every table grows a
+little: the step therefore builds its tables with a ``TableLayout`` (capacity-padded regions in ONE persistent device
+buffer, ``deft_layout_t``) -- the offsets only move when a table outgrows its region (~ every 25 % of growth), and
+only then is the step captured again.  The workspace is owned by the step and sized for the layout's slot capacity.
+This is SURVEY.md 8(f) items 1 (tables that follow the tree incrementally) and 4 (graph'd decode step).
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Sequence
+import ctypes as C
+from collections import OrderedDict
+from typing import Callable, List, Optional
 
 import torch
 
-from . import attention
-from .tree_cache import TreeMetadata
+from . import _lib, attention
+from .tree_cache import BLOCK_CONFIG, TableLayout, TreeMetadata
 
 
 class DecodeStepGraph:
+    MAX_LAYOUTS = 4      # captured layouts kept (least recently used goes first)
+
     def __init__(self, kv_pool, qkv: torch.Tensor, out: torch.Tensor, cache_loc: torch.Tensor, num_heads: int,
                  num_kv_heads: int, head_dim: int, mode: str = "flatten", chunk: int = 8,
                  table_bytes: int = 8 << 20) -> None:
@@ -32,7 +41,9 @@ class DecodeStepGraph:
         self.chunk = max(1, min(chunk, self.layers))
         self.n_chunks = (self.layers + self.chunk - 1) // self.chunk
         self.tables = torch.empty(table_bytes, dtype=torch.uint8, device=qkv.device)
-        self._graphs: Dict[bytes, List[torch.cuda.CUDAGraph]] = {}
+        self.table_layout = TableLayout()
+        self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=qkv.device)
+        self._graphs: "OrderedDict[bytes, List[torch.cuda.CUDAGraph]]" = OrderedDict()
         self.captures = 0
 
     # ---- tables -------------------------------------------------------------------------------
@@ -40,14 +51,37 @@ class DecodeStepGraph:
         """C++ builder + ONE async upload into the persistent table buffer (grown, and the graphs dropped, if the
         tables outgrow it)."""
         single = not isinstance(trees, (list, tuple))
-        for _ in range(2):
-            m = (TreeMetadata.from_tree_cache(trees, device_buffer=self.tables) if single
-                 else TreeMetadata.from_forest(trees, device_buffer=self.tables))
-            if m.packed.data_ptr() == self.tables.data_ptr():
-                return m
-            self.tables = torch.empty(2 * m.packed.numel(), dtype=torch.uint8, device=self.qkv.device)
-            self._graphs.clear()
-        return m
+        if self.mode == "node_chunk":
+            BLOCK_CONFIG["MAX_BLOCK_LEN"] = 128
+        try:
+            for _ in range(2):
+                m = (TreeMetadata.from_tree_cache(trees, device_buffer=self.tables, table_layout=self.table_layout) if single
+                     else TreeMetadata.from_forest(trees, device_buffer=self.tables, table_layout=self.table_layout))
+                if m.packed.data_ptr() == self.tables.data_ptr():
+                    return m
+                self.tables = torch.empty(2 * m.packed.numel(), dtype=torch.uint8, device=self.qkv.device)
+                self._graphs.clear()
+            return m
+        finally:
+            if self.mode == "node_chunk":
+                BLOCK_CONFIG["MAX_BLOCK_LEN"] = -1
+
+    def _plan(self, m: TreeMetadata):
+        return m.flat_plan if self.mode == "flatten" else m.node_plan
+
+    def _size_workspace(self, m: TreeMetadata) -> None:
+        """The step's own partial-softmax buffer, sized for the layout's slot CAPACITY (a graph keeps its address)."""
+        nq = self.qkv.shape[1]
+        plan = self._plan(m)
+        if self.mode == "flatten":
+            need = _lib.lib.deft_b200_flatten_workspace_bytes(nq, self.H, self.HKV, self.D, m.block_q.numel(),
+                                                              m.block_q_cnts.numel(), C.byref(plan))
+        else:
+            need = _lib.lib.deft_b200_node_workspace_bytes(nq, self.H, self.HKV, self.D, m.node_q.numel(),
+                                                           m.node_kv_offset.numel(), m.node_kv.numel(), C.byref(plan))
+        if self.workspace.numel() < need:
+            self.workspace = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=self.qkv.device)
+            self._graphs.clear()          # (the captured launches point into the old buffer)
 
     # ---- the work of one layer ----------------------------------------------------------------
     def _layer(self, l: int, m: TreeMetadata) -> None:
@@ -60,14 +94,14 @@ class DecodeStepGraph:
         K, V = self.kv_pool.get_key_buffer(l), self.kv_pool.get_value_buffer(l)
         if self.mode == "flatten":
             attention.tree_attention_subtree_fwd(q, K, V, self.out[l], m.block_len, m.block_q, m.block_q_cnts,
-                                                 m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens)
+                                                 m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens,
+                                                 workspace=self.workspace)
         else:
             attention.tree_attention_fwd(q, K, V, self.out[l], m.node_kv, m.node_kv_offset, m.node_kv_len, m.node_q,
-                                         m.node_q_offset, m.node_q_len)
+                                         m.node_q_offset, m.node_q_len, workspace=self.workspace)
 
     def _capture(self, m: TreeMetadata) -> List[torch.cuda.CUDAGraph]:
-        for l in range(self.layers):          # eager once: sizes the workspace outside the capture
-            self._layer(l, m)
+        self._layer(0, m)                     # eager once: tensor maps, launch attributes and errors outside the capture
         torch.cuda.current_stream().synchronize()
         graphs = []
         for c in range(self.n_chunks):
@@ -86,9 +120,15 @@ class DecodeStepGraph:
         before / after chunk ``c`` is enqueued (event waits for the chunk's inputs, event records for its outputs)."""
         assert m.packed is not None and m.packed.data_ptr() == self.tables.data_ptr(), \
             "build the step's tables with DecodeStepGraph.metadata()"
-        graphs = self._graphs.get(m.layout)
+        self._size_workspace(m)
+        key = m.layout + self.workspace.data_ptr().to_bytes(8, "little")
+        graphs = self._graphs.get(key)
         if graphs is None:
-            graphs = self._graphs[m.layout] = self._capture(m)
+            graphs = self._graphs[key] = self._capture(m)
+            while len(self._graphs) > self.MAX_LAYOUTS:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
         for c, g in enumerate(graphs):
             if before_chunk is not None:
                 before_chunk(c)

@@ -466,9 +466,29 @@ def sm_count(device: Optional[torch.device]) -> int:
     return _SM_COUNT[idx]
 
 
+class TableLayout:
+    """Capacity-padded packing of the tables (``deft_layout_t``): one per decode loop.  While every table fits its
+    region the packed buffer keeps its offsets from one decode step to the next -- what a captured CUDA graph of the
+    step needs -- although every step appends a page per leaf.  ``version`` moves when a region had to grow."""
+
+    def __init__(self) -> None:
+        self.handle = _lib.lib.deft_b200_layout_new()
+        if not self.handle:
+            raise MemoryError("deft_b200_layout_new failed")
+
+    @property
+    def version(self) -> int:
+        return int(_lib.lib.deft_b200_layout_version(self.handle))
+
+    def __del__(self) -> None:
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None and getattr(_lib, "lib", None) is not None:     # (None at interpreter shutdown)
+            _lib.lib.deft_b200_layout_free(h)
+
+
 def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: int = -1,
                       block_len: int = 128, tree_index_max_ctx: int = 0, node_split: int = NODE_SPLIT,
-                      hkv: int = 0, n_ctas: int = 148, reserve=None):
+                      hkv: int = 0, n_ctas: int = 148, reserve=None, layout: Optional[TableLayout] = None):
     """Runs the C++ builder; returns (packed bytes as numpy uint8, directory, scalars).
 
     ``reserve(nbytes) -> uint8 tensor`` (optional) supplies the destination -- the pinned staging buffer of the
@@ -480,7 +500,7 @@ def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: 
                                         flat["kv"].ctypes.data, flat["q_off"].ctypes.data, flat["qs"].ctypes.data,
                                         flat["tix"].ctypes.data if use_tix else None,
                                         tree_index_max_ctx, query_num, block_len, max_q_len, max_block_len, node_split,
-                                        hkv, n_ctas)
+                                        hkv, n_ctas, layout.handle if layout is not None else None)
     if not h:
         raise _lib.DeftError(f"deft_b200_build_tables failed: {_lib.last_error()}")
     try:
@@ -529,7 +549,7 @@ class TreeMetadata:
 
     @classmethod
     def _assemble(cls, tree, flat, max_q_len: int, max_block_len: int, tree_index: bool,
-                  device_buffer: Optional[torch.Tensor] = None) -> "TreeMetadata":
+                  device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None) -> "TreeMetadata":
         block_len = BLOCK_CONFIG["BLOCK_LEN"]
         if max_block_len == -1:
             max_block_len = BLOCK_CONFIG["MAX_BLOCK_LEN"]
@@ -540,7 +560,7 @@ class TreeMetadata:
         on_gpu = device.type == "cuda"
         data, directory, scalars = build_tables_host(flat, max_q_len, max_block_len, block_len, max_ctx,
                                                      hkv=hkv, n_ctas=sm_count(device),
-                                                     reserve=_STAGING.reserve if on_gpu else None)
+                                                     reserve=_STAGING.reserve if on_gpu else None, layout=table_layout)
         if on_gpu:
             buf, nbytes = data
             if device_buffer is not None and device_buffer.numel() < nbytes:
@@ -568,7 +588,7 @@ class TreeMetadata:
                              n_part_rows=rows, n_units=directory[U][1],
                              units=addr(U), u_csr_off=addr(U + 1), u_csr_rows=addr(U + 2), u_kv=addr(U + 3), u_blk=addr(U + 8),
                              u_mask=addr(U + 4), u_q=addr(U + 5), u_job_off=addr(U + 6), u_jobs=addr(U + 7),
-                             n_unit_slots=int(scalars[6]), n_ctas=int(scalars[7]), hkv=hkv, paired=int(scalars[8]))
+                             n_unit_slots=int(scalars[9]), n_ctas=int(scalars[7]), hkv=hkv, paired=int(scalars[8]))
 
         if tree_index:
             null = torch.empty(0, dtype=torch.int64, device=device)
@@ -576,32 +596,41 @@ class TreeMetadata:
             t["node_kv"] = (tix.device_table() if on_gpu and hasattr(tix, "device_table") else tix.node_to_kv).view(-1)
             for k in ("block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv", "block_lens"):
                 t[k] = null
+        # what a captured graph of the step depends on: where the tables sit, and the few scalars the launches bake in
+        # (grid, cluster pairing, workspace carving).  With a TableLayout the offsets are capacity-padded, and a step
+        # that only appended pages keeps this key although every count has moved.
+        if table_layout is not None:
+            key = np.asarray([d[0] for d in directory] + [int(scalars[0]), int(scalars[7]), int(scalars[8]), int(scalars[9]),
+                                                          table_layout.version, base], dtype=np.int64).tobytes()
+        else:
+            key = dir_bytes + scalars.tobytes() + int(base).to_bytes(8, "little")
         meta = cls(query_num=int(scalars[0]), node_num=int(scalars[1]), total_kv_len=int(scalars[2]),
                    leaf_to_q=flat["leaf_to_q"], block_len=int(scalars[3]), packed=packed,
                    flat_plan=None if tree_index else plan(12, int(scalars[4])), node_plan=plan(16, int(scalars[5])),
-                   layout=dir_bytes + scalars.tobytes() + int(base).to_bytes(8, "little"), **t)
+                   layout=key, **t)
         if on_gpu:
             register_plan(meta)
         return meta
 
     @classmethod
     def from_tree_cache(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1,
-                        device_buffer: Optional[torch.Tensor] = None) -> "TreeMetadata":
+                        device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None) -> "TreeMetadata":
         """Reference signature (tree_cache.py:618-625) + ``device_buffer``: an optional persistent uint8 CUDA tensor
         the packed tables are uploaded into, so that consecutive decode steps find them at the same addresses
         (what a captured CUDA graph of the step needs, see ``decode_step.DecodeStepGraph``)."""
-        return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=False, device_buffer=device_buffer)
+        return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=False, device_buffer=device_buffer,
+                             table_layout=table_layout)
 
     @classmethod
     def from_forest(cls, trees, max_q_len: int = 32, max_block_len: int = -1,
-                    device_buffer: Optional[torch.Tensor] = None) -> "TreeMetadata":
+                    device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None) -> "TreeMetadata":
         """One metadata object (tables + native plan) for several trees sharing one KV pool: the operators
         then attend the whole batch in one launch.  ``leaf_to_q`` is keyed by ``(tree index, leaf id)``."""
         trees = list(trees)
         assert trees and all(t.token_to_kv_pool is trees[0].token_to_kv_pool for t in trees), \
             "the trees of a forest share one TokenToKVPool"
         return cls._assemble(trees[0], flatten_forest(trees), max_q_len, max_block_len, tree_index=False,
-                             device_buffer=device_buffer)
+                             device_buffer=device_buffer, table_layout=table_layout)
 
     @classmethod
     def from_tree_cache_node(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":

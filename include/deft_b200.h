@@ -259,19 +259,30 @@ enum {
 
 typedef struct deft_tables deft_tables_t;
 
+/* Capacity-padded packing.  A decode step appends one page per leaf (tree_generate.py:109), so every table grows a
+ * little from step to step; packed tightly, their offsets move and whatever holds device addresses of the tables (a
+ * captured CUDA graph of the step) dies.  A layout handle remembers a capacity per table: a table that fits keeps its
+ * offset, one that outgrows its region takes ~25 % more than it needs and moves deft_b200_layout_version() on.  NULL
+ * packs tightly.  One handle per decode loop, used by one thread at a time. */
+typedef struct deft_layout deft_layout_t;
+deft_layout_t* deft_b200_layout_new(void);
+void deft_b200_layout_free(deft_layout_t* layout);
+int64_t deft_b200_layout_version(const deft_layout_t* layout);
+
 deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, const int64_t* kv_off,
                                       const int64_t* kv, const int64_t* q_off, const int64_t* qs,
                                       const int64_t* tix_row, int64_t tix_max_ctx,
                                       int32_t query_num, int32_t block_len, int32_t max_q_len,
                                       int32_t max_block_len, int32_t node_split, int32_t hkv,
-                                      int32_t n_ctas);
+                                      int32_t n_ctas, deft_layout_t* layout);
 const void* deft_b200_tables_data(const deft_tables_t* t);  /* packed host buffer */
 size_t deft_b200_tables_bytes(const deft_tables_t* t);
 /* dir[2*i] = byte offset of array i in the packed buffer, dir[2*i+1] = element count */
 int deft_b200_tables_directory(const deft_tables_t* t, int64_t* dir /* [2*DEFT_T_COUNT] */);
 /* scalars: {query_num, node_num, total_kv_len, block_len, flat_part_rows, node_part_rows,
- *           n_unit_slots, n_ctas, paired (1: the job lists are pair-aligned, see deft_job_t.shared)} */
-int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [9] */);
+ *           n_unit_slots, n_ctas, paired (1: the job lists are pair-aligned, see deft_job_t.shared),
+ *           unit-slot capacity (= n_unit_slots without a layout handle: what the workspace is carved for)} */
+int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [10] */);
 void deft_b200_tables_free(deft_tables_t* t);
 
 #ifdef __cplusplus

@@ -39,7 +39,7 @@ def test_argument_errors_are_reported_not_crashed():
         _lib.check(rc)
     rc = _lib.lib.deft_b200_kv_append(None, None, 0, 0, None, None, 0, 0, None, 1, 8, 128, None)
     assert rc == -1
-    assert _lib.lib.deft_b200_build_tables(0, None, None, None, None, None, None, 0, 1, 128, 32, -1, 256, 8, 148) is None
+    assert _lib.lib.deft_b200_build_tables(0, None, None, None, None, None, None, 0, 1, 128, 32, -1, 256, 8, 148, None) is None
     assert "tree" in _lib.last_error()
 
 

@@ -378,3 +378,51 @@ def test_decode_step_graph_replays_with_new_table_contents(dev):
             assert torch.equal(kvp.get_key_buffer(l)[loc.long()], qkv[l, :, H * D: (H + HKV) * D].view(nq, HKV, D))
         assert torch.isfinite(got.float()).all() and torch.equal(got, want), it
     assert len(layouts) == 1 and step.captures == 1, "same shape, other pages: one capture, replayed"
+
+
+@pytest.mark.parametrize("mode", ["flatten", "node"])
+def test_decode_step_graph_survives_the_tree_growing(dev, mode):
+    """A real decode loop (tree_generate.py:109, 128): every step appends a token and a page per leaf, rebuilds the
+    tables, appends K/V and attends.  With capacity-padded tables the captured graphs are replayed across the appends
+    (a handful of captures over 40 steps instead of one per step), and every step equals the eager per-layer calls on
+    a tightly packed build of the same tree."""
+    import deft_b200
+    from deft_b200 import TreeMetadata
+    from deft_b200.workloads import build_tree
+    torch.manual_seed(11)
+    L, H, HKV, D, steps = 2, 32, 8, 128, 40
+    tree = build_tree("cfg3", layers=L, device=dev, headroom=64 * (steps + 2))
+    kvp = tree.token_to_kv_pool
+    for l in range(L):
+        kvp.kv_data[l].normal_()
+    nq = len(tree.leaves)
+    qkv = torch.empty(L, nq, (H + 2 * HKV) * D, dtype=torch.float16, device=dev)
+    out = torch.empty(L, nq, H, D, dtype=torch.float16, device=dev)
+    loc = torch.zeros(nq, dtype=torch.int32, device=dev)
+    step = deft_b200.DecodeStepGraph(kvp, qkv, out, loc, H, HKV, D, mode=mode, chunk=1)
+    for it in range(steps):
+        for leaf in tree.leaves.values():
+            leaf.append_token(7)
+        upd = tree.alloc()
+        loc.copy_(upd.cache_loc)
+        qkv.normal_()
+        m = step.metadata(tree)
+        step.run(m)
+        got = out.clone()
+        m2 = TreeMetadata.from_tree_cache(tree)                 # tight packing, fresh buffer
+        assert m2.total_kv_len == m.total_kv_len == 2048 + 64 * (it + 2)
+        for k in ("block_q", "block_kv", "block_bitmasks", "node_kv", "node_q", "node_kv_len"):
+            assert torch.equal(getattr(m, k), getattr(m2, k)), (it, k)
+        want = torch.empty_like(out)
+        for l in range(L):
+            q = qkv[l, :, : H * D].view(nq, H, D)
+            K, V = kvp.get_key_buffer(l), kvp.get_value_buffer(l)
+            assert torch.equal(K[loc.long()], qkv[l, :, H * D: (H + HKV) * D].view(nq, HKV, D)), "the graph appended this step's K"
+            if mode == "flatten":
+                deft_b200.tree_attention_subtree_fwd(q, K, V, want[l], 128, m2.block_q, m2.block_q_cnts, m2.block_q_offset,
+                                                     m2.block_bitmasks, m2.block_kv, m2.block_lens)
+            else:
+                deft_b200.tree_attention_fwd(q, K, V, want[l], m2.node_kv, m2.node_kv_offset, m2.node_kv_len, m2.node_q,
+                                             m2.node_q_offset, m2.node_q_len)
+        assert torch.isfinite(got.float()).all() and torch.equal(got, want), (mode, it)
+    assert step.captures <= 4, f"{step.captures} captures over {steps} appends"

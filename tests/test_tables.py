@@ -305,3 +305,37 @@ def test_builder_rejects_malformed_trees():
     t, scalars = build(tree)
     assert t["node_kv"].tolist() == [1, 2, 3] and t["block_lens"].tolist() == [3]
     assert t["block_kv"][:4].tolist() == [1, 2, 3, -1] and scalars[2] == 3
+
+
+def test_capacity_padded_layout_keeps_offsets_while_the_tree_grows():
+    """A decode loop appends a page per leaf every step (tree_generate.py:109): every table grows a little.  Built with
+    a TableLayout the packed buffer keeps its offsets for many steps in a row (what a captured CUDA graph of the step
+    needs), every table holds exactly what the tight packing holds, and a table that outgrows its region moves the
+    layout's version on."""
+    from deft_b200.tree_cache import TableLayout
+    from deft_b200.workloads import build_tree
+    tree = build_tree("cfg2", layers=0, device="cpu", H=4, HKV=2, D=16, headroom=64 * 50)
+    lay = TableLayout()
+    offsets, versions = [], []
+    for step in range(48):
+        for leaf in tree.leaves.values():
+            leaf.append_token(7)
+        tree.alloc()
+        flat = flatten_tree(tree)
+        v0 = lay.version
+        d_pad, dir_pad, sc_pad = build_tables_host(flat, hkv=2, n_ctas=148, layout=lay)
+        d_tight, dir_tight, sc_tight = build_tables_host(flat, hkv=2, n_ctas=148)
+        assert np.array_equal(dir_pad[:, 1], dir_tight[:, 1]) and np.array_equal(sc_pad[:9], sc_tight[:9])
+        assert sc_pad[9] >= sc_tight[9] == sc_tight[6], "the slot capacity covers the slots in use"
+        a, b = unpack(d_pad, dir_pad), unpack(d_tight, dir_tight)
+        for name in _lib.T_NAMES:
+            assert np.array_equal(a[name], b[name]), (step, name)
+        assert np.all(np.diff(dir_pad[:, 0]) >= 0) and np.all(dir_pad[:, 0] % 256 == 0)
+        ends = dir_pad[:-1, 0] + dir_pad[:-1, 1] * np.array([a[n].dtype.itemsize for n in _lib.T_NAMES[:-1]])
+        assert np.all(ends <= dir_pad[1:, 0]), "no table runs into the next region"
+        if offsets and tuple(dir_pad[:, 0]) != offsets[-1]:
+            assert lay.version > v0, "offsets only move with the version"
+        offsets.append(tuple(dir_pad[:, 0]))
+        versions.append(lay.version)
+    assert len(set(offsets)) <= 5, "48 decode steps (the subtree's KV grows 2.5x): a handful of layouts"
+    assert len(set(versions)) == len(set(offsets))
