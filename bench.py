@@ -385,7 +385,7 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
         s_in.wait_stream(s_out)
         upload(range(1))                                 # the first chunk of activations goes up under the table build
         # C++ builder + one H2D copy of tables and plan (into the persistent table buffer of the graphed step)
-        m = step.metadata(trees[0] if T == 1 else trees) if graphed else build_meta()
+        m = step.metadata(trees[0] if T == 1 else trees, cache_loc=None if args.e2e_static else host_loc) if graphed else build_meta()
         table_bytes[0] = m.packed.numel()
         loc_dev.copy_(host_loc, non_blocking=True)       # this step's pages (one per leaf)
         if graphed:
@@ -545,9 +545,10 @@ def main():
                         "GROWS: every step appends one token + one page per leaf (TreeCache.alloc) before the tables are rebuilt; "
                         "%d KV tokens per tree at the end of the run" % (r["kv_tokens_end"] // T),
                 "graph_captures": r["captures"],
-                "path": ("TreeCache.alloc + DecodeStepGraph.metadata (TreeMetadata.from_tree_cache: C++ builder, 1 upload into the "
-                         "persistent table buffer; the first chunk of activations goes up under the build, the others queue behind the "
-                         "tables) + pinned H2D of the fused qkv in %d-layer chunks on a copy stream + 32 x (kv_append + tree attention) "
+                "path": ("TreeCache.alloc + DecodeStepGraph.metadata (TreeMetadata.from_tree_cache: C++ builder, capacity-padded tables, 1 "
+                         "upload into the persistent table buffer; the first chunk of activations goes up under the build, the others "
+                         "queue behind the tables) + pinned H2D of the fused qkv in %d-layer chunks on a copy stream + 32 x tree attention "
+                         "with the KV append fused in (this step's K/V read from the activations, written to the pool by stage 2) "
                          "replayed as %d CUDA graphs + D2H of the outputs per chunk on a second copy stream; timed until the last "
                          "output is on the host" % (args.e2e_chunk, r["e2e_chunks"])) if r["graphed"] else
                         "per-layer eager calls (kv_append + attention) between chunked pinned H2D / D2H copies"},

@@ -23,7 +23,7 @@ ITEM_BYTES = 24
 GROUP_BYTES = 24
 UNIT_BYTES = 80
 JOB_BYTES = 96
-N_SCALARS = 10
+N_SCALARS = 11
 
 
 class Plan(C.Structure):
@@ -32,7 +32,14 @@ class Plan(C.Structure):
                 ("n_items", C.c_int32), ("n_groups", C.c_int32), ("n_part_rows", C.c_int32), ("n_units", C.c_int32),
                 ("units", C.c_void_p), ("u_csr_off", C.c_void_p), ("u_csr_rows", C.c_void_p), ("u_kv", C.c_void_p),
                 ("u_blk", C.c_void_p), ("u_mask", C.c_void_p), ("u_q", C.c_void_p), ("u_job_off", C.c_void_p), ("u_jobs", C.c_void_p),
-                ("n_unit_slots", C.c_int32), ("n_ctas", C.c_int32), ("hkv", C.c_int32), ("paired", C.c_int32)]
+                ("n_unit_slots", C.c_int32), ("n_ctas", C.c_int32), ("hkv", C.c_int32), ("paired", C.c_int32),
+                ("fresh", C.c_int32), ("pad", C.c_int32)]
+
+
+class Append(C.Structure):
+    """``deft_append_t``"""
+    _fields_ = [("new_k", C.c_void_p), ("new_v", C.c_void_p), ("new_row_stride", C.c_int64), ("new_head_stride", C.c_int64),
+                ("cache_loc", C.c_void_p)]
 
 
 class DeftError(RuntimeError):
@@ -63,7 +70,11 @@ def _load() -> C.CDLL:
         "deft_b200_node_fwd": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, i32,
                                          vp, i32, vp, vp, vp, i64, vp, vp, i64, i64, C.POINTER(Plan), vp, sz, vp]),
         "deft_b200_kv_append": (C.c_int, [vp, vp, i64, i64, vp, vp, i64, i64, vp, i32, i32, i32, vp]),
-        "deft_b200_build_tables": (vp, [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
+        "deft_b200_build_tables": (vp, [i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
+        "deft_b200_flatten_fwd_append": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, i32,
+                                                   i32, vp, i64, vp, vp, vp, i64, vp, vp, C.POINTER(Plan), C.POINTER(Append), vp, sz, vp]),
+        "deft_b200_node_fwd_append": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, i32,
+                                                vp, i32, vp, vp, vp, i64, vp, vp, i64, i64, C.POINTER(Plan), C.POINTER(Append), vp, sz, vp]),
         "deft_b200_layout_new": (vp, []),
         "deft_b200_layout_free": (None, [vp]),
         "deft_b200_layout_version": (i64, [vp]),
@@ -86,7 +97,7 @@ lib = _load()
 EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_set_stages", "deft_b200_set_stage1_impl",
            "deft_b200_set_debug_buffer", "deft_b200_set_trace_buffer", "deft_b200_set_tma", "deft_b200_set_pdl", "deft_b200_set_gather4", "deft_b200_set_experiment",
            "deft_b200_flatten_workspace_bytes",
-           "deft_b200_flatten_fwd", "deft_b200_node_workspace_bytes", "deft_b200_node_fwd", "deft_b200_kv_append",
+           "deft_b200_flatten_fwd", "deft_b200_node_workspace_bytes", "deft_b200_node_fwd", "deft_b200_flatten_fwd_append", "deft_b200_node_fwd_append", "deft_b200_kv_append",
            "deft_b200_build_tables", "deft_b200_layout_new", "deft_b200_layout_free", "deft_b200_layout_version",
            "deft_b200_tables_data", "deft_b200_tables_bytes",
            "deft_b200_tables_directory", "deft_b200_tables_scalars", "deft_b200_tables_free"]

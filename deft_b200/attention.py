@@ -78,6 +78,14 @@ def _check_qkvo(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tens
     return nq, H, HKV, D
 
 
+def _append_struct(append, nq: int, HKV: int, D: int) -> "_lib.Append":
+    new_k, new_v, loc = append
+    assert new_k.is_cuda and new_v.is_cuda and loc.is_cuda and loc.dtype == torch.int32 and loc.is_contiguous()
+    assert new_k.dtype == torch.float16 and tuple(new_k.shape) == (nq, HKV, D) == tuple(new_v.shape) and loc.numel() == nq
+    assert new_k.stride() == new_v.stride() and new_k.stride(2) == 1
+    return _lib.Append(new_k.data_ptr(), new_v.data_ptr(), new_k.stride(0), new_k.stride(1), loc.data_ptr())
+
+
 def _i64(t: torch.Tensor) -> torch.Tensor:
     assert t.dtype == torch.int64 and t.is_cuda
     return t if t.is_contiguous() else t.contiguous()
@@ -107,10 +115,13 @@ def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Ten
                                output: torch.Tensor, block_len: int, block_q: torch.Tensor,
                                block_q_cnts: torch.Tensor, block_q_offset: torch.Tensor,
                                block_bitmasks: torch.Tensor, block_kv: torch.Tensor, block_lens: torch.Tensor,
-                               plan: Optional[Plan] = None, workspace: Optional[torch.Tensor] = None) -> None:
+                               plan: Optional[Plan] = None, workspace: Optional[torch.Tensor] = None,
+                               append: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None) -> None:
     """DeFT-Flatten attention; writes ``output`` in place (tree_attention.py:552-667).  ``workspace``: an optional
     caller-owned uint8 CUDA tensor for the partial-softmax buffers (a captured CUDA graph keeps its address); by
-    default a per-(device, stream) buffer that grows on demand."""
+    default a per-(device, stream) buffer that grows on demand.  ``append`` = ``(new_k, new_v, cache_loc)``: fused KV
+    append -- the tables must have been built with ``fresh_page``; this step's tokens are read from ``new_k / new_v``
+    ([nq, HKV, D] views of the fused qkv output) and written to the pool pages ``cache_loc`` (int32, device)."""
     nq, H, HKV, D = _check_qkvo(query_states, key_buffer, value_buffer, output)
     (p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, ws_need, _keep) = _flat_tables(
         block_q, block_q_cnts, block_q_offset, block_bitmasks, block_kv, block_lens, plan)
@@ -122,10 +133,17 @@ def tree_attention_subtree_fwd(query_states: torch.Tensor, key_buffer: torch.Ten
     ws = workspace if workspace is not None else _workspace(query_states.device, stream, need)
     qs, ks, os_ = query_states.stride(), key_buffer.stride(), output.stride()
     with _on_device(query_states):
-        rc = _lib.lib.deft_b200_flatten_fwd(
-            query_states.data_ptr(), qs[0], qs[1], key_buffer.data_ptr(), value_buffer.data_ptr(), ks[0], ks[1],
-            key_buffer.shape[0], output.data_ptr(), os_[0], os_[1], nq, H, HKV, D, int(block_len),
-            p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, ws.data_ptr(), ws.numel(), stream)
+        if append is None:
+            rc = _lib.lib.deft_b200_flatten_fwd(
+                query_states.data_ptr(), qs[0], qs[1], key_buffer.data_ptr(), value_buffer.data_ptr(), ks[0], ks[1],
+                key_buffer.shape[0], output.data_ptr(), os_[0], os_[1], nq, H, HKV, D, int(block_len),
+                p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, ws.data_ptr(), ws.numel(), stream)
+        else:
+            rc = _lib.lib.deft_b200_flatten_fwd_append(
+                query_states.data_ptr(), qs[0], qs[1], key_buffer.data_ptr(), value_buffer.data_ptr(), ks[0], ks[1],
+                key_buffer.shape[0], output.data_ptr(), os_[0], os_[1], nq, H, HKV, D, int(block_len),
+                p_bq, n_partials, p_bc, p_bo, p_bl, n_blocks, p_bm, p_bk, plan_ref, C.byref(_append_struct(append, nq, HKV, D)),
+                ws.data_ptr(), ws.numel(), stream)
     if rc:
         _lib.check(rc)
 
@@ -134,7 +152,8 @@ def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, val
                        output: torch.Tensor, KV_indices: torch.Tensor, KV_indices_offset: torch.Tensor,
                        KV_len: torch.Tensor, KVMapQ_List: torch.Tensor, KVMapQ_List_Offset: torch.Tensor,
                        KVMapQ_List_Len: torch.Tensor, plan: Optional[Plan] = None,
-                       workspace: Optional[torch.Tensor] = None) -> None:
+                       workspace: Optional[torch.Tensor] = None,
+                       append: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None) -> None:
     """DeFT-Node / Node-Chunk / Tree-Index attention; writes ``output`` in place (tree_attention.py:14-68)."""
     from .tree_cache import lookup_plan
     nq, H, HKV, D = _check_qkvo(query_states, key_buffer, value_buffer, output)
@@ -154,14 +173,17 @@ def tree_attention_fwd(query_states: torch.Tensor, key_buffer: torch.Tensor, val
     need = _lib.lib.deft_b200_node_workspace_bytes(nq, H, HKV, D, n_partials, n_entries, total_kv_bound,
                                                    C.byref(plan) if plan is not None else None)
     ws = workspace if workspace is not None else _workspace(query_states.device, stream, need)
-    with _on_device(query_states):
-        rc = _lib.lib.deft_b200_node_fwd(
-            query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
+    args = (query_states.data_ptr(), query_states.stride(0), query_states.stride(1),
             key_buffer.data_ptr(), value_buffer.data_ptr(), key_buffer.stride(0), key_buffer.stride(1), key_buffer.shape[0],
             output.data_ptr(), output.stride(0), output.stride(1), nq, H, HKV, D,
             KV_indices.data_ptr(), KV_indices.element_size(), kv_off.data_ptr(), kv_len.data_ptr(), node_q.data_ptr(),
             n_partials, q_off.data_ptr(), q_len.data_ptr(), n_entries, total_kv_bound,
-            C.byref(plan) if plan is not None else None, ws.data_ptr(), ws.numel(), stream)
+            C.byref(plan) if plan is not None else None)
+    with _on_device(query_states):
+        if append is None:
+            rc = _lib.lib.deft_b200_node_fwd(*args, ws.data_ptr(), ws.numel(), stream)
+        else:
+            rc = _lib.lib.deft_b200_node_fwd_append(*args, C.byref(_append_struct(append, nq, HKV, D)), ws.data_ptr(), ws.numel(), stream)
     _lib.check(rc)
 
 

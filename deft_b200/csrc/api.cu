@@ -114,6 +114,35 @@ void setup_tma(AttnParams& p, int64_t kv_pool_tokens) {
     p.tma_q = make_map(&p.tmap_q, MapKey{p.q, p.D, p.H, p.nq, p.q_head_stride, p.q_row_stride, G, 32});
 }
 
+// Fused append: tensor maps over the step's new K / V rows, the mirror image of the pool's
+int setup_append(AttnParams& p, const deft_append_t* a) {
+  DEFT_CHECK_ARG(a->new_k && a->new_v && a->cache_loc, "append: null pointer");
+  DEFT_CHECK_ARG(((uintptr_t)a->new_k | (uintptr_t)a->new_v) % 16 == 0 && (a->new_row_stride | a->new_head_stride) % 8 == 0,
+                 "append: new_k / new_v must be 16-byte aligned with strides in multiples of 8 elements");
+  DEFT_CHECK_ARG(p.tma_kv && p.tma_gather, "append: needs the TMA paths of the tensor-core kernel");
+  const int64_t ratio = a->new_head_stride > 0 ? a->new_row_stride / a->new_head_stride : 0;
+  DEFT_CHECK_ARG(a->new_head_stride >= p.D && ratio >= p.HKV && ratio * a->new_head_stride == a->new_row_stride,
+                 "append: the row stride of new_k / new_v must be a whole number of head strides");
+  const int64_t rows = (int64_t)(p.nq - 1) * ratio + p.HKV;
+  p.new_k = static_cast<const __half*>(a->new_k);
+  p.new_v = static_cast<const __half*>(a->new_v);
+  p.new_row_stride = a->new_row_stride; p.new_head_stride = a->new_head_stride;
+  p.cache_loc = a->cache_loc;
+  p.new_row_ratio = (int32_t)ratio; p.new_rows = (int32_t)rows;
+  bool ok = true;
+  const int boxes[3] = {32, 16, 8};
+  CUtensorMap* km[3] = {&p.tmap_nk, &p.tmap_nk16, &p.tmap_nk8};
+  CUtensorMap* vm[3] = {&p.tmap_nv, &p.tmap_nv16, &p.tmap_nv8};
+  for (int i = 0; i < 3; ++i) {
+    ok = ok && make_map(km[i], MapKey{a->new_k, p.D, p.HKV, p.nq, a->new_head_stride, a->new_row_stride, 1, boxes[i]});
+    ok = ok && make_map(vm[i], MapKey{a->new_v, p.D, p.HKV, p.nq, a->new_head_stride, a->new_row_stride, 1, boxes[i]});
+  }
+  ok = ok && make_map(&p.tmap_nkg, MapKey{a->new_k, p.D, rows, 0, a->new_head_stride, 0, 1, 0});
+  ok = ok && make_map(&p.tmap_nvg, MapKey{a->new_v, p.D, rows, 0, a->new_head_stride, 0, 1, 0});
+  DEFT_CHECK_ARG(ok, "append: could not encode the tensor maps of new_k / new_v");
+  return DEFT_OK;
+}
+
 // Which stage-1 kernel a call of this thread runs (the stage-2 kernel and the partial layout follow it).
 bool use_umma(int32_t H, int32_t HKV, int32_t D) {
   if (g_stage1_impl == DEFT_STAGE1_FMA) return false;
@@ -335,6 +364,22 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
                           const int64_t* block_bitmasks, const int64_t* block_kv,
                           const deft_plan_t* plan, void* workspace, size_t workspace_bytes,
                           void* stream_) {
+  return deft_b200_flatten_fwd_append(q, q_row_stride, q_head_stride, k, v, kv_tok_stride, kv_head_stride, kv_pool_tokens, o,
+                                      o_row_stride, o_head_stride, nq, H, HKV, D, block_len, block_q, n_partials, block_q_cnts,
+                                      block_q_offset, block_lens, n_blocks, block_bitmasks, block_kv, plan, nullptr, workspace,
+                                      workspace_bytes, stream_);
+}
+
+int deft_b200_flatten_fwd_append(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                                 const void* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                                 int64_t kv_pool_tokens, void* o,
+                                 int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
+                                 int32_t HKV, int32_t D, int32_t block_len, const int64_t* block_q,
+                                 int64_t n_partials, const int64_t* block_q_cnts,
+                                 const int64_t* block_q_offset, const int64_t* block_lens, int64_t n_blocks,
+                                 const int64_t* block_bitmasks, const int64_t* block_kv,
+                                 const deft_plan_t* plan, const deft_append_t* append, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_common(q, k, v, o, nq, H, HKV, D, q_row_stride, q_head_stride, kv_tok_stride,
                         kv_head_stride, o_row_stride, o_head_stride);
@@ -357,6 +402,12 @@ int deft_b200_flatten_fwd(const void* q, int64_t q_row_stride, int64_t q_head_st
   p.po = w.po; p.plse = w.plse; p.po16 = w.po16; p.plse16 = w.plse16;
   if (umma) setup_tma(p, kv_pool_tokens);
   p.pdl = g_no_pdl ? 0 : 1;
+  if (append) {
+    DEFT_CHECK_ARG(umma && plan && plan->u_blk && plan->fresh, "append: needs the tensor-core path and a host-built plan (tables built with fresh_page)");
+    rc = setup_append(p, append);
+    if (rc) return rc;
+  }
+  DEFT_CHECK_ARG(!(plan && plan->fresh && !append), "this plan reads the step's tokens from the activations: call the *_append form");
   if (plan) {
     rc = use_plan(p, plan, umma);
     if (rc) return rc;
@@ -380,6 +431,21 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
                        int64_t n_partials, const int64_t* q_offset, const int64_t* q_len,
                        int64_t n_entries, int64_t total_kv_bound, const deft_plan_t* plan,
                        void* workspace, size_t workspace_bytes, void* stream_) {
+  return deft_b200_node_fwd_append(q, q_row_stride, q_head_stride, k, v, kv_tok_stride, kv_head_stride, kv_pool_tokens, o,
+                                   o_row_stride, o_head_stride, nq, H, HKV, D, kv_indices, kv_index_bytes, kv_offset, kv_len, node_q,
+                                   n_partials, q_offset, q_len, n_entries, total_kv_bound, plan, nullptr, workspace,
+                                   workspace_bytes, stream_);
+}
+
+int deft_b200_node_fwd_append(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                              const void* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                              int64_t kv_pool_tokens, void* o,
+                              int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
+                              int32_t HKV, int32_t D, const void* kv_indices, int32_t kv_index_bytes,
+                              const int64_t* kv_offset, const int64_t* kv_len, const int64_t* node_q,
+                              int64_t n_partials, const int64_t* q_offset, const int64_t* q_len,
+                              int64_t n_entries, int64_t total_kv_bound, const deft_plan_t* plan,
+                              const deft_append_t* append, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_common(q, k, v, o, nq, H, HKV, D, q_row_stride, q_head_stride, kv_tok_stride,
                         kv_head_stride, o_row_stride, o_head_stride);
@@ -403,6 +469,12 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
   p.po = w.po; p.plse = w.plse; p.po16 = w.po16; p.plse16 = w.plse16;
   if (umma) setup_tma(p, kv_pool_tokens);
   p.pdl = g_no_pdl ? 0 : 1;
+  if (append) {
+    DEFT_CHECK_ARG(umma && plan && plan->u_blk && plan->fresh, "append: needs the tensor-core path and a host-built plan (tables built with fresh_page)");
+    rc = setup_append(p, append);
+    if (rc) return rc;
+  }
+  DEFT_CHECK_ARG(!(plan && plan->fresh && !append), "this plan reads the step's tokens from the activations: call the *_append form");
   if (plan) {
     rc = use_plan(p, plan, umma);
     if (rc) return rc;

@@ -279,32 +279,39 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           if (lane == 0) mbar_expect_tx(full, 64 * D * 2);
           if (mine) {
             const uint32_t dst = base + (kv == 0 ? L::kK : L::kV) + st * L::kOperandBytes + (w * 64 + c * 8) * 128;
-            const int kind = desc >> 28, page = desc & 0x0fffffff;
+            // bit 27: the chunk holds tokens of THIS step -- rows of the step's new K / V (fused append), "page" = query id
+            const int kind = (desc >> 28) & 3, page = desc & 0x07ffffff;
+            const bool fresh = (desc >> 27) & 1;
             if (kind == 3) {
               if ((c & 3) == 0 && li < NP) {
-                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m32, full, li * 64, hkv, page, 0x3);
-                else tma_load_3d(dst + li * kPanelBytes, m32, full, li * 64, hkv, page);
+                const CUtensorMap* m = fresh ? (kv == 0 ? &p.tmap_nk : &p.tmap_nv) : m32;
+                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m, full, li * 64, hkv, page, 0x3);
+                else tma_load_3d(dst + li * kPanelBytes, m, full, li * 64, hkv, page);
               }
             } else if (kind == 2) {
               if ((c & 1) == 0 && li < NP) {
-                const CUtensorMap* m16 = kv == 0 ? &p.tmap_k16 : &p.tmap_v16;
-                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m16, full, li * 64, hkv, page, 0x3);
-                else tma_load_3d(dst + li * kPanelBytes, m16, full, li * 64, hkv, page);
+                const CUtensorMap* m = fresh ? (kv == 0 ? &p.tmap_nk16 : &p.tmap_nv16) : (kv == 0 ? &p.tmap_k16 : &p.tmap_v16);
+                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m, full, li * 64, hkv, page, 0x3);
+                else tma_load_3d(dst + li * kPanelBytes, m, full, li * 64, hkv, page);
               }
             } else if (kind == 1) {
               if (li < NP) {
-                const CUtensorMap* m8 = kv == 0 ? &p.tmap_k8 : &p.tmap_v8;
-                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m8, full, li * 64, hkv, page, 0x3);
-                else tma_load_3d(dst + li * kPanelBytes, m8, full, li * 64, hkv, page);
+                const CUtensorMap* m = fresh ? (kv == 0 ? &p.tmap_nk8 : &p.tmap_nv8) : (kv == 0 ? &p.tmap_k8 : &p.tmap_v8);
+                if (shared) tma_load_3d_mc(dst + li * kPanelBytes, m, full, li * 64, hkv, page, 0x3);
+                else tma_load_3d(dst + li * kPanelBytes, m, full, li * 64, hkv, page);
               }
             } else if (li < 2 * NP) {
+              // (the builder keeps this step's tokens in chunks of their own: four rows are all fresh -- or dummies -- or none)
               const int row = w * 64 + c * 8 + g4 * 4;   // my four rows of the tile
-              const int r0 = row + 0 < tlen && pg.x >= 0 ? pg.x * p.kv_row_ratio + hkv : p.kv_rows;
-              const int r1 = row + 1 < tlen && pg.y >= 0 ? pg.y * p.kv_row_ratio + hkv : p.kv_rows;
-              const int r2 = row + 2 < tlen && pg.z >= 0 ? pg.z * p.kv_row_ratio + hkv : p.kv_rows;
-              const int r3 = row + 3 < tlen && pg.w >= 0 ? pg.w * p.kv_row_ratio + hkv : p.kv_rows;
-              if (shared) tma_gather4_mc(dst + pn * kPanelBytes + g4 * 4 * 128, mg, full, pn * 64, r0, r1, r2, r3, 0x3);
-              else tma_gather4(dst + pn * kPanelBytes + g4 * 4 * 128, mg, full, pn * 64, r0, r1, r2, r3);
+              constexpr int kFresh = 1 << 30;
+              auto is_fresh = [](int v) { return v >= 0 && (v & kFresh) != 0; };   // (a dummy is -1: every bit set)
+              const bool fr = is_fresh(pg.x) || is_fresh(pg.y) || is_fresh(pg.z) || is_fresh(pg.w);
+              const int ratio = fr ? p.new_row_ratio : p.kv_row_ratio, oob = fr ? p.new_rows : p.kv_rows;
+              auto row_of = [&](int v, int i) { return row + i < tlen && v >= 0 ? (v & ~kFresh) * ratio + hkv : oob; };
+              const int r0 = row_of(pg.x, 0), r1 = row_of(pg.y, 1), r2 = row_of(pg.z, 2), r3 = row_of(pg.w, 3);
+              const CUtensorMap* m = fr ? (kv == 0 ? &p.tmap_nkg : &p.tmap_nvg) : mg;
+              if (shared) tma_gather4_mc(dst + pn * kPanelBytes + g4 * 4 * 128, m, full, pn * 64, r0, r1, r2, r3, 0x3);
+              else tma_gather4(dst + pn * kPanelBytes + g4 * 4 * 128, m, full, pn * 64, r0, r1, r2, r3);
             }
           }
           mbar_arrive(full);

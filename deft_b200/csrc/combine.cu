@@ -74,6 +74,21 @@ __global__ void __launch_bounds__(kThreads) stage2_tiles_kernel(const AttnParams
   griddep_launch_dependents();  // the next kernel of the stream may start its own prologue
   const int64_t w = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (w >= (int64_t)p.nq * p.HKV * CombineShape<D, G>::NCG) return;
+  if (p.new_k != nullptr) {
+    // Fused KV append (KVCacheUpdater.update, tree_cache.py:67-76): stage 1 has read this step's K / V rows straight
+    // from the activations; here they go to their pages for the steps to come.  Warp (query, kv-head, chunk group)
+    // copies its chunks of the row -- nothing of this call reads these pages, so no need to wait for anything.
+    using S = CombineShape<D, G>;
+    const int lane = threadIdx.x & 31;
+    const int cg = (int)(w % S::NCG), kvh = (int)((w / S::NCG) % p.HKV), q = (int)(w / ((int64_t)S::NCG * p.HKV));
+    const int c = cg * S::CPW + lane;
+    if (lane < S::CPW && c < S::CH) {
+      const int64_t src = (int64_t)q * p.new_row_stride + (int64_t)kvh * p.new_head_stride + c * 8;
+      const int64_t dst = (int64_t)p.cache_loc[q] * p.kv_tok_stride + (int64_t)kvh * p.kv_head_stride + c * 8;
+      *reinterpret_cast<uint4*>(const_cast<__half*>(p.k) + dst) = *reinterpret_cast<const uint4*>(p.new_k + src);
+      *reinterpret_cast<uint4*>(const_cast<__half*>(p.v) + dst) = *reinterpret_cast<const uint4*>(p.new_v + src);
+    }
+  }
   combine_tiles_item<D, G, true, kBatch>(p, w, threadIdx.x & 31);
 }
 

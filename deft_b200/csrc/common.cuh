@@ -56,6 +56,14 @@ struct AttnParams {
   //                    row of (page, kv-head) = page * kv_row_ratio + kv-head, rows >= kv_rows read as zeros
   CUtensorMap tmap_k, tmap_v, tmap_q, tmap_kg, tmap_vg;
   CUtensorMap tmap_k16, tmap_v16, tmap_k8, tmap_v8;  // tmap_k / tmap_v with boxes of 16 and 8 pages (aligned runs inside a block)
+  // fused KV append: the same six box maps and two gather maps over the step's new K / V rows ([nq][HKV][D] views of the
+  // fused qkv output; "page" = query id), valid when new_k != nullptr
+  CUtensorMap tmap_nk, tmap_nv, tmap_nk16, tmap_nv16, tmap_nk8, tmap_nv8, tmap_nkg, tmap_nvg;
+  const __half* new_k;
+  const __half* new_v;
+  int64_t new_row_stride, new_head_stride;
+  const int32_t* cache_loc;   // [nq] page of every query's new row (stage 2 writes the rows there)
+  int32_t new_row_ratio, new_rows;
   int32_t tma_kv, tma_q, tma_gather;
   int32_t kv_row_ratio, kv_rows;
   const __half* q;

@@ -66,7 +66,7 @@ std::vector<i64> offsets_of(const std::vector<i64>& lens) {  // cat([0], cumsum(
 struct deft_tables {
   std::vector<unsigned char> packed;
   i64 dir[2 * DEFT_T_COUNT];
-  i64 scalars[10];
+  i64 scalars[11];
 };
 
 // Capacities of the packed buffer's regions, kept from one build to the next (deft_b200_layout_new): a table that
@@ -79,6 +79,7 @@ struct deft_layout {
 };
 
 namespace {
+constexpr i32 kFreshToken = 1 << 30;   // u_kv entry of a token of THIS step: the bit + its query id (deft_plan_t.u_kv)
 // Storage kept from one call to the next (per thread): the tables of a decode step are a few hundred KB, and fresh
 // allocations of that size are handed back to the kernel at every free and page-faulted in again at the next build
 // (measured: a third of the build time).  Everything is cleared, nothing is read, at the start of a build.
@@ -87,6 +88,9 @@ struct Scratch {
   std::vector<i64> block_q, block_q_cnts, block_kv, block_masks, block_lens;
   std::vector<i32> u_kv, u_blk;             // native tiles: page id per token slot, load descriptor per chunk of 8 slots
   std::vector<i32> tok_page, tok_node;      // the trees' tokens in DFS order (page id, node)
+  std::vector<i32> nw_off, nw_slot;         // per node: the slots its queries sit in ...
+  std::vector<uint32_t> nw_word;            // ... and their rows in each
+  std::vector<i64> node_sig;
   std::vector<uint32_t> u_mask;
   std::vector<i64> kvs;
   deft_tables* spare = nullptr;   // a freed handle whose packed buffer is reused by the next build
@@ -105,7 +109,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
                                       const int64_t* tix_row, int64_t tix_max_ctx,
                                       int32_t query_num, int32_t block_len, int32_t max_q_len,
                                       int32_t max_block_len, int32_t node_split, int32_t hkv,
-                                      int32_t n_ctas, deft_layout_t* layout) {
+                                      int32_t n_ctas, deft_layout_t* layout, const int32_t* fresh_page) {
   if (n_nodes <= 0 || !parent || !kv_off || !kv || !q_off || !qs) {
     deft::set_error("build_tables: null or empty tree");
     return nullptr;
@@ -234,6 +238,12 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
 
   auto& kvs = S.kvs;
   std::vector<i64> q;
+  std::vector<std::pair<i32, i32>> fresh_sorted;   // (page, query) of this step's tokens (fused KV append)
+  if (fresh_page) {
+    for (i32 qv = 0; qv < query_num; ++qv)
+      if (fresh_page[qv] >= 0) fresh_sorted.emplace_back(fresh_page[qv], qv);
+    std::sort(fresh_sorted.begin(), fresh_sorted.end());
+  }
   for (i32 n = 0; n < n_nodes; ++n) {  // pre-order visit == the reference's recursive dfs (:725-791)
     const i64 k0 = kv_off[n], k1 = kv_off[n + 1], q0 = q_off[n], q1 = q_off[n + 1];
     if (k1 < k0 || q1 <= q0) {
@@ -270,7 +280,15 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
     }
     if (tix_row && !kv_sorted) std::sort(kvs.begin(), kvs.end());
-    for (i64 kvp : kvs) { tok_page.push_back((i32)kvp); tok_node.push_back(n); }   // the native tiler's token stream (DFS order)
+    for (i64 kvp : kvs) {   // the native tiler's token stream (DFS order); this step's tokens name their query instead of a page
+      i32 v = (i32)kvp;
+      if (fresh_page) {
+        auto it = std::lower_bound(fresh_sorted.begin(), fresh_sorted.end(), std::make_pair((i32)kvp, (i32)-1));
+        if (it != fresh_sorted.end() && it->first == (i32)kvp) v = kFreshToken | it->second;
+      }
+      tok_page.push_back(v);
+      tok_node.push_back(n);
+    }
     // flatten packing (:763-788)
     i64 room = block_len - (i64)seg_tokens.size();
     i64 done = 0;
@@ -297,6 +315,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   std::vector<i64> node_kv_offset = tix_row ? node_kv_offset_ti : offsets_of(node_kv_len);
   std::vector<i64> block_q_offset = offsets_of(block_q_cnts);
 
+  lap("dfs + reference tables");
   // ---- native plan, part 1b: the native tiles.
   // The reference cuts the DFS-ordered token stream of the whole table into blocks of 128 (block_kv above, bit for bit).
   // The native tiles are cut from the same tokens, tree by tree, with two freedoms the kernel's arithmetic allows (a
@@ -315,66 +334,75 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   //    tokens (page -1: a zero row nobody attends).  DEFT_PLAN_REGROUP=0: the rest keeps its DFS order.
   {
     const char* env_r = std::getenv("DEFT_PLAN_REGROUP");
-    const bool regroup = !(env_r && env_r[0] == '0');
-    // per node (lazily): the words of its attending ranks, slot by slot
-    std::vector<std::vector<std::pair<i32, uint32_t>>> node_words((size_t)n_nodes);
-    std::vector<char> node_done((size_t)n_nodes, 0);
-    const std::vector<std::pair<i32, uint32_t>> no_words;
-    auto words_of = [&](i32 n) -> const std::vector<std::pair<i32, uint32_t>>& {
-      if (n < 0) return no_words;
-      if (!node_done[(size_t)n]) {
-        auto& w = node_words[(size_t)n];
-        for (i64 i = q_off[n]; i < q_off[n + 1]; ++i) {
-          const i32 rk = rank_of[(size_t)qs[i]];
-          auto it = std::find_if(w.begin(), w.end(), [&](const std::pair<i32, uint32_t>& e) { return e.first == rk / 32; });
-          if (it == w.end()) w.emplace_back(rk / 32, 1u << (rk % 32));
-          else it->second |= 1u << (rk % 32);
-        }
-        std::sort(w.begin(), w.end());
-        node_done[(size_t)n] = 1;
+    const bool regroup = fresh_page != nullptr || !(env_r && env_r[0] == '0');   // (fresh tokens need chunks of their own)
+    // per node: the words of its attending ranks, slot by slot (CSR over the nodes), and the slots it touches as a key
+    auto& nw_off = S.nw_off; auto& nw_slot = S.nw_slot; auto& nw_word = S.nw_word; auto& node_sig = S.node_sig;
+    nw_off.assign((size_t)n_nodes + 1, 0);
+    nw_slot.clear();
+    nw_word.clear();
+    node_sig.assign((size_t)n_nodes, -1);
+    for (i32 n = 0; n < n_nodes; ++n) {
+      const size_t w0 = nw_slot.size();
+      for (i64 i = q_off[n]; i < q_off[n + 1]; ++i) {
+        const i32 rk = rank_of[(size_t)qs[i]];
+        size_t k = w0;
+        while (k < nw_slot.size() && nw_slot[k] != rk / 32) ++k;
+        if (k == nw_slot.size()) { nw_slot.push_back(rk / 32); nw_word.push_back(0u); }
+        nw_word[k] |= 1u << (rk % 32);
       }
-      return node_words[(size_t)n];
-    };
-    auto sig_of = [&](i32 n) -> i64 {
-      const auto& w = words_of(n);
-      return w.empty() ? -1 : ((i64)w.front().first << 32) | (i64)w.back().first;
-    };
+      for (size_t i = w0 + 1; i < nw_slot.size(); ++i)          // (a node touches one or two slots, rarely more: insertion sort)
+        for (size_t j = i; j > w0 && nw_slot[j] < nw_slot[j - 1]; --j) { std::swap(nw_slot[j], nw_slot[j - 1]); std::swap(nw_word[j], nw_word[j - 1]); }
+      nw_off[(size_t)n + 1] = (i32)nw_slot.size();
+      if (nw_slot.size() > w0) node_sig[(size_t)n] = ((i64)nw_slot[w0] << 32) | (i64)nw_slot.back();
+    }
+    auto sig_of = [&](i32 n) -> i64 { return n < 0 ? -1 : node_sig[(size_t)n]; };
     // one native tile from up to 128 (page, node) tokens; node < 0: a dummy token
     auto emit_tile = [&](const i32* pages, const i32* nodes, i32 n_live) {
-      Tile tl;
+      tiles.emplace_back();
+      Tile& tl = tiles.back();
       tl.n_live = n_live;
       const size_t k0 = u_kv.size();
       u_kv.resize(k0 + 128, 0);
       i32 last_node = -2;
       for (i32 i = 0; i < n_live; ++i) {
         u_kv[k0 + (size_t)i] = pages[i];
-        if (nodes[i] == last_node) continue;     // (tokens come node by node)
+        if (nodes[i] == last_node || nodes[i] < 0) continue;
         last_node = nodes[i];
-        for (const auto& e : words_of(nodes[i]))
-          if (std::find(tl.slots.begin(), tl.slots.end(), e.first) == tl.slots.end()) tl.slots.push_back(e.first);
+        for (i32 k = nw_off[(size_t)last_node]; k < nw_off[(size_t)last_node + 1]; ++k)
+          if (std::find(tl.slots.begin(), tl.slots.end(), nw_slot[(size_t)k]) == tl.slots.end()) tl.slots.push_back(nw_slot[(size_t)k]);
       }
       std::sort(tl.slots.begin(), tl.slots.end());
-      tl.masks.assign(tl.slots.size() * 128, 0u);
-      tl.rows_or.assign(tl.slots.size(), 0u);
-      tl.dense.assign(tl.slots.size(), n_live == 128 ? 1 : 0);
-      for (size_t si = 0; si < tl.slots.size(); ++si) {
+      const size_t ns = tl.slots.size();
+      tl.masks.assign(ns * 128, 0u);
+      tl.rows_or.assign(ns, 0u);
+      tl.dense.assign(ns, n_live == 128 ? 1 : 0);
+      uint32_t full[8], all_and[8];    // per touched slot (a tile touches a handful): the slot's live rows, AND over the tokens
+      std::vector<uint32_t> full_v, and_v;
+      uint32_t* fullp = full; uint32_t* andp = all_and;
+      if (ns > 8) { full_v.resize(ns); and_v.resize(ns); fullp = full_v.data(); andp = and_v.data(); }
+      for (size_t si = 0; si < ns; ++si) {
         const i32 cnt = std::min(32, query_num - 32 * tl.slots[si]);
-        const uint32_t full = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
-        i32 cached_node = -2;
-        uint32_t word = 0;
-        for (i32 i = 0; i < n_live; ++i) {
-          if (nodes[i] != cached_node) {
-            cached_node = nodes[i];
-            word = 0;
-            for (const auto& e : words_of(nodes[i]))
-              if (e.first == tl.slots[si]) word = e.second;
-          }
-          tl.masks[si * 128 + (size_t)i] = word;
-          tl.rows_or[si] |= word;
-          if ((word & full) != full) tl.dense[si] = 0;
-        }
+        fullp[si] = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+        andp[si] = 0xffffffffu;
       }
-      tiles.push_back(std::move(tl));
+      for (i32 i = 0; i < n_live;) {    // tokens of one node in a row share their words
+        i32 j = i + 1;
+        while (j < n_live && nodes[j] == nodes[i]) ++j;
+        size_t si = 0;
+        if (nodes[i] >= 0)
+          for (i32 k = nw_off[(size_t)nodes[i]]; k < nw_off[(size_t)nodes[i] + 1]; ++k) {
+            while (tl.slots[si] != nw_slot[(size_t)k]) { andp[si] = 0; ++si; }   // slots the node does not touch
+            const uint32_t word = nw_word[(size_t)k];
+            std::fill(tl.masks.begin() + (long)(si * 128 + (size_t)i), tl.masks.begin() + (long)(si * 128 + (size_t)j), word);
+            tl.rows_or[si] |= word;
+            andp[si] &= word;
+            ++si;
+          }
+        for (; si < ns; ++si) andp[si] = 0;
+        i = j;
+      }
+      for (size_t si = 0; si < ns; ++si)
+        if ((andp[si] & fullp[si]) != fullp[si]) tl.dense[si] = 0;
     };
     struct Tok { i32 page, node; i64 sig; };
     struct Chunk { i32 first, len; };       // `len` (a power of two) consecutive pages: tokens [first, first + len) of `rest`
@@ -391,10 +419,12 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       out_node.clear();
       for (size_t i = a; i < b;) {
         // a stretch of consecutive pages attended by one set of slots
-        const i64 sig = sig_of(tok_node[i]);
+        // (this step's tokens are not in the pool yet: they never join a run of pool pages, and get groups of their own)
+        const bool fresh = (tok_page[i] & kFreshToken) != 0;
+        const i64 sig = sig_of(tok_node[i]) | (fresh ? (i64)1 << 62 : 0);
         size_t j = i + 1;
-        while (j < b && tok_page[j] == tok_page[j - 1] + 1 && (tok_node[j] == tok_node[j - 1] || sig_of(tok_node[j]) == sig)) ++j;
-        const size_t whole = (j - i) / 128 * 128;
+        while (j < b && tok_page[j] == tok_page[j - 1] + 1 && (tok_node[j] == tok_node[j - 1] || sig_of(tok_node[j]) == (sig & ~((i64)1 << 62)))) ++j;
+        const size_t whole = fresh ? 0 : (j - i) / 128 * 128;
         for (size_t k = i; k < i + whole; k += 128) emit_tile(&tok_page[k], &tok_node[k], 128);   // RUN tiles
         for (size_t k = i + whole; k < j; ++k) rest.push_back({tok_page[k], tok_node[k], sig});
         i = j;
@@ -438,6 +468,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     }
   }
 
+  lap("native tiler");
   // per chunk of 8 token slots: how the kernel's producers load it (deft_plan_t.u_blk)
   auto& u_blk = S.u_blk;
   u_blk.assign(tiles.size() * 16, 0);
@@ -451,11 +482,12 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     for (size_t c = 0; c < 16; ++c) {
       const i32 kind = runs(c / 4 * 32, 32) ? 3 : runs(c / 2 * 16, 16) ? 2 : runs(c * 8, 8) ? 1 : 0;
       const i32 page = u_kv[t * 128 + c * 8];
-      if (page >= (1 << 28)) {
-        deft::set_error("build_tables: page id %d does not fit the 28 bits of a load descriptor", page);
+      const i32 fresh = page >= 0 && (page & kFreshToken) ? 1 : 0;
+      if (page >= 0 && (page & ~kFreshToken) >= (1 << 27)) {
+        deft::set_error("build_tables: page id %d does not fit the 27 bits of a load descriptor", page);
         return nullptr;
       }
-      u_blk[t * 16 + c] = (kind << 28) | (kind ? page : 0);
+      u_blk[t * 16 + c] = (kind << 28) | (fresh << 27) | (kind ? (page & ~kFreshToken) : 0);
     }
   }
 
@@ -755,7 +787,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         }
         {  // shortcut: all tiles full and on consecutive pages
           const size_t k0 = ta * 128, k1 = tb * 128;
-          bool runp = tiles[tb - 1].n_live == 128;
+          bool runp = tiles[tb - 1].n_live == 128 && u_kv[k0] >= 0 && !(u_kv[k0] & kFreshToken);
           for (size_t kk = k0 + 1; kk < k1 && runp; ++kk) runp = u_kv[kk] == u_kv[k0] + (i32)(kk - k0);
           u.page0 = runp ? u_kv[k0] : -1;
         }
@@ -932,6 +964,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   t->scalars[7] = u_job_off.empty() ? 0 : (i64)u_job_off.size() - 1;
   t->scalars[8] = plan_paired ? 1 : 0;
   t->scalars[9] = layout ? layout->slot_cap : n_unit_slots;
+  t->scalars[10] = fresh_page ? 1 : 0;
   return t;
 }
 

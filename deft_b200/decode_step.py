@@ -30,14 +30,17 @@ class DecodeStepGraph:
 
     def __init__(self, kv_pool, qkv: torch.Tensor, out: torch.Tensor, cache_loc: torch.Tensor, num_heads: int,
                  num_kv_heads: int, head_dim: int, mode: str = "flatten", chunk: int = 8,
-                 table_bytes: int = 8 << 20) -> None:
+                 table_bytes: int = 8 << 20, fused_append: bool = True) -> None:
         """``qkv``: [layers, nq, (H + 2 HKV) D] fp16 device buffer the fused projections land in; ``out``: [layers, nq,
         H, D]; ``cache_loc``: [nq] int32 device buffer with this step's page per query (all three keep their
-        addresses; their contents change every step).  ``mode``: flatten | node | node_chunk."""
+        addresses; their contents change every step).  ``mode``: flatten | node | node_chunk.  ``fused_append``: the
+        step's K/V rows are read by the attention straight from ``qkv`` and written to their pages by its second
+        kernel (``metadata(trees, cache_loc=...)`` marks them), instead of a ``kv_append`` launch per layer."""
         assert mode in ("flatten", "node", "node_chunk")
         self.kv_pool, self.qkv, self.out, self.loc = kv_pool, qkv, out, cache_loc
         self.H, self.HKV, self.D, self.mode = num_heads, num_kv_heads, head_dim, mode
         self.layers = qkv.shape[0]
+        self.fused_append = fused_append
         self.chunk = max(1, min(chunk, self.layers))
         self.n_chunks = (self.layers + self.chunk - 1) // self.chunk
         self.tables = torch.empty(table_bytes, dtype=torch.uint8, device=qkv.device)
@@ -47,16 +50,19 @@ class DecodeStepGraph:
         self.captures = 0
 
     # ---- tables -------------------------------------------------------------------------------
-    def metadata(self, trees) -> TreeMetadata:
+    def metadata(self, trees, cache_loc=None) -> TreeMetadata:
         """C++ builder + ONE async upload into the persistent table buffer (grown, and the graphs dropped, if the
-        tables outgrow it)."""
+        tables outgrow it).  ``cache_loc``: this step's page per query on the HOST (``TreeCache.alloc().cache_loc``, the
+        trees' one after the other) -- needed for the fused append; without it the step appends with ``kv_append``."""
         single = not isinstance(trees, (list, tuple))
+        fresh = cache_loc if self.fused_append else None
         if self.mode == "node_chunk":
             BLOCK_CONFIG["MAX_BLOCK_LEN"] = 128
         try:
             for _ in range(2):
-                m = (TreeMetadata.from_tree_cache(trees, device_buffer=self.tables, table_layout=self.table_layout) if single
-                     else TreeMetadata.from_forest(trees, device_buffer=self.tables, table_layout=self.table_layout))
+                m = (TreeMetadata.from_tree_cache(trees, device_buffer=self.tables, table_layout=self.table_layout, fresh_page=fresh)
+                     if single else
+                     TreeMetadata.from_forest(trees, device_buffer=self.tables, table_layout=self.table_layout, fresh_page=fresh))
                 if m.packed.data_ptr() == self.tables.data_ptr():
                     return m
                 self.tables = torch.empty(2 * m.packed.numel(), dtype=torch.uint8, device=self.qkv.device)
@@ -88,17 +94,19 @@ class DecodeStepGraph:
         H, HKV, D = self.H, self.HKV, self.D
         nq = self.qkv.shape[1]
         row = self.qkv[l]
-        attention.kv_append(self.kv_pool.kv_data[l], row[:, H * D: (H + HKV) * D].view(nq, HKV, D),
-                            row[:, (H + HKV) * D:].view(nq, HKV, D), self.loc)
+        k_new, v_new = row[:, H * D: (H + HKV) * D].view(nq, HKV, D), row[:, (H + HKV) * D:].view(nq, HKV, D)
+        append = (k_new, v_new, self.loc) if self._plan(m).fresh else None
+        if append is None:
+            attention.kv_append(self.kv_pool.kv_data[l], k_new, v_new, self.loc)
         q = row[:, : H * D].view(nq, H, D)
         K, V = self.kv_pool.get_key_buffer(l), self.kv_pool.get_value_buffer(l)
         if self.mode == "flatten":
             attention.tree_attention_subtree_fwd(q, K, V, self.out[l], m.block_len, m.block_q, m.block_q_cnts,
                                                  m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens,
-                                                 workspace=self.workspace)
+                                                 workspace=self.workspace, append=append)
         else:
             attention.tree_attention_fwd(q, K, V, self.out[l], m.node_kv, m.node_kv_offset, m.node_kv_len, m.node_q,
-                                         m.node_q_offset, m.node_q_len, workspace=self.workspace)
+                                         m.node_q_offset, m.node_q_len, workspace=self.workspace, append=append)
 
     def _capture(self, m: TreeMetadata) -> List[torch.cuda.CUDAGraph]:
         self._layer(0, m)                     # eager once: tensor maps, launch attributes and errors outside the capture

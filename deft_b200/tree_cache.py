@@ -174,13 +174,20 @@ class TreeCache:
 
     def alloc(self) -> KVCacheUpdater:
         """One new page per leaf, leaves in ascending id order (tree_cache.py:261-283)."""
-        leaves = sorted(self.leaves.values(), key=lambda x: x.id)
+        leaves = [self.leaves[i] for i in sorted(self.leaves)]
         out_cache_loc = self.token_to_kv_pool.alloc(len(leaves))
         assert out_cache_loc is not None
-        table = self.req_to_token_pool.req_to_token
-        for leaf, loc in zip(leaves, out_cache_loc.tolist()):
-            leaf.append_index(loc)
-            table[self.leaf_to_req[leaf.id], leaf.positions[-1]] = loc
+        locs = out_cache_loc.tolist()
+        if self.use_tree_index:
+            for leaf, loc in zip(leaves, locs):
+                leaf.append_index(loc)
+        else:
+            for leaf, loc in zip(leaves, locs):
+                leaf.kv_indices.append(loc)
+        # the page table of the sequence-based baseline, in one indexed store (the host tensor and the array share memory)
+        table = self.req_to_token_pool.req_to_token.numpy()
+        l2r = self.leaf_to_req
+        table[[l2r[leaf.id] for leaf in leaves], [leaf.positions[-1] for leaf in leaves]] = locs
         return KVCacheUpdater(self.token_to_kv_pool, out_cache_loc, is_prompt=False)
 
     # ---- mutation -------------------------------------------------------------------------
@@ -488,7 +495,8 @@ class TableLayout:
 
 def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: int = -1,
                       block_len: int = 128, tree_index_max_ctx: int = 0, node_split: int = NODE_SPLIT,
-                      hkv: int = 0, n_ctas: int = 148, reserve=None, layout: Optional[TableLayout] = None):
+                      hkv: int = 0, n_ctas: int = 148, reserve=None, layout: Optional[TableLayout] = None,
+                      fresh_page: Optional[np.ndarray] = None):
     """Runs the C++ builder; returns (packed bytes as numpy uint8, directory, scalars).
 
     ``reserve(nbytes) -> uint8 tensor`` (optional) supplies the destination -- the pinned staging buffer of the
@@ -496,11 +504,15 @@ def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: 
     ``(tensor, nbytes)`` instead of an array."""
     query_num = len(flat["leaf_to_q"])
     use_tix = tree_index_max_ctx > 0
+    if fresh_page is not None:
+        fresh_page = np.ascontiguousarray(fresh_page, dtype=np.int32)
+        assert fresh_page.shape == (query_num,), "fresh_page: one page per query"
     h = _lib.lib.deft_b200_build_tables(len(flat["parent"]), flat["parent"].ctypes.data, flat["kv_off"].ctypes.data,
                                         flat["kv"].ctypes.data, flat["q_off"].ctypes.data, flat["qs"].ctypes.data,
                                         flat["tix"].ctypes.data if use_tix else None,
                                         tree_index_max_ctx, query_num, block_len, max_q_len, max_block_len, node_split,
-                                        hkv, n_ctas, layout.handle if layout is not None else None)
+                                        hkv, n_ctas, layout.handle if layout is not None else None,
+                                        fresh_page.ctypes.data if fresh_page is not None else None)
     if not h:
         raise _lib.DeftError(f"deft_b200_build_tables failed: {_lib.last_error()}")
     try:
@@ -549,8 +561,11 @@ class TreeMetadata:
 
     @classmethod
     def _assemble(cls, tree, flat, max_q_len: int, max_block_len: int, tree_index: bool,
-                  device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None) -> "TreeMetadata":
+                  device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None,
+                  fresh_page=None) -> "TreeMetadata":
         block_len = BLOCK_CONFIG["BLOCK_LEN"]
+        if fresh_page is not None:
+            fresh_page = (fresh_page.detach().cpu().numpy() if isinstance(fresh_page, torch.Tensor) else np.asarray(fresh_page)).astype(np.int32)
         if max_block_len == -1:
             max_block_len = BLOCK_CONFIG["MAX_BLOCK_LEN"]
         max_ctx = tree.tree_index_pool.node_to_kv.shape[1] if tree_index else 0
@@ -560,7 +575,8 @@ class TreeMetadata:
         on_gpu = device.type == "cuda"
         data, directory, scalars = build_tables_host(flat, max_q_len, max_block_len, block_len, max_ctx,
                                                      hkv=hkv, n_ctas=sm_count(device),
-                                                     reserve=_STAGING.reserve if on_gpu else None, layout=table_layout)
+                                                     reserve=_STAGING.reserve if on_gpu else None, layout=table_layout,
+                                                     fresh_page=fresh_page)
         if on_gpu:
             buf, nbytes = data
             if device_buffer is not None and device_buffer.numel() < nbytes:
@@ -588,7 +604,8 @@ class TreeMetadata:
                              n_part_rows=rows, n_units=directory[U][1],
                              units=addr(U), u_csr_off=addr(U + 1), u_csr_rows=addr(U + 2), u_kv=addr(U + 3), u_blk=addr(U + 8),
                              u_mask=addr(U + 4), u_q=addr(U + 5), u_job_off=addr(U + 6), u_jobs=addr(U + 7),
-                             n_unit_slots=int(scalars[9]), n_ctas=int(scalars[7]), hkv=hkv, paired=int(scalars[8]))
+                             n_unit_slots=int(scalars[9]), n_ctas=int(scalars[7]), hkv=hkv, paired=int(scalars[8]),
+                             fresh=int(scalars[10]))
 
         if tree_index:
             null = torch.empty(0, dtype=torch.int64, device=device)
@@ -600,7 +617,7 @@ class TreeMetadata:
         # (grid, cluster pairing, workspace carving).  With a TableLayout the offsets are capacity-padded, and a step
         # that only appended pages keeps this key although every count has moved.
         if table_layout is not None:
-            key = np.asarray([d[0] for d in directory] + [int(scalars[0]), int(scalars[7]), int(scalars[8]), int(scalars[9]),
+            key = np.asarray([d[0] for d in directory] + [int(scalars[0]), int(scalars[7]), int(scalars[8]), int(scalars[9]), int(scalars[10]),
                                                           table_layout.version, base], dtype=np.int64).tobytes()
         else:
             key = dir_bytes + scalars.tobytes() + int(base).to_bytes(8, "little")
@@ -614,23 +631,27 @@ class TreeMetadata:
 
     @classmethod
     def from_tree_cache(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1,
-                        device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None) -> "TreeMetadata":
+                        device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None,
+                        fresh_page=None) -> "TreeMetadata":
         """Reference signature (tree_cache.py:618-625) + ``device_buffer``: an optional persistent uint8 CUDA tensor
         the packed tables are uploaded into, so that consecutive decode steps find them at the same addresses
-        (what a captured CUDA graph of the step needs, see ``decode_step.DecodeStepGraph``)."""
+        (what a captured CUDA graph of the step needs, see ``decode_step.DecodeStepGraph``); ``table_layout``:
+        capacity-padded packing; ``fresh_page``: this step's page per query (``TreeCache.alloc().cache_loc``) -- the
+        native plan then reads those tokens from the step's activations (fused KV append: ``attention.Append``)."""
         return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=False, device_buffer=device_buffer,
-                             table_layout=table_layout)
+                             table_layout=table_layout, fresh_page=fresh_page)
 
     @classmethod
     def from_forest(cls, trees, max_q_len: int = 32, max_block_len: int = -1,
-                    device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None) -> "TreeMetadata":
+                    device_buffer: Optional[torch.Tensor] = None, table_layout: Optional[TableLayout] = None,
+                    fresh_page=None) -> "TreeMetadata":
         """One metadata object (tables + native plan) for several trees sharing one KV pool: the operators
         then attend the whole batch in one launch.  ``leaf_to_q`` is keyed by ``(tree index, leaf id)``."""
         trees = list(trees)
         assert trees and all(t.token_to_kv_pool is trees[0].token_to_kv_pool for t in trees), \
             "the trees of a forest share one TokenToKVPool"
         return cls._assemble(trees[0], flatten_forest(trees), max_q_len, max_block_len, tree_index=False,
-                             device_buffer=device_buffer, table_layout=table_layout)
+                             device_buffer=device_buffer, table_layout=table_layout, fresh_page=fresh_page)
 
     @classmethod
     def from_tree_cache_node(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":

@@ -152,10 +152,13 @@ typedef struct {
   const deft_unit_t* units;
   const int32_t* u_csr_off;   /* nq+1 */
   const int32_t* u_csr_rows;
-  const int32_t* u_kv;        /* page id per token slot, tiles of 128; -1 = dummy token (a zero row nobody attends) */
+  const int32_t* u_kv;        /* page id per token slot, tiles of 128; -1 = dummy token (a zero row nobody attends);
+                                 bit 30 set: a token of THIS decode step, the low bits are its query id (its K/V row is
+                                 read from the step's activations, see deft_append_t) */
   const int32_t* u_blk;       /* per chunk of 8 token slots (16 per tile): how the chunk is loaded, (kind << 28) | first page.
                                  kind 3 / 2 / 1: the chunk lies in an aligned run of 32 / 16 / 8 consecutive pages (one TMA
-                                 box per panel for the whole run), 0: gathered four rows at a time.  May be NULL. */
+                                 box per panel for the whole run), 0: gathered four rows at a time; bit 27: the chunk holds
+                                 tokens of this step (rows of the activations, "page" = first query id).  May be NULL. */
   const uint32_t* u_mask;     /* 128 words per (tile, slot): bit r = row r of the slot attends */
   const int32_t* u_q;         /* query id per (slot, row) */
   const int32_t* u_job_off;   /* n_ctas+1: CTA c has u_job_off[c+1] - u_job_off[c] jobs (u_jobs carries the lists) */
@@ -164,6 +167,8 @@ typedef struct {
   int32_t n_ctas;             /* CTAs the job lists were balanced for */
   int32_t hkv;                /* kv-head count the job lists were built for */
   int32_t paired;             /* 1: pair-aligned job lists (deft_job_t.shared): the kernel is launched as clusters of 2 */
+  int32_t fresh;              /* 1: the tables were built with fresh_page: the plan can only run through the *_append forms */
+  int32_t pad;
 } deft_plan_t;
 
 /* ------------------------------------------------------------------------------------------
@@ -219,6 +224,44 @@ int deft_b200_node_fwd(const void* q, int64_t q_row_stride, int64_t q_head_strid
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused KV append.  Inside a decode step the reference first scatters the step's K/V rows into the pool
+ * (KVCacheUpdater.update, tree_decoding/tree_cache.py:67-76, called from deft_attention.py:121) and then attends over the
+ * pool.  The *_append forms below do both in the attention's own two launches: wherever the plan marks a token as this
+ * step's (tables built with `fresh_page`, see deft_b200_build_tables) stage 1 reads its K/V row straight from the
+ * activations, and stage 2 writes the rows to their pages cache_loc[i] for the steps to come.  Pool contents after
+ * the call are those of the reference's two index_puts.  Needs a host-built plan and the tensor-core path.
+ *   new_k / new_v [nq, HKV, D] fp16 views of the fused qkv output (strides in elements), cache_loc [nq] int32 [dev]
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* new_k;
+  const void* new_v;
+  int64_t new_row_stride;
+  int64_t new_head_stride;
+  const int32_t* cache_loc;
+} deft_append_t;
+
+int deft_b200_flatten_fwd_append(const void* q, int64_t q_row_stride, int64_t q_head_stride,
+                                 const void* k, const void* v, int64_t kv_tok_stride,
+                                 int64_t kv_head_stride, int64_t kv_pool_tokens, void* o, int64_t o_row_stride,
+                                 int64_t o_head_stride, int32_t nq, int32_t H, int32_t HKV, int32_t D,
+                                 int32_t block_len, const int64_t* block_q, int64_t n_partials,
+                                 const int64_t* block_q_cnts, const int64_t* block_q_offset,
+                                 const int64_t* block_lens, int64_t n_blocks,
+                                 const int64_t* block_bitmasks, const int64_t* block_kv,
+                                 const deft_plan_t* plan, const deft_append_t* append, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
+int deft_b200_node_fwd_append(const void* q, int64_t q_row_stride, int64_t q_head_stride, const void* k,
+                              const void* v, int64_t kv_tok_stride, int64_t kv_head_stride,
+                              int64_t kv_pool_tokens, void* o,
+                              int64_t o_row_stride, int64_t o_head_stride, int32_t nq, int32_t H,
+                              int32_t HKV, int32_t D, const void* kv_indices, int32_t kv_index_bytes,
+                              const int64_t* kv_offset, const int64_t* kv_len, const int64_t* node_q,
+                              int64_t n_partials, const int64_t* q_offset, const int64_t* q_len,
+                              int64_t n_entries, int64_t total_kv_bound, const deft_plan_t* plan,
+                              const deft_append_t* append, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * KV append.  Replaces KVCacheUpdater.update (tree_decoding/tree_cache.py:67-76):
  *   key_buffer[cache_loc] = cache_k; value_buffer[cache_loc] = cache_v   in ONE launch.
  *   new_k/new_v [n, HKV, D] fp16 (row stride in elements), cache_loc [n] int32.
@@ -244,6 +287,8 @@ int deft_b200_kv_append(void* k, void* v, int64_t kv_tok_stride, int64_t kv_head
  *   tix_row[n]       tree-index mode only: node.node_indices_id, else NULL
  * hkv / n_ctas: kv-head count and CTA count (SMs) the native unit plan is balanced for: the
  * builder cuts long KV chains into pieces and assigns (unit, kv-head) jobs to CTAs (longest first).
+ * fresh_page [query_num] or NULL: the page this decode step appends for every query (TreeCache.alloc's cache_loc,
+ *   -1: none).  The native plan then reads those tokens from the step's activations (deft_b200_*_fwd_append).
  * The result is one packed host buffer (upload with a single copy) + a directory.
  * ------------------------------------------------------------------------------------------ */
 enum {
@@ -274,15 +319,16 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
                                       const int64_t* tix_row, int64_t tix_max_ctx,
                                       int32_t query_num, int32_t block_len, int32_t max_q_len,
                                       int32_t max_block_len, int32_t node_split, int32_t hkv,
-                                      int32_t n_ctas, deft_layout_t* layout);
+                                      int32_t n_ctas, deft_layout_t* layout, const int32_t* fresh_page);
 const void* deft_b200_tables_data(const deft_tables_t* t);  /* packed host buffer */
 size_t deft_b200_tables_bytes(const deft_tables_t* t);
 /* dir[2*i] = byte offset of array i in the packed buffer, dir[2*i+1] = element count */
 int deft_b200_tables_directory(const deft_tables_t* t, int64_t* dir /* [2*DEFT_T_COUNT] */);
 /* scalars: {query_num, node_num, total_kv_len, block_len, flat_part_rows, node_part_rows,
  *           n_unit_slots, n_ctas, paired (1: the job lists are pair-aligned, see deft_job_t.shared),
- *           unit-slot capacity (= n_unit_slots without a layout handle: what the workspace is carved for)} */
-int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [10] */);
+ *           unit-slot capacity (= n_unit_slots without a layout handle: what the workspace is carved for),
+ *           fresh (1: built with fresh_page)} */
+int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out /* [11] */);
 void deft_b200_tables_free(deft_tables_t* t);
 
 #ifdef __cplusplus

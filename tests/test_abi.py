@@ -27,7 +27,8 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_abi_version_and_struct_layout():
     assert _lib.lib.deft_b200_abi_version() == _lib.ABI_VERSION
-    assert C.sizeof(_lib.Plan) == 136      # deft_plan_t: item/group layer (48 bytes) + unit layer (9 pointers + 4 ints)
+    assert C.sizeof(_lib.Plan) == 144      # deft_plan_t: item/group layer (48 bytes) + unit layer (9 pointers + 6 ints)
+    assert C.sizeof(_lib.Append) == 40
 
 
 def test_argument_errors_are_reported_not_crashed():
@@ -39,7 +40,7 @@ def test_argument_errors_are_reported_not_crashed():
         _lib.check(rc)
     rc = _lib.lib.deft_b200_kv_append(None, None, 0, 0, None, None, 0, 0, None, 1, 8, 128, None)
     assert rc == -1
-    assert _lib.lib.deft_b200_build_tables(0, None, None, None, None, None, None, 0, 1, 128, 32, -1, 256, 8, 148, None) is None
+    assert _lib.lib.deft_b200_build_tables(0, None, None, None, None, None, None, 0, 1, 128, 32, -1, 256, 8, 148, None, None) is None
     assert "tree" in _lib.last_error()
 
 

@@ -339,3 +339,38 @@ def test_capacity_padded_layout_keeps_offsets_while_the_tree_grows():
         versions.append(lay.version)
     assert len(set(offsets)) <= 5, "48 decode steps (the subtree's KV grows 2.5x): a handful of layouts"
     assert len(set(versions)) == len(set(offsets))
+
+
+@pytest.mark.parametrize("name", ["toy_binary", "wide40", "ragged_cut", "llama_flat8"])
+def test_fresh_tokens_of_a_decode_step_are_marked_for_the_fused_append(golden_dir, name):
+    """Tables built with ``fresh_page`` (the pages TreeCache.alloc just handed out): in the native tables those tokens
+    name their QUERY (bit 30 + query id: the kernel reads the row from the step's activations), they sit in chunks of
+    their own (a gather4 instruction takes four rows of ONE tensor), the load descriptors say so (bit 27), and with
+    the pages put back the plan covers the tree exactly as the plain build does.  The reference tables do not change."""
+    z, tree = load(golden_dir, name)
+    leaves = sorted(tree.leaves.values(), key=lambda x: x.id)
+    fresh = np.asarray([leaf.kv_indices[-1] for leaf in leaves], dtype=np.int32)      # the last page of every leaf
+    flat = flatten_tree(tree)
+    plain, dir0, sc0 = build_tables_host(flat, hkv=2, n_ctas=148)
+    data, directory, scalars = build_tables_host(flat, hkv=2, n_ctas=148, fresh_page=fresh)
+    t0, t = unpack(plain, dir0), unpack(data, directory)
+    assert int(scalars[10]) == 1 and int(sc0[10]) == 0
+    for k in TABLE_KEYS:
+        assert np.array_equal(t[k], t0[k]), k
+    FRESH = 1 << 30
+    u_kv = t["u_kv"].copy()
+    is_fresh = (u_kv >= 0) & ((u_kv & FRESH) != 0)
+    assert sorted((u_kv[is_fresh] & ~FRESH).tolist()) == list(range(len(leaves))), "every query's new token exactly once"
+    for c4 in np.flatnonzero(is_fresh.reshape(-1, 4).any(axis=1)):       # gather granularity: all fresh, or dummies
+        four = u_kv[4 * c4: 4 * c4 + 4]
+        assert np.all(((four & FRESH) != 0) | (four < 0)), four
+    blk = t["u_blk"]
+    for c8 in range(len(blk)):
+        eight = u_kv[8 * c8: 8 * c8 + 8]
+        kind, fr, first = (int(blk[c8]) >> 28) & 3, (int(blk[c8]) >> 27) & 1, int(blk[c8]) & ((1 << 27) - 1)
+        if kind:
+            assert fr == int((eight[0] & FRESH) != 0) and first == int(eight[0]) & ~FRESH
+            assert np.array_equal(eight, eight[0] + np.arange(8)), "a box chunk is a run"
+    decoded = u_kv.copy()
+    decoded[is_fresh] = fresh[u_kv[is_fresh] & ~FRESH]
+    check_unit_plan({**t, "u_kv": decoded}, scalars, tree, 2, 148)
