@@ -9,7 +9,7 @@ from deft_b200.workloads import build_tree
 
 dev = torch.device("cuda:0")
 L, H, HKV, D, CH = 32, 32, 8, 128, int(os.environ.get("CH", "8"))
-tree = build_tree("cfg2", layers=L, device=dev)
+tree = build_tree("cfg2", layers=L, device=dev, headroom=64 * 64)
 kvp = tree.token_to_kv_pool
 for l in range(L):
     kvp.kv_data[l].normal_()
@@ -43,7 +43,12 @@ def one(record):
                 ev_in[c].record(s_in)
     upload(range(1) if not os.environ.get("ALL_FIRST") else range(NC))
     stamps["h2d_enqueued"] = time.perf_counter() - t0
-    m = step.metadata(tree)
+    if not os.environ.get("STATIC"):        # a real decode step: a token and a page per leaf first (tree_generate.py:109)
+        for leaf in tree.leaves.values():
+            leaf.append_token(7)
+        host_loc.copy_(tree.alloc().cache_loc)
+        stamps["alloc_done"] = time.perf_counter() - t0
+    m = step.metadata(tree, cache_loc=None if os.environ.get("STATIC") else host_loc)
     stamps["metadata_done"] = time.perf_counter() - t0
     g["tables_up"].record(main)
     loc_dev.copy_(host_loc, non_blocking=True)
