@@ -335,9 +335,9 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
     n_host = n_chunks if nq <= 256 else 1                     # distinct pinned chunks (forests cycle ONE: the bytes copied are the same)
     host_qkv = torch.randn(n_host * CH, nq, (H + 2 * HKV) * D, dtype=torch.float16).pin_memory()
     host_out = torch.empty(n_host * CH, nq, H, D, dtype=torch.float16).pin_memory()
-    dev_qkv = torch.empty(LAYERS if n_act == LAYERS else 2 * CH, nq, (H + 2 * HKV) * D, dtype=torch.float16, device=dev)
-    dev_out = out if n_act == LAYERS else torch.empty(2 * CH, nq, H, D, dtype=torch.float16, device=dev)
-    n_dev = dev_qkv.shape[0] // CH                             # device chunk buffers (a ring of 2 for big forests)
+    dev_qkv = torch.empty(LAYERS if n_act == LAYERS else 4 * CH, nq, (H + 2 * HKV) * D, dtype=torch.float16, device=dev)
+    dev_out = out if n_act == LAYERS else torch.empty(4 * CH, nq, H, D, dtype=torch.float16, device=dev)
+    n_dev = dev_qkv.shape[0] // CH                             # device chunk buffers (a ring of 4 for big forests)
     leaves = [leaf for t in trees for leaf in sorted(t.leaves.values(), key=lambda x: x.id)]
     host_loc = torch.tensor([leaf.kv_indices[-1] for leaf in leaves], dtype=torch.int32).pin_memory()
     table_bytes = [0]
