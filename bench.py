@@ -476,8 +476,10 @@ def main():
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     # every rank builds tables and drives copies from Python: keep the ranks off each other's cores
+    all_cores = None
     try:
         cores = sorted(os.sched_getaffinity(0))
+        all_cores = set(cores)
         if world > 1 and len(cores) >= 2 * world:
             per = len(cores) // world
             os.sched_setaffinity(0, set(cores[local_rank * per: (local_rank + 1) * per]))
@@ -490,6 +492,8 @@ def main():
         deft_b200._lib.lib.deft_b200_set_experiment(int(os.environ["DEFT_EXPERIMENT"]))
     if os.environ.get("DEFT_PDL"):
         deft_b200._lib.lib.deft_b200_set_pdl(int(os.environ["DEFT_PDL"]))
+    if os.environ.get("DEFT_STAGE1_IMPL"):           # 1 = warp-FMA kernel, 2 = tensor-core kernel (A/B runs)
+        deft_b200._lib.lib.deft_b200_set_stage1_impl(int(os.environ["DEFT_STAGE1_IMPL"]))
     ws = _scripts()
 
     warm = max(args.warmup, 3)
@@ -557,7 +561,7 @@ def main():
     }
     if cfg5 is not None:
         line["cfg5"] = cfg5
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # (the CPU baseline is a rank-0, N = 1 number: it wants every host core)
         line["cpu_baseline"] = cpu_baseline(args.workload)
     print(json.dumps(line), file=json_out, flush=True)
     if world > 1:

@@ -67,6 +67,7 @@ class TokenToKVPool:
         self.device = torch.device(device)
         self.mem_state = np.zeros(size, dtype=np.int16)
         self.alloc_ct = 0
+        self._low = 0          # no free page below this index (first-free search starts here instead of at page 0)
         # [size, key/value, head_num, head_dim] per layer -- the layout the kernels index
         self.kv_data = [torch.empty((size, 2, head_num, head_dim), dtype=dtype, device=self.device)
                         for _ in range(layer_num)]
@@ -78,9 +79,23 @@ class TokenToKVPool:
         return self.kv_data[layer_id][:, 1]
 
     def alloc(self, need_size: int) -> Optional[torch.Tensor]:
-        sel = np.flatnonzero(self.mem_state == 0)[:need_size]
-        if len(sel) < need_size:
+        """The first ``need_size`` free pages in ascending order (memory_pool.py:74-80), found window by window from
+        the lowest page that can be free -- the reference scans the whole pool with ``nonzero`` at every call."""
+        n, lo, found, got = len(self.mem_state), self._low, [], 0
+        win = max(4096, 4 * need_size)
+        first_free = None
+        while lo < n and got < need_size:
+            idx = np.flatnonzero(self.mem_state[lo: lo + win] == 0)
+            if len(idx):
+                if first_free is None:
+                    first_free = lo + int(idx[0])
+                found.append(idx[: need_size - got] + lo)
+                got += len(found[-1])
+            lo += win
+        self._low = first_free if first_free is not None else n
+        if got < need_size:
             return None
+        sel = found[0] if len(found) == 1 else np.concatenate(found)
         self.add_refs(sel)
         return torch.from_numpy(sel.astype(np.int32))
 
@@ -104,11 +119,14 @@ class TokenToKVPool:
         idx = _as_index(token_index)
         self.alloc_ct -= len(idx)
         self.mem_state[idx] -= 1           # once per distinct page, like the reference (memory_pool.py:96-98)
+        if len(idx):
+            self._low = min(self._low, int(idx.min()))
         return int(np.count_nonzero(self.mem_state[idx] == 0))
 
     def clear(self) -> None:
         self.mem_state[:] = 0
         self.alloc_ct = 0
+        self._low = 0
 
 
 class TreeIndexPool:
