@@ -14,6 +14,9 @@ echo "== bench"
 for W in cfg1 cfg3 cfg3b cfg4; do
   timeout 300 python bench.py --workload $W --steps 20 --no-cpu-baseline --no-cfg5 > $OUT/bench_$W.json 2>> $OUT/bench.err; cat $OUT/bench_$W.json
 done
+for W in cfg2 cfg4; do
+  DEFT_PLAN_REGROUP=0 timeout 300 python bench.py --workload $W --steps 20 --no-cpu-baseline --no-cfg5 --e2e-static > $OUT/bench_${W}_noregroup.json 2>> $OUT/bench.err; cat $OUT/bench_${W}_noregroup.json
+done
 DEFT_STAGE1_IMPL=1 timeout 300 python bench.py --workload cfg1 --steps 20 --no-cpu-baseline --no-cfg5 --e2e-static > $OUT/bench_cfg1_fma.json 2>> $OUT/bench.err; cat $OUT/bench_cfg1_fma.json
 for M in node node_chunk seq; do
   timeout 300 python bench.py --mode $M --steps 20 --no-cpu-baseline --no-cfg5 > $OUT/bench_$M.json 2>> $OUT/bench.err; cat $OUT/bench_$M.json
