@@ -587,6 +587,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     // + epilogue.
     const char* env_g = std::getenv("DEFT_PLAN_GATHER_COST");
     const double gather_cost = env_g ? std::atof(env_g) : 2.2;
+    const char* env_m = std::getenv("DEFT_PLAN_MASK_COST");
+    const double mask_cost = env_m ? std::atof(env_m) : 0.5;
     std::vector<double> tile_cost(tiles.size());
     for (size_t t = 0; t < tiles.size(); ++t) {
       // what a tile costs the copy engine goes with its TMA instructions per panel: one box per aligned run of 32 / 16 / 8
@@ -597,7 +599,10 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         const double instr = kind == 3 ? 0.25 : kind == 2 ? 0.5 : kind == 1 ? 1.0 : 2.0;   // of this chunk
         scattered += (instr - 0.25) / (2.0 - 0.25) / 4.0;
       }
-      tile_cost[t] = 1.0 + (gather_cost - 1.0) * scattered / 4.0;
+      // ... and a tile some row of which does not attend every token costs the softmax warps a pass over the mask
+      bool masked = false;
+      for (uint8_t d : tiles[t].dense) masked = masked || d == 0;
+      tile_cost[t] = 1.0 + (masked ? mask_cost : 0.0) + (gather_cost - 1.0) * scattered / 4.0;
     }
     // (DEFT_PLAN_JOB_CONST / DEFT_PLAN_GATHER_COST: calibration overrides for A/B runs on one box)
     const char* env_c = std::getenv("DEFT_PLAN_JOB_CONST");
@@ -697,6 +702,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       uint64_t bj, bg;
       std::memcpy(&bj, &kJobConst, 8);
       std::memcpy(&bg, &gather_cost, 8);
+      bg ^= (uint64_t)(mask_cost * 1024.0);
       key = {hsh, (uint64_t)chains.size(), (uint64_t)tiles.size(), (uint64_t)n_slots, (uint64_t)query_num,
              (uint64_t)heads, (uint64_t)ctas, bj, bg};
     }
