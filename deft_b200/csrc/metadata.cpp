@@ -282,7 +282,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     if (tix_row && !kv_sorted) std::sort(kvs.begin(), kvs.end());
     for (i64 kvp : kvs) {   // the native tiler's token stream (DFS order); this step's tokens name their query instead of a page
       i32 v = (i32)kvp;
-      if (fresh_page) {
+      if (fresh_page && !fresh_sorted.empty() && kvp >= fresh_sorted.front().first && kvp <= fresh_sorted.back().first) {
         auto it = std::lower_bound(fresh_sorted.begin(), fresh_sorted.end(), std::make_pair((i32)kvp, (i32)-1));
         if (it != fresh_sorted.end() && it->first == (i32)kvp) v = kFreshToken | it->second;
       }
