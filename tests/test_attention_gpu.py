@@ -482,4 +482,4 @@ def test_decode_step_graph_survives_the_tree_growing(dev, mode, fused):
             assert torch.allclose(got.float(), want.float(), atol=5e-4, rtol=5e-3), (mode, it)
         else:
             assert torch.equal(got, want), (mode, it)
-    assert step.captures <= 4, f"{step.captures} captures over {steps} appends"
+    assert step.captures <= 8, f"{step.captures} captures over {steps} appends (the subtree grows 40-fold)"
