@@ -202,8 +202,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
   const uint32_t crank = p.clustered ? cluster_ctarank() : 0u;
 
   // Programmatic dependent launch: everything up to here (barrier init, TMEM allocation, job list) overlapped
-  // the tail of the preceding kernel; q, the KV pool and the partial workspace may still be in its hands.
-  griddep_wait();
+  // the tail of the preceding kernel; q, the KV pool and the partial workspace may still be in its hands.  The K / V
+  // producers go further before they wait: their first job's record, load descriptors and page ids are plan data
+  // (nothing of this stream's recent past writes them), and reading them is two dependent trips to memory.
+  if (warp < kKvWarp0 && warp != kMaskWarp) griddep_wait();   // (the mask warp reads plan data only: it never waits)
   if (tid == 0) DEFT_TRACE(kTrStart);
   if (warp >= 8) {
   reg_dealloc<kProducerRegs>();  // warps 8-15: two whole warpgroups give registers away
@@ -229,6 +231,11 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
     const CUtensorMap* mg = kv == 0 ? &p.tmap_kg : &p.tmap_vg;
     const bool native = p.u_blk != nullptr && p.u_kv_bytes == 4 && p.tma_kv != 0 && p.tma_gather != 0;
     uint32_t cnt = 0;  // tiles produced
+    bool waited = false;
+    auto dep_wait = [&]() {   // the preceding kernel's memory, once, before the first byte of q / K / V moves
+      if (!waited) griddep_wait();
+      waited = true;
+    };
     if (warp == kKvWarp0 && lane == 0) DEFT_TRACE(kTrKRole);
     for (int ji = 0; ji < jobs.n; ++ji) {
       deft_unit_t u; int hkv, k; bool shared;
@@ -239,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
       const bool mine = !shared || (uint32_t)w == crank;
       if (known_run) {
         // ---- (a)
+        dep_wait();
         for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
           const int st = cnt % stages;
           mbar_wait<64>(bar(EMPTY + st), ((cnt / stages) & 1) ^ 1);
@@ -265,6 +273,10 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
         auto pages_of = [&](int t) { return t < u.n_tiles ? *reinterpret_cast<const int4*>(pgs + t * kTileN) : make_int4(-1, -1, -1, -1); };
         int d_next = desc_of(0), d_after = desc_of(1);
         int4 g_next = pages_of(0), g_after = pages_of(1);
+        if (!waited) {   // (the loads above are on their way while the preceding kernel drains; they have landed by the wait's end)
+          asm volatile("" ::"r"(d_next), "r"(g_next.x));
+          dep_wait();
+        }
         for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
           const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
           const int st = cnt % stages;
@@ -324,6 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) stage1_umma_kernel(const __grid_c
           return t < u.n_tiles && row < tlen ? (int)load_index(p.u_kv, p.u_kv_bytes, u.kv_off + (int64_t)t * u.kv_tile_stride + row) : -1;
         };
         int pg_next0 = page_of(0, w * 64 + lane), pg_next1 = page_of(0, w * 64 + 32 + lane);
+        dep_wait();
         for (int t = 0; t < u.n_tiles; ++t, ++cnt) {
           const int tlen = t == u.n_tiles - 1 ? u.last_len : kTileN;
           const int st = cnt % stages;
