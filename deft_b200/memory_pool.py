@@ -137,6 +137,9 @@ class TreeIndexPool:
         self.mem_state = np.ones(size, dtype=bool)
         self.can_use_mem_size = size
         self.node_to_kv = torch.zeros((size, max_context_len), dtype=torch.int32)
+        self._dev: Optional[torch.Tensor] = None      # device mirror of node_to_kv ...
+        self._dev_version = -1                        # ... as of this version of the host table
+        self.version = 0                              # bumped by whoever writes node_to_kv (TreeCache does)
 
     def alloc(self, need_size: int) -> Optional[torch.Tensor]:
         if need_size > self.can_use_mem_size:
@@ -158,5 +161,22 @@ class TreeIndexPool:
     def get_offset(self, node_id: int) -> int:
         return node_id * self.node_to_kv.shape[1]
 
+    def touch(self) -> None:
+        """The host table has been written (rows are written through ``TreeNode.node_indices`` views)."""
+        self.version += 1
+
     def device_table(self) -> torch.Tensor:
-        return self.node_to_kv.to(self.device, non_blocking=True)
+        """Persistent device mirror of ``node_to_kv`` (the reference keeps the table on the GPU); uploaded again only
+        after the host table changed, through pinned memory so that the copy is asynchronous."""
+        if self._dev is None or self._dev_version != self.version:
+            if self._dev is None:
+                self._dev = torch.empty(self.node_to_kv.shape, dtype=torch.int32, device=self.device)
+                self._pinned = torch.empty(self.node_to_kv.shape, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else None
+            if self._pinned is not None:
+                torch.cuda.current_stream(self.device).synchronize()      # (the previous upload has left the staging buffer)
+                self._pinned.copy_(self.node_to_kv)
+                self._dev.copy_(self._pinned, non_blocking=True)
+            else:
+                self._dev.copy_(self.node_to_kv)
+            self._dev_version = self.version
+        return self._dev

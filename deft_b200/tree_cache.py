@@ -82,6 +82,7 @@ class TreeNode:
         self._paused = False
         self.node_indices_id = node_indices_id
         self.node_indices = node_indices
+        self.index_pool = None                # set by TreeCache in tree-index mode: told when node_indices is written
         self.cumulative_logprob = 0.0
 
     def get_len(self) -> int:
@@ -97,6 +98,8 @@ class TreeNode:
         self.kv_indices.append(index)
         if self.node_indices is not None:
             self.node_indices[len(self.kv_indices) - 1] = index
+            if self.index_pool is not None:
+                self.index_pool.touch()
 
 
 class TreeCache:
@@ -143,6 +146,7 @@ class TreeCache:
         rid, row = self._take_index_row()
         self._topo_version += 1
         root = TreeNode(0, rid, row)
+        root.index_pool = self.tree_index_pool if self.use_tree_index else None
         root.token_ids = ids
         root.positions = list(range(n))
         self.root = root
@@ -159,12 +163,14 @@ class TreeCache:
         self.req_to_token_pool.req_to_token[req_id, :n] = cache_loc
         if row is not None:
             row[:n] = cache_loc
+            self.tree_index_pool.touch()
         return KVCacheUpdater(self.token_to_kv_pool, cache_loc, is_prompt=True)
 
     def new_node(self, parent: TreeNode) -> TreeNode:
         self._topo_version += 1
         rid, row = self._take_index_row()
         node = TreeNode(self.node_cnt, rid, row)
+        node.index_pool = self.tree_index_pool if self.use_tree_index else None
         self.node_cnt += 1
         node.parent = parent
         node.position_offset = parent.position_offset + len(parent.positions)
