@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--cfg5-trees", type=int, default=CFG5_TREES, help="trees of the cfg5 block over ALL ranks")
     ap.add_argument("--e2e-chunk", type=int, default=8, choices=[1, 2, 4, 8, 16, 32],
                     help="layers per H2D / graph / D2H chunk of the end-to-end leg")
+    ap.add_argument("--e2e-serial", action="store_true", help="end-to-end leg without the table build of step t+1 under step t")
     ap.add_argument("--e2e-static", action="store_true", help="end-to-end leg over a tree that does NOT grow (r1 behaviour)")
     ap.add_argument("--trees-per-gpu", type=int, default=1,
                     help="independent trees of the workload batched into ONE launch per layer")
@@ -244,7 +245,7 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
     from deft_b200.workloads import build_forest, n_leaves
 
     torch.manual_seed(1234 + rank)
-    grow_steps = 0 if args.e2e_static else 3 + e2e_steps + 1
+    grow_steps = 0 if args.e2e_static else 2 * (3 + e2e_steps) + 2      # pipelined + serial legs
     trees = build_forest(workload, T, layers=pools, device=dev, headroom=64 + n_leaves(workload) * grow_steps)
     kvp = trees[0].token_to_kv_pool
     for l in range(pools):
@@ -350,6 +351,7 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
     graphed = args.mode != "seq" and n_dev == n_chunks
     if graphed:      # the step's launches (per layer: kv_append + attention) as CUDA graphs, one per chunk of layers
         step = deft_b200.DecodeStepGraph(kv_view, dev_qkv, dev_out, loc_dev, H, HKV, D, mode=args.mode, chunk=CH)
+        pipe = deft_b200.DecodeStepPipeline(kv_view, dev_qkv, dev_out, H, HKV, D, mode=args.mode, chunk=CH)
 
     def grow():
         """One decode step of the reference loop on the host side: a token and a page per leaf (tree_generate.py:109)."""
@@ -420,12 +422,39 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
         main.wait_stream(s_out)                          # the step ends when the last output is on the host
         main.synchronize()                               # the caller reads the result on the host
 
-    ms_e2e = timed(step_e2e, e2e_steps, 3)
+    def prepare_next():
+        """Host side of the NEXT step (alloc + tables + their upload), enqueued behind the running step."""
+        if not args.e2e_static:
+            grow()
+        m = pipe.prepare(trees[0] if T == 1 else trees, cache_loc=host_loc, fused=not args.e2e_static)
+        table_bytes[0] = m.packed.numel()
+
+    def step_e2e_pipelined():
+        """The same step with the host work of step t+1 (a token and a page per leaf, C++ builder, table upload) done
+        while the layers of step t run: the tables depend on the tree, not on the tokens step t samples.  The step still
+        ends with its outputs on the host, and the next step's activations only go up after that."""
+        s_in.wait_stream(main)
+        s_in.wait_stream(s_out)
+        upload(range(1))
+        pipe.run(before_chunk=lambda c: main.wait_event(ev_in[c]),
+                 after_chunk=lambda c: (upload(range(1, n_chunks)) if c == 0 else None, download(c)))
+        prepare_next()                                   # under the GPU time of this step
+        main.wait_stream(s_out)
+        main.synchronize()                               # the caller reads the result on the host
+
+    ms_serial = None
+    if graphed and not args.e2e_serial:
+        ms_serial = timed(step_e2e, e2e_steps, 3)
+        prepare_next()
+        ms_e2e = timed(step_e2e_pipelined, e2e_steps, 3)
+    else:
+        ms_e2e = timed(step_e2e, e2e_steps, 3)
     h2d = LAYERS * nq * (H + 2 * HKV) * D * 2 + table_bytes[0] + host_loc.numel() * 4
     d2h = LAYERS * nq * H * D * 2
-    res = dict(ms_step=ms_step, ms_s1=ms_s1, ms_s2=ms_s2, ms_e2e=ms_e2e, h2d=h2d, d2h=d2h, nq=nq, clocks=clocks,
+    res = dict(ms_step=ms_step, ms_s1=ms_s1, ms_s2=ms_s2, ms_e2e=ms_e2e, ms_e2e_serial=ms_serial,
+               h2d=h2d, d2h=d2h, nq=nq, clocks=clocks,
                pool_mb=kvp.kv_data[0].numel() * 2 / 1e6, graphed=graphed,
-               captures=step.captures if graphed else None, e2e_chunks=n_chunks, e2e_steps=e2e_steps,
+               captures=(step.captures + pipe.captures) if graphed else None, e2e_chunks=n_chunks, e2e_steps=e2e_steps,
                kv_tokens_end=sum(len(n.kv_indices) for t in trees for n in t.nodes.values()))
     if args.mode == "node_chunk":
         BLOCK_CONFIG["MAX_BLOCK_LEN"] = -1
@@ -549,6 +578,12 @@ def main():
                         "GROWS: every step appends one token + one page per leaf (TreeCache.alloc) before the tables are rebuilt; "
                         "%d KV tokens per tree at the end of the run" % (r["kv_tokens_end"] // T),
                 "graph_captures": r["captures"],
+                "ms_per_step_serial": r["ms_e2e_serial"],
+                "pipelining": ("DecodeStepPipeline: alloc + table build + table upload of step t+1 run on the host while the layers of "
+                               "step t run (two table buffers; the tables depend on the tree, not on the tokens step t samples); every "
+                               "step still ends with its outputs on the host before the next step's activations go up; "
+                               "ms_per_step_serial = the same loop with the build in line") if r["ms_e2e_serial"] is not None else
+                              "none (table build in line)",
                 "path": ("TreeCache.alloc + DecodeStepGraph.metadata (TreeMetadata.from_tree_cache: C++ builder, capacity-padded tables, 1 "
                          "upload into the persistent table buffer; the first chunk of activations goes up under the build, the others "
                          "queue behind the tables) + pinned H2D of the fused qkv in %d-layer chunks on a copy stream + 32 x tree attention "

@@ -19,7 +19,7 @@ if "deft_b200.build" in getattr(_sys, "orig_argv", []):      # `python -m deft_b
 
 from . import _lib  # noqa: F401,E402  (raises ImportError when libdeft_b200.so is absent)
 from .attention import kv_append, token_attention_fwd, tree_attention_fwd, tree_attention_subtree_fwd  # noqa: F401
-from .decode_step import DecodeStepGraph  # noqa: F401,E402
+from .decode_step import DecodeStepGraph, DecodeStepPipeline  # noqa: F401,E402
 from .memory_pool import ReqToTokenPool, TokenToKVPool, TreeIndexPool  # noqa: F401
 from .tree_cache import (BLOCK_CONFIG, KVCacheUpdater, TreeCache, TreeMetadata, TreeNode,  # noqa: F401
                          get_global_tree_metadata, register_tree_metadata, unregister_tree_metadata)

@@ -143,3 +143,49 @@ class DecodeStepGraph:
             g.replay()
             if after_chunk is not None:
                 after_chunk(c)
+
+
+class DecodeStepPipeline:
+    """Two ``DecodeStepGraph`` used alternately, so that the tables of step t+1 are built and uploaded while the layers
+    of step t run on the GPU.
+
+    What the tables of a decode step depend on is the TREE (topology and pages), not the token values the previous
+    step sampled: ``TreeCache.alloc`` hands every leaf a page whatever its token turns out to be (tree_cache.py:401-444).
+    So as long as the branch controller leaves the topology alone (the common step), the host work of step t+1
+    (alloc, flatten_tree, C++ builder, one H2D copy) can run under the GPU time of step t.  Each half owns its table
+    buffer, layout, ``cache_loc`` buffer and workspace; they share the activation / output buffers and the KV pool
+    (the steps themselves stay serial on the stream).  A step whose topology changed after ``prepare`` simply calls
+    ``prepare`` again before ``run`` -- that step then pays the table build in line, like the unpipelined step."""
+
+    def __init__(self, kv_pool, qkv: torch.Tensor, out: torch.Tensor, num_heads: int, num_kv_heads: int,
+                 head_dim: int, **kw) -> None:
+        nq = qkv.shape[1]
+        self.halves = [DecodeStepGraph(kv_pool, qkv, out, torch.zeros(nq, dtype=torch.int32, device=qkv.device),
+                                       num_heads, num_kv_heads, head_dim, **kw) for _ in range(2)]
+        self._turn = 0
+        self._ready = None
+
+    @property
+    def captures(self) -> int:
+        return sum(h.captures for h in self.halves)
+
+    def prepare(self, trees, cache_loc: Optional[torch.Tensor] = None, fused: bool = True) -> TreeMetadata:
+        """Host side of the NEXT step: tables + their upload (and this step's pages, ``cache_loc`` on the host) into the
+        half that the running step does not read.  Enqueued on the current stream, i.e. behind the running step.
+        ``fused=False``: the step appends with ``kv_append`` launches (the tables do not mark the fresh tokens)."""
+        half = self.halves[self._turn]
+        m = half.metadata(trees, cache_loc=cache_loc if fused else None)
+        if cache_loc is not None:
+            half.loc.copy_(cache_loc, non_blocking=True)
+        self._ready = (half, m)
+        return m
+
+    def run(self, before_chunk: Optional[Callable[[int], None]] = None,
+            after_chunk: Optional[Callable[[int], None]] = None) -> TreeMetadata:
+        """Replays the prepared step and hands the turn to the other half."""
+        assert self._ready is not None, "DecodeStepPipeline.prepare() first"
+        half, m = self._ready
+        self._ready = None
+        self._turn ^= 1
+        half.run(m, before_chunk=before_chunk, after_chunk=after_chunk)
+        return m

@@ -483,3 +483,56 @@ def test_decode_step_graph_survives_the_tree_growing(dev, mode, fused):
         else:
             assert torch.equal(got, want), (mode, it)
     assert step.captures <= 8, f"{step.captures} captures over {steps} appends (the subtree grows 40-fold)"
+
+
+@pytest.mark.parametrize("mode", ["flatten", "node"])
+def test_decode_step_pipeline_prepares_the_next_step_under_the_running_one(dev, mode):
+    """DecodeStepPipeline: alloc + table build + upload of step t+1 are issued right after step t is enqueued (no
+    synchronisation in between: the two halves own their table buffers), and every step still equals the eager calls on
+    a tight build of the tree as it was for THAT step."""
+    import deft_b200
+    from deft_b200 import TreeMetadata
+    from deft_b200.workloads import build_tree
+    torch.manual_seed(12)
+    L, H, HKV, D, steps = 2, 32, 8, 128, 24
+    tree = build_tree("cfg3", layers=L, device=dev, headroom=64 * (steps + 3))
+    kvp = tree.token_to_kv_pool
+    for l in range(L):
+        kvp.kv_data[l].normal_()
+    nq = len(tree.leaves)
+    qkv = torch.empty(L, nq, (H + 2 * HKV) * D, dtype=torch.float16, device=dev)
+    out = torch.empty(L, nq, H, D, dtype=torch.float16, device=dev)
+    pipe = deft_b200.DecodeStepPipeline(kvp, qkv, out, H, HKV, D, mode=mode, chunk=1)
+
+    def host_side():
+        for leaf in tree.leaves.values():
+            leaf.append_token(7)
+        upd = tree.alloc()
+        m = pipe.prepare(tree, cache_loc=upd.cache_loc)
+        assert m.flat_plan.fresh == 1
+        return upd.cache_loc.clone(), TreeMetadata.from_tree_cache(tree)
+
+    with pytest.raises(AssertionError):
+        pipe.run()                                        # nothing prepared yet
+    nxt = host_side()
+    for it in range(steps):
+        locs, m2 = nxt
+        qkv.normal_()
+        pipe.run()
+        nxt = host_side()                                 # the tree already holds step it+1 while step `it` runs
+        torch.cuda.synchronize()
+        got = out.clone()
+        want = torch.empty_like(out)
+        for l in range(L):
+            q = qkv[l, :, : H * D].view(nq, H, D)
+            K, V = kvp.get_key_buffer(l), kvp.get_value_buffer(l)
+            assert torch.equal(K[locs.to(dev).long()], qkv[l, :, H * D: (H + HKV) * D].view(nq, HKV, D)), "this step's K is in the pool"
+            if mode == "flatten":
+                deft_b200.tree_attention_subtree_fwd(q, K, V, want[l], 128, m2.block_q, m2.block_q_cnts, m2.block_q_offset,
+                                                     m2.block_bitmasks, m2.block_kv, m2.block_lens)
+            else:
+                deft_b200.tree_attention_fwd(q, K, V, want[l], m2.node_kv, m2.node_kv_offset, m2.node_kv_len, m2.node_q,
+                                             m2.node_q_offset, m2.node_q_len)
+        assert torch.isfinite(got.float()).all(), (mode, it)
+        assert torch.allclose(got.float(), want.float(), atol=5e-4, rtol=5e-3), (mode, it)
+    assert pipe.captures <= 10, pipe.captures
