@@ -17,7 +17,7 @@ import torch
 from . import _lib
 from ._lib import Plan
 
-_SUPPORTED_HEAD_DIMS = (32, 64, 128)
+_SUPPORTED_HEAD_DIMS = (16, 32, 64, 128)     # the reference's own list (tree_attention.py:100,305,582)
 
 try:                                      # raw handle of the current stream without building a Stream object
     _raw_stream = torch._C._cuda_getCurrentRawStream

@@ -224,7 +224,7 @@ int check_common(const void* q, const void* k, const void* v, const void* o, int
   DEFT_CHECK_ARG(q && k && v && o, "null tensor pointer");
   DEFT_CHECK_ARG(nq > 0 && H > 0 && HKV > 0 && H % HKV == 0, "bad head geometry nq=%d H=%d HKV=%d", nq, H, HKV);
   // the reference asserts head_dim in {16, 32, 64, 128} (tree_attention.py:100,305,582)
-  DEFT_CHECK_ARG(D == 32 || D == 64 || D == 128, "head_dim %d not supported (32, 64, 128)", D);
+  DEFT_CHECK_ARG(D == 16 || D == 32 || D == 64 || D == 128, "head_dim %d not supported (16, 32, 64, 128)", D);
   DEFT_CHECK_ARG(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) % 16 == 0,
                  "q/k/v/o must be 16-byte aligned");
   DEFT_CHECK_ARG((q_row_stride | q_head_stride | kv_tok_stride | kv_head_stride | o_row_stride | o_head_stride) % 8 == 0,

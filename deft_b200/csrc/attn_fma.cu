@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kThreads) stage1_fma_kernel(const AttnParams p
   const int hkv = blockIdx.y;
   const deft_item_t item = p.items[item_id];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int DL = D / 32;       // output dims owned by a lane
+  constexpr int DL = D >= 32 ? D / 32 : 1;   // output dims owned by a lane (head_dim 16: the upper lanes own none)
   constexpr int CH = D / 8;        // 16-byte chunks per row
 
   for (int gi = 0; gi < item.n_grp; ++gi) {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads) stage1_fma_kernel(const AttnParams p
             float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&sm.v[t][lane * 2]));
             vf[0] = a0.x; vf[1] = a0.y;
           } else {
-            vf[0] = __half2float(sm.v[t][lane]);
+            vf[0] = lane < D ? __half2float(sm.v[t][lane]) : 0.f;
           }
 #pragma unroll
           for (int g = 0; g < G; ++g)
@@ -208,8 +208,10 @@ __global__ void __launch_bounds__(kThreads) stage1_fma_kernel(const AttnParams p
         const float l = l_run[a][g];
         const float inv = l > 0.f ? 1.f / l : 0.f;
         float* dst = p.po + (prow * p.H + h) * D + lane * DL;
+        if (lane * DL < D) {
 #pragma unroll
-        for (int i = 0; i < DL; ++i) dst[i] = acc[a][g][i] * inv;
+          for (int i = 0; i < DL; ++i) dst[i] = acc[a][g][i] * inv;
+        }
         if (lane == 0) p.plse[prow * p.H + h] = l > 0.f ? m_run[a][g] + __logf(l) : -INFINITY;
       }
     }
@@ -249,11 +251,12 @@ int launch_d(const AttnParams& p, cudaStream_t stream) {
 int launch_stage1_fma(const AttnParams& p, cudaStream_t stream) {
   if (p.n_items <= 0) return DEFT_OK;
   switch (p.D) {
+    case 16: return launch_d<16>(p, stream);
     case 32: return launch_d<32>(p, stream);
     case 64: return launch_d<64>(p, stream);
     case 128: return launch_d<128>(p, stream);
   }
-  set_error("unsupported head_dim %d (supported: 32, 64, 128)", p.D);
+  set_error("unsupported head_dim %d (supported: 16, 32, 64, 128)", p.D);
   return DEFT_E_ARG;
 }
 

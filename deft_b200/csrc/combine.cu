@@ -15,7 +15,7 @@ constexpr int kThreads = 256;
 
 template <int D>
 __global__ void __launch_bounds__(kThreads) stage2_kernel(const AttnParams p) {
-  constexpr int DL = D / 32;
+  constexpr int DL = D >= 32 ? D / 32 : 1;   // head_dim 16: lanes 16-31 own no output dim
   const int lane = threadIdx.x & 31;
   const int64_t w = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (w >= (int64_t)p.nq * p.H) return;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads) stage2_kernel(const AttnParams p) {
         const float2 x = *reinterpret_cast<const float2*>(src);
         acc[0] = fmaf(wgt, x.x, acc[0]); acc[1] = fmaf(wgt, x.y, acc[1]);
       } else {
-        acc[0] = fmaf(wgt, src[0], acc[0]);
+        if (lane < D) acc[0] = fmaf(wgt, src[0], acc[0]);
       }
     }
   }
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kThreads) stage2_kernel(const AttnParams p) {
   } else if constexpr (DL == 2) {
     *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(acc[0] * inv, acc[1] * inv);
   } else {
-    dst[0] = __float2half_rn(acc[0] * inv);
+    if (lane < D) dst[0] = __float2half_rn(acc[0] * inv);
   }
 }
 
@@ -124,6 +124,7 @@ int launch_t(const AttnParams& p, cudaStream_t stream) {
 int launch_stage2(const AttnParams& p, cudaStream_t stream) {
   if (p.nq <= 0) return DEFT_OK;
   switch (p.D) {
+    case 16: return launch_t<16>(p, stream);
     case 32: return launch_t<32>(p, stream);
     case 64: return launch_t<64>(p, stream);
     case 128: return launch_t<128>(p, stream);

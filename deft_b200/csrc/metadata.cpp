@@ -79,6 +79,26 @@ struct deft_layout {
 };
 
 namespace {
+template <class T>
+struct Span {   // a stretch of one of the pooled arrays below
+  T* p = nullptr;
+  size_t n = 0;
+  T* begin() const { return p; }
+  T* end() const { return p + n; }
+  T* data() const { return p; }
+  size_t size() const { return n; }
+  T& operator[](size_t i) const { return p[i]; }
+};
+// native tile (one per 128 token slots, KV NOT duplicated per 32-query sub-block); the arrays live in the Scratch pools
+struct Tile {
+  i32 n_live;
+  size_t s0;                 // first entry of the tile in the pools
+  Span<i32> slots;           // query slots with at least one attending row, ascending
+  Span<uint32_t> masks;      // [touched slot][128]: bit r = rank 32*slot + r attends the token
+  Span<uint32_t> rows_or;    // [touched slot]: OR of the slot's words over the live tokens
+  Span<uint8_t> dense;       // [touched slot]: 128 live tokens, every row of the slot attends every one
+};
+struct RestTok { uint64_t key; i32 page, node; };   // a token outside the RUN tiles; key = (group of slots, page)
 constexpr i32 kFreshToken = 1 << 30;   // u_kv entry of a token of THIS step: the bit + its query id (deft_plan_t.u_kv)
 // Storage kept from one call to the next (per thread): the tables of a decode step are a few hundred KB, and fresh
 // allocations of that size are handed back to the kernel at every free and page-faulted in again at the next build
@@ -93,6 +113,12 @@ struct Scratch {
   std::vector<i64> node_sig;
   std::vector<uint32_t> u_mask;
   std::vector<i64> kvs;
+  std::vector<Tile> tiles;                  // native tiles and their pooled arrays (one entry per (tile, touched slot))
+  std::vector<i32> tp_slots;
+  std::vector<uint32_t> tp_masks, tp_rows_or;
+  std::vector<uint8_t> tp_dense;
+  std::vector<RestTok> rest, rest_tmp;      // the native tiler's subtree tokens (radix-sorted by group and page)
+  std::vector<i32> out_page, out_node;
   deft_tables* spare = nullptr;   // a freed handle whose packed buffer is reused by the next build
   // the last plan search: the piece length depends only on the chains' shape, which most decode steps keep
   std::vector<uint64_t> plan_key;
@@ -170,15 +196,9 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     for (i32 qv = 0; qv < query_num; ++qv)
       if (rank_of[(size_t)qv] < 0) rank_of[(size_t)qv] = next++;
   }
-  // native tiles (one per 128-token block, KV NOT duplicated per 32-query sub-block)
-  struct Tile {
-    i32 n_live;
-    std::vector<i32> slots;        // query slots with at least one attending row, ascending
-    std::vector<uint32_t> masks;   // [touched slot][128]: bit r = rank 32*slot + r attends the token
-    std::vector<uint32_t> rows_or; // [touched slot]: OR of the slot's words over the live tokens
-    std::vector<uint8_t> dense;    // [touched slot]: 128 live tokens, every row of the slot attends every one
-  };
-  std::vector<Tile> tiles;
+  auto& tiles = S.tiles;
+  auto& tp_slots = S.tp_slots; auto& tp_masks = S.tp_masks; auto& tp_rows_or = S.tp_rows_or; auto& tp_dense = S.tp_dense;
+  tiles.clear(); tp_slots.clear(); tp_masks.clear(); tp_rows_or.clear(); tp_dense.clear();
   auto& u_kv = S.u_kv;
   auto& tok_page = S.tok_page;
   auto& tok_node = S.tok_node;
@@ -361,27 +381,31 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       tiles.emplace_back();
       Tile& tl = tiles.back();
       tl.n_live = n_live;
+      const size_t s0 = tl.s0 = tp_slots.size();
       const size_t k0 = u_kv.size();
       u_kv.resize(k0 + 128, 0);
+      std::copy(pages, pages + n_live, u_kv.begin() + (long)k0);
       i32 last_node = -2;
       for (i32 i = 0; i < n_live; ++i) {
-        u_kv[k0 + (size_t)i] = pages[i];
         if (nodes[i] == last_node || nodes[i] < 0) continue;
         last_node = nodes[i];
         for (i32 k = nw_off[(size_t)last_node]; k < nw_off[(size_t)last_node + 1]; ++k)
-          if (std::find(tl.slots.begin(), tl.slots.end(), nw_slot[(size_t)k]) == tl.slots.end()) tl.slots.push_back(nw_slot[(size_t)k]);
+          if (std::find(tp_slots.begin() + (long)s0, tp_slots.end(), nw_slot[(size_t)k]) == tp_slots.end()) tp_slots.push_back(nw_slot[(size_t)k]);
       }
-      std::sort(tl.slots.begin(), tl.slots.end());
-      const size_t ns = tl.slots.size();
-      tl.masks.assign(ns * 128, 0u);
-      tl.rows_or.assign(ns, 0u);
-      tl.dense.assign(ns, n_live == 128 ? 1 : 0);
+      std::sort(tp_slots.begin() + (long)s0, tp_slots.end());
+      const size_t ns = tp_slots.size() - s0;
+      tp_masks.resize((s0 + ns) * 128, 0u);
+      tp_rows_or.resize(s0 + ns, 0u);
+      tp_dense.resize(s0 + ns, n_live == 128 ? 1 : 0);
+      const i32* slots = tp_slots.data() + s0;
+      uint32_t* masks = tp_masks.data() + s0 * 128;
+      uint32_t* rows_or = tp_rows_or.data() + s0;
       uint32_t full[8], all_and[8];    // per touched slot (a tile touches a handful): the slot's live rows, AND over the tokens
       std::vector<uint32_t> full_v, and_v;
       uint32_t* fullp = full; uint32_t* andp = all_and;
       if (ns > 8) { full_v.resize(ns); and_v.resize(ns); fullp = full_v.data(); andp = and_v.data(); }
       for (size_t si = 0; si < ns; ++si) {
-        const i32 cnt = std::min(32, query_num - 32 * tl.slots[si]);
+        const i32 cnt = std::min(32, query_num - 32 * slots[si]);
         fullp[si] = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
         andp[si] = 0xffffffffu;
       }
@@ -391,10 +415,10 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         size_t si = 0;
         if (nodes[i] >= 0)
           for (i32 k = nw_off[(size_t)nodes[i]]; k < nw_off[(size_t)nodes[i] + 1]; ++k) {
-            while (tl.slots[si] != nw_slot[(size_t)k]) { andp[si] = 0; ++si; }   // slots the node does not touch
+            while (slots[si] != nw_slot[(size_t)k]) { andp[si] = 0; ++si; }   // slots the node does not touch
             const uint32_t word = nw_word[(size_t)k];
-            std::fill(tl.masks.begin() + (long)(si * 128 + (size_t)i), tl.masks.begin() + (long)(si * 128 + (size_t)j), word);
-            tl.rows_or[si] |= word;
+            std::fill(masks + si * 128 + (size_t)i, masks + si * 128 + (size_t)j, word);
+            rows_or[si] |= word;
             andp[si] &= word;
             ++si;
           }
@@ -402,13 +426,13 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         i = j;
       }
       for (size_t si = 0; si < ns; ++si)
-        if ((andp[si] & fullp[si]) != fullp[si]) tl.dense[si] = 0;
+        if ((andp[si] & fullp[si]) != fullp[si]) tp_dense[s0 + si] = 0;
     };
-    struct Tok { i32 page, node; i64 sig; };
     struct Chunk { i32 first, len; };       // `len` (a power of two) consecutive pages: tokens [first, first + len) of `rest`
-    std::vector<Tok> rest;
+    auto& rest = S.rest; auto& rest_tmp = S.rest_tmp; auto& out_page = S.out_page; auto& out_node = S.out_node;
     std::vector<Chunk> chunks;
-    std::vector<i32> out_page, out_node;
+    std::vector<i64> sigs;                  // the distinct slot sets of one tree's subtree tokens (a handful)
+    std::vector<i32> sig_rank;
     const size_t n_tok = tok_page.size();
     for (size_t a = 0; a < n_tok;) {
       // the tokens [a, b) of one tree (its nodes are consecutive in the pre-order; parent -1 starts the next tree)
@@ -417,6 +441,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       rest.clear();
       out_page.clear();
       out_node.clear();
+      sigs.clear();
       for (size_t i = a; i < b;) {
         // a stretch of consecutive pages attended by one set of slots
         // (this step's tokens are not in the pool yet: they never join a run of pool pages, and get groups of their own)
@@ -426,14 +451,47 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         while (j < b && tok_page[j] == tok_page[j - 1] + 1 && (tok_node[j] == tok_node[j - 1] || sig_of(tok_node[j]) == (sig & ~((i64)1 << 62)))) ++j;
         const size_t whole = fresh ? 0 : (j - i) / 128 * 128;
         for (size_t k = i; k < i + whole; k += 128) emit_tile(&tok_page[k], &tok_node[k], 128);   // RUN tiles
-        for (size_t k = i + whole; k < j; ++k) rest.push_back({tok_page[k], tok_node[k], sig});
+        if (i + whole < j) {
+          size_t gi = 0;
+          while (gi < sigs.size() && sigs[gi] != sig) ++gi;
+          if (gi == sigs.size()) sigs.push_back(sig);
+          // (a fresh token's "page" is its query id with a flag: the flag is in the group already)
+          for (size_t k = i + whole; k < j; ++k)
+            rest.push_back({((uint64_t)gi << 32) | (uint32_t)(tok_page[k] & ~kFreshToken), tok_page[k], tok_node[k]});
+        }
         i = j;
       }
       if (regroup) {
-        std::stable_sort(rest.begin(), rest.end(), [](const Tok& x, const Tok& y) { return x.sig != y.sig ? x.sig < y.sig : x.page < y.page; });
-        for (size_t g0 = 0; g0 < rest.size();) {                // one group of slots at a time
+        // groups in ascending order of their slot sets, pages ascending inside a group: a byte-wise radix sort of the
+        // keys (LSD, bytes that are the same for all keys skipped: two or three passes for a pool of < 16 M pages)
+        const size_t n_rest = rest.size();
+        sig_rank.assign(sigs.size(), 0);
+        for (size_t x = 0; x < sigs.size(); ++x)
+          for (size_t y = 0; y < sigs.size(); ++y) sig_rank[x] += sigs[y] < sigs[x] ? 1 : 0;
+        uint32_t hist[5][256] = {};
+        for (RestTok& tk : rest) {
+          tk.key = ((uint64_t)sig_rank[(size_t)(tk.key >> 32)] << 32) | (tk.key & 0xffffffffu);
+          for (int d = 0; d < 5; ++d) ++hist[d][(tk.key >> (8 * d)) & 0xff];
+        }
+        if (sigs.size() > 256) {            // (more slot sets than a byte counts: never seen; the comparison sort is the fallback)
+          std::sort(rest.begin(), rest.end(), [](const RestTok& x, const RestTok& y) { return x.key < y.key; });
+        } else {
+          rest_tmp.resize(n_rest);
+          RestTok* src = rest.data();
+          RestTok* dst = rest_tmp.data();
+          for (int d = 0; d < 5 && n_rest > 1; ++d) {
+            uint32_t* h = hist[d];
+            if (h[(src[0].key >> (8 * d)) & 0xff] == n_rest) continue;   // every key has this byte
+            uint32_t sum = 0;
+            for (int v = 0; v < 256; ++v) { const uint32_t c = h[v]; h[v] = sum; sum += c; }
+            for (size_t x = 0; x < n_rest; ++x) dst[h[(src[x].key >> (8 * d)) & 0xff]++] = src[x];
+            std::swap(src, dst);
+          }
+          if (src != rest.data()) rest.swap(rest_tmp);
+        }
+        for (size_t g0 = 0; g0 < n_rest;) {                     // one group of slots at a time
           size_t g1 = g0;
-          while (g1 < rest.size() && rest[g1].sig == rest[g0].sig) ++g1;
+          while (g1 < n_rest && (rest[g1].key >> 32) == (rest[g0].key >> 32)) ++g1;
           chunks.clear();
           for (size_t i = g0; i < g1;) {                         // runs of consecutive pages -> power-of-two chunks
             size_t j = i + 1;
@@ -446,13 +504,15 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
               }
             i = j;
           }
-          std::stable_sort(chunks.begin(), chunks.end(), [](const Chunk& x, const Chunk& y) { return x.len > y.len; });
-          for (const Chunk& c : chunks)
-            for (i32 k = 0; k < c.len; ++k) {
-              out_page.push_back(rest[(size_t)(c.first + k)].page);
-              out_node.push_back(rest[(size_t)(c.first + k)].node);
+          for (i32 len = 32; len >= 1; len >>= 1)                // longest chunks first, in page order among equals
+            for (const Chunk& c : chunks) {
+              if (c.len != len) continue;
+              for (i32 k = 0; k < len; ++k) {
+                out_page.push_back(rest[(size_t)(c.first + k)].page);
+                out_node.push_back(rest[(size_t)(c.first + k)].node);
+              }
             }
-          if (g1 < rest.size())
+          if (g1 < n_rest)
             while (out_page.size() % 32) {                       // whole blocks per group: the next group's runs stay aligned
               out_page.push_back(-1);
               out_node.push_back(-1);
@@ -460,11 +520,19 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
           g0 = g1;
         }
       } else {
-        for (const Tok& tk : rest) { out_page.push_back(tk.page); out_node.push_back(tk.node); }
+        for (const RestTok& tk : rest) { out_page.push_back(tk.page); out_node.push_back(tk.node); }
       }
       for (size_t k = 0; k < out_page.size(); k += 128)
         emit_tile(&out_page[k], &out_node[k], (i32)std::min<size_t>(128, out_page.size() - k));
       a = b;
+    }
+    for (size_t t = 0; t < tiles.size(); ++t) {   // the pools no longer move: hand every tile its stretches
+      Tile& tl = tiles[t];
+      const size_t ns = (t + 1 < tiles.size() ? tiles[t + 1].s0 : tp_slots.size()) - tl.s0;
+      tl.slots = {tp_slots.data() + tl.s0, ns};
+      tl.masks = {tp_masks.data() + tl.s0 * 128, ns * 128};
+      tl.rows_or = {tp_rows_or.data() + tl.s0, ns};
+      tl.dense = {tp_dense.data() + tl.s0, ns};
     }
   }
 
@@ -563,7 +631,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         r.run_n = 0;
       };
       for (size_t t = 0; t < tiles.size(); ++t) {
-        const std::vector<i32>& sl = tiles[t].slots;  // ascending
+        const Span<i32>& sl = tiles[t].slots;  // ascending
         for (size_t i = 0; i < sl.size();) {
           const i32 pr = sl[i] / 2;
           int sig = 0;

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 ATOL, RTOL = 1e-3, 1e-2
 TABLE_KEYS = ["node_q", "node_kv", "node_q_len", "node_kv_len", "node_q_offset", "node_kv_offset",
               "block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv", "block_lens"]
-GEOMS = [(32, 8, 128), (8, 2, 64), (16, 4, 128), (8, 8, 64), (4, 2, 128)]
+GEOMS = [(32, 8, 128), (8, 2, 64), (16, 4, 128), (8, 8, 64), (4, 2, 128), (4, 2, 16), (8, 1, 32)]
 
 
 def random_tree(rng, pool, r2t, layers, HKV, D):
@@ -59,7 +59,7 @@ def per_leaf(q, K, V, paths):
     return out
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(14))
 def test_random_trees_and_forests(seed, monkeypatch):
     import deft_b200
     from deft_b200 import TreeMetadata
