@@ -379,6 +379,34 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
                                                                      non_blocking=True)
             ev_free[c].record(s_out)
 
+    def run_ring(m):
+        """Per-layer eager calls (kv_append + attention) over a ring of device chunk buffers (forests too big to keep 32
+        layers of activations on the device)."""
+        upload(range(1, min(n_dev, n_chunks)))
+        for l in range(LAYERS):
+            c = l // CH
+            if l % CH == 0:
+                main.wait_event(ev_in[c])
+            ld = (c % n_dev) * CH + l % CH
+            k_new = dev_qkv[ld, :, H * D: (H + HKV) * D].view(nq, HKV, D)
+            v_new = dev_qkv[ld, :, (H + HKV) * D:].view(nq, HKV, D)
+            deft_b200.kv_append(kv_view.kv_data[l], k_new, v_new, loc_dev)
+            K, V = kv_view.get_key_buffer(l), kv_view.get_value_buffer(l)
+            qv = dev_qkv[ld, :, : H * D].view(nq, H, D)
+            if args.mode == "seq":
+                deft_b200.token_attention_fwd(qv, K, V, dev_out[ld], r2t_dev, req_idx, start_loc, seq_lens,
+                                              max(seq_len_host), None, sum(seq_len_host))
+            elif args.mode == "flatten":
+                deft_b200.tree_attention_subtree_fwd(qv, K, V, dev_out[ld], m.block_len, m.block_q, m.block_q_cnts,
+                                                     m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens)
+            else:
+                deft_b200.tree_attention_fwd(qv, K, V, dev_out[ld], m.node_kv, m.node_kv_offset, m.node_kv_len,
+                                             m.node_q, m.node_q_offset, m.node_q_len)
+            if l % CH == CH - 1:
+                download(c)
+                if c + n_dev < n_chunks:
+                    upload([c + n_dev])
+
     def step_e2e():
         """Chunk c+1 of the activations comes up while chunk c attends and chunk c-1's outputs go down."""
         if not args.e2e_static:
@@ -395,30 +423,7 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
             step.run(m, before_chunk=lambda c: main.wait_event(ev_in[c]),
                      after_chunk=lambda c: (upload(range(1, n_chunks)) if c == 0 else None, download(c)))
         else:
-            upload(range(1, min(n_dev, n_chunks)))
-            for l in range(LAYERS):
-                c = l // CH
-                if l % CH == 0:
-                    main.wait_event(ev_in[c])
-                ld = (c % n_dev) * CH + l % CH
-                k_new = dev_qkv[ld, :, H * D: (H + HKV) * D].view(nq, HKV, D)
-                v_new = dev_qkv[ld, :, (H + HKV) * D:].view(nq, HKV, D)
-                deft_b200.kv_append(kv_view.kv_data[l], k_new, v_new, loc_dev)
-                K, V = kv_view.get_key_buffer(l), kv_view.get_value_buffer(l)
-                qv = dev_qkv[ld, :, : H * D].view(nq, H, D)
-                if args.mode == "seq":
-                    deft_b200.token_attention_fwd(qv, K, V, dev_out[ld], r2t_dev, req_idx, start_loc, seq_lens,
-                                                  max(seq_len_host), None, sum(seq_len_host))
-                elif args.mode == "flatten":
-                    deft_b200.tree_attention_subtree_fwd(qv, K, V, dev_out[ld], m.block_len, m.block_q, m.block_q_cnts,
-                                                         m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens)
-                else:
-                    deft_b200.tree_attention_fwd(qv, K, V, dev_out[ld], m.node_kv, m.node_kv_offset, m.node_kv_len,
-                                                 m.node_q, m.node_q_offset, m.node_q_len)
-                if l % CH == CH - 1:
-                    download(c)
-                    if c + n_dev < n_chunks:
-                        upload([c + n_dev])
+            run_ring(m)
         main.wait_stream(s_out)                          # the step ends when the last output is on the host
         main.synchronize()                               # the caller reads the result on the host
 
@@ -426,7 +431,11 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
         """Host side of the NEXT step (alloc + tables + their upload), enqueued behind the running step."""
         if not args.e2e_static:
             grow()
-        m = pipe.prepare(trees[0] if T == 1 else trees, cache_loc=host_loc, fused=not args.e2e_static)
+        if graphed:
+            m = pipe.prepare(trees[0] if T == 1 else trees, cache_loc=host_loc, fused=not args.e2e_static)
+        else:       # (stream-ordered behind the running step's launches: fresh table tensor, the one cache_loc buffer)
+            m = ring_ready[0] = build_meta()
+            loc_dev.copy_(host_loc, non_blocking=True)
         table_bytes[0] = m.packed.numel()
 
     def step_e2e_pipelined():
@@ -436,15 +445,20 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
         s_in.wait_stream(main)
         s_in.wait_stream(s_out)
         upload(range(1))
-        pipe.run(before_chunk=lambda c: main.wait_event(ev_in[c]),
-                 after_chunk=lambda c: (upload(range(1, n_chunks)) if c == 0 else None, download(c)))
+        if graphed:
+            pipe.run(before_chunk=lambda c: main.wait_event(ev_in[c]),
+                     after_chunk=lambda c: (upload(range(1, n_chunks)) if c == 0 else None, download(c)))
+        else:
+            run_ring(ring_ready[0])
         prepare_next()                                   # under the GPU time of this step
         main.wait_stream(s_out)
         main.synchronize()                               # the caller reads the result on the host
 
     ms_serial = None
-    if graphed and not args.e2e_serial:
-        ms_serial = timed(step_e2e, e2e_steps, 3)
+    ring_ready = [None]
+    if args.mode != "seq" and not args.e2e_serial:
+        if graphed:                                      # (the ring path of a 512-tree forest: one leg is long enough)
+            ms_serial = timed(step_e2e, e2e_steps, 3)
         prepare_next()
         ms_e2e = timed(step_e2e_pipelined, e2e_steps, 3)
     else:
@@ -453,7 +467,7 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
     d2h = LAYERS * nq * H * D * 2
     res = dict(ms_step=ms_step, ms_s1=ms_s1, ms_s2=ms_s2, ms_e2e=ms_e2e, ms_e2e_serial=ms_serial,
                h2d=h2d, d2h=d2h, nq=nq, clocks=clocks,
-               pool_mb=kvp.kv_data[0].numel() * 2 / 1e6, graphed=graphed,
+               pool_mb=kvp.kv_data[0].numel() * 2 / 1e6, graphed=graphed, pipelined=args.mode != "seq" and not args.e2e_serial,
                captures=(step.captures + pipe.captures) if graphed else None, e2e_chunks=n_chunks, e2e_steps=e2e_steps,
                kv_tokens_end=sum(len(n.kv_indices) for t in trees for n in t.nodes.values()))
     if args.mode == "node_chunk":
@@ -550,7 +564,9 @@ def main():
                 "aggregate_hbm_gbs": world * rf["hbm_gbs"], "roofline_frac_stage1": rf["hbm_frac"],
                 "roofline_frac_operator": rf["algorithmic_bytes_per_launch"] / (c["ms_step"] / LAYERS * 1e-3) / 1e9 / rf["peak"],
                 "e2e": {"trees_per_s": world * T5 / (c["ms_e2e"] * 1e-3), "ms_per_step": c["ms_e2e"], "steps": e2e5,
-                        "h2d_bytes_per_step": c["h2d"], "d2h_bytes_per_step": c["d2h"], "graph_captures": c["captures"]}}
+                        "h2d_bytes_per_step": c["h2d"], "d2h_bytes_per_step": c["d2h"], "graph_captures": c["captures"],
+                        "pipelining": "tables of step t+1 (C++ builder over the forest) built while the copies and layers of step t "
+                                      "run" if c["pipelined"] else "none"}}
 
     if rank != 0:
         if world > 1:
@@ -582,7 +598,7 @@ def main():
                 "pipelining": ("DecodeStepPipeline: alloc + table build + table upload of step t+1 run on the host while the layers of "
                                "step t run (two table buffers; the tables depend on the tree, not on the tokens step t samples); every "
                                "step still ends with its outputs on the host before the next step's activations go up; "
-                               "ms_per_step_serial = the same loop with the build in line") if r["ms_e2e_serial"] is not None else
+                               "ms_per_step_serial = the same loop with the build in line") if r["pipelined"] else
                               "none (table build in line)",
                 "path": ("TreeCache.alloc + DecodeStepGraph.metadata (TreeMetadata.from_tree_cache: C++ builder, capacity-padded tables, 1 "
                          "upload into the persistent table buffer; the first chunk of activations goes up under the build, the others "

@@ -40,7 +40,8 @@ class DecodeStepGraph:
         self.kv_pool, self.qkv, self.out, self.loc = kv_pool, qkv, out, cache_loc
         self.H, self.HKV, self.D, self.mode = num_heads, num_kv_heads, head_dim, mode
         self.layers = qkv.shape[0]
-        self.fused_append = fused_append
+        # (the fused append lives in the tensor-core kernels: other geometries append with kv_append launches)
+        self.fused_append = fused_append and head_dim in (64, 128) and num_heads // num_kv_heads in (1, 2, 4)
         self.chunk = max(1, min(chunk, self.layers))
         self.n_chunks = (self.layers + self.chunk - 1) // self.chunk
         self.tables = torch.empty(table_bytes, dtype=torch.uint8, device=qkv.device)

@@ -116,11 +116,20 @@ def test_random_trees_and_forests(seed, monkeypatch):
     expect_pool[loc.long(), 0] = k_new
     expect_pool[loc.long(), 1] = v_new
     pool.kv_data[0][loc.long()] = float("nan")
-    mf = (TreeMetadata.from_tree_cache(trees[0], fresh_page=loc_host) if len(trees) == 1
-          else TreeMetadata.from_forest(trees, fresh_page=loc_host))
+    fused = D in (64, 128) and H // HKV in (1, 2, 4)      # the fused append lives in the tensor-core kernels
+    mf = (TreeMetadata.from_tree_cache(trees[0], fresh_page=loc_host if fused else None) if len(trees) == 1
+          else TreeMetadata.from_forest(trees, fresh_page=loc_host if fused else None))
     o4 = torch.full((nq, H, D), float("nan"), dtype=torch.float16, device=dev)
-    deft_b200.tree_attention_subtree_fwd(q, K, V, o4, 128, mf.block_q, mf.block_q_cnts, mf.block_q_offset, mf.block_bitmasks,
-                                         mf.block_kv, mf.block_lens, append=(k_new, v_new, loc))
+    if fused:
+        deft_b200.tree_attention_subtree_fwd(q, K, V, o4, 128, mf.block_q, mf.block_q_cnts, mf.block_q_offset, mf.block_bitmasks,
+                                             mf.block_kv, mf.block_lens, append=(k_new, v_new, loc))
+    else:
+        with pytest.raises(deft_b200._lib.DeftError):    # ... and says so for the other geometries
+            deft_b200.tree_attention_subtree_fwd(q, K, V, o4, 128, mf.block_q, mf.block_q_cnts, mf.block_q_offset,
+                                                 mf.block_bitmasks, mf.block_kv, mf.block_lens, append=(k_new, v_new, loc))
+        deft_b200.kv_append(pool.kv_data[0], k_new, v_new, loc)
+        deft_b200.tree_attention_subtree_fwd(q, K, V, o4, 128, mf.block_q, mf.block_q_cnts, mf.block_q_offset, mf.block_bitmasks,
+                                             mf.block_kv, mf.block_lens)
     torch.cuda.synchronize()
     assert torch.equal(pool.kv_data[0], expect_pool), (seed, "pool after the fused append")
     paths = [p for t_ in trees for p in orc.leaf_paths(t_)]
