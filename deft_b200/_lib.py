@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DEFT_B200_LIB") or os.path.join(_HERE, "lib", "libdeft_b200.so")   # (override: A/B of two builds)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 T_NAMES = ["node_q", "node_kv", "node_q_len", "node_kv_len", "node_q_offset", "node_kv_offset",
            "block_q", "block_q_cnts", "block_q_offset", "block_bitmasks", "block_kv", "block_lens",
            "flat_items", "flat_groups", "flat_csr_off", "flat_csr_rows",
@@ -75,6 +75,12 @@ def _load() -> C.CDLL:
                                                    i32, vp, i64, vp, vp, vp, i64, vp, vp, C.POINTER(Plan), C.POINTER(Append), vp, sz, vp]),
         "deft_b200_node_fwd_append": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, i32,
                                                 vp, i32, vp, vp, vp, i64, vp, vp, i64, i64, C.POINTER(Plan), C.POINTER(Append), vp, sz, vp]),
+        "deft_b200_tree_new": (vp, []),
+        "deft_b200_tree_free": (None, [vp]),
+        "deft_b200_tree_set": (C.c_int, [vp, i32, vp, vp, vp, vp, vp, vp, i32]),
+        "deft_b200_tree_append": (C.c_int, [vp, i32, vp, vp]),
+        "deft_b200_tree_pages": (i64, [vp]),
+        "deft_b200_build_tables_trees": (vp, [vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, vp]),
         "deft_b200_layout_new": (vp, []),
         "deft_b200_layout_free": (None, [vp]),
         "deft_b200_layout_version": (i64, [vp]),
@@ -98,7 +104,8 @@ EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_set_stage
            "deft_b200_set_debug_buffer", "deft_b200_set_trace_buffer", "deft_b200_set_tma", "deft_b200_set_pdl", "deft_b200_set_gather4", "deft_b200_set_experiment",
            "deft_b200_flatten_workspace_bytes",
            "deft_b200_flatten_fwd", "deft_b200_node_workspace_bytes", "deft_b200_node_fwd", "deft_b200_flatten_fwd_append", "deft_b200_node_fwd_append", "deft_b200_kv_append",
-           "deft_b200_build_tables", "deft_b200_layout_new", "deft_b200_layout_free", "deft_b200_layout_version",
+           "deft_b200_build_tables", "deft_b200_tree_new", "deft_b200_tree_free", "deft_b200_tree_set", "deft_b200_tree_append",
+           "deft_b200_tree_pages", "deft_b200_build_tables_trees", "deft_b200_layout_new", "deft_b200_layout_free", "deft_b200_layout_version",
            "deft_b200_tables_data", "deft_b200_tables_bytes",
            "deft_b200_tables_directory", "deft_b200_tables_scalars", "deft_b200_tables_free"]
 

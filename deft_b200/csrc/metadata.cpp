@@ -78,6 +78,16 @@ struct deft_layout {
   i64 version = 0;
 };
 
+// Native mirror of one decoding tree (deft_b200_tree_new): topology and per-node page lists kept on this side of the
+// ABI, so that a decode step only hands over the pages it appended (TreeCache.alloc) instead of the whole tree.
+struct deft_tree {
+  std::vector<i32> parent;                 // DFS pre-order, -1 for the root
+  std::vector<std::vector<i64>> pages;     // per node, in the order they were handed out
+  std::vector<i64> q_off, qs, tix;
+  i32 query_num = 0;
+  i64 n_pages = 0;
+};
+
 namespace {
 template <class T>
 struct Span {   // a stretch of one of the pooled arrays below
@@ -1055,6 +1065,95 @@ int deft_b200_tables_scalars(const deft_tables_t* t, int64_t* out) {
   if (!t || !out) return DEFT_E_ARG;
   std::memcpy(out, t->scalars, sizeof(t->scalars));
   return DEFT_OK;
+}
+
+deft_tree_t* deft_b200_tree_new(void) { return new (std::nothrow) deft_tree_t(); }
+void deft_b200_tree_free(deft_tree_t* t) { delete t; }
+int64_t deft_b200_tree_pages(const deft_tree_t* t) { return t ? t->n_pages : -1; }
+
+int deft_b200_tree_set(deft_tree_t* t, int32_t n_nodes, const int32_t* parent, const int64_t* kv_off, const int64_t* kv,
+                       const int64_t* q_off, const int64_t* qs, const int64_t* tix_row, int32_t query_num) {
+  if (!t || n_nodes <= 0 || !parent || !kv_off || !kv || !q_off || !qs || query_num <= 0) {
+    deft::set_error("tree_set: null or empty tree");
+    return DEFT_E_ARG;
+  }
+  for (i32 n = 0; n < n_nodes; ++n)
+    if (kv_off[n + 1] < kv_off[n] || q_off[n + 1] < q_off[n]) {
+      deft::set_error("tree_set: offsets of node %d decrease", n);
+      return DEFT_E_ARG;
+    }
+  t->parent.assign(parent, parent + n_nodes);
+  t->pages.resize((size_t)n_nodes);
+  for (i32 n = 0; n < n_nodes; ++n) t->pages[(size_t)n].assign(kv + kv_off[n], kv + kv_off[n + 1]);
+  t->q_off.assign(q_off, q_off + n_nodes + 1);
+  t->qs.assign(qs, qs + q_off[n_nodes]);
+  if (tix_row) t->tix.assign(tix_row, tix_row + n_nodes);
+  else t->tix.clear();
+  t->query_num = query_num;
+  t->n_pages = kv_off[n_nodes] - kv_off[0];
+  return DEFT_OK;
+}
+
+int deft_b200_tree_append(deft_tree_t* t, int32_t n, const int32_t* node, const int64_t* page) {
+  if (!t || n < 0 || (n > 0 && (!node || !page))) {
+    deft::set_error("tree_append: null argument");
+    return DEFT_E_ARG;
+  }
+  for (i32 i = 0; i < n; ++i)
+    if (node[i] >= (i32)t->pages.size()) {
+      deft::set_error("tree_append: node %d of a tree of %zu nodes", node[i], t->pages.size());
+      return DEFT_E_ARG;
+    }
+  for (i32 i = 0; i < n; ++i) {
+    if (node[i] < 0) continue;            // a leaf the walk left out (paused)
+    t->pages[(size_t)node[i]].push_back(page[i]);
+    ++t->n_pages;
+  }
+  return DEFT_OK;
+}
+
+deft_tables_t* deft_b200_build_tables_trees(deft_tree_t* const* trees, int32_t n_trees, int64_t tix_max_ctx,
+                                            int32_t block_len, int32_t max_q_len, int32_t max_block_len,
+                                            int32_t node_split, int32_t hkv, int32_t n_ctas, deft_layout_t* layout,
+                                            const int32_t* fresh_page) {
+  if (!trees || n_trees <= 0) {
+    deft::set_error("build_tables_trees: no trees");
+    return nullptr;
+  }
+  // the flat arrays of deft_b200_build_tables: the trees one after the other (nodes, pages and queries offset)
+  thread_local std::vector<i32> parent;
+  thread_local std::vector<i64> kv_off, kv, q_off, qs, tix;
+  parent.clear(); kv.clear(); qs.clear(); tix.clear();
+  kv_off.assign(1, 0);
+  q_off.assign(1, 0);
+  i64 query_base = 0;
+  bool all_tix = tix_max_ctx > 0;
+  for (i32 ti = 0; ti < n_trees; ++ti) {
+    const deft_tree_t* t = trees[ti];
+    if (!t || t->parent.empty()) {
+      deft::set_error("build_tables_trees: tree %d is empty (deft_b200_tree_set first)", ti);
+      return nullptr;
+    }
+    const i32 node_base = (i32)parent.size();
+    const i64 qs_base = (i64)qs.size();
+    for (size_t n = 0; n < t->parent.size(); ++n) {
+      parent.push_back(t->parent[n] < 0 ? -1 : t->parent[n] + node_base);
+      kv.insert(kv.end(), t->pages[n].begin(), t->pages[n].end());
+      kv_off.push_back((i64)kv.size());
+      q_off.push_back(qs_base + t->q_off[n + 1] - t->q_off[0]);
+    }
+    for (i64 qv : t->qs) qs.push_back(qv + query_base);
+    if (t->tix.size() == t->parent.size()) tix.insert(tix.end(), t->tix.begin(), t->tix.end());
+    else all_tix = false;
+    query_base += t->query_num;
+  }
+  if (tix_max_ctx > 0 && !all_tix) {
+    deft::set_error("build_tables_trees: tree-index mode needs the index rows of every tree");
+    return nullptr;
+  }
+  return deft_b200_build_tables((i32)parent.size(), parent.data(), kv_off.data(), kv.data(), q_off.data(), qs.data(),
+                                tix_max_ctx > 0 ? tix.data() : nullptr, tix_max_ctx, (i32)query_base, block_len, max_q_len,
+                                max_block_len, node_split, hkv, n_ctas, layout, fresh_page);
 }
 
 deft_layout_t* deft_b200_layout_new(void) { return new (std::nothrow) deft_layout_t(); }

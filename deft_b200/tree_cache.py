@@ -19,6 +19,7 @@ What is different underneath:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from dataclasses import dataclass, field
 from itertools import chain
@@ -57,12 +58,31 @@ class KVCacheUpdater:
 
 
 _PAUSE_EPOCH = [0]     # moved whenever a node's ``paused`` flag changes (part of flatten_tree's cache key)
+_PAGES_EPOCH = [0]     # moved when a node outside any TreeCache swaps or appends to its page list
 
 
 class TreeNode:
     @property
     def paused(self) -> bool:
         return self._paused
+
+    @property
+    def kv_indices(self) -> List[int]:
+        return self._kv_indices
+
+    @kv_indices.setter
+    def kv_indices(self, value: List[int]) -> None:
+        """A page list swapped for another object (init_prompt, reset_node_KV, or the caller's own code): whatever
+        mirrors the tree's pages (``TreeCache.native_tree``) is out of date."""
+        self._kv_indices = value
+        self._touch_pages()
+
+    def _touch_pages(self) -> None:
+        owner = self._owner
+        if owner is not None:
+            owner._pages_epoch += 1
+        else:
+            _PAGES_EPOCH[0] += 1
 
     @paused.setter
     def paused(self, value: bool) -> None:
@@ -72,11 +92,12 @@ class TreeNode:
     def __init__(self, id: int, node_indices_id: Optional[int] = None,
                  node_indices: Optional[torch.Tensor] = None) -> None:
         self.id = id
+        self._owner = None                    # the TreeCache that made the node (told when the page list changes)
         self.children: Dict[int, "TreeNode"] = {}
         self.token_ids: List[int] = []
         self.positions: List[int] = []
         self.position_offset = 0
-        self.kv_indices: List[int] = []
+        self._kv_indices: List[int] = []
         self.parent: Optional["TreeNode"] = None
         self.refs: Set["TreeNode"] = set()
         self._paused = False
@@ -95,9 +116,10 @@ class TreeNode:
             self.cumulative_logprob += logprob
 
     def append_index(self, index: int) -> None:
-        self.kv_indices.append(index)
+        self._kv_indices.append(index)
+        self._touch_pages()                  # (``TreeCache.alloc`` appends in bulk and tells the mirror itself)
         if self.node_indices is not None:
-            self.node_indices[len(self.kv_indices) - 1] = index
+            self.node_indices[len(self._kv_indices) - 1] = index
             if self.index_pool is not None:
                 self.index_pool.touch()
 
@@ -130,6 +152,8 @@ class TreeCache:
         self.layer_num = layer_num
         self.deleted_token_num = 0
         self._topo_version = 0      # bumped by every change of nodes / leaves / refs: flatten_tree keeps the walk
+        self._pages_epoch = 0       # bumped when a node's page list changes other than through alloc()
+        self._mirror: Optional["_NativeTree"] = None
 
     # ---- construction -------------------------------------------------------------------
     def _take_index_row(self):
@@ -146,6 +170,7 @@ class TreeCache:
         rid, row = self._take_index_row()
         self._topo_version += 1
         root = TreeNode(0, rid, row)
+        root._owner = self
         root.index_pool = self.tree_index_pool if self.use_tree_index else None
         root.token_ids = ids
         root.positions = list(range(n))
@@ -170,6 +195,7 @@ class TreeCache:
         self._topo_version += 1
         rid, row = self._take_index_row()
         node = TreeNode(self.node_cnt, rid, row)
+        node._owner = self
         node.index_pool = self.tree_index_pool if self.use_tree_index else None
         self.node_cnt += 1
         node.parent = parent
@@ -184,17 +210,39 @@ class TreeCache:
         out_cache_loc = self.token_to_kv_pool.alloc(len(leaves))
         assert out_cache_loc is not None
         locs = out_cache_loc.tolist()
+        mirror = self._mirror
+        in_sync = mirror is not None and mirror.key == self._mirror_key()
         if self.use_tree_index:
             for leaf, loc in zip(leaves, locs):
                 leaf.append_index(loc)
         else:
             for leaf, loc in zip(leaves, locs):
-                leaf.kv_indices.append(loc)
+                leaf._kv_indices.append(loc)
+        if in_sync:       # the native mirror follows: one call with the step's pages (deft_b200_tree_append)
+            mirror.append(locs)
+            mirror.key = self._mirror_key()
         # the page table of the sequence-based baseline, in one indexed store (the host tensor and the array share memory)
         table = self.req_to_token_pool.req_to_token.numpy()
         l2r = self.leaf_to_req
         table[[l2r[leaf.id] for leaf in leaves], [leaf.positions[-1] for leaf in leaves]] = locs
         return KVCacheUpdater(self.token_to_kv_pool, out_cache_loc, is_prompt=False)
+
+    # ---- native mirror --------------------------------------------------------------------
+    def _mirror_key(self):
+        return (self._topo_version, self._pages_epoch, _PAUSE_EPOCH[0], _PAGES_EPOCH[0], id(self.root))
+
+    def native_tree(self) -> "_NativeTree":
+        """The C++ mirror of this tree (``deft_tree_t``), brought up to date: a decode loop that only
+        calls ``alloc`` between builds keeps it in step with one ``deft_b200_tree_append`` per ``alloc``; anything else
+        (branch, cut, merge, pause, a swapped page list) is followed by a full ``deft_b200_tree_set`` here."""
+        m = self._mirror
+        if m is None:
+            m = self._mirror = _NativeTree()
+        key = self._mirror_key()
+        if m.key != key or m.n_pages != sum(map(len, m.lists)):     # (the sum catches in-place edits of a page list)
+            m.sync(self, flatten_tree(self))
+            m.key = key
+        return m
 
     # ---- mutation -------------------------------------------------------------------------
     def merge_nodes(self, node_A: TreeNode, node_B: TreeNode, pruneB_flag: Optional[bool] = True) -> None:
@@ -479,6 +527,75 @@ def sm_count(device: Optional[torch.device]) -> int:
     return _SM_COUNT[idx]
 
 
+class _NativeTree:
+    """Handle + bookkeeping of one tree's C++ mirror (``deft_tree_t``); owned by ``TreeCache.native_tree``."""
+
+    def __init__(self) -> None:
+        self.handle = _lib.lib.deft_b200_tree_new()
+        if not self.handle:
+            raise MemoryError("deft_b200_tree_new failed")
+        self.key = None                  # TreeCache._mirror_key() the mirror was last in step with
+        self.lists: List[List[int]] = [] # the page lists of the walked nodes (their lengths are checked against n_pages)
+        self.n_pages = -1
+        self.leaf_idx = np.zeros(0, dtype=np.int32)   # DFS index of every leaf, leaves in ascending id order (-1: not walked)
+        self.n_live = 0
+        self.leaf_to_q: Dict[int, int] = {}
+        self.syncs = 0                   # full hand-overs so far (a decode loop that only allocs needs one)
+
+    def sync(self, tree, flat: Dict[str, Any]) -> None:
+        """Full hand-over of the tree (``deft_b200_tree_set``) from the arrays ``flatten_tree`` made."""
+        self.syncs += 1
+        use_tix = bool(getattr(tree, "use_tree_index", False))
+        _lib.check(_lib.lib.deft_b200_tree_set(self.handle, len(flat["parent"]), flat["parent"].ctypes.data,
+                                               flat["kv_off"].ctypes.data, flat["kv"].ctypes.data, flat["q_off"].ctypes.data,
+                                               flat["qs"].ctypes.data, flat["tix"].ctypes.data if use_tix else None,
+                                               len(flat["leaf_to_q"])))
+        nodes = tree._flat_topo[1][0]
+        self.lists = [n.kv_indices for n in nodes]
+        self.n_pages = int(flat["kv_off"][-1])
+        at = {id(n): i for i, n in enumerate(nodes)}
+        self.leaf_idx = np.asarray([at.get(id(tree.leaves[l]), -1) for l in sorted(tree.leaves)], dtype=np.int32)
+        self.n_live = int((self.leaf_idx >= 0).sum())
+        self.leaf_to_q = flat["leaf_to_q"]
+
+    def append(self, pages: List[int]) -> None:
+        """A decode step: one page per leaf, leaves in ascending id order (``TreeCache.alloc``)."""
+        arr = np.asarray(pages, dtype=np.int64)
+        assert arr.shape[0] == self.leaf_idx.shape[0]
+        _lib.check(_lib.lib.deft_b200_tree_append(self.handle, arr.shape[0], self.leaf_idx.ctypes.data, arr.ctypes.data))
+        self.n_pages += self.n_live
+
+    def __del__(self) -> None:
+        if getattr(self, "handle", None) and _lib is not None and getattr(_lib, "lib", None) is not None:
+            _lib.lib.deft_b200_tree_free(self.handle)
+            self.handle = None
+
+
+def _native_trees_enabled() -> bool:
+    return os.environ.get("DEFT_NATIVE_TREE", "1") != "0"
+
+
+def mirror_flat(trees) -> Optional[Dict[str, Any]]:
+    """The builder's input as native mirrors instead of flat arrays, when every tree keeps one (our ``TreeCache``)."""
+    if not _native_trees_enabled() or not all(hasattr(t, "native_tree") for t in trees):
+        return None
+    mirrors = [t.native_tree() for t in trees]
+    if len(trees) == 1:
+        return dict(trees=mirrors, leaf_to_q=mirrors[0].leaf_to_q, query_num=len(mirrors[0].leaf_to_q))
+    # (tree index, leaf id) -> query: kept while no tree of the forest changes its leaves
+    key = tuple(id(m.leaf_to_q) for m in mirrors)
+    cached = getattr(trees[0], "_forest_leaf_to_q", None)
+    if cached is None or cached[0] != key:
+        leaf_to_q: Dict[Any, int] = {}
+        base = 0
+        for i, m in enumerate(mirrors):
+            for leaf, q in m.leaf_to_q.items():
+                leaf_to_q[(i, leaf)] = q + base
+            base += len(m.leaf_to_q)
+        cached = trees[0]._forest_leaf_to_q = (key, leaf_to_q, base, [m.leaf_to_q for m in mirrors])   # (keeps the ids alive)
+    return dict(trees=mirrors, leaf_to_q=cached[1], query_num=cached[2])
+
+
 class TableLayout:
     """Capacity-padded packing of the tables (``deft_layout_t``): one per decode loop.  While every table fits its
     region the packed buffer keeps its offsets from one decode step to the next -- what a captured CUDA graph of the
@@ -508,17 +625,25 @@ def build_tables_host(flat: Dict[str, Any], max_q_len: int = 32, max_block_len: 
     ``reserve(nbytes) -> uint8 tensor`` (optional) supplies the destination -- the pinned staging buffer of the
     upload -- so that the tables are copied once, straight out of the builder; the first return value is then
     ``(tensor, nbytes)`` instead of an array."""
-    query_num = len(flat["leaf_to_q"])
+    query_num = flat["query_num"] if "trees" in flat else len(flat["leaf_to_q"])
     use_tix = tree_index_max_ctx > 0
     if fresh_page is not None:
         fresh_page = np.ascontiguousarray(fresh_page, dtype=np.int32)
         assert fresh_page.shape == (query_num,), "fresh_page: one page per query"
-    h = _lib.lib.deft_b200_build_tables(len(flat["parent"]), flat["parent"].ctypes.data, flat["kv_off"].ctypes.data,
-                                        flat["kv"].ctypes.data, flat["q_off"].ctypes.data, flat["qs"].ctypes.data,
-                                        flat["tix"].ctypes.data if use_tix else None,
-                                        tree_index_max_ctx, query_num, block_len, max_q_len, max_block_len, node_split,
-                                        hkv, n_ctas, layout.handle if layout is not None else None,
-                                        fresh_page.ctypes.data if fresh_page is not None else None)
+    if "trees" in flat:       # native mirrors (TreeCache.native_tree): nothing of the tree crosses the ABI again
+        mirrors = flat["trees"]
+        handles = (C.c_void_p * len(mirrors))(*[m.handle for m in mirrors])
+        h = _lib.lib.deft_b200_build_tables_trees(handles, len(mirrors), tree_index_max_ctx, block_len, max_q_len,
+                                                  max_block_len, node_split, hkv, n_ctas,
+                                                  layout.handle if layout is not None else None,
+                                                  fresh_page.ctypes.data if fresh_page is not None else None)
+    else:
+        h = _lib.lib.deft_b200_build_tables(len(flat["parent"]), flat["parent"].ctypes.data, flat["kv_off"].ctypes.data,
+                                            flat["kv"].ctypes.data, flat["q_off"].ctypes.data, flat["qs"].ctypes.data,
+                                            flat["tix"].ctypes.data if use_tix else None,
+                                            tree_index_max_ctx, query_num, block_len, max_q_len, max_block_len, node_split,
+                                            hkv, n_ctas, layout.handle if layout is not None else None,
+                                            fresh_page.ctypes.data if fresh_page is not None else None)
     if not h:
         raise _lib.DeftError(f"deft_b200_build_tables failed: {_lib.last_error()}")
     try:
@@ -644,8 +769,8 @@ class TreeMetadata:
         (what a captured CUDA graph of the step needs, see ``decode_step.DecodeStepGraph``); ``table_layout``:
         capacity-padded packing; ``fresh_page``: this step's page per query (``TreeCache.alloc().cache_loc``) -- the
         native plan then reads those tokens from the step's activations (fused KV append: ``attention.Append``)."""
-        return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=False, device_buffer=device_buffer,
-                             table_layout=table_layout, fresh_page=fresh_page)
+        return cls._assemble(tree, mirror_flat([tree]) or flatten_tree(tree), max_q_len, max_block_len, tree_index=False,
+                             device_buffer=device_buffer, table_layout=table_layout, fresh_page=fresh_page)
 
     @classmethod
     def from_forest(cls, trees, max_q_len: int = 32, max_block_len: int = -1,
@@ -656,13 +781,13 @@ class TreeMetadata:
         trees = list(trees)
         assert trees and all(t.token_to_kv_pool is trees[0].token_to_kv_pool for t in trees), \
             "the trees of a forest share one TokenToKVPool"
-        return cls._assemble(trees[0], flatten_forest(trees), max_q_len, max_block_len, tree_index=False,
+        return cls._assemble(trees[0], mirror_flat(trees) or flatten_forest(trees), max_q_len, max_block_len, tree_index=False,
                              device_buffer=device_buffer, table_layout=table_layout, fresh_page=fresh_page)
 
     @classmethod
     def from_tree_cache_node(cls, tree, tile_num: int = 8, max_q_len: int = 32, max_block_len: int = -1) -> "TreeMetadata":
         assert tree.use_tree_index and tree.tree_index_pool is not None
-        return cls._assemble(tree, flatten_tree(tree), max_q_len, max_block_len, tree_index=True)
+        return cls._assemble(tree, mirror_flat([tree]) or flatten_tree(tree), max_q_len, max_block_len, tree_index=True)
 
 
 def register_plan(meta: TreeMetadata) -> None:

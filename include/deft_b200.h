@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEFT_B200_ABI_VERSION 4
+#define DEFT_B200_ABI_VERSION 5
 
 enum {
   DEFT_OK = 0,
@@ -320,6 +320,25 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
                                       int32_t query_num, int32_t block_len, int32_t max_q_len,
                                       int32_t max_block_len, int32_t node_split, int32_t hkv,
                                       int32_t n_ctas, deft_layout_t* layout, const int32_t* fresh_page);
+
+/* Native tree mirror: SURVEY.md 8(f).1 "keep topology / page lists in C++".  What TreeCache holds as Python objects
+ * (tree_cache.py:94-129: TreeNode.kv_indices, .refs, .children) is mirrored here once (deft_b200_tree_set, the flat arrays
+ * of deft_b200_build_tables for ONE tree), after which a decode step only reports the page it appended to each leaf
+ * (TreeCache.alloc, tree_cache.py:261-283 -> deft_b200_tree_append: node = DFS index, -1 entries are skipped) and the
+ * tables are built straight from the mirrors (deft_b200_build_tables_trees: the trees one after the other, queries of
+ * tree t after those of tree t-1; fresh_page indexed by that global query id).  Any structural change (branch, cut,
+ * merge) is followed by another deft_b200_tree_set.  One thread at a time per handle. */
+typedef struct deft_tree deft_tree_t;
+deft_tree_t* deft_b200_tree_new(void);
+void deft_b200_tree_free(deft_tree_t* tree);
+int deft_b200_tree_set(deft_tree_t* tree, int32_t n_nodes, const int32_t* parent, const int64_t* kv_off, const int64_t* kv,
+                       const int64_t* q_off, const int64_t* qs, const int64_t* tix_row /* or NULL */, int32_t query_num);
+int deft_b200_tree_append(deft_tree_t* tree, int32_t n, const int32_t* node, const int64_t* page);
+int64_t deft_b200_tree_pages(const deft_tree_t* tree);   /* pages held (consistency check of the caller) */
+deft_tables_t* deft_b200_build_tables_trees(deft_tree_t* const* trees, int32_t n_trees, int64_t tix_max_ctx,
+                                            int32_t block_len, int32_t max_q_len, int32_t max_block_len,
+                                            int32_t node_split, int32_t hkv, int32_t n_ctas, deft_layout_t* layout,
+                                            const int32_t* fresh_page);
 const void* deft_b200_tables_data(const deft_tables_t* t);  /* packed host buffer */
 size_t deft_b200_tables_bytes(const deft_tables_t* t);
 /* dir[2*i] = byte offset of array i in the packed buffer, dir[2*i+1] = element count */

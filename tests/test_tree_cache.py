@@ -279,3 +279,113 @@ def test_cfg3b_is_a_medusa_style_sparse_tree():
     assert tree.root.kv_indices == list(range(2048))
     m = TreeMetadata.from_tree_cache(tree)
     assert m.query_num == len(tree.leaves) == 29 and m.total_kv_len == 2048 + 63
+
+
+def _tables_equal(a, b):
+    """Two (data, directory, scalars) results of build_tables_host hold the same bytes."""
+    assert np.array_equal(a[1], b[1]), "directory"
+    assert np.array_equal(a[2], b[2]), "scalars"
+    assert np.array_equal(a[0], b[0]), "packed tables"
+
+
+def test_native_tree_mirror_follows_the_tree(monkeypatch):
+    """the C++ mirror (deft_tree_t) is fed one deft_b200_tree_append per alloc() and gives, after every
+    kind of change -- alloc, branch, cut, merge with and without pruning, reset_node_KV, pause, a page list edited or
+    swapped behind the TreeCache's back -- the tables the flat arrays of a fresh walk give, byte for byte."""
+    import random
+    from deft_b200.tree_cache import build_tables_host, mirror_flat
+    rng = random.Random(3)
+    r2t = ReqToTokenPool(size=256, max_context_len=1024, device="cpu")
+    kvp = TokenToKVPool(size=16384, dtype=torch.float16, head_num=2, head_dim=16, layer_num=1, device="cpu")
+    tree = TreeCache(torch.float16, 2, 16, 1, r2t, kvp, None, True, False)
+    tree.init_prompt(torch.arange(1, 301, dtype=torch.int32))
+
+    def check(what):
+        flat = mirror_flat([tree])
+        assert flat is not None and "trees" in flat
+        got = build_tables_host(flat, hkv=2)
+        want = build_tables_host(_fresh_flat(tree), hkv=2)
+        _tables_equal(got, want)
+        assert flat["leaf_to_q"] == {lid: i for i, lid in enumerate(sorted(tree.leaves))}, what
+        assert _lib.lib.deft_b200_tree_pages(tree.native_tree().handle) == sum(
+            len(n.kv_indices) for n in tree.nodes.values() if not n.paused)
+
+    def step():
+        for leaf in tree.leaves.values():
+            leaf.append_token(1)
+        return tree.alloc()
+
+    check("prompt")
+    syncs = tree.native_tree().syncs
+    for _ in range(10):                         # a decode loop: alloc only -> no further hand-over of the tree
+        step()
+        check("alloc")
+    assert tree.native_tree().syncs == syncs
+    for it in range(50):
+        op = rng.random()
+        leaves = sorted(tree.leaves.values(), key=lambda x: x.id)
+        if op < 0.25 and len(leaves) < 40:
+            tree.branch(rng.choice(leaves), rng.choice((2, 3, 5)))
+            what = "branch"
+        elif op < 0.35 and len(leaves) > 2:
+            tree.cut(rng.choice(leaves))
+            what = "cut"
+        elif op < 0.45 and len(leaves) > 3:
+            a, b = rng.sample(leaves, 2)
+            tree.merge_nodes(a, b, pruneB_flag=rng.random() < 0.5)
+            what = "merge"
+        elif op < 0.50:
+            rng.choice(leaves).kv_indices.append(kvp.alloc(1).tolist()[0])       # edited in place, behind the tree's back
+            what = "foreign append"
+        elif op < 0.55:
+            leaf = rng.choice(leaves)
+            leaf.kv_indices = list(leaf.kv_indices) + kvp.alloc(2).tolist()      # swapped for another list
+            what = "foreign swap"
+        elif op < 0.65:
+            rng.choice(leaves).paused = False    # (the reference never pauses a node; the setter still moves the epoch)
+            what = "pause epoch"
+        else:
+            what = "alloc"
+        step()
+        check(what)
+        step()                                  # (and the append path right after the re-sync)
+        check(what + " + alloc")
+    monkeypatch.setenv("DEFT_NATIVE_TREE", "0")
+    assert mirror_flat([tree]) is None          # the switch: flat arrays, as for a foreign tree object
+
+
+def test_native_tree_mirrors_of_a_forest_and_of_tree_index_mode():
+    from deft_b200.tree_cache import build_tables_host, flatten_forest, flatten_tree, mirror_flat
+    from deft_b200.workloads import build_forest
+    trees = build_forest("cfg3", 5, layers=1, device=torch.device("cpu"), headroom=64 * 8)
+    for it in range(4):
+        locs = []
+        for t in trees:
+            for leaf in t.leaves.values():
+                leaf.append_token(1)
+            locs.append(t.alloc().cache_loc)
+        fresh = torch.cat(locs).numpy()
+        flat = mirror_flat(trees)
+        _tables_equal(build_tables_host(flat, hkv=8, fresh_page=fresh), build_tables_host(flatten_forest(trees), hkv=8, fresh_page=fresh))
+        assert flat["leaf_to_q"] == flatten_forest(trees)["leaf_to_q"]
+        if it == 1:
+            trees[2].branch(sorted(trees[2].leaves.values(), key=lambda x: x.id)[0], 2)   # one tree of the forest changes shape
+    assert sum(t.native_tree().syncs for t in trees) == 6        # one hand-over per tree + one for the branch
+    # tree-index mode: the index rows travel with the mirror
+    r2t = ReqToTokenPool(size=64, max_context_len=512, device="cpu")
+    kvp = TokenToKVPool(size=4096, dtype=torch.float16, head_num=2, head_dim=16, layer_num=1, device="cpu")
+    tix = TreeIndexPool(size=32, max_context_len=512, device="cpu")
+    tree = TreeCache(torch.float16, 2, 16, 1, r2t, kvp, tix, True, True)
+    tree.init_prompt(torch.arange(1, 150, dtype=torch.int32))
+    tree.branch(tree.root, 3)
+    BLOCK_CONFIG["MAX_BLOCK_LEN"] = 128
+    try:
+        for _ in range(3):
+            for leaf in tree.leaves.values():
+                leaf.append_token(1)
+            tree.alloc()
+            _tables_equal(build_tables_host(mirror_flat([tree]), max_block_len=128, tree_index_max_ctx=512, hkv=2),
+                          build_tables_host(flatten_tree(tree), max_block_len=128, tree_index_max_ctx=512, hkv=2))
+        assert tree.native_tree().syncs == 1
+    finally:
+        BLOCK_CONFIG["MAX_BLOCK_LEN"] = -1
