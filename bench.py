@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--cfg5-trees", type=int, default=CFG5_TREES, help="trees of the cfg5 block over ALL ranks")
     ap.add_argument("--e2e-chunk", type=int, default=8, choices=[1, 2, 4, 8, 16, 32],
                     help="layers per H2D / graph / D2H chunk of the end-to-end leg")
+    ap.add_argument("--profile-e2e", default=None, metavar="FILE",
+                    help="cProfile of 50 end-to-end steps (host side) written to FILE; diagnostic, not a bench value")
     ap.add_argument("--e2e-serial", action="store_true", help="end-to-end leg without the table build of step t+1 under step t")
     ap.add_argument("--e2e-static", action="store_true", help="end-to-end leg over a tree that does NOT grow (r1 behaviour)")
     ap.add_argument("--trees-per-gpu", type=int, default=1,
@@ -245,7 +247,7 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
     from deft_b200.workloads import build_forest, n_leaves
 
     torch.manual_seed(1234 + rank)
-    grow_steps = 0 if args.e2e_static else 2 * (3 + e2e_steps) + 2      # pipelined + serial legs
+    grow_steps = 0 if args.e2e_static else 2 * (3 + e2e_steps) + 2 + (50 if args.profile_e2e else 0)     # pipelined + serial legs
     trees = build_forest(workload, T, layers=pools, device=dev, headroom=64 + n_leaves(workload) * grow_steps)
     kvp = trees[0].token_to_kv_pool
     for l in range(pools):
@@ -461,6 +463,16 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
             ms_serial = timed(step_e2e, e2e_steps, 3)
         prepare_next()
         ms_e2e = timed(step_e2e_pipelined, e2e_steps, 3)
+        if args.profile_e2e and rank == 0 and graphed and not args.e2e_static:
+            import cProfile
+            import pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            for _ in range(50):
+                step_e2e_pipelined()
+            pr.disable()
+            with open(args.profile_e2e, "w") as f:
+                pstats.Stats(pr, stream=f).sort_stats("tottime").print_stats(40)
     else:
         ms_e2e = timed(step_e2e, e2e_steps, 3)
     h2d = LAYERS * nq * (H + 2 * HKV) * D * 2 + table_bytes[0] + host_loc.numel() * 4

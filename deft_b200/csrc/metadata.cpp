@@ -80,12 +80,29 @@ struct deft_layout {
 
 // Native mirror of one decoding tree (deft_b200_tree_new): topology and per-node page lists kept on this side of the
 // ABI, so that a decode step only hands over the pages it appended (TreeCache.alloc) instead of the whole tree.
+// What the native tiler keeps per tree from one build to the next (valid while the tree only grows by appends): the
+// token order of its tiles.  A build then lays out only the tokens appended since -- its cost no longer grows with
+// the tree -- and cuts the tiles from the kept order.
+struct deft_tiler_cache {
+  bool valid = false;
+  i32 query_base = 0;                      // rank of the tree's first query in the build the order was made for
+  std::vector<i32> run_page, run_node;     // tokens of the RUN tiles (128 each), nodes tree-local
+  struct Group {                           // tokens attended by one set of slots, in tile order (-1: dummy)
+    i64 sig;
+    i32 max_page;
+    std::vector<i32> page, node;
+  };
+  std::vector<Group> groups;               // ascending sig
+  std::vector<std::pair<i32, i64>> pending;   // (node, page) appended since the kept order was last brought up to date
+};
+
 struct deft_tree {
   std::vector<i32> parent;                 // DFS pre-order, -1 for the root
   std::vector<std::vector<i64>> pages;     // per node, in the order they were handed out
   std::vector<i64> q_off, qs, tix;
   i32 query_num = 0;
   i64 n_pages = 0;
+  deft_tiler_cache tiler;
 };
 
 namespace {
@@ -136,6 +153,9 @@ struct Scratch {
   ~Scratch() { delete spare; }
 };
 thread_local Scratch g_scratch;
+// the mirrors the flat arrays of the running build were made from, tree by tree (deft_b200_build_tables_trees), or null
+thread_local deft_tree_t* const* g_tree_hints = nullptr;
+thread_local i32 g_n_tree_hints = 0;
 }  // namespace
 
 extern "C" {
@@ -438,16 +458,238 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       for (size_t si = 0; si < ns; ++si)
         if ((andp[si] & fullp[si]) != fullp[si]) tp_dense[s0 + si] = 0;
     };
-    struct Chunk { i32 first, len; };       // `len` (a power of two) consecutive pages: tokens [first, first + len) of `rest`
+    struct Chunk { i32 first, len; };       // `len` (a power of two) consecutive pages: tokens [first, first + len) of a sorted list
     auto& rest = S.rest; auto& rest_tmp = S.rest_tmp; auto& out_page = S.out_page; auto& out_node = S.out_node;
     std::vector<Chunk> chunks;
     std::vector<i64> sigs;                  // the distinct slot sets of one tree's subtree tokens (a handful)
     std::vector<i32> sig_rank;
+    std::vector<i32> gseq_page, gseq_node;  // one group's tokens in tile order
+    // power-of-two chunks of the runs of consecutive pages of tokens [g0, g1) of `rest` (sorted by page)
+    auto chunk_runs = [&](size_t g0, size_t g1) {
+      chunks.clear();
+      for (size_t i = g0; i < g1;) {
+        size_t j = i + 1;
+        while (j < g1 && rest[j].page == rest[j - 1].page + 1) ++j;
+        size_t at = i;
+        for (i32 len = 32; len >= 1; len >>= 1)
+          while (j - at >= (size_t)len) {
+            chunks.push_back({(i32)at, len});
+            at += (size_t)len;
+          }
+        i = j;
+      }
+    };
+    // `rest` by ascending key: a byte-wise radix sort (LSD, bytes that are the same for all keys skipped: two or three
+    // passes for a pool of < 16 M pages)
+    auto sort_rest = [&]() {
+      const size_t n_rest = rest.size();
+      uint32_t hist[5][256] = {};
+      uint64_t any = 0;
+      for (const RestTok& tk : rest) {
+        any |= tk.key;
+        for (int d = 0; d < 5; ++d) ++hist[d][(tk.key >> (8 * d)) & 0xff];
+      }
+      if ((any >> 40) != 0) {             // (more slot sets than a byte counts: never seen; the comparison sort is the fallback)
+        std::sort(rest.begin(), rest.end(), [](const RestTok& x, const RestTok& y) { return x.key < y.key; });
+        return;
+      }
+      rest_tmp.resize(n_rest);
+      RestTok* src = rest.data();
+      RestTok* dst = rest_tmp.data();
+      for (int d = 0; d < 5 && n_rest > 1; ++d) {
+        uint32_t* h = hist[d];
+        if (h[(src[0].key >> (8 * d)) & 0xff] == n_rest) continue;   // every key has this byte
+        uint32_t sum = 0;
+        for (int v = 0; v < 256; ++v) { const uint32_t c = h[v]; h[v] = sum; sum += c; }
+        for (size_t x = 0; x < n_rest; ++x) dst[h[(src[x].key >> (8 * d)) & 0xff]++] = src[x];
+        std::swap(src, dst);
+      }
+      if (src != rest.data()) rest.swap(rest_tmp);
+    };
+    // the groups of `rest` (sorted) one after the other into out_page / out_node: inside a group the chunks longest
+    // first (in page order among equals), between groups dummies up to a whole block of 32.  `keep`: where the
+    // groups without the fresh flag are also kept for the builds to come (nodes tree-local).
+    auto layout_rest = [&](deft_tiler_cache* keep, i32 node_base) {
+      const size_t n_rest = rest.size();
+      for (size_t g0 = 0; g0 < n_rest;) {
+        size_t g1 = g0;
+        while (g1 < n_rest && (rest[g1].key >> 32) == (rest[g0].key >> 32)) ++g1;
+        chunk_runs(g0, g1);
+        gseq_page.clear();
+        gseq_node.clear();
+        for (i32 len = 32; len >= 1; len >>= 1)
+          for (const Chunk& c : chunks) {
+            if (c.len != len) continue;
+            for (i32 k = 0; k < len; ++k) {
+              gseq_page.push_back(rest[(size_t)(c.first + k)].page);
+              gseq_node.push_back(rest[(size_t)(c.first + k)].node);
+            }
+          }
+        out_page.insert(out_page.end(), gseq_page.begin(), gseq_page.end());
+        out_node.insert(out_node.end(), gseq_node.begin(), gseq_node.end());
+        const i64 sig = sigs[(size_t)sig_rank[(size_t)(rest[g0].key >> 32)]];
+        if (keep && !((sig >> 62) & 1)) {
+          keep->groups.emplace_back();
+          deft_tiler_cache::Group& g = keep->groups.back();
+          g.sig = sig;
+          g.max_page = rest[g1 - 1].page;
+          g.page = gseq_page;
+          g.node.resize(gseq_node.size());
+          for (size_t k = 0; k < gseq_node.size(); ++k) g.node[k] = gseq_node[k] - node_base;
+        }
+        if (g1 < n_rest)
+          while (out_page.size() % 32) {                       // whole blocks per group: the next group's runs stay aligned
+            out_page.push_back(-1);
+            out_node.push_back(-1);
+          }
+        g0 = g1;
+      }
+    };
+    // rest tokens carry the index of their slot set in `sigs`; the sort wants the RANK of the set (ascending sig)
+    auto rank_sigs = [&]() {
+      sig_rank.assign(sigs.size(), 0);       // sig_rank[rank] = index in sigs (after the loop below: inverted)
+      std::vector<i32> rk(sigs.size(), 0);
+      for (size_t x = 0; x < sigs.size(); ++x)
+        for (size_t y = 0; y < sigs.size(); ++y) rk[x] += sigs[y] < sigs[x] ? 1 : 0;
+      for (RestTok& tk : rest) tk.key = ((uint64_t)rk[(size_t)(tk.key >> 32)] << 32) | (tk.key & 0xffffffffu);
+      for (size_t x = 0; x < sigs.size(); ++x) sig_rank[(size_t)rk[x]] = (i32)x;
+    };
+    auto fresh_query = [&](i64 page) -> i32 {     // the query whose page of this step `page` is, or -1
+      if (!fresh_page || fresh_sorted.empty() || page < fresh_sorted.front().first || page > fresh_sorted.back().first) return -1;
+      auto it = std::lower_bound(fresh_sorted.begin(), fresh_sorted.end(), std::make_pair((i32)page, (i32)-1));
+      return it != fresh_sorted.end() && it->first == (i32)page ? it->second : -1;
+    };
+    // A tree whose tile order was kept (deft_tiler_cache): the tokens appended since go to the END of their groups, the
+    // ones of this very step (fresh_page) into groups of their own as ever, and the tiles are cut from the kept order.
+    // false: the kept order cannot serve this build (nothing has been touched).
+    struct Incoming { i32 group, page, node; };
+    std::vector<Incoming> incoming;
+    std::vector<std::pair<i32, i64>> still_pending;
+    auto serve_kept = [&](deft_tree_t* ht, i32 node_base, i32 query_base) -> bool {
+      deft_tiler_cache& c = ht->tiler;
+      if (!c.valid || c.query_base != query_base) return false;
+      size_t named = 0, found = 0;
+      if (fresh_page)
+        for (i32 qv = query_base; qv < query_base + ht->query_num; ++qv) named += fresh_page[qv] >= 0 ? 1 : 0;
+      incoming.clear();
+      still_pending.clear();
+      rest.clear();
+      sigs.clear();
+      for (const auto& pn : c.pending) {
+        const i64 sig = sig_of(node_base + pn.first);
+        const i32 fq = fresh_query(pn.second);
+        if (fq >= 0) {                      // of this step: read from the activations, kept pending for the next build
+          ++found;
+          still_pending.push_back(pn);
+          const i64 fsig = sig | ((i64)1 << 62);
+          size_t gi = 0;
+          while (gi < sigs.size() && sigs[gi] != fsig) ++gi;
+          if (gi == sigs.size()) sigs.push_back(fsig);
+          rest.push_back({((uint64_t)gi << 32) | (uint32_t)fq, kFreshToken | fq, node_base + pn.first});
+          continue;
+        }
+        size_t g = 0;
+        while (g < c.groups.size() && c.groups[g].sig != sig) ++g;
+        if (g < c.groups.size() && pn.second <= (i64)c.groups[g].max_page) return false;   // not an append in page order
+        if (pn.second >= ((i64)1 << 27)) return false;
+        incoming.push_back({g < c.groups.size() ? (i32)g : -1, (i32)pn.second, pn.first});
+      }
+      if (found != named) return false;     // fresh_page names tokens the kept order already holds as pool pages
+      for (Incoming& in : incoming)         // slot sets seen for the first time get (empty) groups, kept in ascending order
+        if (in.group < 0) {
+          const i64 sig = sig_of(node_base + in.node);
+          size_t g = 0;
+          while (g < c.groups.size() && c.groups[g].sig < sig) ++g;
+          if (g == c.groups.size() || c.groups[g].sig != sig) {
+            deft_tiler_cache::Group ng;
+            ng.sig = sig;
+            ng.max_page = -1;
+            c.groups.insert(c.groups.begin() + (long)g, std::move(ng));
+            for (Incoming& o : incoming)
+              if (o.group >= (i32)g) ++o.group;
+          }
+          in.group = (i32)g;
+        }
+      // per group: the new tokens by page, runs -> power-of-two chunks, longest first, at the end of the group.  A chunk
+      // of 8 or more is aligned with dummies when the whole batch is a multiple of it (the alignment then lasts: one
+      // page per leaf and step), so that it loads as one TMA box per panel.
+      std::sort(incoming.begin(), incoming.end(), [](const Incoming& x, const Incoming& y) { return x.group != y.group ? x.group < y.group : x.page < y.page; });
+      std::vector<RestTok> batch;
+      for (size_t i0 = 0; i0 < incoming.size();) {
+        size_t i1 = i0;
+        while (i1 < incoming.size() && incoming[i1].group == incoming[i0].group) ++i1;
+        deft_tiler_cache::Group& g = c.groups[(size_t)incoming[i0].group];
+        batch.clear();
+        for (size_t i = i0; i < i1; ++i) batch.push_back({0, incoming[i].page, incoming[i].node});
+        batch.swap(rest);                   // (chunk_runs reads `rest`)
+        chunk_runs(0, rest.size());
+        const size_t batch_len = rest.size();
+        for (i32 len = 32; len >= 1; len >>= 1)
+          for (const Chunk& ch : chunks) {
+            if (ch.len != len) continue;
+            if (len >= 8 && batch_len % (size_t)len == 0)
+              while (g.page.size() % (size_t)len) { g.page.push_back(-1); g.node.push_back(-1); }
+            for (i32 k = 0; k < len; ++k) {
+              g.page.push_back(rest[(size_t)(ch.first + k)].page);
+              g.node.push_back(rest[(size_t)(ch.first + k)].node);
+            }
+          }
+        g.max_page = rest.back().page;
+        batch.swap(rest);
+        i0 = i1;
+      }
+      c.pending.swap(still_pending);
+      // the tiles: RUN tiles, the kept groups, this step's groups
+      out_page.clear();
+      out_node.clear();
+      for (size_t k = 0; k < c.run_page.size(); k += 128) {
+        out_node.resize(128);
+        for (size_t x = 0; x < 128; ++x) out_node[x] = c.run_node[k + x] + node_base;
+        emit_tile(&c.run_page[k], out_node.data(), 128);
+      }
+      out_node.clear();
+      rank_sigs();
+      sort_rest();
+      bool first = true;
+      for (const deft_tiler_cache::Group& g : c.groups) {
+        if (g.page.empty()) continue;
+        if (!first)
+          while (out_page.size() % 32) { out_page.push_back(-1); out_node.push_back(-1); }
+        first = false;
+        out_page.insert(out_page.end(), g.page.begin(), g.page.end());
+        for (i32 nd : g.node) out_node.push_back(nd < 0 ? -1 : nd + node_base);
+      }
+      if (!rest.empty()) {
+        if (!first)
+          while (out_page.size() % 32) { out_page.push_back(-1); out_node.push_back(-1); }
+        layout_rest(nullptr, node_base);
+      }
+      for (size_t k = 0; k < out_page.size(); k += 128)
+        emit_tile(&out_page[k], &out_node[k], (i32)std::min<size_t>(128, out_page.size() - k));
+      return true;
+    };
     const size_t n_tok = tok_page.size();
-    for (size_t a = 0; a < n_tok;) {
+    i32 tree_i = 0, query_base = 0, nodes_before = 0;
+    for (size_t a = 0; a < n_tok; ++tree_i) {
       // the tokens [a, b) of one tree (its nodes are consecutive in the pre-order; parent -1 starts the next tree)
+      deft_tree_t* ht = g_tree_hints && tree_i < g_n_tree_hints ? g_tree_hints[tree_i] : nullptr;
       size_t b = a + 1;
-      while (b < n_tok && !(tok_node[b] != tok_node[b - 1] && parent[tok_node[b]] == -1)) ++b;
+      if (ht) b = a + (size_t)ht->n_pages;
+      else
+        while (b < n_tok && !(tok_node[b] != tok_node[b - 1] && parent[tok_node[b]] == -1)) ++b;
+      const i32 node_base = ht ? nodes_before : tok_node[a];
+      if (ht) nodes_before += (i32)ht->parent.size();
+      if (ht && regroup && serve_kept(ht, node_base, query_base)) {
+        query_base += ht->query_num;
+        a = b;
+        continue;
+      }
+      deft_tiler_cache* keep = nullptr;
+      if (ht && regroup) {                   // this build's order is kept for the builds to come
+        keep = &ht->tiler;
+        *keep = deft_tiler_cache();
+        keep->query_base = query_base;
+      }
       rest.clear();
       out_page.clear();
       out_node.clear();
@@ -461,6 +703,15 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         while (j < b && tok_page[j] == tok_page[j - 1] + 1 && (tok_node[j] == tok_node[j - 1] || sig_of(tok_node[j]) == (sig & ~((i64)1 << 62)))) ++j;
         const size_t whole = fresh ? 0 : (j - i) / 128 * 128;
         for (size_t k = i; k < i + whole; k += 128) emit_tile(&tok_page[k], &tok_node[k], 128);   // RUN tiles
+        if (keep) {
+          for (size_t k = i; k < i + whole; ++k) {
+            keep->run_page.push_back(tok_page[k]);
+            keep->run_node.push_back(tok_node[k] - node_base);
+          }
+          if (fresh)                         // this step's tokens join the kept order at the next build
+            for (size_t k = i; k < j; ++k)
+              keep->pending.emplace_back(tok_node[k] - node_base, (i64)fresh_page[tok_page[k] & ~kFreshToken]);
+        }
         if (i + whole < j) {
           size_t gi = 0;
           while (gi < sigs.size() && sigs[gi] != sig) ++gi;
@@ -472,68 +723,20 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         i = j;
       }
       if (regroup) {
-        // groups in ascending order of their slot sets, pages ascending inside a group: a byte-wise radix sort of the
-        // keys (LSD, bytes that are the same for all keys skipped: two or three passes for a pool of < 16 M pages)
-        const size_t n_rest = rest.size();
-        sig_rank.assign(sigs.size(), 0);
-        for (size_t x = 0; x < sigs.size(); ++x)
-          for (size_t y = 0; y < sigs.size(); ++y) sig_rank[x] += sigs[y] < sigs[x] ? 1 : 0;
-        uint32_t hist[5][256] = {};
-        for (RestTok& tk : rest) {
-          tk.key = ((uint64_t)sig_rank[(size_t)(tk.key >> 32)] << 32) | (tk.key & 0xffffffffu);
-          for (int d = 0; d < 5; ++d) ++hist[d][(tk.key >> (8 * d)) & 0xff];
-        }
-        if (sigs.size() > 256) {            // (more slot sets than a byte counts: never seen; the comparison sort is the fallback)
-          std::sort(rest.begin(), rest.end(), [](const RestTok& x, const RestTok& y) { return x.key < y.key; });
-        } else {
-          rest_tmp.resize(n_rest);
-          RestTok* src = rest.data();
-          RestTok* dst = rest_tmp.data();
-          for (int d = 0; d < 5 && n_rest > 1; ++d) {
-            uint32_t* h = hist[d];
-            if (h[(src[0].key >> (8 * d)) & 0xff] == n_rest) continue;   // every key has this byte
-            uint32_t sum = 0;
-            for (int v = 0; v < 256; ++v) { const uint32_t c = h[v]; h[v] = sum; sum += c; }
-            for (size_t x = 0; x < n_rest; ++x) dst[h[(src[x].key >> (8 * d)) & 0xff]++] = src[x];
-            std::swap(src, dst);
-          }
-          if (src != rest.data()) rest.swap(rest_tmp);
-        }
-        for (size_t g0 = 0; g0 < n_rest;) {                     // one group of slots at a time
-          size_t g1 = g0;
-          while (g1 < n_rest && (rest[g1].key >> 32) == (rest[g0].key >> 32)) ++g1;
-          chunks.clear();
-          for (size_t i = g0; i < g1;) {                         // runs of consecutive pages -> power-of-two chunks
-            size_t j = i + 1;
-            while (j < g1 && rest[j].page == rest[j - 1].page + 1) ++j;
-            size_t at = i;
-            for (i32 len = 32; len >= 1; len >>= 1)
-              while (j - at >= (size_t)len) {
-                chunks.push_back({(i32)at, len});
-                at += (size_t)len;
-              }
-            i = j;
-          }
-          for (i32 len = 32; len >= 1; len >>= 1)                // longest chunks first, in page order among equals
-            for (const Chunk& c : chunks) {
-              if (c.len != len) continue;
-              for (i32 k = 0; k < len; ++k) {
-                out_page.push_back(rest[(size_t)(c.first + k)].page);
-                out_node.push_back(rest[(size_t)(c.first + k)].node);
-              }
-            }
-          if (g1 < n_rest)
-            while (out_page.size() % 32) {                       // whole blocks per group: the next group's runs stay aligned
-              out_page.push_back(-1);
-              out_node.push_back(-1);
-            }
-          g0 = g1;
+        rank_sigs();
+        sort_rest();
+        layout_rest(keep, node_base);
+        if (keep) {
+          keep->valid = true;
+          for (const RestTok& tk : rest)     // (a page that does not fit a load descriptor fails the build further down)
+            if (!(tk.page & kFreshToken) && tk.page >= (1 << 27)) keep->valid = false;
         }
       } else {
         for (const RestTok& tk : rest) { out_page.push_back(tk.page); out_node.push_back(tk.node); }
       }
       for (size_t k = 0; k < out_page.size(); k += 128)
         emit_tile(&out_page[k], &out_node[k], (i32)std::min<size_t>(128, out_page.size() - k));
+      if (ht) query_base += ht->query_num;
       a = b;
     }
     for (size_t t = 0; t < tiles.size(); ++t) {   // the pools no longer move: hand every tile its stretches
@@ -1091,6 +1294,7 @@ int deft_b200_tree_set(deft_tree_t* t, int32_t n_nodes, const int32_t* parent, c
   else t->tix.clear();
   t->query_num = query_num;
   t->n_pages = kv_off[n_nodes] - kv_off[0];
+  t->tiler = deft_tiler_cache();          // (another topology: the kept tile order is void)
   return DEFT_OK;
 }
 
@@ -1108,6 +1312,7 @@ int deft_b200_tree_append(deft_tree_t* t, int32_t n, const int32_t* node, const 
     if (node[i] < 0) continue;            // a leaf the walk left out (paused)
     t->pages[(size_t)node[i]].push_back(page[i]);
     ++t->n_pages;
+    if (t->tiler.valid) t->tiler.pending.emplace_back(node[i], page[i]);
   }
   return DEFT_OK;
 }
@@ -1151,9 +1356,14 @@ deft_tables_t* deft_b200_build_tables_trees(deft_tree_t* const* trees, int32_t n
     deft::set_error("build_tables_trees: tree-index mode needs the index rows of every tree");
     return nullptr;
   }
-  return deft_b200_build_tables((i32)parent.size(), parent.data(), kv_off.data(), kv.data(), q_off.data(), qs.data(),
-                                tix_max_ctx > 0 ? tix.data() : nullptr, tix_max_ctx, (i32)query_base, block_len, max_q_len,
-                                max_block_len, node_split, hkv, n_ctas, layout, fresh_page);
+  g_tree_hints = trees;
+  g_n_tree_hints = n_trees;
+  deft_tables_t* out = deft_b200_build_tables((i32)parent.size(), parent.data(), kv_off.data(), kv.data(), q_off.data(),
+                                              qs.data(), tix_max_ctx > 0 ? tix.data() : nullptr, tix_max_ctx, (i32)query_base,
+                                              block_len, max_q_len, max_block_len, node_split, hkv, n_ctas, layout, fresh_page);
+  g_tree_hints = nullptr;
+  g_n_tree_hints = 0;
+  return out;
 }
 
 deft_layout_t* deft_b200_layout_new(void) { return new (std::nothrow) deft_layout_t(); }

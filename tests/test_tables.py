@@ -374,3 +374,134 @@ def test_fresh_tokens_of_a_decode_step_are_marked_for_the_fused_append(golden_di
     decoded = u_kv.copy()
     decoded[is_fresh] = fresh[u_kv[is_fresh] & ~FRESH]
     check_unit_plan({**t, "u_kv": decoded}, scalars, tree, 2, 148)
+
+
+def _decode_fresh(t, fresh):
+    """Native tables with the tokens of this step put back as pages + the layout rules of fresh tokens and box chunks."""
+    FRESH = 1 << 30
+    u_kv = t["u_kv"].copy()
+    is_fresh = (u_kv >= 0) & ((u_kv & FRESH) != 0)
+    if fresh is None:
+        assert not is_fresh.any()
+    else:
+        assert sorted((u_kv[is_fresh] & ~FRESH).tolist()) == list(range(len(fresh))), "every query's new token exactly once"
+        tail = np.ones(len(u_kv), dtype=bool)                                 # past the live tokens of a tree's last tile: zeros
+        for u in t["u_units"]:
+            n_tok = (int(u["n_tiles"]) - 1) * 128 + int(u["last_len"])
+            tail[int(u["kv_off"]): int(u["kv_off"]) + n_tok] = False
+        for c4 in np.flatnonzero(is_fresh.reshape(-1, 4).any(axis=1)):       # gather granularity: all fresh, or dummies
+            four = u_kv[4 * c4: 4 * c4 + 4]
+            assert np.all(((four & FRESH) != 0) | (four < 0) | tail[4 * c4: 4 * c4 + 4]), four
+    blk = t["u_blk"]
+    kinds = np.zeros(4, dtype=np.int64)
+    for c8 in range(len(blk)):
+        eight = u_kv[8 * c8: 8 * c8 + 8]
+        kind, fr, first = (int(blk[c8]) >> 28) & 3, (int(blk[c8]) >> 27) & 1, int(blk[c8]) & ((1 << 27) - 1)
+        kinds[kind] += 1
+        if kind:
+            assert fr == int((eight[0] & FRESH) != 0) and first == int(eight[0]) & ~FRESH
+            assert np.array_equal(eight, eight[0] + np.arange(8)), "a box chunk is a run"
+    decoded = u_kv.copy()
+    if fresh is not None:
+        decoded[is_fresh] = fresh[u_kv[is_fresh] & ~FRESH]
+    return {**t, "u_kv": decoded}, kinds
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_kept_tile_order_of_a_growing_tree(seed):
+    """SURVEY 8(f).1, incremental tables: a tree that only grows by alloc() keeps the token order of its native tiles
+    in its C++ mirror; a build lays out the appended tokens only.  After every step -- with the step's tokens read from
+    the activations or from the pool, on trees of every shape, across branches and cuts (which void the kept order) --
+    the reference tables are the flat-array builder's byte for byte and the native plan attends every (query, page)
+    pair exactly once; the tiles are as well loadable (TMA boxes against gathers) as the ones laid out from scratch."""
+    import torch
+    from deft_b200.memory_pool import ReqToTokenPool, TokenToKVPool
+    from deft_b200.tree_cache import TreeCache, mirror_flat
+    rng = random.Random(seed)
+    r2t = ReqToTokenPool(size=512, max_context_len=4096, device="cpu")
+    kvp = TokenToKVPool(size=1 << 16, dtype=torch.float16, head_num=2, head_dim=16, layer_num=1, device="cpu")
+    tree = TreeCache(torch.float16, 2, 16, 1, r2t, kvp, None, True, False)
+    tree.init_prompt(torch.arange(rng.choice([5, 130, 300, 700]), dtype=torch.int32))
+
+    def step():
+        for leaf in tree.leaves.values():
+            leaf.append_token(1)
+        return tree.alloc().cache_loc.numpy().astype(np.int32)
+
+    def branch_some(width):
+        for leaf in sorted(tree.leaves.values(), key=lambda x: x.id):
+            if len(tree.leaves) < 90 and rng.random() < 0.7:
+                tree.branch(leaf, rng.choice(width))
+
+    branch_some((2, 3))
+    for _ in range(rng.choice([1, 16])):
+        step()
+    branch_some((2, 3, 4) if seed % 2 else (2,))
+    kept_steps = 0
+    for it in range(45):
+        if it in (17, 31):                     # the topology moves: the mirror is handed over again, the order made anew
+            leaves = sorted(tree.leaves.values(), key=lambda x: x.id)
+            if it == 17:
+                tree.branch(rng.choice(leaves), 2)
+            elif len(leaves) > 2:
+                tree.cut(rng.choice(leaves))
+        fresh = step()
+        use_fresh = rng.random() < 0.7
+        syncs = tree.native_tree().syncs
+        got = build_tables_host(mirror_flat([tree]), hkv=2, n_ctas=148, fresh_page=fresh if use_fresh else None)
+        want = build_tables_host(flatten_tree(tree), hkv=2, n_ctas=148, fresh_page=fresh if use_fresh else None)
+        kept_steps += int(tree.native_tree().syncs == syncs)
+        t, t0 = unpack(got[0], got[1]), unpack(want[0], want[1])
+        for k in TABLE_KEYS:
+            assert np.array_equal(t[k], t0[k]), (it, k)
+        dec, kinds = _decode_fresh(t, fresh if use_fresh else None)
+        check_unit_plan(dec, got[2], tree, 2, 148)
+        _, kinds0 = _decode_fresh(t0, fresh if use_fresh else None)
+        # load instructions per panel: box32 = 1/4 per chunk of 8, box16 = 1/2, box8 = 1, gathered = 2
+        cost, cost0 = (k @ np.array([2.0, 1.0, 0.5, 0.25]) for k in (kinds, kinds0))
+        assert cost <= 1.25 * cost0 + 8, (it, kinds, kinds0)
+        if rng.random() < 0.3:                 # a second build of the same step, the other way round
+            again = build_tables_host(mirror_flat([tree]), hkv=2, n_ctas=148, fresh_page=None if use_fresh else fresh)
+            dec2, _ = _decode_fresh(unpack(again[0], again[1]), None if use_fresh else fresh)
+            check_unit_plan(dec2, again[2], tree, 2, 148)
+    assert kept_steps >= 40
+
+
+def test_kept_tile_order_of_a_forest():
+    """The same for several trees over one pool: every tree keeps its own order (slots are counted over the whole
+    forest, so a tree whose first query moves -- a neighbour branched -- starts over)."""
+    import torch
+    from deft_b200.memory_pool import ReqToTokenPool, TokenToKVPool
+    from deft_b200.tree_cache import TreeCache, flatten_forest, mirror_flat
+    rng = random.Random(11)
+    r2t = ReqToTokenPool(size=512, max_context_len=4096, device="cpu")
+    kvp = TokenToKVPool(size=1 << 16, dtype=torch.float16, head_num=2, head_dim=16, layer_num=1, device="cpu")
+    trees = []
+    for i in range(4):
+        tree = TreeCache(torch.float16, 2, 16, 1, r2t, kvp, None, True, False)
+        tree.init_prompt(torch.arange((40, 260, 131, 512)[i], dtype=torch.int32))
+        for _ in range(2):
+            for leaf in sorted(tree.leaves.values(), key=lambda x: x.id):
+                if rng.random() < 0.8:
+                    tree.branch(leaf, rng.choice((2, 3, 5)))
+            for leaf in tree.leaves.values():
+                leaf.append_token(1)
+            tree.alloc()
+        trees.append(tree)
+    for it in range(24):
+        if it == 9:
+            trees[1].branch(sorted(trees[1].leaves.values(), key=lambda x: x.id)[0], 3)   # the queries of trees 2, 3 move up
+        locs = []
+        for tree in trees:
+            for leaf in tree.leaves.values():
+                leaf.append_token(1)
+            locs.append(tree.alloc().cache_loc.numpy().astype(np.int32))
+        fresh = np.concatenate(locs) if it % 3 else None
+        got = build_tables_host(mirror_flat(trees), hkv=2, n_ctas=148, fresh_page=fresh)
+        want = build_tables_host(flatten_forest(trees), hkv=2, n_ctas=148, fresh_page=fresh)
+        t, t0 = unpack(got[0], got[1]), unpack(want[0], want[1])
+        for k in TABLE_KEYS:
+            assert np.array_equal(t[k], t0[k]), (it, k)
+        dec, _ = _decode_fresh(t, fresh)
+        check_unit_plan(dec, got[2], trees, 2, 148)
+    assert sum(t.native_tree().syncs for t in trees) == 5
