@@ -84,6 +84,7 @@ def _load() -> C.CDLL:
         "deft_b200_layout_new": (vp, []),
         "deft_b200_layout_free": (None, [vp]),
         "deft_b200_layout_version": (i64, [vp]),
+        "deft_b200_layout_set_native_only": (None, [vp, C.c_int]),
         "deft_b200_tables_data": (vp, [vp]),
         "deft_b200_tables_bytes": (sz, [vp]),
         "deft_b200_tables_directory": (C.c_int, [vp, vp]),
@@ -105,7 +106,7 @@ EXPORTS = ["deft_b200_abi_version", "deft_b200_last_error", "deft_b200_set_stage
            "deft_b200_flatten_workspace_bytes",
            "deft_b200_flatten_fwd", "deft_b200_node_workspace_bytes", "deft_b200_node_fwd", "deft_b200_flatten_fwd_append", "deft_b200_node_fwd_append", "deft_b200_kv_append",
            "deft_b200_build_tables", "deft_b200_tree_new", "deft_b200_tree_free", "deft_b200_tree_set", "deft_b200_tree_append",
-           "deft_b200_tree_pages", "deft_b200_build_tables_trees", "deft_b200_layout_new", "deft_b200_layout_free", "deft_b200_layout_version",
+           "deft_b200_tree_pages", "deft_b200_build_tables_trees", "deft_b200_layout_new", "deft_b200_layout_free", "deft_b200_layout_version", "deft_b200_layout_set_native_only",
            "deft_b200_tables_data", "deft_b200_tables_bytes",
            "deft_b200_tables_directory", "deft_b200_tables_scalars", "deft_b200_tables_free"]
 

@@ -385,11 +385,13 @@ int deft_b200_flatten_fwd_append(const void* q, int64_t q_row_stride, int64_t q_
                         kv_head_stride, o_row_stride, o_head_stride);
   if (rc) return rc;
   DEFT_CHECK_ARG(block_len == 128, "block_len must be 128 (got %d): the reference Flatten kernel hard-wires it", block_len);
-  DEFT_CHECK_ARG(block_q && block_q_cnts && block_q_offset && block_lens && block_bitmasks && block_kv,
-                 "null table pointer");
-  DEFT_CHECK_ARG(n_blocks > 0 && n_partials > 0, "empty tables");
-  DEFT_CHECK_ARG(workspace, "null workspace");
   const bool umma = use_umma(H, HKV, D);
+  // (a native-only build, deft_b200_layout_set_native_only: the unit plan is all the tensor-core path reads)
+  const bool plan_only = umma && plan && plan->units && plan->u_blk && n_blocks == 0 && n_partials == 0;
+  DEFT_CHECK_ARG(plan_only || (block_q && block_q_cnts && block_q_offset && block_lens && block_bitmasks && block_kv),
+                 "null table pointer");
+  DEFT_CHECK_ARG(plan_only || (n_blocks > 0 && n_partials > 0), "empty tables");
+  DEFT_CHECK_ARG(workspace, "null workspace");
   Workspace w = carve(workspace, flatten_sizes(plan, n_partials, n_blocks), umma, plan == nullptr, nq, H, HKV, D);
   if (w.bytes > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
@@ -451,10 +453,11 @@ int deft_b200_node_fwd_append(const void* q, int64_t q_row_stride, int64_t q_hea
                         kv_head_stride, o_row_stride, o_head_stride);
   if (rc) return rc;
   DEFT_CHECK_ARG(kv_index_bytes == 8 || kv_index_bytes == 4, "kv_index_bytes must be 8 or 4");
-  DEFT_CHECK_ARG(kv_indices && kv_offset && kv_len && node_q && q_offset && q_len, "null table pointer");
-  DEFT_CHECK_ARG(n_entries > 0 && n_partials > 0, "empty tables");
-  DEFT_CHECK_ARG(workspace, "null workspace");
   const bool umma = use_umma(H, HKV, D);
+  const bool plan_only = umma && plan && plan->units && plan->u_blk && n_entries == 0 && n_partials == 0;
+  DEFT_CHECK_ARG(plan_only || (kv_indices && kv_offset && kv_len && node_q && q_offset && q_len), "null table pointer");
+  DEFT_CHECK_ARG(plan_only || (n_entries > 0 && n_partials > 0), "empty tables");
+  DEFT_CHECK_ARG(workspace, "null workspace");
   const int64_t items = node_items_bound(n_entries, total_kv_bound);
   Workspace w = carve(workspace, node_sizes(plan, n_partials, n_entries, total_kv_bound), umma, plan == nullptr,
                       nq, H, HKV, D);

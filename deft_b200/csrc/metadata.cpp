@@ -76,6 +76,7 @@ struct deft_layout {
   i64 cap_bytes[DEFT_T_COUNT] = {0};
   i64 slot_cap = 0;      // unit slots (partial tiles per kv-head) the workspace is carved for
   i64 version = 0;
+  int native_only = 0;   // leave the reference tables and the item / group plans empty (deft_b200_layout_set_native_only)
 };
 
 // Native mirror of one decoding tree (deft_b200_tree_new): topology and per-node page lists kept on this side of the
@@ -196,6 +197,9 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     std::fprintf(stderr, "build_tables %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(now - t_prof).count());
     t_prof = now;
   };
+  // A decode loop on the tensor-core kernels reads nothing but the native unit plan: its layout may ask for just that
+  // (the int64 tables of the reference and the item / group plans of the warp-FMA path are then left empty)
+  const bool native_only = layout && layout->native_only && block_len == 128 && hkv > 0;
   Scratch& S = g_scratch;
   auto& node_q = S.node_q; auto& node_kv = S.node_kv; auto& node_q_len = S.node_q_len; auto& node_kv_len = S.node_kv_len;
   auto& node_kv_offset_ti = S.node_kv_offset_ti;
@@ -294,11 +298,52 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       if (fresh_page[qv] >= 0) fresh_sorted.emplace_back(fresh_page[qv], qv);
     std::sort(fresh_sorted.begin(), fresh_sorted.end());
   }
+  const char* env_r = std::getenv("DEFT_PLAN_REGROUP");
+  const bool regroup = fresh_page != nullptr || !(env_r && env_r[0] == '0');   // (fresh tokens need chunks of their own)
+  // A native-only build of trees that all keep their tile order needs no token stream at all: the tokens of a tree
+  // are then listed only if its kept order turns out not to serve (gen_tokens below).
+  bool lazy_tokens = native_only && regroup && g_tree_hints != nullptr;
+  if (lazy_tokens) {
+    i32 qb = 0;
+    for (i32 ti = 0; ti < g_n_tree_hints && lazy_tokens; ++ti) {
+      lazy_tokens = g_tree_hints[ti]->tiler.valid && g_tree_hints[ti]->tiler.query_base == qb;
+      qb += g_tree_hints[ti]->query_num;
+    }
+  }
+  auto push_tokens = [&]() {   // of the node whose sorted pages are in `kvs`; this step's tokens name their query instead of a page
+    for (i64 kvp : kvs) {
+      i32 v = (i32)kvp;
+      if (fresh_page && !fresh_sorted.empty() && kvp >= fresh_sorted.front().first && kvp <= fresh_sorted.back().first) {
+        auto it = std::lower_bound(fresh_sorted.begin(), fresh_sorted.end(), std::make_pair((i32)kvp, (i32)-1));
+        if (it != fresh_sorted.end() && it->first == (i32)kvp) v = kFreshToken | it->second;
+      }
+      tok_page.push_back(v);
+    }
+  };
+  auto gen_tokens = [&](i32 n0, i32 n1) {
+    tok_page.clear();
+    tok_node.clear();
+    for (i32 n = n0; n < n1; ++n) {
+      kvs.assign(kv + kv_off[n], kv + kv_off[n + 1]);
+      if (!std::is_sorted(kvs.begin(), kvs.end())) std::sort(kvs.begin(), kvs.end());
+      push_tokens();
+      tok_node.insert(tok_node.end(), kvs.size(), n);
+    }
+  };
   for (i32 n = 0; n < n_nodes; ++n) {  // pre-order visit == the reference's recursive dfs (:725-791)
     const i64 k0 = kv_off[n], k1 = kv_off[n + 1], q0 = q_off[n], q1 = q_off[n + 1];
     if (k1 < k0 || q1 <= q0) {
       deft::set_error("build_tables: node %d has no attending query or a negative page count", n);
       return nullptr;
+    }
+    if (lazy_tokens) {
+      for (i64 i = q0; i < q1; ++i)
+        if (qs[i] < 0 || qs[i] >= query_num) {
+          deft::set_error("build_tables: node %d lists query %lld outside [0, %d)", n, (long long)qs[i], query_num);
+          return nullptr;
+        }
+      total_kv_len += k1 - k0;
+      continue;
     }
     kvs.assign(kv + k0, kv + k1);
     const i64 n_kv = (i64)kvs.size();
@@ -318,7 +363,7 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
     const i64 step = max_block_len == -1 ? n_kv : max_block_len;
     const bool kv_sorted = std::is_sorted(kvs.begin(), kvs.end());  // pages of a node are handed out ascending
     if (!tix_row && !kv_sorted) std::sort(kvs.begin(), kvs.end());  // :736 (the tree-index table keeps page order)
-    for (size_t s0 = 0; s0 < q.size(); s0 += (size_t)max_q_len) {
+    for (size_t s0 = 0; s0 < q.size() && !native_only; s0 += (size_t)max_q_len) {
       const size_t s1 = std::min(q.size(), s0 + (size_t)max_q_len);
       for (i64 c0 = 0; c0 < n_kv; c0 += step) {
         const i64 c1 = std::min(n_kv, c0 + step);
@@ -330,18 +375,11 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
     }
     if (tix_row && !kv_sorted) std::sort(kvs.begin(), kvs.end());
-    for (i64 kvp : kvs) {   // the native tiler's token stream (DFS order); this step's tokens name their query instead of a page
-      i32 v = (i32)kvp;
-      if (fresh_page && !fresh_sorted.empty() && kvp >= fresh_sorted.front().first && kvp <= fresh_sorted.back().first) {
-        auto it = std::lower_bound(fresh_sorted.begin(), fresh_sorted.end(), std::make_pair((i32)kvp, (i32)-1));
-        if (it != fresh_sorted.end() && it->first == (i32)kvp) v = kFreshToken | it->second;
-      }
-      tok_page.push_back(v);
-      tok_node.push_back(n);
-    }
+    push_tokens();               // the native tiler's token stream (DFS order)
+    tok_node.insert(tok_node.end(), kvs.size(), n);
     // flatten packing (:763-788)
     i64 room = block_len - (i64)seg_tokens.size();
-    i64 done = 0;
+    i64 done = native_only ? n_kv : 0;
     while (done < n_kv) {
       if (n_kv - done < room) {
         seg_tokens.insert(seg_tokens.end(), kvs.begin() + done, kvs.end());
@@ -383,8 +421,6 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   //    consecutive pages; the DFS order just strings them node by node.  A group is padded to whole blocks with dummy
   //    tokens (page -1: a zero row nobody attends).  DEFT_PLAN_REGROUP=0: the rest keeps its DFS order.
   {
-    const char* env_r = std::getenv("DEFT_PLAN_REGROUP");
-    const bool regroup = fresh_page != nullptr || !(env_r && env_r[0] == '0');   // (fresh tokens need chunks of their own)
     // per node: the words of its attending ranks, slot by slot (CSR over the nodes), and the slots it touches as a key
     auto& nw_off = S.nw_off; auto& nw_slot = S.nw_slot; auto& nw_word = S.nw_word; auto& node_sig = S.node_sig;
     nw_off.assign((size_t)n_nodes + 1, 0);
@@ -668,22 +704,8 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
         emit_tile(&out_page[k], &out_node[k], (i32)std::min<size_t>(128, out_page.size() - k));
       return true;
     };
-    const size_t n_tok = tok_page.size();
-    i32 tree_i = 0, query_base = 0, nodes_before = 0;
-    for (size_t a = 0; a < n_tok; ++tree_i) {
-      // the tokens [a, b) of one tree (its nodes are consecutive in the pre-order; parent -1 starts the next tree)
-      deft_tree_t* ht = g_tree_hints && tree_i < g_n_tree_hints ? g_tree_hints[tree_i] : nullptr;
-      size_t b = a + 1;
-      if (ht) b = a + (size_t)ht->n_pages;
-      else
-        while (b < n_tok && !(tok_node[b] != tok_node[b - 1] && parent[tok_node[b]] == -1)) ++b;
-      const i32 node_base = ht ? nodes_before : tok_node[a];
-      if (ht) nodes_before += (i32)ht->parent.size();
-      if (ht && regroup && serve_kept(ht, node_base, query_base)) {
-        query_base += ht->query_num;
-        a = b;
-        continue;
-      }
+    // the tiles of the tree whose tokens are [a, b) of the stream, laid out from scratch (and the order kept, if it has a mirror)
+    auto layout_tree = [&](size_t a, size_t b, deft_tree_t* ht, i32 node_base, i32 query_base) {
       deft_tiler_cache* keep = nullptr;
       if (ht && regroup) {                   // this build's order is kept for the builds to come
         keep = &ht->tiler;
@@ -736,6 +758,31 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
       }
       for (size_t k = 0; k < out_page.size(); k += 128)
         emit_tile(&out_page[k], &out_node[k], (i32)std::min<size_t>(128, out_page.size() - k));
+    };
+    i32 tree_i = 0, query_base = 0, nodes_before = 0;
+    if (lazy_tokens) {
+      for (; tree_i < g_n_tree_hints; ++tree_i) {
+        deft_tree_t* ht = g_tree_hints[tree_i];
+        const i32 n_nodes_t = (i32)ht->parent.size();
+        if (!serve_kept(ht, nodes_before, query_base)) {
+          gen_tokens(nodes_before, nodes_before + n_nodes_t);
+          layout_tree(0, tok_page.size(), ht, nodes_before, query_base);
+        }
+        nodes_before += n_nodes_t;
+        query_base += ht->query_num;
+      }
+    }
+    const size_t n_tok = lazy_tokens ? 0 : tok_page.size();
+    for (size_t a = 0; a < n_tok; ++tree_i) {
+      // the tokens [a, b) of one tree (its nodes are consecutive in the pre-order; parent -1 starts the next tree)
+      deft_tree_t* ht = g_tree_hints && tree_i < g_n_tree_hints ? g_tree_hints[tree_i] : nullptr;
+      size_t b = a + 1;
+      if (ht) b = a + (size_t)ht->n_pages;
+      else
+        while (b < n_tok && !(tok_node[b] != tok_node[b - 1] && parent[tok_node[b]] == -1)) ++b;
+      const i32 node_base = ht ? nodes_before : tok_node[a];
+      if (ht) nodes_before += (i32)ht->parent.size();
+      if (!(ht && regroup && serve_kept(ht, node_base, query_base))) layout_tree(a, b, ht, node_base, query_base);
       if (ht) query_base += ht->query_num;
       a = b;
     }
@@ -1367,6 +1414,9 @@ deft_tables_t* deft_b200_build_tables_trees(deft_tree_t* const* trees, int32_t n
 }
 
 deft_layout_t* deft_b200_layout_new(void) { return new (std::nothrow) deft_layout_t(); }
+void deft_b200_layout_set_native_only(deft_layout_t* l, int on) {
+  if (l) l->native_only = on ? 1 : 0;
+}
 void deft_b200_layout_free(deft_layout_t* l) { delete l; }
 int64_t deft_b200_layout_version(const deft_layout_t* l) { return l ? l->version : -1; }
 

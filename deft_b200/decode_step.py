@@ -30,12 +30,15 @@ class DecodeStepGraph:
 
     def __init__(self, kv_pool, qkv: torch.Tensor, out: torch.Tensor, cache_loc: torch.Tensor, num_heads: int,
                  num_kv_heads: int, head_dim: int, mode: str = "flatten", chunk: int = 8,
-                 table_bytes: int = 8 << 20, fused_append: bool = True) -> None:
+                 table_bytes: int = 8 << 20, fused_append: bool = True, reference_tables: bool = False) -> None:
         """``qkv``: [layers, nq, (H + 2 HKV) D] fp16 device buffer the fused projections land in; ``out``: [layers, nq,
         H, D]; ``cache_loc``: [nq] int32 device buffer with this step's page per query (all three keep their
         addresses; their contents change every step).  ``mode``: flatten | node | node_chunk.  ``fused_append``: the
         step's K/V rows are read by the attention straight from ``qkv`` and written to their pages by its second
-        kernel (``metadata(trees, cache_loc=...)`` marks them), instead of a ``kv_append`` launch per layer."""
+        kernel (``metadata(trees, cache_loc=...)`` marks them), instead of a ``kv_append`` launch per layer.
+        ``reference_tables``: also build and upload the reference's int64 tables (``block_q``, ``node_kv`` ... of the
+        ``TreeMetadata`` that ``metadata()`` returns); the step itself only reads the native plan, so by default -- on
+        the geometries of the tensor-core kernels -- they are left empty."""
         assert mode in ("flatten", "node", "node_chunk")
         self.kv_pool, self.qkv, self.out, self.loc = kv_pool, qkv, out, cache_loc
         self.H, self.HKV, self.D, self.mode = num_heads, num_kv_heads, head_dim, mode
@@ -45,7 +48,8 @@ class DecodeStepGraph:
         self.chunk = max(1, min(chunk, self.layers))
         self.n_chunks = (self.layers + self.chunk - 1) // self.chunk
         self.tables = torch.empty(table_bytes, dtype=torch.uint8, device=qkv.device)
-        self.table_layout = TableLayout()
+        tensor_core = head_dim in (64, 128) and num_heads // num_kv_heads in (1, 2, 4)
+        self.table_layout = TableLayout(native_only=tensor_core and not reference_tables)
         self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=qkv.device)
         self._graphs: "OrderedDict[bytes, List[torch.cuda.CUDAGraph]]" = OrderedDict()
         self.captures = 0
@@ -104,10 +108,10 @@ class DecodeStepGraph:
         if self.mode == "flatten":
             attention.tree_attention_subtree_fwd(q, K, V, self.out[l], m.block_len, m.block_q, m.block_q_cnts,
                                                  m.block_q_offset, m.block_bitmasks, m.block_kv, m.block_lens,
-                                                 workspace=self.workspace, append=append)
+                                                 plan=m.flat_plan, workspace=self.workspace, append=append)
         else:
             attention.tree_attention_fwd(q, K, V, self.out[l], m.node_kv, m.node_kv_offset, m.node_kv_len, m.node_q,
-                                         m.node_q_offset, m.node_q_len, workspace=self.workspace, append=append)
+                                         m.node_q_offset, m.node_q_len, plan=m.node_plan, workspace=self.workspace, append=append)
 
     def _capture(self, m: TreeMetadata) -> List[torch.cuda.CUDAGraph]:
         self._layer(0, m)                     # eager once: tensor maps, launch attributes and errors outside the capture

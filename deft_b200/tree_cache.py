@@ -601,10 +601,16 @@ class TableLayout:
     region the packed buffer keeps its offsets from one decode step to the next -- what a captured CUDA graph of the
     step needs -- although every step appends a page per leaf.  ``version`` moves when a region had to grow."""
 
-    def __init__(self) -> None:
+    def __init__(self, native_only: bool = False) -> None:
+        """``native_only``: builds with this layout make the native unit plan only -- the reference's twelve tables and
+        the item / group plans of the warp-FMA path stay empty (a third of the build and two thirds of the upload).
+        For decode loops that call the operators themselves on a tensor-core geometry (``DecodeStepGraph``)."""
         self.handle = _lib.lib.deft_b200_layout_new()
         if not self.handle:
             raise MemoryError("deft_b200_layout_new failed")
+        self.native_only = bool(native_only)
+        if native_only:
+            _lib.lib.deft_b200_layout_set_native_only(self.handle, 1)
 
     @property
     def version(self) -> int:

@@ -313,6 +313,11 @@ typedef struct deft_layout deft_layout_t;
 deft_layout_t* deft_b200_layout_new(void);
 void deft_b200_layout_free(deft_layout_t* layout);
 int64_t deft_b200_layout_version(const deft_layout_t* layout);
+/* on != 0 (set before the first build with the handle): builds leave the twelve reference tables and the item / group
+ * plans EMPTY and make the native unit plan only -- all that deft_b200_*_fwd(_append) read on the tensor-core path
+ * when they are given the plan (their table pointers may then be NULL, their counts 0).  For decode loops that call
+ * the operators themselves (DecodeStepGraph); what the reference's own code reads from TreeMetadata is not there. */
+void deft_b200_layout_set_native_only(deft_layout_t* layout, int on);
 
 deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, const int64_t* kv_off,
                                       const int64_t* kv, const int64_t* q_off, const int64_t* qs,

@@ -353,7 +353,7 @@ def test_decode_step_graph_replays_with_new_table_contents(dev):
     qkv = torch.empty(L, nq, (H + 2 * HKV) * D, dtype=torch.float16, device=dev)
     out = torch.empty(L, nq, H, D, dtype=torch.float16, device=dev)
     loc = torch.zeros(nq, dtype=torch.int32, device=dev)
-    step = deft_b200.DecodeStepGraph(kvp, qkv, out, loc, H, HKV, D, mode="flatten", chunk=2)
+    step = deft_b200.DecodeStepGraph(kvp, qkv, out, loc, H, HKV, D, mode="flatten", chunk=2, reference_tables=True)
     layouts = set()
     for it, tree in enumerate([trees[0], trees[1], trees[0]]):
         qkv.normal_()
@@ -451,7 +451,8 @@ def test_decode_step_graph_survives_the_tree_growing(dev, mode, fused):
     qkv = torch.empty(L, nq, (H + 2 * HKV) * D, dtype=torch.float16, device=dev)
     out = torch.empty(L, nq, H, D, dtype=torch.float16, device=dev)
     loc = torch.zeros(nq, dtype=torch.int32, device=dev)
-    step = deft_b200.DecodeStepGraph(kvp, qkv, out, loc, H, HKV, D, mode=mode, chunk=1)
+    # (the unfused variant also keeps the reference's tables in the step's metadata; by default they are left empty)
+    step = deft_b200.DecodeStepGraph(kvp, qkv, out, loc, H, HKV, D, mode=mode, chunk=1, reference_tables=not fused)
     for it in range(steps):
         for leaf in tree.leaves.values():
             leaf.append_token(7)
@@ -465,7 +466,10 @@ def test_decode_step_graph_survives_the_tree_growing(dev, mode, fused):
         m2 = TreeMetadata.from_tree_cache(tree)                 # tight packing, fresh buffer, plain plan
         assert m2.total_kv_len == m.total_kv_len == 2048 + 64 * (it + 2)
         for k in ("block_q", "block_kv", "block_bitmasks", "node_kv", "node_q", "node_kv_len"):
-            assert torch.equal(getattr(m, k), getattr(m2, k)), (it, k)
+            if fused:
+                assert getattr(m, k).numel() == 0, (it, k)
+            else:
+                assert torch.equal(getattr(m, k), getattr(m2, k)), (it, k)
         want = torch.empty_like(out)
         for l in range(L):
             q = qkv[l, :, : H * D].view(nq, H, D)

@@ -437,6 +437,8 @@ def test_kept_tile_order_of_a_growing_tree(seed):
     for _ in range(rng.choice([1, 16])):
         step()
     branch_some((2, 3, 4) if seed % 2 else (2,))
+    from deft_b200.tree_cache import TableLayout
+    lean_layout = TableLayout(native_only=True)
     kept_steps = 0
     for it in range(45):
         if it in (17, 31):                     # the topology moves: the mirror is handed over again, the order made anew
@@ -454,6 +456,12 @@ def test_kept_tile_order_of_a_growing_tree(seed):
         t, t0 = unpack(got[0], got[1]), unpack(want[0], want[1])
         for k in TABLE_KEYS:
             assert np.array_equal(t[k], t0[k]), (it, k)
+        # a native-only layout on the same mirror (no token stream is made at all when the kept order serves): same unit plan
+        lean = build_tables_host(mirror_flat([tree]), hkv=2, n_ctas=148, fresh_page=fresh if use_fresh else None, layout=lean_layout)
+        tl = unpack(lean[0], lean[1])
+        for name in _lib.T_NAMES[20:]:
+            assert np.array_equal(t[name], tl[name]), (it, name)
+        assert all(len(tl[k]) == 0 for k in TABLE_KEYS) and lean[2][2] == got[2][2]
         dec, kinds = _decode_fresh(t, fresh if use_fresh else None)
         check_unit_plan(dec, got[2], tree, 2, 148)
         _, kinds0 = _decode_fresh(t0, fresh if use_fresh else None)
@@ -505,3 +513,31 @@ def test_kept_tile_order_of_a_forest():
         dec, _ = _decode_fresh(t, fresh)
         check_unit_plan(dec, got[2], trees, 2, 148)
     assert sum(t.native_tree().syncs for t in trees) == 5
+
+
+def test_native_only_layout_leaves_the_reference_tables_empty():
+    """deft_b200_layout_set_native_only: the unit plan (all the tensor-core path reads) is byte for byte the one of the
+    full build, the twelve reference tables and the item / group plans are empty, the upload is a third."""
+    import torch
+    from deft_b200.tree_cache import TableLayout
+    from deft_b200.workloads import build_tree
+    tree = build_tree("cfg2", layers=1, device=torch.device("cpu"), headroom=64 * 8)
+    full_l, lean_l = TableLayout(), TableLayout(native_only=True)
+    for it in range(3):
+        for leaf in tree.leaves.values():
+            leaf.append_token(1)
+        fresh = tree.alloc().cache_loc.numpy().astype(np.int32)
+        flat = flatten_tree(tree)
+        full = build_tables_host(flat, hkv=8, n_ctas=148, layout=full_l, fresh_page=fresh)
+        lean = build_tables_host(flat, hkv=8, n_ctas=148, layout=lean_l, fresh_page=fresh)
+        t, tl = unpack(full[0], full[1]), unpack(lean[0], lean[1])
+        for i, name in enumerate(_lib.T_NAMES):
+            if i < 20:
+                assert len(tl[name]) == (65 if name.endswith("csr_off") else 0), name      # (an empty CSR still has its offsets)
+            else:
+                assert np.array_equal(t[name], tl[name]), name
+        assert lean[2][0] == 64 and lean[2][2] == full[2][2] and lean[2][4] == 0 and lean[2][5] == 0
+        assert np.array_equal(full[2][6:], lean[2][6:])
+        dec, _ = _decode_fresh(tl, fresh)
+        check_unit_plan(dec, lean[2], tree, 8, 148)
+        assert len(lean[0]) < 0.45 * len(full[0])
