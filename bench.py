@@ -247,7 +247,7 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
     from deft_b200.workloads import build_forest, n_leaves
 
     torch.manual_seed(1234 + rank)
-    grow_steps = 0 if args.e2e_static else 2 * (3 + e2e_steps) + 2 + (50 if args.profile_e2e else 0)     # pipelined + serial legs
+    grow_steps = 0 if args.e2e_static else 2 * (3 + e2e_steps) + 14 + (50 if args.profile_e2e else 0)     # pipelined + serial legs
     trees = build_forest(workload, T, layers=pools, device=dev, headroom=64 + n_leaves(workload) * grow_steps)
     kvp = trees[0].token_to_kv_pool
     for l in range(pools):
@@ -312,14 +312,19 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_wall = []       # host wall time of every step of the last timed() call (the end-to-end steps end synchronised)
+
     def timed(fn, n, w):
         for _ in range(w):
             fn()
         barrier()
+        del step_wall[:]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
+            t0 = time.perf_counter()
             fn()
+            step_wall.append((time.perf_counter() - t0) * 1e3)
         e1.record()
         barrier()
         return max_over_ranks(e0.elapsed_time(e1), dev) / n
@@ -462,6 +467,13 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
         if graphed:                                      # (the ring path of a 512-tree forest: one leg is long enough)
             ms_serial = timed(step_e2e, e2e_steps, 3)
         prepare_next()
+        if os.environ.get("DEFT_BENCH_STEP_TIMES") and graphed:     # diagnostic: host wall time and captures of every step
+            import time as _time
+            for i in range(12):
+                t0 = _time.perf_counter()
+                step_e2e_pipelined()
+                print("step %d: %.2f ms, captures %d, table bytes %d" % (i, (_time.perf_counter() - t0) * 1e3, pipe.captures, table_bytes[0]),
+                      file=sys.stderr)
         ms_e2e = timed(step_e2e_pipelined, e2e_steps, 3)
         if args.profile_e2e and rank == 0 and graphed and not args.e2e_static:
             import cProfile
@@ -477,7 +489,9 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
         ms_e2e = timed(step_e2e, e2e_steps, 3)
     h2d = LAYERS * nq * (H + 2 * HKV) * D * 2 + table_bytes[0] + host_loc.numel() * 4
     d2h = LAYERS * nq * H * D * 2
+    wall = sorted(step_wall)
     res = dict(ms_step=ms_step, ms_s1=ms_s1, ms_s2=ms_s2, ms_e2e=ms_e2e, ms_e2e_serial=ms_serial,
+               e2e_wall=dict(median_ms=wall[len(wall) // 2], max_ms=wall[-1], min_ms=wall[0]),
                h2d=h2d, d2h=d2h, nq=nq, clocks=clocks,
                pool_mb=kvp.kv_data[0].numel() * 2 / 1e6, graphed=graphed, pipelined=args.mode != "seq" and not args.e2e_serial,
                captures=(step.captures + pipe.captures) if graphed else None, e2e_chunks=n_chunks, e2e_steps=e2e_steps,
@@ -553,7 +567,7 @@ def main():
 
     warm = max(args.warmup, 3)
     T = max(1, args.trees_per_gpu)
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(3 * args.steps, 60))       # (a decode loop: long enough for the rare table re-layouts to weigh what they weigh)
     r = measure(args, dev, rank, world, args.workload, T, LAYERS, args.steps, warm, e2e_steps, args.e2e_chunk, True)
     torch.cuda.empty_cache()
 
@@ -607,6 +621,7 @@ def main():
                         "%d KV tokens per tree at the end of the run" % (r["kv_tokens_end"] // T),
                 "graph_captures": r["captures"],
                 "ms_per_step_serial": r["ms_e2e_serial"],
+                "host_wall_per_step": r["e2e_wall"],
                 "pipelining": ("DecodeStepPipeline: alloc + table build + table upload of step t+1 run on the host while the layers of "
                                "step t run (two table buffers; the tables depend on the tree, not on the tokens step t samples); every "
                                "step still ends with its outputs on the host before the next step's activations go up; "

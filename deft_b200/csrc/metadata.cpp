@@ -1265,12 +1265,16 @@ deft_tables_t* deft_b200_build_tables(int32_t n_nodes, const int32_t* parent, co
   if (layout) {   // capacity-padded regions: offsets only move when a table outgrows its region
     bool grow = n_unit_slots > layout->slot_cap;
     for (int i = 0; i < DEFT_T_COUNT; ++i) grow = grow || (i64)((src[i].n * src[i].elem + 255) / 256 * 256) > layout->cap_bytes[i];
-    if (grow) {     // ... and then every region takes its headroom afresh: the tables grow together, so do the layouts
+    if (grow) {     // ... and then every region takes its headroom afresh: the tables grow together, so do the layouts.
+      // What moving costs is a re-capture of the decode step's CUDA graphs (3-5 ms, measured: more than three steps),
+      // what headroom costs is upload bytes: +50 % for the reference's big int64 tables, +100 % (and 4 KB: the job
+      // and unit tables move in jumps when the plan search changes the piece length) for the small native ones.
       for (int i = 0; i < DEFT_T_COUNT; ++i) {
         const size_t region = (src[i].n * src[i].elem + 255) / 256 * 256;
-        layout->cap_bytes[i] = std::max<i64>(layout->cap_bytes[i], (i64)((region + region / 4 + 1024 + 255) / 256 * 256));
+        const size_t want = i < 12 ? region + region / 2 + 1024 : 2 * region + 4096;
+        layout->cap_bytes[i] = std::max<i64>(layout->cap_bytes[i], (i64)((want + 255) / 256 * 256));
       }
-      layout->slot_cap = std::max<i64>(layout->slot_cap, n_unit_slots + n_unit_slots / 4 + 8);
+      layout->slot_cap = std::max<i64>(layout->slot_cap, n_unit_slots + n_unit_slots / 2 + 8);
       ++layout->version;
     }
   }

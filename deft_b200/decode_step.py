@@ -52,6 +52,7 @@ class DecodeStepGraph:
         self.table_layout = TableLayout(native_only=tensor_core and not reference_tables)
         self.workspace = torch.empty(1 << 20, dtype=torch.uint8, device=qkv.device)
         self._graphs: "OrderedDict[bytes, List[torch.cuda.CUDAGraph]]" = OrderedDict()
+        self._capture_stream: Optional[torch.cuda.Stream] = None
         self.captures = 0
 
     # ---- tables -------------------------------------------------------------------------------
@@ -114,15 +115,30 @@ class DecodeStepGraph:
                                          m.node_q_offset, m.node_q_len, plan=m.node_plan, workspace=self.workspace, append=append)
 
     def _capture(self, m: TreeMetadata) -> List[torch.cuda.CUDAGraph]:
-        self._layer(0, m)                     # eager once: tensor maps, launch attributes and errors outside the capture
-        torch.cuda.current_stream().synchronize()
+        """The step's launches into one CUDA graph per chunk of layers.  A re-capture happens in the middle of a decode
+        loop (a table outgrew its region), so it must not stall it: ``capture_begin`` / ``capture_end`` on a side
+        stream, without the device-wide synchronize + ``empty_cache`` that ``torch.cuda.graph`` puts in front of every
+        capture (measured: 3-20 ms per capture, a 0.8 s stall once) -- the launches allocate nothing."""
+        cur = torch.cuda.current_stream()
+        if self.captures == 0:
+            self._layer(0, m)                 # eager once: launch attributes, tensor maps and errors outside the capture
+            cur.synchronize()
+        if self._capture_stream is None:
+            self._capture_stream = torch.cuda.Stream(device=self.qkv.device)
+        side = self._capture_stream
+        side.wait_stream(cur)
         graphs = []
-        for c in range(self.n_chunks):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for l in range(c * self.chunk, min(self.layers, (c + 1) * self.chunk)):
-                    self._layer(l, m)
-            graphs.append(g)
+        with torch.cuda.stream(side):
+            for c in range(self.n_chunks):
+                g = torch.cuda.CUDAGraph()
+                g.capture_begin(capture_error_mode="thread_local")
+                try:
+                    for l in range(c * self.chunk, min(self.layers, (c + 1) * self.chunk)):
+                        self._layer(l, m)
+                finally:
+                    g.capture_end()
+                graphs.append(g)
+        cur.wait_stream(side)
         self.captures += 1
         return graphs
 
