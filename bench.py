@@ -61,8 +61,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the 512-tree batch block (BASELINE configs[4])")
     ap.add_argument("--cfg5-trees", type=int, default=CFG5_TREES, help="trees of the cfg5 block over ALL ranks")
-    ap.add_argument("--e2e-chunk", type=int, default=8, choices=[1, 2, 4, 8, 16, 32],
-                    help="layers per H2D / graph / D2H chunk of the end-to-end leg")
+    ap.add_argument("--e2e-chunk", type=int, default=4, choices=[1, 2, 4, 8, 16, 32],
+                    help="layers per H2D / graph / D2H chunk of the end-to-end leg (4: what is not overlapped -- the first "
+                         "chunk up, the last one down -- is an eighth of the step's copies; measured 2 / 4 / 8 / 16: "
+                         "cfg2 1.10 / 0.91 / 0.98 / 1.16 ms, cfg4 2.94 / 3.08 / 3.42 / - ms per step)")
     ap.add_argument("--profile-e2e", default=None, metavar="FILE",
                     help="cProfile of 50 end-to-end steps (host side) written to FILE; diagnostic, not a bench value")
     ap.add_argument("--e2e-serial", action="store_true", help="end-to-end leg without the table build of step t+1 under step t")
@@ -577,7 +579,7 @@ def main():
         pool_bytes = (ws.unique_kv_tokens("cfg2") + 64 + 64 * 8) * T5 * 2 * HKV * D * 2
         pools5 = int(max(2, min(LAYERS, (56 << 30) // pool_bytes)))
         steps5, e2e5 = max(3, min(args.steps, 5)), 3
-        c = measure(args, dev, rank, world, "cfg2", T5, pools5, steps5, 3, e2e5, 2 if T5 > 64 else 8, False)
+        c = measure(args, dev, rank, world, "cfg2", T5, pools5, steps5, 3, e2e5, 2 if T5 > 64 else 4, False)
         torch.cuda.empty_cache()
         rf = roofline("cfg2", T5, c["ms_s1"], "flatten")
         cfg5 = {"workload": f"BASELINE configs[4]: {args.cfg5_trees} independent cfg2 trees sharded over {world} GPU(s)",
