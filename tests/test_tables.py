@@ -499,6 +499,8 @@ def test_kept_tile_order_of_a_forest():
     for it in range(24):
         if it == 9:
             trees[1].branch(sorted(trees[1].leaves.values(), key=lambda x: x.id)[0], 3)   # the queries of trees 2, 3 move up
+        if it == 15:       # pages come back to the pool: the next alloc of EVERY tree takes them (lower than what it holds)
+            trees[0].cut(sorted(trees[0].leaves.values(), key=lambda x: x.id)[-1])
         locs = []
         for tree in trees:
             for leaf in tree.leaves.values():
@@ -512,7 +514,7 @@ def test_kept_tile_order_of_a_forest():
             assert np.array_equal(t[k], t0[k]), (it, k)
         dec, _ = _decode_fresh(t, fresh)
         check_unit_plan(dec, got[2], trees, 2, 148)
-    assert sum(t.native_tree().syncs for t in trees) == 5
+    assert sum(t.native_tree().syncs for t in trees) == 6
 
 
 def test_native_only_layout_leaves_the_reference_tables_empty():
