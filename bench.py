@@ -464,10 +464,12 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
         main.synchronize()                               # the caller reads the result on the host
 
     ms_serial = None
+    wall_serial = None
     ring_ready = [None]
     if args.mode != "seq" and not args.e2e_serial:
         if graphed:                                      # (the ring path of a 512-tree forest: one leg is long enough)
             ms_serial = timed(step_e2e, e2e_steps, 3)
+            wall_serial = sorted(step_wall)
         prepare_next()
         if os.environ.get("DEFT_BENCH_STEP_TIMES") and graphed:     # diagnostic: host wall time and captures of every step
             import time as _time
@@ -494,6 +496,8 @@ def measure(args, dev, rank, world, workload: str, T: int, pools: int, steps: in
     wall = sorted(step_wall)
     res = dict(ms_step=ms_step, ms_s1=ms_s1, ms_s2=ms_s2, ms_e2e=ms_e2e, ms_e2e_serial=ms_serial,
                e2e_wall=dict(median_ms=wall[len(wall) // 2], max_ms=wall[-1], min_ms=wall[0]),
+               e2e_wall_serial=None if not wall_serial else dict(median_ms=wall_serial[len(wall_serial) // 2],
+                                                                 max_ms=wall_serial[-1], min_ms=wall_serial[0]),
                h2d=h2d, d2h=d2h, nq=nq, clocks=clocks,
                pool_mb=kvp.kv_data[0].numel() * 2 / 1e6, graphed=graphed, pipelined=args.mode != "seq" and not args.e2e_serial,
                captures=(step.captures + pipe.captures) if graphed else None, e2e_chunks=n_chunks, e2e_steps=e2e_steps,
@@ -624,6 +628,7 @@ def main():
                 "graph_captures": r["captures"],
                 "ms_per_step_serial": r["ms_e2e_serial"],
                 "host_wall_per_step": r["e2e_wall"],
+                "host_wall_per_step_serial": r["e2e_wall_serial"],
                 "pipelining": ("DecodeStepPipeline: alloc + table build + table upload of step t+1 run on the host while the layers of "
                                "step t run (two table buffers; the tables depend on the tree, not on the tokens step t samples); every "
                                "step still ends with its outputs on the host before the next step's activations go up; "
