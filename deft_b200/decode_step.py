@@ -9,8 +9,8 @@ What a captured launch holds is device ADDRESSES (tables, workspace, activations
 pairing); every count the kernels need they read from the tables themselves (job records, CSR bounds).  A real
 decode loop appends a page per leaf every step (``TreeCache.alloc``, tree_generate.py:109), so every table grows a
 little: the step therefore builds its tables with a ``TableLayout`` (capacity-padded regions in ONE persistent device
-buffer, ``deft_layout_t``) -- the offsets only move when a table outgrows its region (~ every 25 % of growth), and
-only then is the step captured again.  The workspace is owned by the step and sized for the layout's slot capacity.
+buffer, ``deft_layout_t``) -- the offsets only move when a table outgrows its region (the small native tables take
+100 % of headroom), and only then is the step captured again.  The workspace is owned by the step and sized for the layout's slot capacity.
 This is SURVEY.md 8(f) items 1 (tables that follow the tree incrementally) and 4 (graph'd decode step).
 """
 from __future__ import annotations

@@ -307,7 +307,7 @@ typedef struct deft_tables deft_tables_t;
 /* Capacity-padded packing.  A decode step appends one page per leaf (tree_generate.py:109), so every table grows a
  * little from step to step; packed tightly, their offsets move and whatever holds device addresses of the tables (a
  * captured CUDA graph of the step) dies.  A layout handle remembers a capacity per table: a table that fits keeps its
- * offset, one that outgrows its region takes ~25 % more than it needs and moves deft_b200_layout_version() on.  NULL
+ * offset, one that outgrows its region takes 50-100 % more than it needs and moves deft_b200_layout_version() on.  NULL
  * packs tightly.  One handle per decode loop, used by one thread at a time. */
 typedef struct deft_layout deft_layout_t;
 deft_layout_t* deft_b200_layout_new(void);
