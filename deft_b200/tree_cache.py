@@ -239,10 +239,16 @@ class TreeCache:
         if m is None:
             m = self._mirror = _NativeTree()
         key = self._mirror_key()
-        if m.key != key or m.n_pages != sum(map(len, m.lists)):     # (the sum catches in-place edits of a page list)
+        # (the sum catches in-place edits of a page list that change its length; code that rewrites pages in place
+        # without going through the tree calls invalidate_native_tree())
+        if m.key != key or m.n_pages != sum(map(len, m.lists)):
             m.sync(self, flatten_tree(self))
             m.key = key
         return m
+
+    def invalidate_native_tree(self) -> None:
+        """Forces a full hand-over of the tree at the next table build."""
+        self._pages_epoch += 1
 
     # ---- mutation -------------------------------------------------------------------------
     def merge_nodes(self, node_A: TreeNode, node_B: TreeNode, pruneB_flag: Optional[bool] = True) -> None:

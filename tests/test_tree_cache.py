@@ -361,6 +361,12 @@ def test_native_tree_mirror_follows_the_tree(monkeypatch):
         check(what)
         step()                                  # (and the append path right after the re-sync)
         check(what + " + alloc")
+    leaf = sorted(tree.leaves.values(), key=lambda x: x.id)[0]
+    leaf.kv_indices[-1], leaf.kv_indices[-2] = leaf.kv_indices[-2], leaf.kv_indices[-1]      # same length: only an explicit call tells
+    syncs = tree.native_tree().syncs
+    tree.invalidate_native_tree()
+    check("rewritten in place")
+    assert tree.native_tree().syncs == syncs + 1
     monkeypatch.setenv("DEFT_NATIVE_TREE", "0")
     assert mirror_flat([tree]) is None          # the switch: flat arrays, as for a foreign tree object
 
