@@ -29,11 +29,12 @@ class DecodeStepGraph:
     MAX_LAYOUTS = 4      # captured layouts kept (least recently used goes first)
 
     def __init__(self, kv_pool, qkv: torch.Tensor, out: torch.Tensor, cache_loc: torch.Tensor, num_heads: int,
-                 num_kv_heads: int, head_dim: int, mode: str = "flatten", chunk: int = 8,
+                 num_kv_heads: int, head_dim: int, mode: str = "flatten", chunk=8,
                  table_bytes: int = 8 << 20, fused_append: bool = True, reference_tables: bool = False) -> None:
         """``qkv``: [layers, nq, (H + 2 HKV) D] fp16 device buffer the fused projections land in; ``out``: [layers, nq,
         H, D]; ``cache_loc``: [nq] int32 device buffer with this step's page per query (all three keep their
-        addresses; their contents change every step).  ``mode``: flatten | node | node_chunk.  ``fused_append``: the
+        addresses; their contents change every step).  ``mode``: flatten | node | node_chunk.  ``chunk``: layers per CUDA
+        graph, or the list of chunk sizes.  ``fused_append``: the
         step's K/V rows are read by the attention straight from ``qkv`` and written to their pages by its second
         kernel (``metadata(trees, cache_loc=...)`` marks them), instead of a ``kv_append`` launch per layer.
         ``reference_tables``: also build and upload the reference's int64 tables (``block_q``, ``node_kv`` ... of the
@@ -45,8 +46,16 @@ class DecodeStepGraph:
         self.layers = qkv.shape[0]
         # (the fused append lives in the tensor-core kernels: other geometries append with kv_append launches)
         self.fused_append = fused_append and head_dim in (64, 128) and num_heads // num_kv_heads in (1, 2, 4)
-        self.chunk = max(1, min(chunk, self.layers))
-        self.n_chunks = (self.layers + self.chunk - 1) // self.chunk
+        if isinstance(chunk, (list, tuple)):          # chunk sizes given one by one (e.g. a short first and last chunk)
+            sizes = [int(c) for c in chunk]
+            assert sizes and min(sizes) >= 1 and sum(sizes) == self.layers, "chunk sizes must add up to the layers"
+        else:
+            size = max(1, min(int(chunk), self.layers))
+            sizes = [min(size, self.layers - l) for l in range(0, self.layers, size)]
+        self.bounds = [0]
+        for c in sizes:
+            self.bounds.append(self.bounds[-1] + c)
+        self.n_chunks = len(sizes)
         self.tables = torch.empty(table_bytes, dtype=torch.uint8, device=qkv.device)
         tensor_core = head_dim in (64, 128) and num_heads // num_kv_heads in (1, 2, 4)
         self.table_layout = TableLayout(native_only=tensor_core and not reference_tables)
@@ -133,7 +142,7 @@ class DecodeStepGraph:
                 g = torch.cuda.CUDAGraph()
                 g.capture_begin(capture_error_mode="thread_local")
                 try:
-                    for l in range(c * self.chunk, min(self.layers, (c + 1) * self.chunk)):
+                    for l in range(self.bounds[c], self.bounds[c + 1]):
                         self._layer(l, m)
                 finally:
                     g.capture_end()
