@@ -385,10 +385,11 @@ def _decode_fresh(t, fresh):
         assert not is_fresh.any()
     else:
         assert sorted((u_kv[is_fresh] & ~FRESH).tolist()) == list(range(len(fresh))), "every query's new token exactly once"
-        tail = np.ones(len(u_kv), dtype=bool)                                 # past the live tokens of a tree's last tile: zeros
-        for u in t["u_units"]:
-            n_tok = (int(u["n_tiles"]) - 1) * 128 + int(u["last_len"])
-            tail[int(u["kv_off"]): int(u["kv_off"]) + n_tok] = False
+        # past the live tokens of a tree's last tile: zeros (nobody attends them; such a tile can sit in the middle of a
+        # chain when small trees share a slot)
+        tiles = u_kv.reshape(-1, 128)
+        n_live = np.where((tiles != 0).any(axis=1), 128 - np.argmax(tiles[:, ::-1] != 0, axis=1), 0)
+        tail = (np.arange(128)[None, :] >= n_live[:, None]).reshape(-1)
         for c4 in np.flatnonzero(is_fresh.reshape(-1, 4).any(axis=1)):       # gather granularity: all fresh, or dummies
             four = u_kv[4 * c4: 4 * c4 + 4]
             assert np.all(((four & FRESH) != 0) | (four < 0) | tail[4 * c4: 4 * c4 + 4]), four
@@ -543,3 +544,48 @@ def test_native_only_layout_leaves_the_reference_tables_empty():
         dec, _ = _decode_fresh(tl, fresh)
         check_unit_plan(dec, lean[2], tree, 8, 148)
         assert len(lean[0]) < 0.45 * len(full[0])
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_kept_tile_order_under_random_operations(seed):
+    """One to three trees over one pool; every step one of branch / cut / merge (or none), a token and a page per leaf,
+    then a build from the mirrors -- with or without the step's tokens marked fresh, tight or native-only, for 148 / 16 /
+    7 CTAs: the plan attends every (query, page) pair once, the reference tables are the flat-array builder's."""
+    import torch
+    from deft_b200.memory_pool import ReqToTokenPool, TokenToKVPool
+    from deft_b200.tree_cache import TableLayout, TreeCache, flatten_forest, mirror_flat
+    rng = random.Random(1000 + seed)
+    r2t = ReqToTokenPool(size=2048, max_context_len=4096, device="cpu")
+    kvp = TokenToKVPool(size=1 << 17, dtype=torch.float16, head_num=2, head_dim=16, layer_num=1, device="cpu")
+    trees = []
+    for _ in range(rng.choice([1, 2, 3])):
+        tree = TreeCache(torch.float16, 2, 16, 1, r2t, kvp, None, True, False)
+        tree.init_prompt(torch.arange(rng.choice([1, 7, 127, 128, 129, 300, 900]), dtype=torch.int32))
+        trees.append(tree)
+    lean = TableLayout(native_only=True)
+    for it in range(40):
+        op, tree = rng.random(), rng.choice(trees)
+        leaves = sorted(tree.leaves.values(), key=lambda x: x.id)
+        if op < 0.12 and sum(len(t.leaves) for t in trees) < 150:
+            tree.branch(rng.choice(leaves), rng.choice((2, 3, 4, 7)))
+        elif op < 0.18 and len(leaves) > 2:
+            tree.cut(rng.choice(leaves))
+        elif op < 0.22 and len(leaves) > 3:
+            a, b = rng.sample(leaves, 2)
+            tree.merge_nodes(a, b, pruneB_flag=True)
+        locs = []
+        for t_ in trees:
+            for leaf in t_.leaves.values():
+                leaf.append_token(1)
+            locs.append(t_.alloc().cache_loc.numpy().astype(np.int32))
+        fresh = np.concatenate(locs) if rng.random() < 0.6 else None
+        layout = lean if rng.random() < 0.5 else None
+        got = build_tables_host(mirror_flat(trees), hkv=2, n_ctas=rng.choice([148, 16, 7]), fresh_page=fresh, layout=layout)
+        t = unpack(got[0], got[1])
+        dec, _ = _decode_fresh(t, fresh)
+        check_unit_plan(dec, got[2], trees if len(trees) > 1 else trees[0], 2, int(got[2][7]))
+        if layout is None:
+            want = build_tables_host(flatten_forest(trees) if len(trees) > 1 else flatten_tree(trees[0]), hkv=2, fresh_page=fresh)
+            t0 = unpack(want[0], want[1])
+            for k in TABLE_KEYS:
+                assert np.array_equal(t[k], t0[k]), (it, k)
